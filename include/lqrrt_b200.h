@@ -1,0 +1,197 @@
+/*
+ * lqrrt_b200 -- C ABI of the B200 tree-expansion engine.
+ *
+ * This is the drop-in boundary for the hot path of jnez71/lqRRT: the body of
+ * the `while True:` loop of Planner.update_plan (reference
+ * lqrrt/planner.py:233-290) and the functions it calls.  The reference is pure
+ * Python and has no FFI of its own; each entry point below names the reference
+ * code it replaces, and INTEGRATION.md shows the ctypes binding a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *   - every function returns int: 0 = LQ_OK, < 0 = error; nothing throws.
+ *     lq_last_error(h) returns a NUL-terminated message owned by the handle
+ *     (or a static string when h is NULL).
+ *   - `h_*` pointers are HOST memory valid for the duration of the call and are
+ *     always float64 / int32 regardless of the engine dtype (the reference's
+ *     own types).  `d_*` pointers are DEVICE memory owned by the caller (e.g. a
+ *     torch tensor's data_ptr) holding the engine dtype (float or double).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - matrices are row-major; node-major host arrays are (count x n).
+ *   - one engine = one GPU = one host thread at a time (the reference runs
+ *     update_plan on the caller's thread, planner.py:104).
+ */
+#ifndef LQRRT_B200_H
+#define LQRRT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LQ_ABI_VERSION 1
+#define LQ_MAX_N 12          /* states   */
+#define LQ_MAX_M 6           /* controls */
+#define LQ_MAX_PRIMS 8
+
+enum { LQ_OK = 0, LQ_ERR_ARG = -1, LQ_ERR_CUDA = -2, LQ_ERR_STATE = -3, LQ_ERR_UNSUPPORTED = -4 };
+enum { LQ_F32 = 0, LQ_F64 = 1 };
+
+/* dynamics(x, u, dt) -- reference contract planner.py:35-37 */
+enum { LQ_SYS_BOAT = 1,              /* demos/demo_boat_{novice,intermediate,advanced}.py dynamics */
+       LQ_SYS_CAR = 2,               /* demos/demo_car.py:46-72 */
+       LQ_SYS_PENDULUM2 = 3,         /* synthetic config C1 */
+       LQ_SYS_DOUBLE_INTEGRATOR = 4  /* synthetic config C5 */ };
+
+/* (S, K) = lqr(x, u) -- reference contract planner.py:39-42 */
+enum { LQ_LQR_PD_ROTATED = 1,        /* demo_boat_novice.py:86-103, demo_car.py:95-113 */
+       LQ_LQR_CONSTANT = 2,          /* demo_pendulum.py:119-126 */
+       LQ_LQR_FD_RICCATI = 3         /* north_star's built-in provider (not in the reference) */ };
+
+/* is_feasible(x, u) primitives -- reference contract constraints.py:29,53-61 */
+enum { LQ_FEAS_STATE_BOX = 1,        /* demo_boat_advanced.py:211-213 */
+       LQ_FEAS_EFFORT_BOX = 2,       /* demo_pendulum.py:154-157 */
+       LQ_FEAS_STATE_REGION = 3,     /* config C1 obstacle region */
+       LQ_FEAS_CIRCLES_POINT = 4,    /* demo_boat_novice.py:160-164 */
+       LQ_FEAS_CIRCLES_CLOUD = 5,    /* demo_boat_intermediate.py:198-210, demo_car.py:168-180 */
+       LQ_FEAS_BOXES_CLOUD = 6,      /* config C2 boxes */
+       LQ_FEAS_SPHERES_POINT = 7     /* config C5 spheres */ };
+
+typedef struct lq_feas_prim {
+    int32_t kind;
+    int32_t n_obs;                 /* rows of obs */
+    int32_t n_verts;               /* columns of verts (2 x V) */
+    int32_t flags;                 /* bit0: demo_car.py:175 doubled-centre vertex */
+    int32_t dims[4];               /* state indices: x, y, (z | heading) */
+    double inflate;
+    const double* obs;             /* n_obs x {3: cx cy r | 4: cx cy hx hy | 4: cx cy cz r} */
+    const double* verts;           /* 2 x n_verts, row-major */
+    const double* lo;              /* box primitives: n (state) or m (effort) entries */
+    const double* hi;
+} lq_feas_prim;
+
+typedef struct lq_config {
+    int32_t abi_version;           /* LQ_ABI_VERSION */
+    int32_t device;                /* CUDA device ordinal */
+    int32_t dtype;                 /* LQ_F32 | LQ_F64: arithmetic type of every kernel */
+    int32_t n, m;                  /* nstates, ncontrols (constraints.py:32-33) */
+    int32_t sys_kind, lqr_kind;
+    int32_t n_sys_params, n_lqr_params;
+    const double* sys_params;      /* blob layouts: lqrrt_b200/models.py */
+    const double* lqr_params;
+    uint32_t angle_mask;           /* erf: bit i set => dim i wraps (demo_boat_novice.py:106-118) */
+    int32_t n_prims;
+    const lq_feas_prim* prims;
+    int32_t horizon_iters;         /* planner.py:549 */
+    double dt;                     /* planner.py:527 */
+    double FPR;                    /* planner.py:530; int(FPR*len) is evaluated in float64 on the device */
+    double error_tol[LQ_MAX_N];    /* planner.py:532-536 (inf allowed) */
+    int32_t node_capacity;         /* tree rows held in HBM */
+    int32_t wave_capacity;         /* most samples one lq_wave_expand may take on this GPU */
+    int32_t tries_capacity;        /* most sampler tries (planner.py:188-191) */
+} lq_config;
+
+typedef struct lq_wave_stats {
+    int32_t tree_size;             /* after commit */
+    int32_t n_sampled;             /* samples expanded by this wave (all ranks) */
+    int32_t n_accepted;            /* nodes appended */
+    int32_t n_goal;                /* goal-region nodes so far this plan */
+    int32_t best_node;             /* node of the fastest plan so far, -1 if none (planner.py:276-281) */
+    int32_t best_cost;             /* its cumulative steps; T = (1 + best_cost) * dt (planner.py:273) */
+    int32_t full;                  /* 1 if node_capacity truncated this wave */
+    int32_t tries_used;            /* sum over samples of sampler tries */
+    int32_t flags;                 /* `flags` rank 0 passed to its lq_wave_expand (host stop protocol) */
+    int32_t reserved[3];
+} lq_wave_stats;
+
+typedef struct lq_engine lq_engine;
+
+/* ---- lifetime ----------------------------------------------------------- */
+int lq_abi_version(void);
+int lq_create(const lq_config* cfg, lq_engine** out);       /* replaces Planner.__init__/set_system/set_resolution, planner.py:85-100,517-592 */
+int lq_destroy(lq_engine* h);
+const char* lq_last_error(const lq_engine* h);
+
+/* ---- problem state ------------------------------------------------------ */
+/* Planner.set_goal, planner.py:468-487: goal and goal region (goal +- buffer, open box). */
+int lq_set_goal(lq_engine* h, const double* h_goal, const double* h_buffer);
+/* default sampler setup, planner.py:178-198: box, goal bias, tries limit. */
+int lq_set_sampling(lq_engine* h, const double* h_lo, const double* h_hi, const double* h_goal_bias, int tries);
+/* Tree.__init__, tree.py:50-73 + planner.py:172-173: new tree seeded at x0, K0 = lqr(x0, 0); clears ignores/best plan. */
+int lq_reset(lq_engine* h, const double* h_x0, void* stream);
+/* test/bench hook: replace the tree with `count` given nodes (K_i = lqr(x_i, 0)). */
+int lq_load_nodes(lq_engine* h, int count, const double* h_state, const int32_t* h_parent,
+                  const int32_t* h_cost, void* stream);
+int lq_tree_size(lq_engine* h, int* out);                   /* Tree.size, tree.py:73 (synchronises the stream) */
+
+/* ---- the hot path, stage by stage ---------------------------------------- */
+/* _costs_to_go + argsort/argmin selection, planner.py:239-247,340-350.
+ * d_queries: n x W (dim-major) engine dtype.  d_idx: W int32, d_cost: W engine dtype (may be NULL). */
+int lq_nearest(lq_engine* h, const void* d_queries, int W, int use_ignore,
+               int32_t* d_idx, void* d_cost, void* stream);
+/* _steer(ID, xtar, force_arrive=False), planner.py:354-438, for W (node, target) pairs.
+ * d_targets: n x W dim-major.  Outputs (may be NULL): d_len W int32;
+ * d_xseq W x H x n, d_useq W x H x m (sample-major) engine dtype. */
+int lq_steer(lq_engine* h, const int32_t* d_ids, const void* d_targets, int W,
+             void* d_xseq, void* d_useq, int32_t* d_len, void* stream);
+
+/* One wave of the expand loop, planner.py:233-283, for samples [first, first+count) of a global
+ * wave of `wave_size` samples: sample (planner.py:201-211; Philox stream keyed by seed/wave_ctr/sample,
+ * or h_samples: count x n float64 when non-NULL, or h_candidates below) -> nearest -> steer ->
+ * pack accepted records, in sample order, into the engine's send buffer.  Nothing is appended yet. */
+int lq_wave_expand(lq_engine* h, uint64_t seed, uint32_t wave_ctr, int first, int count,
+                   const double* h_samples, int use_ignore, int flags, void* stream);
+/* Reference-stream sampling (planner.py:201-211 on NumPy's MT19937): h_candidates holds
+ * `n_candidates` consecutive tries (n_candidates x n float64) in stream order; the engine tests
+ * feasibility of all of them, then walks them in order giving each of `count` samples up to `tries`
+ * tries.  *h_consumed receives how many candidates were used (the host advances its RNG by that). */
+int lq_wave_expand_candidates(lq_engine* h, int count, int tries, const double* h_candidates,
+                              int n_candidates, int use_ignore, int* h_consumed, void* stream);
+/* `flags` above travels in the record header; after lq_wave_commit every rank reads segment 0's
+ * value back in lq_wave_stats.flags -- the host uses it to agree on when to stop without an extra
+ * collective (the reference's stop rules are wall-clock based, planner.py:286-311). */
+/* The packed records of the last lq_wave_expand: device pointer + fixed byte size (the allgather payload). */
+int lq_wave_records(lq_engine* h, void** d_records, uint64_t* bytes);
+/* Tree.add_node for every accepted record of `n_segments` record buffers laid end to end
+ * (segment r = rank r's lq_wave_records), in segment order then record order = global sample order;
+ * then goal test / ignores / best plan (planner.py:253-283, tree.py:77-96).  d_records may be the
+ * engine's own buffer (single GPU). */
+int lq_wave_commit(lq_engine* h, const void* d_records, int n_segments, void* stream);
+/* Blocks until the last commit finished and returns its counters. */
+int lq_wave_stats_get(lq_engine* h, lq_wave_stats* out);
+
+/* closest-to-guide, planner.py:313-318: argmin_i d_i' Sg d_i, Sg = lqr(xguide,0).S with the
+ * columns of dims where h_colmask[i] != 0 zeroed. */
+int lq_closest(lq_engine* h, const double* h_xguide, const uint8_t* h_colmask, int* h_id, void* stream);
+/* _steer(ID, xtar, force_arrive=True), planner.py:296,399-410, with the wall-clock limit replaced by
+ * max_steps; h_x: max_steps x n, h_u: max_steps x m. */
+int lq_steer_force(lq_engine* h, int node, const double* h_xtar, int max_steps,
+                   double* h_x, double* h_u, int* h_len, void* stream);
+/* Tree.add_node with explicit content (finish_on_goal, planner.py:299). */
+int lq_append_node(lq_engine* h, int parent, const double* h_state, const double* h_x, const double* h_u,
+                   int len, void* stream);
+/* planner.py:270 for externally chosen ids (tests). */
+int lq_mark_ignore(lq_engine* h, const int32_t* h_ids, int count, void* stream);
+
+/* ---- read-back (Tree.state / pID / lqr / x_seq / u_seq, tree.py:62-70) --- */
+int lq_download_nodes(lq_engine* h, int first, int count, double* h_state, int32_t* h_parent,
+                      int32_t* h_cost, int32_t* h_edge_len, uint8_t* h_ignore, double* h_K, void* stream);
+/* edges of `count` nodes listed in h_ids: h_x count x H x n, h_u count x H x m (rows past the edge length are zero). */
+int lq_download_edges(lq_engine* h, const int32_t* h_ids, int count, double* h_x, double* h_u, void* stream);
+
+/* ---- the user callbacks themselves, batched (planner.py:35-59) ------------ */
+int lq_eval_dynamics(lq_engine* h, int count, const double* h_x, const double* h_u, double dt, double* h_xnext);
+int lq_eval_lqr(lq_engine* h, int count, const double* h_x, const double* h_u, double* h_S, double* h_K);
+int lq_eval_erf(lq_engine* h, int count, const double* h_xgoal, const double* h_x, double* h_e);
+int lq_eval_feasible(lq_engine* h, int count, const double* h_x, const double* h_u, uint8_t* h_ok);
+
+/* number of kernels this engine has launched since creation (bench.py's gpu_launches) */
+int lq_launch_count(lq_engine* h, uint64_t* out);
+/* tuning knobs: steer lanes per sample (1, 8, 32; 0 keeps), nearest queries per thread (0 = heuristic) */
+int lq_set_tuning(lq_engine* h, int steer_lanes, int nearest_q);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,405 @@
+"""
+ctypes binding of the C ABI in include/lqrrt_b200.h (liblqrrt_b200.so, built
+from csrc/ for sm_100a).  This is the only module that touches the shared
+library; there is no CPU implementation behind it, so a missing library or a
+missing GPU is an error, never a fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import models as M
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'liblqrrt_b200.so')
+
+LQ_ABI_VERSION = 1
+LQ_MAX_N = 12
+LQ_F32, LQ_F64 = 0, 1
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class lq_feas_prim(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('n_obs', C.c_int32), ('n_verts', C.c_int32), ('flags', C.c_int32),
+                ('dims', C.c_int32 * 4), ('inflate', C.c_double),
+                ('obs', C.POINTER(C.c_double)), ('verts', C.POINTER(C.c_double)),
+                ('lo', C.POINTER(C.c_double)), ('hi', C.POINTER(C.c_double))]
+
+
+class lq_config(C.Structure):
+    _fields_ = [('abi_version', C.c_int32), ('device', C.c_int32), ('dtype', C.c_int32),
+                ('n', C.c_int32), ('m', C.c_int32), ('sys_kind', C.c_int32), ('lqr_kind', C.c_int32),
+                ('n_sys_params', C.c_int32), ('n_lqr_params', C.c_int32),
+                ('sys_params', C.POINTER(C.c_double)), ('lqr_params', C.POINTER(C.c_double)),
+                ('angle_mask', C.c_uint32), ('n_prims', C.c_int32), ('prims', C.POINTER(lq_feas_prim)),
+                ('horizon_iters', C.c_int32), ('dt', C.c_double), ('FPR', C.c_double),
+                ('error_tol', C.c_double * LQ_MAX_N),
+                ('node_capacity', C.c_int32), ('wave_capacity', C.c_int32), ('tries_capacity', C.c_int32)]
+
+
+class lq_wave_stats(C.Structure):
+    _fields_ = [('tree_size', C.c_int32), ('n_sampled', C.c_int32), ('n_accepted', C.c_int32),
+                ('n_goal', C.c_int32), ('best_node', C.c_int32), ('best_cost', C.c_int32),
+                ('full', C.c_int32), ('tries_used', C.c_int32), ('flags', C.c_int32),
+                ('reserved', C.c_int32 * 3)]
+
+
+# every symbol include/lqrrt_b200.h declares: (restype, argtypes)
+_P = C.c_void_p
+_D = C.POINTER(C.c_double)
+_I = C.POINTER(C.c_int32)
+_U8 = C.POINTER(C.c_uint8)
+SYMBOLS = {
+    'lq_abi_version': (C.c_int, []),
+    'lq_create': (C.c_int, [C.POINTER(lq_config), C.POINTER(_P)]),
+    'lq_destroy': (C.c_int, [_P]),
+    'lq_last_error': (C.c_char_p, [_P]),
+    'lq_set_goal': (C.c_int, [_P, _D, _D]),
+    'lq_set_sampling': (C.c_int, [_P, _D, _D, _D, C.c_int]),
+    'lq_reset': (C.c_int, [_P, _D, _P]),
+    'lq_load_nodes': (C.c_int, [_P, C.c_int, _D, _I, _I, _P]),
+    'lq_tree_size': (C.c_int, [_P, C.POINTER(C.c_int)]),
+    'lq_nearest': (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P]),
+    'lq_steer': (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P]),
+    'lq_wave_expand': (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_int, C.c_int, _D, C.c_int, C.c_int, _P]),
+    'lq_wave_expand_candidates': (C.c_int, [_P, C.c_int, C.c_int, _D, C.c_int, C.c_int, C.POINTER(C.c_int), _P]),
+    'lq_wave_records': (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64)]),
+    'lq_wave_commit': (C.c_int, [_P, _P, C.c_int, _P]),
+    'lq_wave_stats_get': (C.c_int, [_P, C.POINTER(lq_wave_stats)]),
+    'lq_closest': (C.c_int, [_P, _D, _U8, C.POINTER(C.c_int), _P]),
+    'lq_steer_force': (C.c_int, [_P, C.c_int, _D, C.c_int, _D, _D, C.POINTER(C.c_int), _P]),
+    'lq_append_node': (C.c_int, [_P, C.c_int, _D, _D, _D, C.c_int, _P]),
+    'lq_mark_ignore': (C.c_int, [_P, _I, C.c_int, _P]),
+    'lq_download_nodes': (C.c_int, [_P, C.c_int, C.c_int, _D, _I, _I, _I, _U8, _D, _P]),
+    'lq_download_edges': (C.c_int, [_P, _I, C.c_int, _D, _D, _P]),
+    'lq_eval_dynamics': (C.c_int, [_P, C.c_int, _D, _D, C.c_double, _D]),
+    'lq_eval_lqr': (C.c_int, [_P, C.c_int, _D, _D, _D, _D]),
+    'lq_eval_erf': (C.c_int, [_P, C.c_int, _D, _D, _D]),
+    'lq_eval_feasible': (C.c_int, [_P, C.c_int, _D, _D, _U8]),
+    'lq_launch_count': (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    'lq_set_tuning': (C.c_int, [_P, C.c_int, C.c_int]),
+}
+
+_lib = None
+
+
+def load_library():
+    """dlopen the in-tree shared library and bind every declared symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise NativeError(
+            "{} is missing: build the CUDA extension first (python -c 'import __graft_entry__ as g; "
+            "g.build()' or make -C lqrrt_b200/csrc). lqrrt_b200 has no CPU fallback.".format(LIB_PATH))
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)            # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if lib.lq_abi_version() != LQ_ABI_VERSION:
+        raise NativeError("liblqrrt_b200.so ABI version {} != binding version {}".format(
+            lib.lq_abi_version(), LQ_ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(_D)
+
+
+def _ip(a):
+    return a.ctypes.data_as(_I)
+
+
+def _c64(a, shape=None):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+class Engine(object):
+    """One lq_engine handle: one GPU's replica of the tree plus the wave
+    working set.  Methods map 1:1 onto the C ABI."""
+
+    def __init__(self, system, horizon_iters, dt, FPR, error_tol, node_capacity, wave_capacity,
+                 dtype='f32', device=0, tries_capacity=16):
+        self.lib = load_library()
+        self.system = system
+        self.n = system.nstates; self.m = system.ncontrols
+        self.H = int(horizon_iters)
+        self.dtype = dtype
+        self.np_dtype = np.float32 if dtype == 'f32' else np.float64
+        self.device = int(device)
+        self.node_capacity = int(node_capacity)
+        self.wave_capacity = (int(wave_capacity) + 3) & ~3
+        if dtype not in ('f32', 'f64'):
+            raise ValueError("dtype must be 'f32' or 'f64'")
+
+        keep = []          # keep numpy buffers alive across lq_create
+        cfg = lq_config()
+        cfg.abi_version = LQ_ABI_VERSION
+        cfg.device = self.device
+        cfg.dtype = LQ_F32 if dtype == 'f32' else LQ_F64
+        cfg.n = self.n; cfg.m = self.m
+        cfg.sys_kind = system.dynamics.kind; cfg.lqr_kind = system.lqr.kind
+        sp = _c64(system.dynamics.blob()); lp = _c64(system.lqr.blob(self.n, self.m)); keep += [sp, lp]
+        cfg.n_sys_params = len(sp); cfg.n_lqr_params = len(lp)
+        cfg.sys_params = _dp(sp); cfg.lqr_params = _dp(lp)
+        cfg.angle_mask = system.erf.mask(self.n)
+        prims = system.is_feasible.prims
+        arr = (lq_feas_prim * max(1, len(prims)))()
+        for i, p in enumerate(prims):
+            arr[i].kind = p.kind
+            arr[i].flags = p.flags
+            arr[i].inflate = p.inflate
+            for k in range(4):
+                arr[i].dims[k] = p.dims[k]
+            if p.obs is not None:
+                o = _c64(p.obs); keep.append(o)
+                arr[i].n_obs = len(o); arr[i].obs = _dp(o)
+            if p.verts is not None:
+                v = _c64(p.verts); keep.append(v)
+                arr[i].n_verts = v.shape[1]; arr[i].verts = _dp(v)
+            if p.lo is not None:
+                want = self.m if p.kind == M.FEAS_EFFORT_BOX else self.n
+                lo = _c64(p.lo); hi = _c64(p.hi)
+                if len(lo) != want or len(hi) != want:
+                    raise ValueError("box primitive needs {} bounds".format(want))
+                keep += [lo, hi]
+                arr[i].lo = _dp(lo); arr[i].hi = _dp(hi)
+        cfg.n_prims = len(prims); cfg.prims = arr
+        cfg.horizon_iters = self.H
+        cfg.dt = float(dt); cfg.FPR = float(FPR)
+        tol = np.abs(np.asarray(error_tol, dtype=np.float64)) * np.ones(self.n)
+        for i in range(self.n):
+            cfg.error_tol[i] = tol[i]
+        cfg.node_capacity = self.node_capacity
+        cfg.wave_capacity = self.wave_capacity
+        cfg.tries_capacity = int(tries_capacity)
+
+        h = _P()
+        rc = self.lib.lq_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise NativeError("lq_create failed ({}): {}".format(rc, self.lib.lq_last_error(None).decode()))
+        self.h = h
+        del keep
+
+    # ------------------------------------------------------------------ utils
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self.lib.lq_last_error(self.h).decode()
+            if rc == -1:
+                raise ValueError(msg or "invalid argument")
+            raise NativeError("lqrrt_b200 native call failed ({}): {}".format(rc, msg))
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.lq_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _stream(stream):
+        if stream is None:
+            return None
+        return _P(int(stream))
+
+    # -------------------------------------------------------------- problem
+    def set_goal(self, goal, buffer):
+        g = _c64(goal); b = _c64(buffer)
+        self._ck(self.lib.lq_set_goal(self.h, _dp(g), _dp(b)))
+
+    def set_sampling(self, sample_space, goal_bias, tries):
+        ss = _c64(sample_space, (self.n, 2))
+        lo = np.ascontiguousarray(ss[:, 0]); hi = np.ascontiguousarray(ss[:, 1])
+        gb = _c64(goal_bias) * np.ones(self.n)
+        self._ck(self.lib.lq_set_sampling(self.h, _dp(lo), _dp(hi), _dp(gb), int(tries)))
+
+    def reset(self, x0, stream=None):
+        x = _c64(x0)
+        self._ck(self.lib.lq_reset(self.h, _dp(x), self._stream(stream)))
+
+    def load_nodes(self, state, parent=None, cost=None, stream=None):
+        s = _c64(state).reshape(-1, self.n)
+        p = None if parent is None else np.ascontiguousarray(parent, dtype=np.int32)
+        c = None if cost is None else np.ascontiguousarray(cost, dtype=np.int32)
+        self._ck(self.lib.lq_load_nodes(self.h, len(s), _dp(s), None if p is None else _ip(p),
+                                        None if c is None else _ip(c), self._stream(stream)))
+
+    def tree_size(self):
+        out = C.c_int(0)
+        self._ck(self.lib.lq_tree_size(self.h, C.byref(out)))
+        return out.value
+
+    # ------------------------------------------------------------ hot path
+    def nearest(self, d_queries, W, use_ignore, d_idx, d_cost=None, stream=None):
+        """Device pointers (ints): queries n x W dim-major engine dtype; idx W int32."""
+        self._ck(self.lib.lq_nearest(self.h, _P(d_queries), int(W), int(bool(use_ignore)), _P(d_idx),
+                                     _P(d_cost) if d_cost else None, self._stream(stream)))
+
+    def steer(self, d_ids, d_targets, W, d_xseq=None, d_useq=None, d_len=None, stream=None):
+        self._ck(self.lib.lq_steer(self.h, _P(d_ids), _P(d_targets), int(W),
+                                   _P(d_xseq) if d_xseq else None, _P(d_useq) if d_useq else None,
+                                   _P(d_len) if d_len else None, self._stream(stream)))
+
+    def wave_expand(self, seed, wave_ctr, first, count, samples=None, use_ignore=True, flags=0, stream=None):
+        hs = None
+        if samples is not None:
+            hs = _c64(samples).reshape(-1, self.n)
+            if len(hs) != count:
+                raise ValueError("samples must be count x n")
+        self._ck(self.lib.lq_wave_expand(self.h, C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), C.c_uint32(int(wave_ctr) & 0xFFFFFFFF),
+                                         int(first), int(count), None if hs is None else _dp(hs),
+                                         int(bool(use_ignore)), int(flags), self._stream(stream)))
+
+    def wave_expand_candidates(self, count, tries, candidates, use_ignore=True, stream=None):
+        c = _c64(candidates).reshape(-1, self.n)
+        used = C.c_int(0)
+        self._ck(self.lib.lq_wave_expand_candidates(self.h, int(count), int(tries), _dp(c), len(c),
+                                                    int(bool(use_ignore)), C.byref(used), self._stream(stream)))
+        return used.value
+
+    def wave_records(self):
+        p = _P(); b = C.c_uint64(0)
+        self._ck(self.lib.lq_wave_records(self.h, C.byref(p), C.byref(b)))
+        return p.value, b.value
+
+    def wave_commit(self, d_records=None, n_segments=1, stream=None):
+        self._ck(self.lib.lq_wave_commit(self.h, _P(d_records) if d_records else None, int(n_segments), self._stream(stream)))
+
+    def wave_stats(self):
+        st = lq_wave_stats()
+        self._ck(self.lib.lq_wave_stats_get(self.h, C.byref(st)))
+        return st
+
+    def closest(self, xguide, colmask, stream=None):
+        x = _c64(xguide)
+        mk = np.ascontiguousarray(colmask, dtype=np.uint8)
+        out = C.c_int(0)
+        self._ck(self.lib.lq_closest(self.h, _dp(x), mk.ctypes.data_as(_U8), C.byref(out), self._stream(stream)))
+        return out.value
+
+    def steer_force(self, node, xtar, max_steps, stream=None):
+        xt = _c64(xtar)
+        hx = np.zeros((max_steps, self.n)); hu = np.zeros((max_steps, self.m))
+        ln = C.c_int(0)
+        self._ck(self.lib.lq_steer_force(self.h, int(node), _dp(xt), int(max_steps), _dp(hx), _dp(hu), C.byref(ln),
+                                         self._stream(stream)))
+        return hx[:ln.value].copy(), hu[:ln.value].copy()
+
+    def append_node(self, parent, state, x_seq, u_seq, stream=None):
+        s = _c64(state)
+        x = _c64(x_seq).reshape(-1, self.n); u = _c64(u_seq).reshape(-1, self.m)
+        self._ck(self.lib.lq_append_node(self.h, int(parent), _dp(s), _dp(x), _dp(u), len(x), self._stream(stream)))
+
+    def mark_ignore(self, ids, stream=None):
+        a = np.ascontiguousarray(ids, dtype=np.int32)
+        self._ck(self.lib.lq_mark_ignore(self.h, _ip(a), len(a), self._stream(stream)))
+
+    # -------------------------------------------------------------- read-back
+    def download_nodes(self, first, count, want_K=False, stream=None):
+        state = np.zeros((count, self.n)); parent = np.zeros(count, dtype=np.int32)
+        cost = np.zeros(count, dtype=np.int32); elen = np.zeros(count, dtype=np.int32)
+        ign = np.zeros(count, dtype=np.uint8)
+        K = np.zeros((count, self.m, self.n)) if want_K else None
+        self._ck(self.lib.lq_download_nodes(self.h, int(first), int(count), _dp(state), _ip(parent), _ip(cost), _ip(elen),
+                                            ign.ctypes.data_as(_U8), None if K is None else _dp(K), self._stream(stream)))
+        return dict(state=state, parent=parent, cost=cost, edge_len=elen, ignore=ign, K=K)
+
+    def download_edges(self, ids, stream=None):
+        a = np.ascontiguousarray(ids, dtype=np.int32)
+        hx = np.zeros((len(a), self.H, self.n)); hu = np.zeros((len(a), self.H, self.m))
+        if len(a):
+            self._ck(self.lib.lq_download_edges(self.h, _ip(a), len(a), _dp(hx), _dp(hu), self._stream(stream)))
+        return hx, hu
+
+    # -------------------------------------------------------------- callbacks
+    def eval_dynamics(self, x, u, dt):
+        x = _c64(x).reshape(-1, self.n); u = _c64(u).reshape(-1, self.m)
+        out = np.zeros_like(x)
+        self._ck(self.lib.lq_eval_dynamics(self.h, len(x), _dp(x), _dp(u), float(dt), _dp(out)))
+        return out
+
+    def eval_lqr(self, x, u):
+        x = _c64(x).reshape(-1, self.n); u = _c64(u).reshape(-1, self.m)
+        S = np.zeros((len(x), self.n, self.n)); K = np.zeros((len(x), self.m, self.n))
+        self._ck(self.lib.lq_eval_lqr(self.h, len(x), _dp(x), _dp(u), _dp(S), _dp(K)))
+        return S, K
+
+    def eval_erf(self, xgoal, x):
+        xg = _c64(xgoal).reshape(-1, self.n); x = _c64(x).reshape(-1, self.n)
+        out = np.zeros_like(x)
+        self._ck(self.lib.lq_eval_erf(self.h, len(x), _dp(xg), _dp(x), _dp(out)))
+        return out
+
+    def eval_feasible(self, x, u):
+        x = _c64(x).reshape(-1, self.n); u = _c64(u).reshape(-1, self.m)
+        ok = np.zeros(len(x), dtype=np.uint8)
+        self._ck(self.lib.lq_eval_feasible(self.h, len(x), _dp(x), _dp(u), ok.ctypes.data_as(_U8)))
+        return ok.astype(bool)
+
+    def launch_count(self):
+        out = C.c_uint64(0)
+        self._ck(self.lib.lq_launch_count(self.h, C.byref(out)))
+        return out.value
+
+    def set_tuning(self, steer_lanes=0, nearest_q=0):
+        self._ck(self.lib.lq_set_tuning(self.h, int(steer_lanes), int(nearest_q)))
+
+
+class ModelEvaluator(object):
+    """Backs the bare-call form of the specs (`sys.dynamics(x, u, dt)` ...):
+    a minimal float64 engine used only for its lq_eval_* entry points."""
+
+    def __init__(self, system):
+        self.system = system
+        self.engine = Engine(system, horizon_iters=1, dt=system.dt_hint, FPR=0.0,
+                             error_tol=np.zeros(system.nstates), node_capacity=4, wave_capacity=4,
+                             dtype='f64', device=_current_device())
+
+    def dynamics(self, x, u, dt):
+        return self.engine.eval_dynamics(x, np.atleast_1d(u), dt)[0]
+
+    def lqr(self, x, u):
+        u = np.zeros(self.system.ncontrols) + np.asarray(u, dtype=np.float64)
+        S, K = self.engine.eval_lqr(x, u)
+        return S[0], K[0]
+
+    def erf(self, xgoal, x):
+        return self.engine.eval_erf(xgoal, x)[0]
+
+    def is_feasible(self, x, u):
+        u = np.zeros(self.system.ncontrols) + np.asarray(u, dtype=np.float64)
+        return bool(self.engine.eval_feasible(x, u)[0])
+
+
+def _current_device():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return torch.cuda.current_device()
+    except Exception:
+        pass
+    return 0
+
+
+class DevicePointer(object):
+    """Exposes a raw device allocation through __cuda_array_interface__ so torch can wrap it without a
+    copy (torch.as_tensor): the engine's record buffer becomes the allgather input in place."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {'shape': (int(nbytes),), 'typestr': '|u1', 'data': (int(ptr), False),
+                                         'version': 2, 'strides': None}

@@ -1,0 +1,202 @@
+// K4: Tree.add_node for a whole wave + the post-add bookkeeping
+// (reference lqrrt/tree.py:77-96, lqrrt/planner.py:253-283).
+//
+// pack:   compact the wave's accepted samples (edge length > 0), in sample
+//         order, into a fixed-size record buffer -- the multi-GPU allgather
+//         payload (every rank contributes one such segment per wave).
+// commit: append the records of all segments, segment order then record order
+//         (= global sample order), to the SoA tree; goal test, ignore marks
+//         along the new plan, best-plan tracking.
+#pragma once
+#include "steer.cuh"
+
+namespace lq {
+
+constexpr int REC_HEADER_INTS = 32;
+enum { HDR_COUNT = 0, HDR_SAMPLED = 1, HDR_TRIES = 2, HDR_FLAGS = 3 };
+
+template <typename T> struct RecView {
+    int* header;
+    T* state;      // [N][Wc]
+    T* K;          // [M*N][Wc]
+    int* parent;   // [Wc]
+    int* len;      // [Wc]
+    T* ex;         // [Wc][H*N]
+    T* eu;         // [Wc][H*M]
+};
+
+__host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
+
+template <typename T>
+__host__ __device__ inline size_t rec_bytes(int Wc, int N, int M, int H) {
+    size_t b = REC_HEADER_INTS * sizeof(int);
+    b += align16(sizeof(T) * (size_t)N * Wc);
+    b += align16(sizeof(T) * (size_t)M * N * Wc);
+    b += align16(sizeof(int) * (size_t)Wc) * 2;
+    b += align16(sizeof(T) * (size_t)Wc * H * N);
+    b += align16(sizeof(T) * (size_t)Wc * H * M);
+    return b;
+}
+
+template <typename T>
+__host__ __device__ inline RecView<T> rec_view(void* base, int Wc, int N, int M, int H) {
+    RecView<T> v;
+    char* p = (char*)base;
+    v.header = (int*)p; p += REC_HEADER_INTS * sizeof(int);
+    v.state = (T*)p; p += align16(sizeof(T) * (size_t)N * Wc);
+    v.K = (T*)p; p += align16(sizeof(T) * (size_t)M * N * Wc);
+    v.parent = (int*)p; p += align16(sizeof(int) * (size_t)Wc);
+    v.len = (int*)p; p += align16(sizeof(int) * (size_t)Wc);
+    v.ex = (T*)p; p += align16(sizeof(T) * (size_t)Wc * H * N);
+    v.eu = (T*)p;
+    return v;
+}
+
+// Exclusive scan of (len > 0) over the wave -> record slot per sample; one CTA.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+pack_scan_kernel(const int* __restrict__ len, const int* __restrict__ tries_used, int count,
+                 int* __restrict__ slot, int* __restrict__ header, int flags) {
+    __shared__ int wsum[BLOCK / 32];
+    __shared__ int wtries[BLOCK / 32];
+    const int per = (count + BLOCK - 1) / BLOCK;
+    const int j0 = threadIdx.x * per, j1 = min(j0 + per, count);
+    int local = 0, tries = 0;
+    for (int j = j0; j < j1; j++) { local += len[j] > 0; if (tries_used) tries += tries_used[j]; }
+    int incl = local;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tries += __shfl_xor_sync(0xffffffffu, tries, o);
+    if (lane == 31) wsum[warp] = incl;
+    if (lane == 0) wtries[warp] = tries;
+    __syncthreads();
+    int woff = 0, total = 0, ttries = 0;
+    for (int w = 0; w < BLOCK / 32; w++) { if (w < warp) woff += wsum[w]; total += wsum[w]; ttries += wtries[w]; }
+    int run = woff + incl - local;
+    for (int j = j0; j < j1; j++) { slot[j] = run; run += len[j] > 0; }
+    if (threadIdx.x == 0) { header[HDR_COUNT] = total; header[HDR_SAMPLED] = count; header[HDR_TRIES] = ttries; header[HDR_FLAGS] = flags; }
+}
+
+// One warp per sample: copy an accepted sample's node record and edge into its slot.
+template <typename T>
+__global__ void pack_kernel(const int* __restrict__ len, const int* __restrict__ slot, const int* __restrict__ ids,
+                            const T* __restrict__ xnew, const T* __restrict__ Knew, int ostride,
+                            const T* __restrict__ xseq, const T* __restrict__ useq, int count,
+                            RecView<T> rv, int Wc, int N, int M, int H) {
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (j >= count) return;
+    const int L = len[j];
+    if (L <= 0) return;
+    const int s = slot[j];
+    for (int d = lane; d < N; d += 32) rv.state[(size_t)d * Wc + s] = xnew[(size_t)d * ostride + j];
+    for (int k = lane; k < M * N; k += 32) rv.K[(size_t)k * Wc + s] = Knew[(size_t)k * ostride + j];
+    if (lane == 0) { rv.parent[s] = ids[j]; rv.len[s] = L; }
+    const T* sx = xseq + (size_t)j * H * N; T* dx = rv.ex + (size_t)s * H * N;
+    for (int k = lane; k < L * N; k += 32) dx[k] = sx[k];
+    const T* su = useq + (size_t)j * H * M; T* du = rv.eu + (size_t)s * H * M;
+    for (int k = lane; k < L * M; k += 32) du[k] = su[k];
+}
+
+template <typename T> struct TreeView {
+    T* state;          // [N][cap]
+    T* K;              // [M*N][cap]
+    int* parent;       // [cap]
+    int* cost;         // [cap] cumulative recorded steps from the seed; T_plan = (1 + cost) dt
+    int* edge_len;     // [cap]
+    uint8_t* ignore;   // [cap] (word-aligned: marks are set with atomicOr on the containing word)
+    T* edge_x;         // [cap][H*N]
+    T* edge_u;         // [cap][H*M]
+    int* size;         // device scalar
+    int* n_ignored;    // device scalar
+    int* n_goal;       // device scalar
+    unsigned long long* best;   // (cost << 32 | node), ~0 = none
+    int cap;
+};
+
+template <typename T>
+__device__ __forceinline__ void mark_path(const TreeView<T>& tv, int node) {
+    // planner.py:266-270: ignores |= climb(node).  Stops at the first ancestor that is already marked:
+    // whoever marked it also walks (or walked) on to the seed.
+    while (node >= 0) {
+        unsigned* word = (unsigned*)(tv.ignore + (node & ~3));
+        const unsigned bit = 1u << (8 * (node & 3));
+        const unsigned old = atomicOr(word, bit);
+        if (old & bit) break;
+        atomicAdd(tv.n_ignored, 1);
+        node = tv.parent[node];
+    }
+}
+
+// One warp per (segment, record).
+template <typename T>
+__global__ void commit_kernel(TreeView<T> tv, const char* __restrict__ records, size_t seg_bytes, int n_seg,
+                              int Wc, int N, int M, int H,
+                              const T* __restrict__ goal_lo, const T* __restrict__ goal_hi) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int seg = w / Wc, k = w % Wc;
+    if (seg >= n_seg) return;
+    int before = 0, mine = 0;
+    for (int s = 0; s <= seg; s++) {
+        const int c = ((const int*)(records + (size_t)s * seg_bytes))[HDR_COUNT];
+        if (s < seg) before += c; else mine = c;
+    }
+    if (k >= mine) return;
+    const int node = *tv.size + before + k;
+    if (node >= tv.cap) return;
+    const RecView<T> rv = rec_view<T>((void*)(records + (size_t)seg * seg_bytes), Wc, N, M, H);
+    const int L = rv.len[k], par = rv.parent[k];
+    bool in_goal = true;
+    for (int d = lane; d < N; d += 32) {
+        const T v = rv.state[(size_t)d * Wc + k];
+        tv.state[(size_t)d * tv.cap + node] = v;
+        in_goal = in_goal && (goal_lo[d] < v) && (v < goal_hi[d]);      // planner.py:442-447
+    }
+    in_goal = __all_sync(0xffffffffu, in_goal);
+    for (int q = lane; q < M * N; q += 32) tv.K[(size_t)q * tv.cap + node] = rv.K[(size_t)q * Wc + k];
+    const T* sx = rv.ex + (size_t)k * H * N; T* dx = tv.edge_x + (size_t)node * H * N;
+    for (int q = lane; q < L * N; q += 32) dx[q] = sx[q];
+    const T* su = rv.eu + (size_t)k * H * M; T* du = tv.edge_u + (size_t)node * H * M;
+    for (int q = lane; q < L * M; q += 32) du[q] = su[q];
+    if (lane == 0) {
+        const int c = tv.cost[par] + L;
+        tv.parent[node] = par; tv.cost[node] = c; tv.edge_len[node] = L;
+        if (in_goal) {                                                  // planner.py:260-281
+            atomicAdd(tv.n_goal, 1);
+            atomicMin(tv.best, ((unsigned long long)(unsigned)c << 32) | (unsigned)node);
+            mark_path(tv, node);
+        }
+    }
+}
+
+struct DevStats { int v[12]; };
+
+// Single thread: publish the new size and the wave counters.
+template <typename T>
+__global__ void commit_finish_kernel(TreeView<T> tv, const char* __restrict__ records, size_t seg_bytes, int n_seg,
+                                     DevStats* __restrict__ out) {
+    int total = 0, sampled = 0, tries = 0;
+    for (int s = 0; s < n_seg; s++) {
+        const int* h = (const int*)(records + (size_t)s * seg_bytes);
+        total += h[HDR_COUNT]; sampled += h[HDR_SAMPLED]; tries += h[HDR_TRIES];
+    }
+    const int old = *tv.size;
+    const int nsz = min(old + total, tv.cap);
+    *tv.size = nsz;
+    const unsigned long long b = *tv.best;
+    out->v[0] = nsz; out->v[1] = sampled; out->v[2] = nsz - old; out->v[3] = *tv.n_goal;
+    out->v[4] = b == ~0ull ? -1 : (int)(b & 0xffffffffu);
+    out->v[5] = b == ~0ull ? -1 : (int)(b >> 32);
+    out->v[6] = (old + total > tv.cap) ? 1 : 0;
+    out->v[7] = tries;
+    out->v[8] = ((const int*)records)[HDR_FLAGS];
+    out->v[9] = out->v[10] = out->v[11] = 0;
+}
+
+}  // namespace lq

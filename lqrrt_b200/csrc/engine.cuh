@@ -1,0 +1,829 @@
+// The engine behind the C ABI (include/lqrrt_b200.h): owns the tree in HBM as
+// structure-of-arrays and runs the reference's expand loop
+// (lqrrt/planner.py:233-290) one wave at a time:
+//   sample (K3) -> nearest (K1) -> steer (K2) -> pack -> [allgather by the host] -> commit (K4)
+// Templated on arithmetic type and on the compiled device model.
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include <cstring>
+#include <cstdio>
+#include <cmath>
+#include <algorithm>
+
+#include "models.cuh"
+#include "nearest.cuh"
+#include "steer.cuh"
+#include "sample.cuh"
+#include "commit.cuh"
+
+struct lq_engine {
+    std::string err;
+    uint64_t launches = 0;
+    int device = 0;
+    virtual ~lq_engine() {}
+    virtual int set_goal(const double* goal, const double* buf) = 0;
+    virtual int set_sampling(const double* lo, const double* hi, const double* bias, int tries) = 0;
+    virtual int reset(const double* x0, cudaStream_t st) = 0;
+    virtual int load_nodes(int count, const double* state, const int* parent, const int* cost, cudaStream_t st) = 0;
+    virtual int tree_size(int* out) = 0;
+    virtual int nearest(const void* d_q, int W, int use_ignore, int* d_idx, void* d_cost, cudaStream_t st) = 0;
+    virtual int steer(const int* d_ids, const void* d_t, int W, void* d_x, void* d_u, int* d_len, cudaStream_t st) = 0;
+    virtual int wave_expand(uint64_t seed, uint32_t wave, int first, int count, const double* h_samples,
+                            int use_ignore, int flags, cudaStream_t st) = 0;
+    virtual int wave_expand_candidates(int count, int tries, const double* h_cand, int n_cand, int use_ignore,
+                                       int* h_consumed, cudaStream_t st) = 0;
+    virtual int wave_records(void** d, uint64_t* bytes) = 0;
+    virtual int wave_commit(const void* d_records, int n_seg, cudaStream_t st) = 0;
+    virtual int wave_stats(lq_wave_stats* out) = 0;
+    virtual int closest(const double* xg, const uint8_t* colmask, int* id, cudaStream_t st) = 0;
+    virtual int steer_force(int node, const double* xtar, int max_steps, double* hx, double* hu, int* len, cudaStream_t st) = 0;
+    virtual int append_node(int parent, const double* state, const double* hx, const double* hu, int len, cudaStream_t st) = 0;
+    virtual int mark_ignore(const int* ids, int count, cudaStream_t st) = 0;
+    virtual int download_nodes(int first, int count, double* state, int* parent, int* cost, int* elen,
+                               uint8_t* ign, double* K, cudaStream_t st) = 0;
+    virtual int download_edges(const int* ids, int count, double* hx, double* hu, cudaStream_t st) = 0;
+    virtual int eval_dynamics(int count, const double* x, const double* u, double dt, double* xn) = 0;
+    virtual int eval_lqr(int count, const double* x, const double* u, double* S, double* K) = 0;
+    virtual int eval_erf(int count, const double* xg, const double* x, double* e) = 0;
+    virtual int eval_feasible(int count, const double* x, const double* u, uint8_t* ok) = 0;
+    virtual int set_tuning(int steer_lanes, int nearest_q) = 0;
+};
+
+namespace lq {
+
+#define LQ_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            char b_[512];                                                                      \
+            snprintf(b_, sizeof b_, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, #call); \
+            this->err = b_;                                                                    \
+            return LQ_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+#define LQ_FAIL(code, ...)                       \
+    do {                                         \
+        char b_[512];                            \
+        snprintf(b_, sizeof b_, __VA_ARGS__);    \
+        this->err = b_;                          \
+        return code;                             \
+    } while (0)
+
+constexpr int MAX_SPLIT = 128;
+constexpr int NEAR_BLOCK = 128;
+
+// ---- small utility kernels --------------------------------------------------
+template <typename T, class Sys, class Lqr>
+__global__ void init_gain_kernel(Model<T, Sys, Lqr> md, const T* __restrict__ state, T* __restrict__ K, int cap, int count) {
+    constexpr int N = Sys::N, M = Sys::M;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    T x[N], u[M], Kl[M * N];
+    for (int d = 0; d < N; d++) x[d] = state[(size_t)d * cap + i];
+    for (int r = 0; r < M; r++) u[r] = T(0);
+    md.lqr.gain(md.sys, md.dt, x, u, Kl);                         // planner.py:172: lqr(x0, zeros)
+    for (int k = 0; k < M * N; k++) K[(size_t)k * cap + i] = Kl[k];
+}
+
+template <typename T, class Sys, class Lqr>
+__global__ void eval_kernel(Model<T, Sys, Lqr> md, int what, int count, const T* __restrict__ a, const T* __restrict__ b,
+                            T dt, T* __restrict__ o1, T* __restrict__ o2, uint8_t* __restrict__ ob) {
+    constexpr int N = Sys::N, M = Sys::M;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    if (what == 0) {          // dynamics: a = x (count x N), b = u (count x M)
+        T x[N], u[M], xn[N];
+        for (int d = 0; d < N; d++) x[d] = a[i * N + d];
+        for (int r = 0; r < M; r++) u[r] = b[i * M + r];
+        md.sys.step(x, u, dt, xn);
+        for (int d = 0; d < N; d++) o1[i * N + d] = xn[d];
+    } else if (what == 1) {   // lqr: S (N x N), K (M x N)
+        T x[N], u[M], S[N * N], K[M * N];
+        for (int d = 0; d < N; d++) x[d] = a[i * N + d];
+        for (int r = 0; r < M; r++) u[r] = b[i * M + r];
+        md.lqr.metric(md.sys, md.dt, x, S);
+        md.lqr.gain(md.sys, md.dt, x, u, K);
+        for (int k = 0; k < N * N; k++) o1[(size_t)i * N * N + k] = S[k];
+        for (int k = 0; k < M * N; k++) o2[(size_t)i * M * N + k] = K[k];
+    } else if (what == 2) {   // erf: a = xgoal, b = x
+        T xg[N], x[N], e[N];
+        for (int d = 0; d < N; d++) { xg[d] = a[i * N + d]; x[d] = b[i * N + d]; }
+        erf_eval<T, N>(md.angle_mask, xg, x, e);
+        for (int d = 0; d < N; d++) o1[i * N + d] = e[d];
+    } else {                  // is_feasible
+        T x[N], u[M];
+        for (int d = 0; d < N; d++) x[d] = a[i * N + d];
+        for (int r = 0; r < M; r++) u[r] = b[i * M + r];
+        ob[i] = feasible_eval<T, N, M>(md.feas, x, u) ? 1 : 0;
+    }
+}
+
+template <typename T>
+__global__ void mark_ignore_kernel(TreeView<T> tv, const int* __restrict__ ids, int count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int node = ids[i];
+    if (node < 0 || node >= *tv.size) return;
+    unsigned* word = (unsigned*)(tv.ignore + (node & ~3));
+    const unsigned bit = 1u << (8 * (node & 3));
+    if (!(atomicOr(word, bit) & bit)) atomicAdd(tv.n_ignored, 1);
+}
+
+template <typename T>
+__global__ void gather_edges_kernel(TreeView<T> tv, const int* __restrict__ ids, int count, int H, int HN, int HM,
+                                    T* __restrict__ ox, T* __restrict__ ou) {
+    const int r = blockIdx.x;
+    if (r >= count) return;
+    const int node = ids[r];
+    const int L = tv.edge_len[node];
+    const int nx = L * (HN / H), nu = L * (HM / H);      // rows past the edge length read back as zero
+    for (int k = threadIdx.x; k < HN; k += blockDim.x) ox[(size_t)r * HN + k] = k < nx ? tv.edge_x[(size_t)node * HN + k] : T(0);
+    for (int k = threadIdx.x; k < HM; k += blockDim.x) ou[(size_t)r * HM + k] = k < nu ? tv.edge_u[(size_t)node * HM + k] : T(0);
+}
+
+template <typename T>
+__global__ void tree_scalars_kernel(TreeView<T> tv, int size) {
+    *tv.size = size; *tv.n_ignored = 0; *tv.n_goal = 0; *tv.best = ~0ull;
+}
+
+template <typename T> struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc((void**)&p, count * sizeof(T));
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { release(); }
+};
+
+// ---- the engine -----------------------------------------------------------
+template <typename T, class Sys, class Lqr>
+struct EngineImpl : lq_engine {
+    static constexpr int N = Sys::N, M = Sys::M;
+    static constexpr int NS = N * (N + 1) / 2;
+    using Md = Model<T, Sys, Lqr>;
+
+    Md md;
+    SamplerParams<T, N> sp;
+    bool have_goal = false, have_sampling = false;
+    int cap = 0, Wc = 0, H = 0, tries_cap = 10;
+    int size_ub = 0;                 // host upper bound of the device-side tree size
+    int steer_lanes = 1, near_q = 0; // tuning (0 = heuristic)
+    bool metric_diag = true;
+    DiagMetric<T, N> dmet;
+    double Sconst[N * N];
+
+    // tree: dim-major so that a scan reads each dim as one contiguous stream
+    DevBuf<T> t_state, t_K, t_ex, t_eu;
+    DevBuf<int> t_parent, t_cost, t_elen, t_scal;
+    DevBuf<uint8_t> t_ignore;
+    DevBuf<unsigned long long> t_best;
+    TreeView<T> tv;
+    // obstacle tables
+    std::vector<DevBuf<T>*> feas_bufs;
+    // wave working set
+    DevBuf<T> w_samples, w_ncost, w_pcost, w_Sp, w_xs, w_us, w_xnew, w_Knew, w_cand, w_goal;
+    DevBuf<int> w_nidx, w_pidx, w_len, w_slot, w_tries, w_pick, w_misc;
+    DevBuf<uint8_t> w_candok;
+    DevBuf<char> w_rec;
+    DevBuf<DevStats> w_stats;
+    size_t rec_sz = 0;
+    lq_wave_stats* h_stats = nullptr;     // pinned
+    int* h_misc = nullptr;                // pinned
+    cudaEvent_t ev_stats = nullptr;
+    bool stats_pending = false;
+    cudaStream_t last_stream = nullptr;
+
+    ~EngineImpl() override {
+        cudaSetDevice(device);
+        for (auto* b : feas_bufs) delete b;
+        if (h_stats) cudaFreeHost(h_stats);
+        if (h_misc) cudaFreeHost(h_misc);
+        if (ev_stats) cudaEventDestroy(ev_stats);
+    }
+
+    template <typename U>
+    int upload(DevBuf<U>& dst, const std::vector<U>& src) {
+        LQ_CUDA(dst.alloc(src.size()));
+        if (!src.empty()) LQ_CUDA(cudaMemcpy(dst.p, src.data(), src.size() * sizeof(U), cudaMemcpyHostToDevice));
+        return LQ_OK;
+    }
+
+    int init(const lq_config* c) {
+        device = c->device;
+        LQ_CUDA(cudaSetDevice(device));
+        if (c->n != N || c->m != M) LQ_FAIL(LQ_ERR_ARG, "model expects n=%d m=%d, config has n=%d m=%d", N, M, c->n, c->m);
+        if (c->n_sys_params != Sys::NPARAMS) LQ_FAIL(LQ_ERR_ARG, "dynamics blob has %d entries, expected %d", c->n_sys_params, Sys::NPARAMS);
+        if (c->horizon_iters < 1) LQ_FAIL(LQ_ERR_ARG, "horizon_iters must be >= 1");
+        if (c->node_capacity < 1 || c->wave_capacity < 1) LQ_FAIL(LQ_ERR_ARG, "capacities must be >= 1");
+        memset(&md, 0, sizeof md);
+        md.sys.unpack(c->sys_params);
+        if (md.lqr.unpack(c->lqr_params, c->n_lqr_params) != 0) LQ_FAIL(LQ_ERR_ARG, "lqr blob does not fit this provider/model");
+        md.angle_mask = c->angle_mask;
+        md.H = H = c->horizon_iters;
+        md.dt = (T)c->dt;
+        md.FPR = c->FPR;
+        for (int i = 0; i < N; i++) {
+            md.tol[i] = (T)c->error_tol[i];
+            md.goal_lo[i] = -Num<T>::inf(); md.goal_hi[i] = Num<T>::inf();
+        }
+        cap = (c->node_capacity + 3) & ~3;
+        Wc = (c->wave_capacity + 3) & ~3;
+        tries_cap = std::max(1, c->tries_capacity);
+
+        // feasibility tables
+        if (c->n_prims < 0 || c->n_prims > LQ_MAX_PRIMS) LQ_FAIL(LQ_ERR_ARG, "at most %d feasibility primitives", LQ_MAX_PRIMS);
+        md.feas.n_prims = c->n_prims;
+        for (int pi = 0; pi < c->n_prims; pi++) {
+            const lq_feas_prim& s = c->prims[pi];
+            FeasPrim<T>& d = md.feas.prims[pi];
+            d.kind = s.kind; d.n_obs = s.n_obs; d.n_verts = s.n_verts; d.flags = s.flags;
+            for (int k = 0; k < 4; k++) d.dims[k] = s.dims[k];
+            d.inflate = (T)s.inflate; d.bound_r = T(0); d.obs = nullptr; d.verts = nullptr; d.nbox = 0;
+            const bool is_box = s.kind == LQ_FEAS_STATE_BOX || s.kind == LQ_FEAS_STATE_REGION || s.kind == LQ_FEAS_EFFORT_BOX;
+            if (is_box) {
+                d.nbox = s.kind == LQ_FEAS_EFFORT_BOX ? M : N;
+                if (!s.lo || !s.hi) LQ_FAIL(LQ_ERR_ARG, "box primitive %d needs lo/hi", pi);
+                for (int k = 0; k < d.nbox; k++) { d.lo[k] = (T)s.lo[k]; d.hi[k] = (T)s.hi[k]; }
+                continue;
+            }
+            int stride;
+            switch (s.kind) {
+            case LQ_FEAS_CIRCLES_POINT: case LQ_FEAS_CIRCLES_CLOUD: stride = 3; break;
+            case LQ_FEAS_BOXES_CLOUD: case LQ_FEAS_SPHERES_POINT: stride = 4; break;
+            default: LQ_FAIL(LQ_ERR_ARG, "unknown feasibility primitive kind %d", s.kind);
+            }
+            const int nd = s.kind == LQ_FEAS_SPHERES_POINT ? 3 : (s.kind == LQ_FEAS_CIRCLES_POINT ? 2 : 3);
+            for (int k = 0; k < nd; k++)
+                if (s.dims[k] < 0 || s.dims[k] >= N) LQ_FAIL(LQ_ERR_ARG, "primitive %d: state dim %d out of range", pi, s.dims[k]);
+            std::vector<T> obs((size_t)std::max(1, s.n_obs) * 4, T(0));
+            for (int o = 0; o < s.n_obs; o++) {
+                for (int k = 0; k < stride; k++) obs[o * 4 + k] = (T)s.obs[o * stride + k];
+                // point primitives compare against inflate + r (demo_boat_novice.py:162): fold it in float64
+                if (s.kind == LQ_FEAS_CIRCLES_POINT) obs[o * 4 + 2] = (T)(s.inflate + s.obs[o * stride + 2]);
+                if (s.kind == LQ_FEAS_SPHERES_POINT) obs[o * 4 + 3] = (T)(s.inflate + s.obs[o * stride + 3]);
+            }
+            auto* ob = new DevBuf<T>(); feas_bufs.push_back(ob);
+            if (int r = upload(*ob, obs)) return r;
+            d.obs = ob->p;
+            if (s.kind == LQ_FEAS_CIRCLES_CLOUD || s.kind == LQ_FEAS_BOXES_CLOUD) {
+                if (s.n_verts < 1 || !s.verts) LQ_FAIL(LQ_ERR_ARG, "cloud primitive %d needs vertices", pi);
+                std::vector<T> vv((size_t)2 * s.n_verts);
+                double br = 0;
+                for (int v = 0; v < s.n_verts; v++) {
+                    vv[v] = (T)s.verts[v]; vv[s.n_verts + v] = (T)s.verts[s.n_verts + v];
+                    br = std::max(br, std::hypot(s.verts[v], s.verts[s.n_verts + v]));
+                }
+                d.bound_r = (T)br;
+                auto* vb = new DevBuf<T>(); feas_bufs.push_back(vb);
+                if (int r = upload(*vb, vv)) return r;
+                d.verts = vb->p;
+            }
+        }
+
+        // tree
+        LQ_CUDA(t_state.alloc((size_t)N * cap));
+        LQ_CUDA(t_K.alloc((size_t)M * N * cap));
+        LQ_CUDA(t_ex.alloc((size_t)cap * H * N));
+        LQ_CUDA(t_eu.alloc((size_t)cap * H * M));
+        LQ_CUDA(t_parent.alloc(cap)); LQ_CUDA(t_cost.alloc(cap)); LQ_CUDA(t_elen.alloc(cap));
+        LQ_CUDA(t_ignore.alloc(cap)); LQ_CUDA(t_scal.alloc(8)); LQ_CUDA(t_best.alloc(1));
+        tv.state = t_state.p; tv.K = t_K.p; tv.parent = t_parent.p; tv.cost = t_cost.p; tv.edge_len = t_elen.p;
+        tv.ignore = t_ignore.p; tv.edge_x = t_ex.p; tv.edge_u = t_eu.p;
+        tv.size = t_scal.p; tv.n_ignored = t_scal.p + 1; tv.n_goal = t_scal.p + 2; tv.best = t_best.p; tv.cap = cap;
+        LQ_CUDA(cudaMemset(t_scal.p, 0, 8 * sizeof(int)));
+
+        // wave working set
+        LQ_CUDA(w_samples.alloc((size_t)N * Wc)); LQ_CUDA(w_ncost.alloc(Wc)); LQ_CUDA(w_nidx.alloc(Wc));
+        LQ_CUDA(w_pcost.alloc((size_t)MAX_SPLIT * Wc)); LQ_CUDA(w_pidx.alloc((size_t)MAX_SPLIT * Wc));
+        LQ_CUDA(w_xs.alloc((size_t)Wc * H * N)); LQ_CUDA(w_us.alloc((size_t)Wc * H * M));
+        LQ_CUDA(w_len.alloc(Wc)); LQ_CUDA(w_slot.alloc(Wc)); LQ_CUDA(w_tries.alloc(Wc)); LQ_CUDA(w_pick.alloc(Wc));
+        LQ_CUDA(w_xnew.alloc((size_t)N * Wc)); LQ_CUDA(w_Knew.alloc((size_t)M * N * Wc));
+        LQ_CUDA(w_misc.alloc(8)); LQ_CUDA(w_stats.alloc(1)); LQ_CUDA(w_goal.alloc(2 * LQ_MAX_N));
+        rec_sz = rec_bytes<T>(Wc, N, M, H);
+        LQ_CUDA(w_rec.alloc(rec_sz));
+        LQ_CUDA(cudaMemset(w_rec.p, 0, rec_sz));
+        LQ_CUDA(cudaMemset(w_tries.p, 0, Wc * sizeof(int)));
+        LQ_CUDA(cudaMallocHost((void**)&h_stats, sizeof(lq_wave_stats)));
+        LQ_CUDA(cudaMallocHost((void**)&h_misc, 8 * sizeof(int)));
+        memset(h_stats, 0, sizeof(lq_wave_stats));
+        LQ_CUDA(cudaEventCreateWithFlags(&ev_stats, cudaEventDisableTiming));
+
+        // metric: constant providers are classified once (planner.py:348 evaluates lqr at every sample)
+        if (Lqr::CONST_METRIC) {
+            metric_diag = true;
+            const T* S = const_metric_ptr();
+            for (int i = 0; i < N; i++)
+                for (int j = 0; j < N; j++) {
+                    Sconst[i * N + j] = (double)S[i * N + j];
+                    if (i != j && S[i * N + j] != T(0)) metric_diag = false;
+                }
+            for (int i = 0; i < N; i++) if (Sconst[i * N + i] < 0) metric_diag = false;
+        } else {
+            metric_diag = false;
+        }
+        if (metric_diag) {
+            dmet.angle_mask = md.angle_mask;
+            dmet.exact = sizeof(T) == 8 ? 1 : 0;
+            for (int i = 0; i < N; i++) {
+                const double w = std::sqrt(Sconst[i * N + i]);
+                dmet.w[i] = (T)w; dmet.period[i] = (T)(6.283185307179586 * w); dmet.sdiag[i] = (T)Sconst[i * N + i];
+            }
+        } else {
+            LQ_CUDA(w_Sp.alloc((size_t)NS * Wc));
+            if (Lqr::CONST_METRIC) {
+                std::vector<T> sp_h((size_t)NS * Wc);
+                int s = N;
+                for (int a = 0; a < N; a++) {
+                    for (int j = 0; j < Wc; j++) sp_h[(size_t)a * Wc + j] = (T)Sconst[a * N + a];
+                    for (int b = a + 1; b < N; b++, s++)
+                        for (int j = 0; j < Wc; j++) sp_h[(size_t)s * Wc + j] = (T)(Sconst[a * N + b] + Sconst[b * N + a]);
+                }
+                LQ_CUDA(cudaMemcpy(w_Sp.p, sp_h.data(), sp_h.size() * sizeof(T), cudaMemcpyHostToDevice));
+            }
+        }
+        // heuristic: split the obstacle tables over a warp once they dominate a rollout step
+        int obs_work = 0;
+        for (int pi = 0; pi < md.feas.n_prims; pi++) obs_work += md.feas.prims[pi].n_obs;
+        steer_lanes = obs_work >= 256 ? 8 : 1;
+        return LQ_OK;
+    }
+
+    const T* const_metric_ptr() { return const_metric_ptr_impl(md.lqr, 0); }
+    template <class L> static auto const_metric_ptr_impl(L& l, int) -> decltype((const T*)l.S) { return l.S; }
+    template <class L> static const T* const_metric_ptr_impl(L&, long) { return nullptr; }
+
+    // ---- problem state --------------------------------------------------------
+    int set_goal(const double* goal, const double* buf) override {
+        LQ_CUDA(cudaSetDevice(device));
+        std::vector<T> g(2 * LQ_MAX_N, T(0));
+        for (int i = 0; i < N; i++) {
+            // goal region (goal - buff, goal + buff), planner.py:482-484; evaluated in float64 first
+            md.goal_lo[i] = (T)(goal[i] - buf[i]); md.goal_hi[i] = (T)(goal[i] + buf[i]);
+            g[i] = md.goal_lo[i]; g[LQ_MAX_N + i] = md.goal_hi[i];
+            sp.goal[i] = (T)goal[i];
+        }
+        LQ_CUDA(cudaMemcpy(w_goal.p, g.data(), g.size() * sizeof(T), cudaMemcpyHostToDevice));
+        have_goal = true;
+        return LQ_OK;
+    }
+
+    int set_sampling(const double* lo, const double* hi, const double* bias, int tries) override {
+        if (tries < 1 || tries > tries_cap) LQ_FAIL(LQ_ERR_ARG, "tries must be in 1..%d", tries_cap);
+        for (int i = 0; i < N; i++) {
+            sp.center[i] = (T)((lo[i] + hi[i]) / 2.0);      // np.mean(sample_space, axis=1), planner.py:197
+            sp.span[i] = (T)(hi[i] - lo[i]);                 // np.diff, planner.py:198
+            sp.bias[i] = (T)bias[i];
+        }
+        sp.tries = tries;
+        have_sampling = true;
+        return LQ_OK;
+    }
+
+    int reset(const double* x0, cudaStream_t st) override {
+        const int parent = -1, cost = 0;
+        return load_nodes(1, x0, &parent, &cost, st);
+    }
+
+    int load_nodes(int count, const double* state, const int* parent, const int* cost, cudaStream_t st) override {
+        LQ_CUDA(cudaSetDevice(device));
+        if (count < 1 || count > cap) LQ_FAIL(LQ_ERR_ARG, "node count %d outside 1..%d", count, cap);
+        std::vector<T> soa((size_t)N * count);
+        for (int i = 0; i < count; i++)
+            for (int d = 0; d < N; d++) soa[(size_t)d * count + i] = (T)state[(size_t)i * N + d];
+        LQ_CUDA(cudaStreamSynchronize(st));
+        for (int d = 0; d < N; d++)
+            LQ_CUDA(cudaMemcpyAsync(t_state.p + (size_t)d * cap, soa.data() + (size_t)d * count, count * sizeof(T),
+                                    cudaMemcpyHostToDevice, st));
+        std::vector<int> par(count, -1), cst(count, 0);
+        if (parent) par.assign(parent, parent + count);
+        if (cost) cst.assign(cost, cost + count);
+        LQ_CUDA(cudaMemcpyAsync(t_parent.p, par.data(), count * sizeof(int), cudaMemcpyHostToDevice, st));
+        LQ_CUDA(cudaMemcpyAsync(t_cost.p, cst.data(), count * sizeof(int), cudaMemcpyHostToDevice, st));
+        LQ_CUDA(cudaMemsetAsync(t_elen.p, 0, count * sizeof(int), st));
+        LQ_CUDA(cudaMemsetAsync(t_ignore.p, 0, cap, st));
+        tree_scalars_kernel<T><<<1, 1, 0, st>>>(tv, count); launches++;
+        init_gain_kernel<T, Sys, Lqr><<<(count + 127) / 128, 128, 0, st>>>(md, t_state.p, t_K.p, cap, count); launches++;
+        LQ_CUDA(cudaGetLastError());
+        LQ_CUDA(cudaStreamSynchronize(st));     // host staging vectors die here
+        size_ub = count;
+        memset(h_stats, 0, sizeof(lq_wave_stats));
+        h_stats->tree_size = count; h_stats->best_node = -1; h_stats->best_cost = -1;
+        stats_pending = false;
+        return LQ_OK;
+    }
+
+    int tree_size(int* out) override {
+        LQ_CUDA(cudaSetDevice(device));
+        LQ_CUDA(cudaDeviceSynchronize());
+        LQ_CUDA(cudaMemcpy(out, tv.size, sizeof(int), cudaMemcpyDeviceToHost));
+        size_ub = *out;
+        return LQ_OK;
+    }
+
+    // ---- K1 -------------------------------------------------------------------
+    int launch_nearest(const T* q, int qstride, int W, int use_ignore, int* idx, T* cost, cudaStream_t st) {
+        const int Nub = std::max(1, size_ub);
+        const int max_splits = std::min(MAX_SPLIT, (Nub + NEAR_BLOCK - 1) / NEAR_BLOCK);
+        const int target = 148 * 8;
+        int nsplit_used = 1;
+        auto plan = [&](int qper, int& nqb, int& chunk, int& nsplit) {
+            nqb = (W + NEAR_BLOCK * qper - 1) / (NEAR_BLOCK * qper);
+            nsplit = std::max(1, std::min(max_splits, (target + nqb - 1) / nqb));
+            chunk = (Nub + nsplit - 1) / nsplit;
+            chunk = (chunk + NEAR_BLOCK - 1) / NEAR_BLOCK * NEAR_BLOCK;
+            nsplit = (Nub + chunk - 1) / chunk;
+        };
+        if (metric_diag) {
+            constexpr int QBIG = sizeof(T) == 4 ? 4 : 2;
+            int nqb, chunk, nsplit;
+            plan(QBIG, nqb, chunk, nsplit);
+            bool big = (long long)nqb * max_splits >= 148 * 2;
+            if (near_q == 1) big = false;
+            if (near_q > 1) big = true;
+            if (big) {
+                nearest_diag_kernel<T, N, QBIG, NEAR_BLOCK><<<nqb * nsplit, NEAR_BLOCK, 0, st>>>(
+                    t_state.p, cap, t_ignore.p, tv.size, tv.n_ignored, use_ignore, q, qstride, W, dmet, nqb, chunk,
+                    w_pcost.p, w_pidx.p, Wc);
+            } else {
+                plan(1, nqb, chunk, nsplit);
+                nearest_diag_kernel<T, N, 1, NEAR_BLOCK><<<nqb * nsplit, NEAR_BLOCK, 0, st>>>(
+                    t_state.p, cap, t_ignore.p, tv.size, tv.n_ignored, use_ignore, q, qstride, W, dmet, nqb, chunk,
+                    w_pcost.p, w_pidx.p, Wc);
+            }
+            nsplit_used = nsplit;
+        } else {
+            if (qstride != Wc) LQ_FAIL(LQ_ERR_STATE, "dense-metric search needs queries in the engine's wave layout");
+            if (!Lqr::CONST_METRIC) {
+                metric_kernel<T, Sys, Lqr><<<(W + 63) / 64, 64, 0, st>>>(md.sys, md.lqr, md.dt, q, qstride, W, w_Sp.p);
+                launches++;
+            }
+            int nqb, chunk, nsplit;
+            plan(1, nqb, chunk, nsplit);
+            nearest_dense_kernel<T, N, NEAR_BLOCK><<<nqb * nsplit, NEAR_BLOCK, 0, st>>>(
+                t_state.p, cap, t_ignore.p, tv.size, tv.n_ignored, use_ignore, q, qstride, W, w_Sp.p, md.angle_mask,
+                nqb, chunk, w_pcost.p, w_pidx.p, Wc);
+            nsplit_used = nsplit;
+        }
+        launches++;
+        nearest_finalize_kernel<T><<<(W + 127) / 128, 128, 0, st>>>(w_pcost.p, w_pidx.p, Wc, nsplit_used, W, idx, cost);
+        launches++;
+        LQ_CUDA(cudaGetLastError());
+        return LQ_OK;
+    }
+
+    int nearest(const void* d_q, int W, int use_ignore, int* d_idx, void* d_cost, cudaStream_t st) override {
+        LQ_CUDA(cudaSetDevice(device));
+        if (W < 1 || W > Wc) LQ_FAIL(LQ_ERR_ARG, "W=%d outside 1..wave_capacity=%d", W, Wc);
+        const T* q = (const T*)d_q;
+        int qstride = W;
+        if (!metric_diag) {     // dense search reads S in the wave layout: restride the queries
+            for (int d = 0; d < N; d++)
+                LQ_CUDA(cudaMemcpyAsync(w_samples.p + (size_t)d * Wc, q + (size_t)d * W, W * sizeof(T), cudaMemcpyDeviceToDevice, st));
+            q = w_samples.p; qstride = Wc;
+        }
+        return launch_nearest(q, qstride, W, use_ignore, d_idx, (T*)d_cost, st);
+    }
+
+    // ---- K2 -------------------------------------------------------------------
+    template <int LANES>
+    void launch_steer_l(const int* ids, const T* targets, int tstride, int W, T* xs, T* us, int* len, T* xnew, T* Knew,
+                        int ostride, cudaStream_t st) {
+        constexpr int BLOCK = 128;
+        const long long threads = (long long)W * LANES;
+        steer_kernel<T, Sys, Lqr, LANES, BLOCK><<<(unsigned)((threads + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(
+            md, t_state.p, t_K.p, cap, ids, targets, tstride, W, xs, us, len, xnew, Knew, ostride);
+        launches++;
+    }
+    void launch_steer(const int* ids, const T* targets, int tstride, int W, T* xs, T* us, int* len, T* xnew, T* Knew,
+                      int ostride, cudaStream_t st) {
+        if (steer_lanes >= 32) launch_steer_l<32>(ids, targets, tstride, W, xs, us, len, xnew, Knew, ostride, st);
+        else if (steer_lanes >= 8) launch_steer_l<8>(ids, targets, tstride, W, xs, us, len, xnew, Knew, ostride, st);
+        else launch_steer_l<1>(ids, targets, tstride, W, xs, us, len, xnew, Knew, ostride, st);
+    }
+
+    int steer(const int* d_ids, const void* d_t, int W, void* d_x, void* d_u, int* d_len, cudaStream_t st) override {
+        LQ_CUDA(cudaSetDevice(device));
+        if (W < 1 || W > Wc) LQ_FAIL(LQ_ERR_ARG, "W=%d outside 1..wave_capacity=%d", W, Wc);
+        T* xs = d_x ? (T*)d_x : w_xs.p;
+        T* us = d_u ? (T*)d_u : w_us.p;
+        if (d_x) LQ_CUDA(cudaMemsetAsync(xs, 0, (size_t)W * H * N * sizeof(T), st));
+        if (d_u) LQ_CUDA(cudaMemsetAsync(us, 0, (size_t)W * H * M * sizeof(T), st));
+        launch_steer(d_ids, (const T*)d_t, W, W, xs, us, d_len ? d_len : w_len.p, nullptr, nullptr, 0, st);
+        LQ_CUDA(cudaGetLastError());
+        return LQ_OK;
+    }
+
+    // ---- one wave -------------------------------------------------------------
+    int expand_from_samples(int count, int use_ignore, int flags, cudaStream_t st) {
+        if (int r = launch_nearest(w_samples.p, Wc, count, use_ignore, w_nidx.p, w_ncost.p, st)) return r;
+        launch_steer(w_nidx.p, w_samples.p, Wc, count, w_xs.p, w_us.p, w_len.p, w_xnew.p, w_Knew.p, Wc, st);
+        RecView<T> rv = rec_view<T>(w_rec.p, Wc, N, M, H);
+        pack_scan_kernel<1024><<<1, 1024, 0, st>>>(w_len.p, w_tries.p, count, w_slot.p, rv.header, flags); launches++;
+        pack_kernel<T><<<(count * 32 + 255) / 256, 256, 0, st>>>(w_len.p, w_slot.p, w_nidx.p, w_xnew.p, w_Knew.p, Wc,
+                                                                w_xs.p, w_us.p, count, rv, Wc, N, M, H);
+        launches++;
+        LQ_CUDA(cudaGetLastError());
+        last_stream = st;
+        return LQ_OK;
+    }
+
+    int wave_expand(uint64_t seed, uint32_t wave, int first, int count, const double* h_samples, int use_ignore,
+                    int flags, cudaStream_t st) override {
+        LQ_CUDA(cudaSetDevice(device));
+        if (count < 0 || count > Wc) LQ_FAIL(LQ_ERR_ARG, "count=%d outside 0..wave_capacity=%d", count, Wc);
+        if (!have_goal) LQ_FAIL(LQ_ERR_STATE, "lq_set_goal has not been called");
+        if (count == 0) {
+            RecView<T> rv = rec_view<T>(w_rec.p, Wc, N, M, H);
+            int hdr[REC_HEADER_INTS] = {0};
+            hdr[HDR_FLAGS] = flags;
+            LQ_CUDA(cudaMemcpyAsync(rv.header, hdr, sizeof hdr, cudaMemcpyHostToDevice, st));
+            LQ_CUDA(cudaStreamSynchronize(st));
+            last_stream = st;
+            return LQ_OK;
+        }
+        if (h_samples) {
+            std::vector<T> soa((size_t)N * count);
+            for (int j = 0; j < count; j++)
+                for (int d = 0; d < N; d++) soa[(size_t)d * count + j] = (T)h_samples[(size_t)j * N + d];
+            for (int d = 0; d < N; d++)
+                LQ_CUDA(cudaMemcpyAsync(w_samples.p + (size_t)d * Wc, soa.data() + (size_t)d * count, count * sizeof(T),
+                                        cudaMemcpyHostToDevice, st));
+            LQ_CUDA(cudaMemsetAsync(w_tries.p, 0, count * sizeof(int), st));
+            LQ_CUDA(cudaStreamSynchronize(st));
+        } else {
+            if (!have_sampling) LQ_FAIL(LQ_ERR_STATE, "lq_set_sampling has not been called");
+            sample_kernel<T, Sys, Lqr><<<(count + 127) / 128, 128, 0, st>>>(md, sp, seed, wave, first, count,
+                                                                            w_samples.p, Wc, w_tries.p);
+            launches++;
+        }
+        return expand_from_samples(count, use_ignore, flags, st);
+    }
+
+    int wave_expand_candidates(int count, int tries, const double* h_cand, int n_cand, int use_ignore,
+                               int* h_consumed, cudaStream_t st) override {
+        LQ_CUDA(cudaSetDevice(device));
+        if (count < 1 || count > Wc) LQ_FAIL(LQ_ERR_ARG, "count=%d outside 1..wave_capacity=%d", count, Wc);
+        if (tries < 1 || n_cand < (long long)count * tries) LQ_FAIL(LQ_ERR_ARG, "need count*tries candidates");
+        if (!have_goal) LQ_FAIL(LQ_ERR_STATE, "lq_set_goal has not been called");
+        if (w_cand.n < (size_t)N * n_cand) { LQ_CUDA(w_cand.alloc((size_t)N * n_cand)); LQ_CUDA(w_candok.alloc(n_cand)); }
+        std::vector<T> soa((size_t)N * n_cand);
+        for (int j = 0; j < n_cand; j++)
+            for (int d = 0; d < N; d++) soa[(size_t)d * n_cand + j] = (T)h_cand[(size_t)j * N + d];
+        LQ_CUDA(cudaMemcpyAsync(w_cand.p, soa.data(), soa.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+        candidates_feasible_kernel<T, Sys, Lqr><<<(n_cand + 127) / 128, 128, 0, st>>>(md, w_cand.p, n_cand, n_cand, w_candok.p);
+        launches++;
+        candidates_select_kernel<T, N><<<1, 256, 0, st>>>(w_cand.p, n_cand, w_candok.p, n_cand, count, tries,
+                                                          w_samples.p, Wc, w_pick.p, w_misc.p);
+        launches++;
+        LQ_CUDA(cudaMemsetAsync(w_tries.p, 0, count * sizeof(int), st));
+        LQ_CUDA(cudaMemcpyAsync(h_misc, w_misc.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (int r = expand_from_samples(count, use_ignore, 0, st)) return r;
+        LQ_CUDA(cudaStreamSynchronize(st));
+        if (h_consumed) *h_consumed = h_misc[0];
+        return LQ_OK;
+    }
+
+    int wave_records(void** d, uint64_t* bytes) override {
+        if (d) *d = w_rec.p;
+        if (bytes) *bytes = rec_sz;
+        return LQ_OK;
+    }
+
+    int wave_commit(const void* d_records, int n_seg, cudaStream_t st) override {
+        LQ_CUDA(cudaSetDevice(device));
+        if (n_seg < 1) LQ_FAIL(LQ_ERR_ARG, "n_segments must be >= 1");
+        const char* rec = d_records ? (const char*)d_records : w_rec.p;
+        const long long warps = (long long)n_seg * Wc;
+        commit_kernel<T><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(tv, rec, rec_sz, n_seg, Wc, N, M, H,
+                                                                                w_goal.p, w_goal.p + LQ_MAX_N);
+        launches++;
+        commit_finish_kernel<T><<<1, 1, 0, st>>>(tv, rec, rec_sz, n_seg, w_stats.p); launches++;
+        LQ_CUDA(cudaGetLastError());
+        LQ_CUDA(cudaMemcpyAsync(h_stats, w_stats.p, sizeof(DevStats), cudaMemcpyDeviceToHost, st));
+        LQ_CUDA(cudaEventRecord(ev_stats, st));
+        stats_pending = true;
+        size_ub = std::min(cap, size_ub + n_seg * Wc);
+        return LQ_OK;
+    }
+
+    int wave_stats(lq_wave_stats* out) override {
+        LQ_CUDA(cudaSetDevice(device));
+        if (stats_pending) { LQ_CUDA(cudaEventSynchronize(ev_stats)); stats_pending = false; }
+        size_ub = h_stats->tree_size;
+        if (out) *out = *h_stats;
+        return LQ_OK;
+    }
+
+    // ---- close-out ------------------------------------------------------------
+    int closest(const double* xg, const uint8_t* colmask, int* id, cudaStream_t st) override {
+        LQ_CUDA(cudaSetDevice(device));
+        // Sguide = lqr(xguide, 0).S with masked columns zeroed (planner.py:313-316)
+        FullMetric<T, N> fm;
+        double S[N * N], K[M * N], u0[M] = {0};
+        if (int r = eval_lqr(1, xg, u0, S, K)) return r;
+        for (int i = 0; i < N; i++) {
+            fm.x[i] = (T)xg[i];
+            for (int j = 0; j < N; j++) fm.S[i * N + j] = (colmask && colmask[j]) ? T(0) : (T)S[i * N + j];
+        }
+        fm.angle_mask = md.angle_mask;
+        closest_kernel<T, N><<<1, 1024, 0, st>>>(t_state.p, cap, tv.size, fm, w_misc.p + 1); launches++;
+        LQ_CUDA(cudaGetLastError());
+        LQ_CUDA(cudaMemcpyAsync(h_misc + 1, w_misc.p + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        LQ_CUDA(cudaStreamSynchronize(st));
+        *id = h_misc[1];
+        return LQ_OK;
+    }
+
+    int steer_force(int node, const double* xtar, int max_steps, double* hx, double* hu, int* len, cudaStream_t st) override {
+        LQ_CUDA(cudaSetDevice(device));
+        if (max_steps < 1) LQ_FAIL(LQ_ERR_ARG, "max_steps must be >= 1");
+        int sz = 0;
+        if (int r = tree_size(&sz)) return r;
+        if (node < 0 || node >= sz) LQ_FAIL(LQ_ERR_ARG, "The given ID, %d, doesn't exist.", node);
+        DevBuf<T> xt, xs, us;
+        std::vector<T> xth(N);
+        for (int d = 0; d < N; d++) xth[d] = (T)xtar[d];
+        if (int r = upload(xt, xth)) return r;
+        LQ_CUDA(xs.alloc((size_t)max_steps * N)); LQ_CUDA(us.alloc((size_t)max_steps * M));
+        steer_force_kernel<T, Sys, Lqr><<<1, 32, 0, st>>>(md, t_state.p, t_K.p, cap, node, xt.p, max_steps, xs.p, us.p, w_misc.p + 2);
+        launches++;
+        LQ_CUDA(cudaGetLastError());
+        LQ_CUDA(cudaStreamSynchronize(st));
+        int L = 0;
+        LQ_CUDA(cudaMemcpy(&L, w_misc.p + 2, sizeof(int), cudaMemcpyDeviceToHost));
+        std::vector<T> bx((size_t)std::max(1, L) * N), bu((size_t)std::max(1, L) * M);
+        if (L > 0) {
+            LQ_CUDA(cudaMemcpy(bx.data(), xs.p, (size_t)L * N * sizeof(T), cudaMemcpyDeviceToHost));
+            LQ_CUDA(cudaMemcpy(bu.data(), us.p, (size_t)L * M * sizeof(T), cudaMemcpyDeviceToHost));
+            for (size_t k = 0; k < (size_t)L * N; k++) hx[k] = (double)bx[k];
+            for (size_t k = 0; k < (size_t)L * M; k++) hu[k] = (double)bu[k];
+        }
+        *len = L;
+        return LQ_OK;
+    }
+
+    int append_node(int parent, const double* state, const double* hx, const double* hu, int len, cudaStream_t st) override {
+        LQ_CUDA(cudaSetDevice(device));
+        int sz = 0;
+        if (int r = tree_size(&sz)) return r;
+        if (parent < 0 || parent >= sz) LQ_FAIL(LQ_ERR_ARG, "The given parent ID, %d, doesn't exist.", parent);   // tree.py:83-84
+        if (sz >= cap) LQ_FAIL(LQ_ERR_STATE, "tree is at node_capacity=%d", cap);
+        // edges longer than the horizon (force-arrive) keep only their length on the device; the host
+        // planner holds the full sequence (planner.py:299-303 extends its own lists)
+        const int keep = std::min(len, H);
+        std::vector<T> ex((size_t)H * N, T(0)), eu((size_t)H * M, T(0)), xs(N);
+        for (int k = 0; k < keep * N; k++) ex[k] = (T)hx[k];
+        for (int k = 0; k < keep * M; k++) eu[k] = (T)hu[k];
+        for (int d = 0; d < N; d++) xs[d] = (T)state[d];
+        for (int d = 0; d < N; d++) LQ_CUDA(cudaMemcpy(t_state.p + (size_t)d * cap + sz, &xs[d], sizeof(T), cudaMemcpyHostToDevice));
+        LQ_CUDA(cudaMemcpy(t_ex.p + (size_t)sz * H * N, ex.data(), ex.size() * sizeof(T), cudaMemcpyHostToDevice));
+        LQ_CUDA(cudaMemcpy(t_eu.p + (size_t)sz * H * M, eu.data(), eu.size() * sizeof(T), cudaMemcpyHostToDevice));
+        int pc = 0;
+        LQ_CUDA(cudaMemcpy(&pc, t_cost.p + parent, sizeof(int), cudaMemcpyDeviceToHost));
+        const int c = pc + len;
+        LQ_CUDA(cudaMemcpy(t_parent.p + sz, &parent, sizeof(int), cudaMemcpyHostToDevice));
+        LQ_CUDA(cudaMemcpy(t_cost.p + sz, &c, sizeof(int), cudaMemcpyHostToDevice));
+        LQ_CUDA(cudaMemcpy(t_elen.p + sz, &keep, sizeof(int), cudaMemcpyHostToDevice));
+        // the reference stores lqr=None for this node (planner.py:299); K = lqr(state, 0) keeps it steerable
+        init_gain_kernel<T, Sys, Lqr><<<1, 32, 0, st>>>(md, t_state.p + sz, t_K.p + sz, cap, 1); launches++;
+        const int nsz = sz + 1;
+        LQ_CUDA(cudaMemcpyAsync(tv.size, &nsz, sizeof(int), cudaMemcpyHostToDevice, st));
+        LQ_CUDA(cudaStreamSynchronize(st));
+        size_ub = nsz; h_stats->tree_size = nsz;
+        return LQ_OK;
+    }
+
+    int mark_ignore(const int* ids, int count, cudaStream_t st) override {
+        LQ_CUDA(cudaSetDevice(device));
+        if (count <= 0) return LQ_OK;
+        DevBuf<int> d;
+        std::vector<int> v(ids, ids + count);
+        if (int r = upload(d, v)) return r;
+        mark_ignore_kernel<T><<<(count + 127) / 128, 128, 0, st>>>(tv, d.p, count); launches++;
+        LQ_CUDA(cudaGetLastError());
+        LQ_CUDA(cudaStreamSynchronize(st));
+        return LQ_OK;
+    }
+
+    // ---- read-back --------------------------------------------------------------
+    int download_nodes(int first, int count, double* state, int* parent, int* cost, int* elen, uint8_t* ign, double* K,
+                       cudaStream_t st) override {
+        LQ_CUDA(cudaSetDevice(device));
+        LQ_CUDA(cudaStreamSynchronize(st));
+        int sz = 0;
+        LQ_CUDA(cudaMemcpy(&sz, tv.size, sizeof(int), cudaMemcpyDeviceToHost));
+        if (first < 0 || count < 0 || first + count > sz) LQ_FAIL(LQ_ERR_ARG, "node range [%d,%d) outside tree of %d", first, first + count, sz);
+        if (count == 0) return LQ_OK;
+        if (state) {
+            std::vector<T> b((size_t)N * count);
+            for (int d = 0; d < N; d++)
+                LQ_CUDA(cudaMemcpy(b.data() + (size_t)d * count, t_state.p + (size_t)d * cap + first, count * sizeof(T), cudaMemcpyDeviceToHost));
+            for (int i = 0; i < count; i++)
+                for (int d = 0; d < N; d++) state[(size_t)i * N + d] = (double)b[(size_t)d * count + i];
+        }
+        if (K) {
+            std::vector<T> b((size_t)M * N * count);
+            for (int k = 0; k < M * N; k++)
+                LQ_CUDA(cudaMemcpy(b.data() + (size_t)k * count, t_K.p + (size_t)k * cap + first, count * sizeof(T), cudaMemcpyDeviceToHost));
+            for (int i = 0; i < count; i++)
+                for (int k = 0; k < M * N; k++) K[(size_t)i * M * N + k] = (double)b[(size_t)k * count + i];
+        }
+        if (parent) LQ_CUDA(cudaMemcpy(parent, t_parent.p + first, count * sizeof(int), cudaMemcpyDeviceToHost));
+        if (cost) LQ_CUDA(cudaMemcpy(cost, t_cost.p + first, count * sizeof(int), cudaMemcpyDeviceToHost));
+        if (elen) LQ_CUDA(cudaMemcpy(elen, t_elen.p + first, count * sizeof(int), cudaMemcpyDeviceToHost));
+        if (ign) LQ_CUDA(cudaMemcpy(ign, t_ignore.p + first, count, cudaMemcpyDeviceToHost));
+        return LQ_OK;
+    }
+
+    int download_edges(const int* ids, int count, double* hx, double* hu, cudaStream_t st) override {
+        LQ_CUDA(cudaSetDevice(device));
+        if (count <= 0) return LQ_OK;
+        int sz = 0;
+        LQ_CUDA(cudaStreamSynchronize(st));
+        LQ_CUDA(cudaMemcpy(&sz, tv.size, sizeof(int), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < count; i++)
+            if (ids[i] < 0 || ids[i] >= sz) LQ_FAIL(LQ_ERR_ARG, "The given ID, %d, doesn't exist.", ids[i]);
+        DevBuf<int> d;
+        std::vector<int> v(ids, ids + count);
+        if (int r = upload(d, v)) return r;
+        DevBuf<T> ox, ou;
+        LQ_CUDA(ox.alloc((size_t)count * H * N)); LQ_CUDA(ou.alloc((size_t)count * H * M));
+        gather_edges_kernel<T><<<count, 128, 0, st>>>(tv, d.p, count, H, H * N, H * M, ox.p, ou.p); launches++;
+        LQ_CUDA(cudaGetLastError());
+        std::vector<T> bx((size_t)count * H * N), bu((size_t)count * H * M);
+        LQ_CUDA(cudaStreamSynchronize(st));
+        LQ_CUDA(cudaMemcpy(bx.data(), ox.p, bx.size() * sizeof(T), cudaMemcpyDeviceToHost));
+        LQ_CUDA(cudaMemcpy(bu.data(), ou.p, bu.size() * sizeof(T), cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < bx.size(); k++) hx[k] = (double)bx[k];
+        for (size_t k = 0; k < bu.size(); k++) hu[k] = (double)bu[k];
+        return LQ_OK;
+    }
+
+    // ---- the callbacks, batched ---------------------------------------------------
+    int eval_generic(int what, int count, const double* a, int na, const double* b, int nb, double dt,
+                     double* o1, int n1, double* o2, int n2, uint8_t* ob) {
+        LQ_CUDA(cudaSetDevice(device));
+        if (count <= 0) return LQ_OK;
+        std::vector<T> ha((size_t)count * na), hb((size_t)count * nb);
+        for (size_t k = 0; k < ha.size(); k++) ha[k] = (T)a[k];
+        for (size_t k = 0; k < hb.size(); k++) hb[k] = (T)b[k];
+        DevBuf<T> da, db, d1, d2;
+        DevBuf<uint8_t> dob;
+        if (int r = upload(da, ha)) return r;
+        if (int r = upload(db, hb)) return r;
+        LQ_CUDA(d1.alloc((size_t)count * std::max(1, n1))); LQ_CUDA(d2.alloc((size_t)count * std::max(1, n2)));
+        LQ_CUDA(dob.alloc(count));
+        eval_kernel<T, Sys, Lqr><<<(count + 63) / 64, 64>>>(md, what, count, da.p, db.p, (T)dt, d1.p, d2.p, dob.p);
+        launches++;
+        LQ_CUDA(cudaGetLastError());
+        LQ_CUDA(cudaDeviceSynchronize());
+        if (o1 && n1) {
+            std::vector<T> h((size_t)count * n1);
+            LQ_CUDA(cudaMemcpy(h.data(), d1.p, h.size() * sizeof(T), cudaMemcpyDeviceToHost));
+            for (size_t k = 0; k < h.size(); k++) o1[k] = (double)h[k];
+        }
+        if (o2 && n2) {
+            std::vector<T> h((size_t)count * n2);
+            LQ_CUDA(cudaMemcpy(h.data(), d2.p, h.size() * sizeof(T), cudaMemcpyDeviceToHost));
+            for (size_t k = 0; k < h.size(); k++) o2[k] = (double)h[k];
+        }
+        if (ob) LQ_CUDA(cudaMemcpy(ob, dob.p, count, cudaMemcpyDeviceToHost));
+        return LQ_OK;
+    }
+    int eval_dynamics(int count, const double* x, const double* u, double dt, double* xn) override {
+        return eval_generic(0, count, x, N, u, M, dt, xn, N, nullptr, 0, nullptr);
+    }
+    int eval_lqr(int count, const double* x, const double* u, double* S, double* K) override {
+        return eval_generic(1, count, x, N, u, M, 0.0, S, N * N, K, M * N, nullptr);
+    }
+    int eval_erf(int count, const double* xg, const double* x, double* e) override {
+        return eval_generic(2, count, xg, N, x, N, 0.0, e, N, nullptr, 0, nullptr);
+    }
+    int eval_feasible(int count, const double* x, const double* u, uint8_t* ok) override {
+        return eval_generic(3, count, x, N, u, M, 0.0, nullptr, 0, nullptr, 0, ok);
+    }
+
+    int set_tuning(int lanes, int nq) override {
+        if (lanes == 1 || lanes == 8 || lanes == 32) steer_lanes = lanes;
+        else if (lanes != 0) LQ_FAIL(LQ_ERR_ARG, "steer lanes must be 0 (keep), 1, 8 or 32");
+        near_q = nq;
+        return LQ_OK;
+    }
+};
+
+template <typename T, class Sys, class Lqr>
+lq_engine* make_engine(const lq_config* cfg, std::string& err, int* rc) {
+    auto* e = new EngineImpl<T, Sys, Lqr>();
+    *rc = e->init(cfg);
+    if (*rc != LQ_OK) { err = e->err; delete e; return nullptr; }
+    return e;
+}
+
+}  // namespace lq

@@ -1,0 +1,4 @@
+#include "inst.cuh"
+namespace lq {
+lq_engine* make_dint_f64(const lq_config* c, std::string& err, int* rc) { return make_dint<double>(c, err, rc); }
+}

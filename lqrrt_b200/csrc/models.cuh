@@ -1,0 +1,510 @@
+// Device twins of the user callbacks on the reference's hot path
+// (dynamics / lqr / erf / is_feasible; contract: reference lqrrt/planner.py:35-59,
+// constraints.py:29).  Everything here is register-resident, per-thread code:
+// n <= 12 states, m <= 6 controls, no tensor cores.  T is float or double.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include "../../include/lqrrt_b200.h"
+
+namespace lq {
+
+template <typename T> struct Num;
+template <> struct Num<float> {
+    static __host__ __device__ __forceinline__ float inf() { return INFINITY; }
+    static __device__ __forceinline__ float two_pi() { return 6.283185307179586f; }
+    static __device__ __forceinline__ float inv_two_pi() { return 0.15915494309189535f; }
+};
+template <> struct Num<double> {
+    static __host__ __device__ __forceinline__ double inf() { return (double)INFINITY; }
+    static __device__ __forceinline__ double two_pi() { return 6.283185307179586; }
+    static __device__ __forceinline__ double inv_two_pi() { return 0.15915494309189535; }
+};
+
+__device__ __forceinline__ void sincos_t(float a, float* s, float* c) { sincosf(a, s, c); }
+__device__ __forceinline__ void sincos_t(double a, double* s, double* c) { sincos(a, s, c); }
+__device__ __forceinline__ float atan2_t(float y, float x) { return atan2f(y, x); }
+__device__ __forceinline__ double atan2_t(double y, double x) { return atan2(y, x); }
+__device__ __forceinline__ float rint_t(float a) { return rintf(a); }
+__device__ __forceinline__ double rint_t(double a) { return rint(a); }
+__device__ __forceinline__ float abs_t(float a) { return fabsf(a); }
+__device__ __forceinline__ double abs_t(double a) { return fabs(a); }
+__device__ __forceinline__ float min_t(float a, float b) { return fminf(a, b); }
+__device__ __forceinline__ double min_t(double a, double b) { return fmin(a, b); }
+__device__ __forceinline__ float max_t(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double max_t(double a, double b) { return fmax(a, b); }
+__device__ __forceinline__ float sqrt_t(float a) { return sqrtf(a); }
+__device__ __forceinline__ double sqrt_t(double a) { return sqrt(a); }
+
+// Signed angle a_to - a_from on the circle in the reference's form
+// atan2(sg*c - cg*s, cg*c + sg*s) (demos/demo_boat_novice.py:112-117).
+template <typename T>
+__device__ __forceinline__ T wrap_sc(T s_from, T c_from, T s_to, T c_to) {
+    return atan2_t(s_to * c_from - c_to * s_from, c_to * c_from + s_to * s_from);
+}
+
+// ---------------------------------------------------------------------------
+// dynamics (reference a5).  step(): x (in) -> xn (out); u is a private copy
+// the model may saturate in place, exactly as the demos mutate their copy
+// (planner.py:390 passes np.copy(u)), so the caller's recorded u stays raw.
+// ---------------------------------------------------------------------------
+
+template <typename T> struct BoatSys {            // demos/demo_boat_{novice,intermediate,advanced}.py
+    static constexpr int N = 6, M = 3;
+    static constexpr int KIND = LQ_SYS_BOAT;
+    T invM[3], Dpos[3], Dneg[3], umax[3], B[12], invB[12], tmax[4];
+    T rudder, vpos0, vneg0;
+    int thruster_clip, carlike, use_rudder;
+
+    __host__ void unpack(const double* p) {
+        int k = 0;
+        for (int i = 0; i < 3; i++) invM[i] = (T)p[k++];
+        for (int i = 0; i < 3; i++) Dpos[i] = (T)p[k++];
+        for (int i = 0; i < 3; i++) Dneg[i] = (T)p[k++];
+        for (int i = 0; i < 3; i++) umax[i] = (T)p[k++];
+        for (int i = 0; i < 12; i++) B[i] = (T)p[k++];
+        for (int i = 0; i < 12; i++) invB[i] = (T)p[k++];
+        for (int i = 0; i < 4; i++) tmax[i] = (T)p[k++];
+        rudder = (T)p[k++]; vpos0 = (T)p[k++]; vneg0 = (T)p[k++];
+        thruster_clip = p[k++] != 0.0; carlike = p[k++] != 0.0; use_rudder = p[k++] != 0.0;
+    }
+    static constexpr int NPARAMS = 46;
+
+    __device__ __forceinline__ void step(const T* x, T* u, T dt, T* xn) const {
+        T s, c;
+        sincos_t(x[2], &s, &c);
+        const T vx = x[3], vy = x[4], vh = x[5];
+        const T D0 = vx >= T(0) ? Dpos[0] : Dneg[0];
+        const T D1 = vy >= T(0) ? Dpos[1] : Dneg[1];
+        const T D2 = vh >= T(0) ? Dpos[2] : Dneg[2];
+        const T wx = c * vx - s * vy;               // R(h) v, world-frame velocity
+        const T wy = s * vx + c * vy;
+        if (use_rudder) {                           // intermediate:71-77, advanced:101-108
+            const T ang = atan2_t(wy, wx);
+            T sg, cg;
+            sincos_t(ang, &sg, &cg);
+            u[2] = u[2] + rudder * wrap_sc(s, c, sg, cg);
+        }
+        if (thruster_clip) {                        // advanced:111  u = B clip(invB u, +-tmax)
+            T th[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                T t = invB[i * 3 + 0] * u[0] + invB[i * 3 + 1] * u[1] + invB[i * 3 + 2] * u[2];
+                th[i] = min_t(max_t(t, -tmax[i]), tmax[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+                u[i] = B[i * 4 + 0] * th[0] + B[i * 4 + 1] * th[1] + B[i * 4 + 2] * th[2] + B[i * 4 + 3] * th[3];
+        } else {                                    // novice:67-69
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+                if (abs_t(u[i]) > umax[i]) u[i] = u[i] > T(0) ? umax[i] : -umax[i];
+        }
+        xn[0] = x[0] + wx * dt;
+        xn[1] = x[1] + wy * dt;
+        xn[2] = x[2] + vh * dt;
+        xn[3] = vx + (invM[0] * (u[0] - D0 * vx)) * dt;
+        xn[4] = vy + (invM[1] * (u[1] - D1 * vy)) * dt;
+        xn[5] = vh + (invM[2] * (u[2] - D2 * vh)) * dt;
+        if (carlike) {                              // intermediate:88-98, advanced:120-128
+            if (vx > T(0)) xn[5] = min_t(abs_t(xn[3] / vpos0), T(1)) * xn[5];
+            else if (vx < T(0)) xn[5] = min_t(abs_t(xn[3] / vneg0), T(1)) * xn[5];
+            if (xn[3] < T(0)) xn[3] = T(0);
+        }
+    }
+};
+
+template <typename T> struct CarSys {             // demos/demo_car.py:46-72
+    static constexpr int N = 5, M = 2;
+    static constexpr int KIND = LQ_SYS_CAR;
+    T invM[2], D[2], ulo[2], uhi[2], velmax0;
+    static constexpr int NPARAMS = 9;
+    __host__ void unpack(const double* p) {
+        int k = 0;
+        for (int i = 0; i < 2; i++) invM[i] = (T)p[k++];
+        for (int i = 0; i < 2; i++) D[i] = (T)p[k++];
+        for (int i = 0; i < 2; i++) ulo[i] = (T)p[k++];
+        for (int i = 0; i < 2; i++) uhi[i] = (T)p[k++];
+        velmax0 = (T)p[k++];
+    }
+    __device__ __forceinline__ void step(const T* x, T* u, T dt, T* xn) const {
+        T s, c;
+        sincos_t(x[2], &s, &c);
+        u[0] = min_t(max_t(u[0], ulo[0]), uhi[0]);
+        u[1] = min_t(max_t(u[1], ulo[1]), uhi[1]);
+        xn[0] = x[0] + (c * x[3]) * dt;
+        xn[1] = x[1] + (s * x[3]) * dt;
+        xn[2] = x[2] + x[4] * dt;
+        xn[3] = x[3] + (invM[0] * (u[0] - D[0] * x[3])) * dt;
+        xn[4] = x[4] + (invM[1] * (u[1] - D[1] * x[4])) * dt;
+        if (xn[3] < T(0)) xn[3] = T(0);
+        xn[4] = min_t(abs_t(xn[3] / velmax0), T(1)) * xn[4];
+    }
+};
+
+template <typename T> struct PendulumSys {        // config C1
+    static constexpr int N = 2, M = 1;
+    static constexpr int KIND = LQ_SYS_PENDULUM2;
+    T ml2, mgl, damping, tau_max;
+    static constexpr int NPARAMS = 5;
+    __host__ void unpack(const double* p) {
+        ml2 = (T)(p[0] * p[1] * p[1]); mgl = (T)(p[0] * p[3] * p[1]); damping = (T)p[2]; tau_max = (T)p[4];
+    }
+    __device__ __forceinline__ void step(const T* x, T* u, T dt, T* xn) const {
+        T s, c;
+        sincos_t(x[0], &s, &c);
+        const T tau = min_t(max_t(u[0], -tau_max), tau_max);
+        const T wdot = (tau - damping * x[1] - mgl * s) / ml2;
+        xn[0] = x[0] + x[1] * dt;
+        xn[1] = x[1] + wdot * dt;
+    }
+};
+
+template <typename T, int D> struct DoubleIntSys { // config C5
+    static constexpr int N = 2 * D, M = D;
+    static constexpr int KIND = LQ_SYS_DOUBLE_INTEGRATOR;
+    int axes;
+    static constexpr int NPARAMS = 1;
+    __host__ void unpack(const double* p) { axes = (int)p[0]; }
+    __device__ __forceinline__ void step(const T* x, T* u, T dt, T* xn) const {
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+            xn[i] = x[i] + x[D + i] * dt;
+            xn[D + i] = x[D + i] + u[i] * dt;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------
+// erf (reference a7): e = xgoal - x, masked dims wrapped.
+// ---------------------------------------------------------------------------
+template <typename T, int N>
+__device__ __forceinline__ void erf_eval(uint32_t angle_mask, const T* xgoal, const T* x, T* e) {
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        if (angle_mask & (1u << i)) {
+            T s, c, sg, cg;
+            sincos_t(x[i], &s, &c);
+            sincos_t(xgoal[i], &sg, &cg);
+            e[i] = wrap_sc(s, c, sg, cg);
+        } else {
+            e[i] = xgoal[i] - x[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// lqr providers (reference a6).  gain(): K (M x N row-major) at (x,u);
+// metric(): S (N x N row-major) at x with u = 0 (planner.py:348).
+// ---------------------------------------------------------------------------
+template <typename T, class Sys> struct PdRotatedLqr {
+    static constexpr int N = Sys::N, M = Sys::M;
+    static constexpr int KIND = LQ_LQR_PD_ROTATED;
+    static constexpr bool CONST_METRIC = true;
+    T kp[M * M], kd[M * M], S[N * N];
+    __host__ int unpack(const double* p, int count) {
+        if (count != 2 * M * M + N * N) return -1;
+        if (!((N == 6 && M == 3) || (N == 5 && M == 2))) return -1;
+        int k = 0;
+        for (int i = 0; i < M * M; i++) kp[i] = (T)p[k++];
+        for (int i = 0; i < M * M; i++) kd[i] = (T)p[k++];
+        for (int i = 0; i < N * N; i++) S[i] = (T)p[k++];
+        return 0;
+    }
+    __device__ __forceinline__ void gain(const Sys&, T, const T* x, const T*, T* K) const {
+        T s, c;
+        sincos_t(x[2], &s, &c);
+        if (M == 3) {                               // K = [kp R(h)^T, kd], demo_boat_novice.py:86-103
+#pragma unroll
+            for (int i = 0; i < M; i++) {
+                K[i * N + 0] = kp[i * M + 0] * c - kp[i * M + 1] * s;
+                K[i * N + 1] = kp[i * M + 0] * s + kp[i * M + 1] * c;
+                K[i * N + 2] = kp[i * M + 2 % M];
+#pragma unroll
+                for (int j = 0; j < M; j++) K[i * N + 3 + j] = kd[i * M + j];
+            }
+        } else {                                    // K = [kp [[c,s,0],[0,0,1]], kd], demo_car.py:95-113
+#pragma unroll
+            for (int i = 0; i < M; i++) {
+                K[i * N + 0] = kp[i * M + 0] * c;
+                K[i * N + 1] = kp[i * M + 0] * s;
+                K[i * N + 2] = kp[i * M + 1 % M];
+#pragma unroll
+                for (int j = 0; j < M; j++) K[i * N + 3 + j] = kd[i * M + j];
+            }
+        }
+    }
+    __device__ __forceinline__ void metric(const Sys&, T, const T*, T* Sout) const {
+#pragma unroll
+        for (int i = 0; i < N * N; i++) Sout[i] = S[i];
+    }
+};
+
+template <typename T, class Sys> struct ConstantLqr {
+    static constexpr int N = Sys::N, M = Sys::M;
+    static constexpr int KIND = LQ_LQR_CONSTANT;
+    static constexpr bool CONST_METRIC = true;
+    T S[N * N], K0[M * N];
+    __host__ int unpack(const double* p, int count) {
+        if (count != N * N + M * N) return -1;
+        int k = 0;
+        for (int i = 0; i < N * N; i++) S[i] = (T)p[k++];
+        for (int i = 0; i < M * N; i++) K0[i] = (T)p[k++];
+        return 0;
+    }
+    __device__ __forceinline__ void gain(const Sys&, T, const T*, const T*, T* K) const {
+#pragma unroll
+        for (int i = 0; i < M * N; i++) K[i] = K0[i];
+    }
+    __device__ __forceinline__ void metric(const Sys&, T, const T*, T* Sout) const {
+#pragma unroll
+        for (int i = 0; i < N * N; i++) Sout[i] = S[i];
+    }
+};
+
+// Finite-difference Jacobian + backward finite-horizon discrete Riccati sweep
+// (BASELINE.json north_star; oracle twin oracle/models.py fd_jacobians /
+// riccati_sweep).  All matrices are thread-private; loops are fully unrolled
+// for small N so they live in registers, larger N spills to L1-backed local.
+template <typename T, class Sys> struct FdRiccatiLqr {
+    static constexpr int N = Sys::N, M = Sys::M;
+    static constexpr int KIND = LQ_LQR_FD_RICCATI;
+    static constexpr bool CONST_METRIC = false;
+    T Q[N * N], R[M * M];
+    T eps;
+    int steps;
+    __host__ int unpack(const double* p, int count) {
+        if (count != N * N + M * M + 2) return -1;
+        int k = 0;
+        for (int i = 0; i < N * N; i++) Q[i] = (T)p[k++];
+        for (int i = 0; i < M * M; i++) R[i] = (T)p[k++];
+        eps = (T)p[k++]; steps = (int)p[k++];
+        return 0;
+    }
+
+    __device__ void solve(const Sys& sys, T dt, const T* x, const T* u, T* P, T* K) const {
+        T A[N * N], Bm[N * M];
+        const T inv2e = T(1) / (T(2) * eps);
+        // central differences of the discrete map (n + m column pairs)
+        for (int j = 0; j < N; j++) {
+            T xp[N], xm[N], up[M], um[M], fp[N], fm[N];
+#pragma unroll
+            for (int i = 0; i < N; i++) { xp[i] = x[i]; xm[i] = x[i]; }
+#pragma unroll
+            for (int i = 0; i < M; i++) { up[i] = u[i]; um[i] = u[i]; }
+            xp[j] += eps; xm[j] -= eps;
+            sys.step(xp, up, dt, fp);
+            sys.step(xm, um, dt, fm);
+#pragma unroll
+            for (int i = 0; i < N; i++) A[i * N + j] = (fp[i] - fm[i]) * inv2e;
+        }
+        for (int j = 0; j < M; j++) {
+            T xp[N], xm[N], up[M], um[M], fp[N], fm[N];
+#pragma unroll
+            for (int i = 0; i < N; i++) { xp[i] = x[i]; xm[i] = x[i]; }
+#pragma unroll
+            for (int i = 0; i < M; i++) { up[i] = u[i]; um[i] = u[i]; }
+            up[j] += eps; um[j] -= eps;
+            sys.step(xp, up, dt, fp);
+            sys.step(xm, um, dt, fm);
+#pragma unroll
+            for (int i = 0; i < N; i++) Bm[i * M + j] = (fp[i] - fm[i]) * inv2e;
+        }
+#pragma unroll
+        for (int i = 0; i < N * N; i++) P[i] = Q[i];
+#pragma unroll
+        for (int i = 0; i < M * N; i++) K[i] = T(0);
+        for (int it = 0; it < steps; it++) {
+            T BtP[M * N];                           // B' P        (M x N)
+            for (int i = 0; i < M; i++)
+                for (int j = 0; j < N; j++) {
+                    T a = T(0);
+                    for (int k = 0; k < N; k++) a += Bm[k * M + i] * P[k * N + j];
+                    BtP[i * N + j] = a;
+                }
+            T G[M * M], Rhs[M * N];                 // G = R + B'PB, Rhs = B'PA
+            for (int i = 0; i < M; i++) {
+                for (int j = 0; j < M; j++) {
+                    T a = R[i * M + j];
+                    for (int k = 0; k < N; k++) a += BtP[i * N + k] * Bm[k * M + j];
+                    G[i * M + j] = a;
+                }
+                for (int j = 0; j < N; j++) {
+                    T a = T(0);
+                    for (int k = 0; k < N; k++) a += BtP[i * N + k] * A[k * N + j];
+                    Rhs[i * N + j] = a;
+                }
+            }
+            // K = G^-1 Rhs by Gaussian elimination with partial pivoting (as LAPACK gesv in the oracle)
+            for (int col = 0; col < M; col++) {
+                int piv = col;
+                T big = abs_t(G[col * M + col]);
+                for (int r = col + 1; r < M; r++) {
+                    T v = abs_t(G[r * M + col]);
+                    if (v > big) { big = v; piv = r; }
+                }
+                if (piv != col) {
+                    for (int j = 0; j < M; j++) { T t = G[col * M + j]; G[col * M + j] = G[piv * M + j]; G[piv * M + j] = t; }
+                    for (int j = 0; j < N; j++) { T t = Rhs[col * N + j]; Rhs[col * N + j] = Rhs[piv * N + j]; Rhs[piv * N + j] = t; }
+                }
+                const T inv = T(1) / G[col * M + col];
+                for (int r = col + 1; r < M; r++) {
+                    const T f = G[r * M + col] * inv;
+                    for (int j = col; j < M; j++) G[r * M + j] -= f * G[col * M + j];
+                    for (int j = 0; j < N; j++) Rhs[r * N + j] -= f * Rhs[col * N + j];
+                }
+            }
+            for (int r = M - 1; r >= 0; r--) {
+                const T inv = T(1) / G[r * M + r];
+                for (int j = 0; j < N; j++) {
+                    T a = Rhs[r * N + j];
+                    for (int k = r + 1; k < M; k++) a -= G[r * M + k] * K[k * N + j];
+                    K[r * N + j] = a * inv;
+                }
+            }
+            // P = Q + A' P (A - B K)
+            T AmBK[N * N];
+            for (int i = 0; i < N; i++)
+                for (int j = 0; j < N; j++) {
+                    T a = A[i * N + j];
+                    for (int k = 0; k < M; k++) a -= Bm[i * M + k] * K[k * N + j];
+                    AmBK[i * N + j] = a;
+                }
+            T AtP[N * N];
+            for (int i = 0; i < N; i++)
+                for (int j = 0; j < N; j++) {
+                    T a = T(0);
+                    for (int k = 0; k < N; k++) a += A[k * N + i] * P[k * N + j];
+                    AtP[i * N + j] = a;
+                }
+            for (int i = 0; i < N; i++)
+                for (int j = 0; j < N; j++) {
+                    T a = Q[i * N + j];
+                    for (int k = 0; k < N; k++) a += AtP[i * N + k] * AmBK[k * N + j];
+                    P[i * N + j] = a;
+                }
+        }
+    }
+    __device__ void gain(const Sys& sys, T dt, const T* x, const T* u, T* K) const {
+        T P[N * N];
+        solve(sys, dt, x, u, P, K);
+    }
+    __device__ void metric(const Sys& sys, T dt, const T* x, T* Sout) const {
+        T K[M * N], u0[M];
+#pragma unroll
+        for (int i = 0; i < M; i++) u0[i] = T(0);
+        solve(sys, dt, x, u0, Sout, K);
+    }
+};
+
+// ---------------------------------------------------------------------------
+// feasibility (reference a8): conjunction of primitives, obstacle tables in
+// global memory (read-only path; every lane of a warp walks the same table).
+// ---------------------------------------------------------------------------
+template <typename T> struct FeasPrim {
+    int kind, n_obs, n_verts, flags;
+    int dims[4];
+    T inflate;
+    T bound_r;            // cloud: max vertex norm (broad phase)
+    const T* obs;         // n_obs x stride (row-major, stride 4)
+    const T* verts;       // 2 x n_verts
+    T lo[LQ_MAX_N], hi[LQ_MAX_N];
+    int nbox;
+};
+
+template <typename T> struct FeasSet {
+    int n_prims;
+    FeasPrim<T> prims[LQ_MAX_PRIMS];
+};
+
+// lane / lanes: cooperative evaluation by `lanes` threads that all hold the
+// same (x,u); obstacle loops are strided by lane.  Returns this lane's verdict;
+// the caller combines lanes (AND).  lanes == 1 is the scalar case.
+template <typename T, int N, int M>
+__device__ __forceinline__ bool feasible_eval(const FeasSet<T>& fs, const T* x, const T* u, int lane = 0, int lanes = 1) {
+    for (int pi = 0; pi < fs.n_prims; pi++) {
+        const FeasPrim<T>& p = fs.prims[pi];
+        switch (p.kind) {
+        case LQ_FEAS_STATE_BOX:
+#pragma unroll
+            for (int i = 0; i < N; i++)
+                if (i < p.nbox && (x[i] > p.hi[i] || x[i] < p.lo[i])) return false;
+            break;
+        case LQ_FEAS_EFFORT_BOX:
+#pragma unroll
+            for (int i = 0; i < M; i++)
+                if (i < p.nbox && abs_t(u[i]) > p.hi[i]) return false;
+            break;
+        case LQ_FEAS_STATE_REGION: {
+            bool inside = true;
+#pragma unroll
+            for (int i = 0; i < N; i++)
+                if (i < p.nbox && !(x[i] >= p.lo[i] && x[i] <= p.hi[i])) inside = false;
+            if (inside) return false;
+            break;
+        }
+        case LQ_FEAS_CIRCLES_POINT: {               // demo_boat_novice.py:160-164
+            T px = T(0), py = T(0);
+#pragma unroll
+            for (int i = 0; i < N; i++) { if (i == p.dims[0]) px = x[i]; if (i == p.dims[1]) py = x[i]; }
+            for (int o = lane; o < p.n_obs; o += lanes) {
+                const T dx = px - p.obs[o * 4 + 0], dy = py - p.obs[o * 4 + 1];
+                const T rr = p.obs[o * 4 + 2];      // inflate + r, host-added
+                if (dx * dx + dy * dy <= rr * rr) return false;
+            }
+            break;
+        }
+        case LQ_FEAS_SPHERES_POINT: {
+            T px = T(0), py = T(0), pz = T(0);
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                if (i == p.dims[0]) px = x[i];
+                if (i == p.dims[1]) py = x[i];
+                if (i == p.dims[2]) pz = x[i];
+            }
+            for (int o = lane; o < p.n_obs; o += lanes) {
+                const T dx = px - p.obs[o * 4 + 0], dy = py - p.obs[o * 4 + 1], dz = pz - p.obs[o * 4 + 2];
+                const T rr = p.obs[o * 4 + 3];
+                if (dx * dx + dy * dy + dz * dz <= rr * rr) return false;
+            }
+            break;
+        }
+        case LQ_FEAS_CIRCLES_CLOUD:                 // demo_boat_intermediate.py:198-210, demo_car.py:168-180
+        case LQ_FEAS_BOXES_CLOUD: {
+            T px = T(0), py = T(0), ph = T(0);
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                if (i == p.dims[0]) px = x[i];
+                if (i == p.dims[1]) py = x[i];
+                if (i == p.dims[2]) ph = x[i];
+            }
+            T s, c;
+            sincos_t(ph, &s, &c);
+            const bool circ = p.kind == LQ_FEAS_CIRCLES_CLOUD;
+            for (int o = lane; o < p.n_obs; o += lanes) {
+                const T ox = p.obs[o * 4 + 0], oy = p.obs[o * 4 + 1];
+                const T a = p.obs[o * 4 + 2], b = p.obs[o * 4 + 3];
+                if (p.flags & 1) {                  // demo_car.py:175: vertex at 2 * position
+                    const T ex = px + px - ox, ey = py + py - oy;
+                    if (circ ? (ex * ex + ey * ey <= a * a) : (abs_t(ex) <= a && abs_t(ey) <= b)) return false;
+                }
+                // broad phase: hull bounding circle vs obstacle bounding circle (conservative)
+                const T dx = px - ox, dy = py - oy;
+                const T reach = (circ ? a : sqrt_t(a * a + b * b)) + p.bound_r;
+                if (dx * dx + dy * dy > reach * reach * T(1.0001)) continue;
+                for (int v = 0; v < p.n_verts; v++) {
+                    const T bx = p.verts[v], by = p.verts[p.n_verts + v];
+                    const T ex = dx + (c * bx - s * by), ey = dy + (s * bx + c * by);
+                    if (circ ? (ex * ex + ey * ey <= a * a) : (abs_t(ex) <= a && abs_t(ey) <= b)) return false;
+                }
+            }
+            break;
+        }
+        default: break;
+        }
+    }
+    return true;
+}
+
+}  // namespace lq

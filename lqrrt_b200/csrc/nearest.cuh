@@ -1,0 +1,290 @@
+// K1: nearest-node search = Planner._costs_to_go + argmin/argsort selection
+// (reference lqrrt/planner.py:239-247, 340-350, erf_v :585-588), for a whole
+// wave of queries against the SoA tree in HBM.
+//
+// Brute force on the FP32/FP64 pipes (no tensor cores: the angle wrap is not a
+// bilinear form and K = n <= 12 would waste the MMA tile).  Work item =
+// (query block, node split); node tiles are staged from the dim-major tree
+// into shared memory once per CTA and broadcast to all lanes, every thread
+// keeps Q queries and their running (min, argmin) in registers, partial
+// results per split are reduced by nearest_finalize_kernel.
+//
+// Ignore semantics (planner.py:240-245: first node in cost order that is not
+// on a finished plan, plain argmin if every node is ignored): ignored nodes are
+// staged as +inf so they can never win; the "all ignored" case is detected from
+// the engine's ignored-node counter and handled by scanning with the mask off.
+#pragma once
+#include "models.cuh"
+
+namespace lq {
+
+// Diagonal metric in pre-scaled form: cost = sum_i (w_i * wrap_i(q_i - v_i))^2,
+// w_i = sqrt(S_ii); for an angle dim the wrapped magnitude of the scaled
+// difference is min(|d|, P_i - |d|) with P_i = 2 pi w_i once both operands are
+// reduced to one period.
+template <typename T, int N> struct DiagMetric {
+    T w[N];
+    T period[N];
+    uint32_t angle_mask;
+    int exact;            // 1: unscaled d*S*d with rint wrap (float64 parity mode)
+    T sdiag[N];
+};
+
+template <int N> struct PadDim { static constexpr int V = (N + 3) / 4 * 4; };
+
+template <typename T>
+__device__ __forceinline__ T reduce_period(T a) {   // a -> a - 2 pi rint(a / 2 pi)
+    return a - Num<T>::two_pi() * rint_t(a * Num<T>::inv_two_pi());
+}
+
+template <typename T, int N, int Q, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+nearest_diag_kernel(const T* __restrict__ state, int cap, const uint8_t* __restrict__ ignore,
+                    const int* __restrict__ d_size, const int* __restrict__ d_nignored, int use_ignore,
+                    const T* __restrict__ queries, int qstride, int W,
+                    DiagMetric<T, N> met, int nqb, int chunk,
+                    T* __restrict__ pcost, int* __restrict__ pidx, int pstride) {
+    constexpr int NP = PadDim<N>::V;
+    constexpr int TILE = BLOCK;
+    __shared__ __align__(16) T tile[TILE * NP];
+
+    const int qb = blockIdx.x % nqb;
+    const int split = blockIdx.x / nqb;
+    const int size = *d_size;
+    const bool mask_on = use_ignore && (*d_nignored < size);
+    const int n0 = split * chunk;
+    const int n1 = min(n0 + chunk, size);
+
+    T q[Q][N];
+    T best[Q];
+    int bidx[Q];
+    const int qbase = qb * (BLOCK * Q) + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < Q; k++) {
+        const int j = qbase + k * BLOCK;
+        best[k] = Num<T>::inf();
+        bidx[k] = -1;
+#pragma unroll
+        for (int d = 0; d < N; d++) {
+            T v = j < W ? queries[(size_t)d * qstride + j] : T(0);
+            if (!met.exact) {
+                if (met.angle_mask & (1u << d)) v = reduce_period(v);
+                v *= met.w[d];
+            }
+            q[k][d] = v;
+        }
+    }
+
+    for (int base = n0; base < n1; base += TILE) {
+        __syncthreads();
+        {   // stage one node per thread: coalesced along the node index for every dim
+            const int node = base + threadIdx.x;
+            const bool live = node < n1 && !(mask_on && ignore[node]);
+            T v[NP];
+#pragma unroll
+            for (int d = 0; d < N; d++) {
+                T a = live ? state[(size_t)d * cap + node] : Num<T>::inf();
+                if (!met.exact) {
+                    if (met.angle_mask & (1u << d)) a = reduce_period(a);
+                    a *= met.w[d];
+                    if (!live) a = Num<T>::inf();
+                }
+                v[d] = a;
+            }
+#pragma unroll
+            for (int d = N; d < NP; d++) v[d] = T(0);
+#pragma unroll
+            for (int d = 0; d < NP; d++) tile[threadIdx.x * NP + d] = v[d];
+        }
+        __syncthreads();
+        const int cnt = min(TILE, n1 - base);
+#pragma unroll 2
+        for (int i = 0; i < cnt; i++) {
+            T v[NP];
+#pragma unroll
+            for (int d = 0; d < NP; d++) v[d] = tile[i * NP + d];   // same address in every lane: broadcast
+            const int node = base + i;
+#pragma unroll
+            for (int k = 0; k < Q; k++) {
+                T c = T(0);
+                if (met.exact) {
+#pragma unroll
+                    for (int d = 0; d < N; d++) {
+                        T e = q[k][d] - v[d];
+                        if (met.angle_mask & (1u << d)) e = reduce_period(e);
+                        c += e * met.sdiag[d] * e;
+                    }
+                } else {
+#pragma unroll
+                    for (int d = 0; d < N; d++) {
+                        T e = q[k][d] - v[d];
+                        if (met.angle_mask & (1u << d)) {
+                            const T a = abs_t(e);
+                            e = min_t(a, met.period[d] - a);
+                        }
+                        c = fma(e, e, c);
+                    }
+                }
+                if (c < best[k]) { best[k] = c; bidx[k] = node; }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < Q; k++) {
+        const int j = qbase + k * BLOCK;
+        if (j < W) {
+            pcost[(size_t)split * pstride + j] = best[k];
+            pidx[(size_t)split * pstride + j] = bidx[k];
+        }
+    }
+}
+
+// Dense per-query metric: cost = d' S d with S symmetrised and packed
+// (diagonal, then doubled upper triangle), NS = N (N + 1) / 2 coefficients per
+// query held in registers.
+template <typename T, int N, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+nearest_dense_kernel(const T* __restrict__ state, int cap, const uint8_t* __restrict__ ignore,
+                     const int* __restrict__ d_size, const int* __restrict__ d_nignored, int use_ignore,
+                     const T* __restrict__ queries, int qstride, int W,
+                     const T* __restrict__ Spacked, uint32_t angle_mask, int nqb, int chunk,
+                     T* __restrict__ pcost, int* __restrict__ pidx, int pstride) {
+    constexpr int NP = PadDim<N>::V;
+    constexpr int NS = N * (N + 1) / 2;
+    constexpr int TILE = BLOCK;
+    __shared__ __align__(16) T tile[TILE * NP];
+
+    const int qb = blockIdx.x % nqb;
+    const int split = blockIdx.x / nqb;
+    const int size = *d_size;
+    const bool mask_on = use_ignore && (*d_nignored < size);
+    const int n0 = split * chunk;
+    const int n1 = min(n0 + chunk, size);
+    const int j = qb * BLOCK + threadIdx.x;
+
+    T q[N], S[NS];
+#pragma unroll
+    for (int d = 0; d < N; d++) q[d] = j < W ? queries[(size_t)d * qstride + j] : T(0);
+#pragma unroll
+    for (int s = 0; s < NS; s++) S[s] = j < W ? Spacked[(size_t)s * qstride + j] : T(0);
+    T best = Num<T>::inf();
+    int bidx = -1;
+
+    for (int base = n0; base < n1; base += TILE) {
+        __syncthreads();
+        {
+            const int node = base + threadIdx.x;
+            const bool live = node < n1 && !(mask_on && ignore[node]);
+#pragma unroll
+            for (int d = 0; d < NP; d++)
+                tile[threadIdx.x * NP + d] = d < N ? (live ? state[(size_t)d * cap + node] : Num<T>::inf()) : T(0);
+        }
+        __syncthreads();
+        const int cnt = min(TILE, n1 - base);
+        for (int i = 0; i < cnt; i++) {
+            T e[N];
+#pragma unroll
+            for (int d = 0; d < N; d++) {
+                e[d] = q[d] - tile[i * NP + d];
+                if (angle_mask & (1u << d)) e[d] = reduce_period(e[d]);
+            }
+            T c = T(0);
+            int s = N;
+#pragma unroll
+            for (int a = 0; a < N; a++) {
+                T r = S[a] * e[a];
+#pragma unroll
+                for (int b = a + 1; b < N; b++) r = fma(S[s++], e[b], r);
+                c = fma(e[a], r, c);
+            }
+            // a dead (inf) node yields inf or NaN; neither compares below best
+            if (c < best) { best = c; bidx = base + i; }
+        }
+    }
+    if (j < W) {
+        pcost[(size_t)split * pstride + j] = best;
+        pidx[(size_t)split * pstride + j] = bidx;
+    }
+}
+
+// Reduce the per-split partials in ascending split order with a strict '<':
+// lowest node index wins ties, as NumPy's argmin / first-in-argsort does.
+template <typename T>
+__global__ void nearest_finalize_kernel(const T* __restrict__ pcost, const int* __restrict__ pidx, int pstride,
+                                        int nsplit, int W, int* __restrict__ idx, T* __restrict__ cost) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= W) return;
+    T best = Num<T>::inf();
+    int b = -1;
+    for (int s = 0; s < nsplit; s++) {
+        const T c = pcost[(size_t)s * pstride + j];
+        const int i = pidx[(size_t)s * pstride + j];
+        if (i >= 0 && (b < 0 || c < best)) { best = c; b = i; }
+    }
+    idx[j] = b < 0 ? 0 : b;
+    if (cost) cost[j] = best;
+}
+
+// Per-query metric for state-dependent providers (planner.py:348: S = lqr(x, 0)[0]
+// at the sample), packed for nearest_dense_kernel.
+template <typename T, class Sys, class Lqr>
+__global__ void metric_kernel(Sys sys, Lqr lqr, T dt, const T* __restrict__ queries, int qstride, int W,
+                              T* __restrict__ Spacked) {
+    constexpr int N = Sys::N;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= W) return;
+    T x[N], S[N * N];
+#pragma unroll
+    for (int d = 0; d < N; d++) x[d] = queries[(size_t)d * qstride + j];
+    lqr.metric(sys, dt, x, S);
+    int s = N;
+    for (int a = 0; a < N; a++) {
+        Spacked[(size_t)a * qstride + j] = S[a * N + a];
+        for (int b = a + 1; b < N; b++) Spacked[(size_t)(s++) * qstride + j] = S[a * N + b] + S[b * N + a];
+    }
+}
+
+// K5: closest-to-guide (planner.py:313-318), one query, full (possibly
+// column-zeroed, hence asymmetric) S.  Single CTA; once per plan.
+template <typename T, int N>
+struct FullMetric { T S[N * N]; T x[N]; uint32_t angle_mask; };
+
+template <typename T, int N>
+__global__ void closest_kernel(const T* __restrict__ state, int cap, const int* __restrict__ d_size,
+                               FullMetric<T, N> fm, int* __restrict__ out) {
+    __shared__ T sc[1024];
+    __shared__ int si[1024];
+    const int size = *d_size;
+    T best = Num<T>::inf();
+    int b = -1;
+    for (int node = threadIdx.x; node < size; node += blockDim.x) {
+        T e[N];
+#pragma unroll
+        for (int d = 0; d < N; d++) {
+            e[d] = fm.x[d] - state[(size_t)d * cap + node];
+            if (fm.angle_mask & (1u << d)) e[d] = reduce_period(e[d]);
+        }
+        T c = T(0);
+#pragma unroll
+        for (int k = 0; k < N; k++) {      // sum_k (sum_j e_j S_jk) e_k  (tensordot(diffs, S) * diffs)
+            T r = T(0);
+#pragma unroll
+            for (int jj = 0; jj < N; jj++) r = fma(e[jj], fm.S[jj * N + k], r);
+            c = fma(r, e[k], c);
+        }
+        if (b < 0 || c < best) { best = c; b = node; }
+    }
+    sc[threadIdx.x] = best; si[threadIdx.x] = b;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            const T c2 = sc[threadIdx.x + s]; const int i2 = si[threadIdx.x + s];
+            const T c1 = sc[threadIdx.x]; const int i1 = si[threadIdx.x];
+            if (i2 >= 0 && (i1 < 0 || c2 < c1 || (c2 == c1 && i2 < i1))) { sc[threadIdx.x] = c2; si[threadIdx.x] = i2; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = si[0] < 0 ? 0 : si[0];
+}
+
+}  // namespace lq

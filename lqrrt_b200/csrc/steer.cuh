@@ -1,0 +1,159 @@
+// K2: Planner._steer(ID, xtar, force_arrive=False) for a whole wave
+// (reference lqrrt/planner.py:354-438; exact control flow SURVEY.md section 3.2),
+// fused with the lqr provider, the dynamics step and is_feasible.
+//
+// One sample per group of LANES threads.  All lanes of a group carry the same
+// state/gain in registers and execute the same instruction stream (results are
+// bitwise identical across lanes); only the obstacle tables of is_feasible are
+// split across the lanes, and the verdict is combined with a group ballot.
+// LANES = 1 is thread-per-sample; LANES = 32 is warp-per-sample for heavy
+// collision fields.  Rollout is latency/issue bound: tiny matrices, no tensor
+// cores.
+#pragma once
+#include <cooperative_groups.h>
+#include "models.cuh"
+
+namespace lq {
+namespace cg = cooperative_groups;
+
+template <typename T, class Sys, class Lqr> struct Model {
+    Sys sys;
+    Lqr lqr;
+    FeasSet<T> feas;
+    uint32_t angle_mask;
+    int H;                       // horizon_iters (planner.py:549)
+    T dt;
+    T tol[LQ_MAX_N];             // error_tol (planner.py:532-536)
+    T goal_lo[LQ_MAX_N], goal_hi[LQ_MAX_N];   // goal region, open box (planner.py:442-447, 482-486)
+    double FPR;                  // int(FPR * len) is evaluated in float64 as Python does (planner.py:394-395)
+};
+
+template <typename T, class Sys, class Lqr>
+__device__ __forceinline__ int fpr_keep(const Model<T, Sys, Lqr>& md, int len) { return (int)(md.FPR * (double)len); }
+
+template <int LANES>
+__device__ __forceinline__ bool group_all(bool ok) {
+    if (LANES == 1) return ok;
+    // control flow is uniform inside a group, so the tile collective is convergent
+    return cg::tiled_partition<LANES>(cg::this_thread_block()).all(ok);
+}
+
+// Outputs per sample j (all optional except len):
+//   xseq [j][H][N], useq [j][H][M]   recorded edge (sample-major)
+//   len  [j]                          kept length after the FPR cut
+//   xnew [N][ostride], Knew [M*N][ostride]   final state and K = lqr(xnew, u_last).K (planner.py:256-257)
+template <typename T, class Sys, class Lqr, int LANES, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+steer_kernel(Model<T, Sys, Lqr> md,
+             const T* __restrict__ tstate, const T* __restrict__ tK, int cap,
+             const int* __restrict__ ids, const T* __restrict__ targets, int tstride, int W,
+             T* __restrict__ xseq, T* __restrict__ useq, int* __restrict__ len_out,
+             T* __restrict__ xnew_out, T* __restrict__ Knew_out, int ostride) {
+    constexpr int N = Sys::N, M = Sys::M;
+    const int gid = (blockIdx.x * BLOCK + threadIdx.x) / LANES;
+    const int lane = threadIdx.x % LANES;
+    if (gid >= W) return;                  // whole groups leave together (BLOCK % LANES == 0)
+    const int j = gid;
+    const int id = ids[j];
+
+    T x[N], xt[N], K[M * N];
+#pragma unroll
+    for (int d = 0; d < N; d++) { x[d] = tstate[(size_t)d * cap + id]; xt[d] = targets[(size_t)d * tstride + j]; }
+#pragma unroll
+    for (int k = 0; k < M * N; k++) K[k] = tK[(size_t)k * cap + id];
+
+    int len = 0, nrec = 0, i = 0;
+    T* xrow = xseq + (size_t)j * md.H * N;      // never NULL: the engine supplies scratch
+    T* urow = useq + (size_t)j * md.H * M;
+
+    while (true) {
+        T e[N], u[M], uw[M], xn[N];
+        erf_eval<T, N>(md.angle_mask, xt, x, e);                 // planner.py:386
+#pragma unroll
+        for (int r = 0; r < M; r++) {                            // u = K e, planner.py:387
+            T a = T(0);
+#pragma unroll
+            for (int d = 0; d < N; d++) a += K[r * N + d] * e[d];
+            u[r] = a; uw[r] = a;
+        }
+        md.sys.step(x, uw, md.dt, xn);                           // planner.py:390 (uw = the copy dynamics may clip)
+        const bool ok = group_all<LANES>(feasible_eval<T, N, M>(md.feas, xn, u, lane, LANES));   // planner.py:393
+        if (!ok) { len = fpr_keep(md, nrec); break; }            // planner.py:394-396
+        i += 1;                                                  // planner.py:414
+        bool conv = true;
+#pragma unroll
+        for (int d = 0; d < N; d++) conv = conv && (abs_t(e[d]) <= md.tol[d]);
+        if (i > md.H || conv) { len = nrec; break; }             // planner.py:428-429
+#pragma unroll
+        for (int d = 0; d < N; d++) x[d] = xn[d];
+        if (lane == 0) {                                         // planner.py:432-433
+#pragma unroll
+            for (int d = 0; d < N; d++) xrow[nrec * N + d] = x[d];
+#pragma unroll
+            for (int r = 0; r < M; r++) urow[nrec * M + r] = u[r];
+        }
+        nrec += 1;
+        md.lqr.gain(md.sys, md.dt, x, u, K);                     // planner.py:436
+    }
+
+    if (lane == 0) {
+        len_out[j] = len;
+        if (xnew_out && len > 0) {
+            // The node is the last KEPT state and its gain is lqr(xnew, u_seq[-1]).K (planner.py:256-257).
+            // Without an FPR cut, x / K already hold exactly that; after a cut (len < nrec) the
+            // kept tail is re-read from this thread's own edge rows and the gain recomputed.
+            if (len < nrec) {
+                T uk[M];
+#pragma unroll
+                for (int d = 0; d < N; d++) x[d] = xrow[(len - 1) * N + d];
+#pragma unroll
+                for (int r = 0; r < M; r++) uk[r] = urow[(len - 1) * M + r];
+                md.lqr.gain(md.sys, md.dt, x, uk, K);
+            }
+#pragma unroll
+            for (int d = 0; d < N; d++) xnew_out[(size_t)d * ostride + j] = x[d];
+#pragma unroll
+            for (int k = 0; k < M * N; k++) Knew_out[(size_t)k * ostride + j] = K[k];
+        }
+    }
+}
+
+// _steer(..., force_arrive=True) (planner.py:296, 399-410) for one (node, target): the reference bounds
+// it by wall-clock (:402-406); here by max_steps.  Sequential by nature: one thread.
+template <typename T, class Sys, class Lqr>
+__global__ void steer_force_kernel(Model<T, Sys, Lqr> md, const T* __restrict__ tstate, const T* __restrict__ tK,
+                                   int cap, int id, const T* __restrict__ xtar, int max_steps,
+                                   T* __restrict__ xs, T* __restrict__ us, int* __restrict__ len_out) {
+    constexpr int N = Sys::N, M = Sys::M;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    T x[N], xt[N], K[M * N];
+    for (int d = 0; d < N; d++) { x[d] = tstate[(size_t)d * cap + id]; xt[d] = xtar[d]; }
+    for (int k = 0; k < M * N; k++) K[k] = tK[(size_t)k * cap + id];
+    int len = 0, steps = 0;
+    while (true) {
+        T e[N], u[M], uw[M], xn[N];
+        erf_eval<T, N>(md.angle_mask, xt, x, e);
+        for (int r = 0; r < M; r++) {
+            T a = T(0);
+            for (int d = 0; d < N; d++) a += K[r * N + d] * e[d];
+            u[r] = a; uw[r] = a;
+        }
+        md.sys.step(x, uw, md.dt, xn);
+        if (!feasible_eval<T, N, M>(md.feas, xn, u)) {
+            len = fpr_keep(md, len);
+            break;
+        }
+        steps += 1;
+        if (steps > max_steps) break;
+        bool close = true;                                        // np.allclose(x, xtar, 1e-4, 1e-4), planner.py:409
+        for (int d = 0; d < N; d++) close = close && (abs_t(xn[d] - xt[d]) <= T(1e-4) + T(1e-4) * abs_t(xt[d]));
+        if (close) break;
+        for (int d = 0; d < N; d++) { x[d] = xn[d]; xs[len * N + d] = xn[d]; }
+        for (int r = 0; r < M; r++) us[len * M + r] = u[r];
+        len += 1;
+        md.lqr.gain(md.sys, md.dt, x, u, K);
+    }
+    *len_out = len;
+}
+
+}  // namespace lq

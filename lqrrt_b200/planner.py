@@ -1,0 +1,438 @@
+"""
+Planner: the reference's public planning class (lqrrt/planner.py) with its
+expand loop moved onto the GPU.
+
+Same constructor, setters, result attributes and error messages as the
+reference (planner.py:85-100, 468-610); `update_plan` keeps the reference's
+stop rules and close-out paths (planner.py:286-336) but each pass of its loop
+expands a *wave* of samples through the C ABI (sample -> nearest -> steer ->
+commit, include/lqrrt_b200.h) instead of one sample in Python.
+
+New keyword arguments (all optional, defaults keep reference call sites valid):
+  wave      None = adaptive wave size, int = fixed global wave size
+            (1 reproduces the reference's sequential semantics)
+  wave_max  cap of the adaptive wave size
+  dtype     'f32' (throughput) or 'f64' (reference-parity arithmetic)
+  rng       'philox' = counter-based device sampler; 'numpy' = the reference's
+            global MT19937 stream, drawn on the host in the reference's order
+  seed      Philox key
+  device    CUDA ordinal (default: torch's current device)
+  comm      torch.distributed process group (or True for WORLD): the wave is
+            sharded over the ranks and accepted nodes are all-gathered so every
+            rank's tree stays identical
+
+dynamics / lqr / erf / constraints.is_feasible must be `lqrrt_b200.models`
+specs; there is no CPU fallback for arbitrary Python callables.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import scipy.interpolate
+
+from . import models as _models
+from . import waves as _waves
+from .constraints import Constraints
+from .tree import Tree
+
+
+class Planner(object):
+
+    def __init__(self, dynamics, lqr, constraints,
+                 horizon, dt=0.05, FPR=0,
+                 error_tol=0.05, erf=np.subtract,
+                 min_time=0.5, max_time=1, max_nodes=1E5,
+                 goal0=None, sys_time=time.time, printing=True,
+                 wave=None, wave_max=8192, dtype='f32', rng='philox', seed=0, device=None, comm=None):
+        self._engine = None
+        self._engine_key = None
+        self._exchange = None
+        self.wave = wave
+        self.wave_max = int(wave_max)
+        self.dtype = dtype
+        if rng not in ('philox', 'numpy'):
+            raise ValueError("rng must be 'philox' or 'numpy'")
+        self.rng = rng
+        self.seed = int(seed)
+        self.device = device
+        self._set_comm(comm)
+
+        self.set_system(dynamics, lqr, constraints, erf)
+        self.set_resolution(horizon, dt, FPR, error_tol)
+        self.set_runtime(min_time, max_time, max_nodes, sys_time)
+        self.set_goal(goal0)
+        self.printing = printing
+        self.killed = False
+        self.stats = {}
+
+    # ------------------------------------------------------------------ comm
+    def _set_comm(self, comm):
+        self.comm = None
+        self.world = 1
+        self.rank = 0
+        if comm is None or comm is False:
+            return
+        import torch.distributed as dist
+        if comm is True:
+            comm = dist.group.WORLD
+        self.comm = comm
+        self.world = dist.get_world_size(comm)
+        self.rank = dist.get_rank(comm)
+
+    # ---------------------------------------------------------------- engine
+    def _device(self):
+        if self.device is not None:
+            return int(self.device)
+        from ._native import _current_device
+        return _current_device()
+
+    def _wave_capacity(self):
+        top = self.wave_max if self.wave is None else max(1, int(self.wave))
+        return _waves.local_capacity(top, self.world)
+
+    def _ensure_engine(self):
+        """(Re)build the device engine when anything baked into it changed; `dt` and friends are plain
+        attributes in the reference (lqrrt_node.py:259 assigns planner.dt directly), so compare by value."""
+        from ._native import Engine
+        if self.hfactor:
+            raise NotImplementedError("adaptive horizon (horizon=(min, max), planner.py:418-425) is not "
+                                      "available on the GPU path yet; pass a scalar horizon")
+        # constraints.set_feasibility_function may have swapped the spec since set_system
+        self._system = _models.bundle_of(self.dynamics, self.lqr, self.erf, self.constraints.is_feasible)
+        tol = np.abs(np.asarray(self.error_tol, dtype=np.float64)) * np.ones(self.nstates)
+        key = (id(self._system), int(self.horizon_iters), float(self.dt), float(self.FPR), tuple(tol.tolist()),
+               int(self.max_nodes) + 1, self._wave_capacity(), self.dtype, self._device())
+        if self._engine is None or key != self._engine_key:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = Engine(self._system, self.horizon_iters, self.dt, self.FPR, tol,
+                                  node_capacity=int(self.max_nodes) + 1, wave_capacity=self._wave_capacity(),
+                                  dtype=self.dtype, device=self._device())
+            self._engine_key = key
+            self._exchange = None
+        return self._engine
+
+    @staticmethod
+    def _cuda_stream():
+        try:
+            import torch
+            if torch.cuda.is_available():
+                return torch.cuda.current_stream().cuda_stream
+        except ImportError:
+            pass
+        return None
+
+    # ----------------------------------------------------------- update_plan
+    def update_plan(self, x0, sample_space, goal_bias=0,
+                    guide=None, xrand_gen=None, pruning=True,
+                    finish_on_goal=False, specific_time=None):
+        """
+        Grows a new tree from x0 toward the goal and prepares get_state(t) /
+        get_effort(t); arguments and return value as reference planner.py:104-154.
+        Returns False if it was killed, if the tree exceeded max_nodes, or if no
+        goal has been set.
+        """
+        x0 = np.array(x0, dtype=np.float64)
+        if self.goal is None:
+            print("No goal has been set yet!")
+            self.get_state = lambda t: x0
+            self.get_effort = lambda t: np.zeros(self.ncontrols)
+            return False
+
+        if specific_time is None:
+            min_time, max_time = self.min_time, self.max_time
+        else:
+            min_time = max_time = specific_time
+
+        # ---- sampler (planner.py:176-216)
+        mode = None
+        tries_limit = 10
+        if xrand_gen is None or type(xrand_gen) is int:
+            if goal_bias is None:
+                goal_bias = [0] * self.nstates
+            elif hasattr(goal_bias, '__contains__'):
+                if len(goal_bias) != self.nstates:
+                    raise ValueError("Expected goal_bias to be scalar or have same length as state.")
+            else:
+                goal_bias = [goal_bias] * self.nstates
+            # the reference leans on Python 2's `None > 0 == False` here (planner.py:188-191)
+            if xrand_gen is not None and xrand_gen > 0:
+                tries_limit = int(xrand_gen)
+            sample_space = np.array(sample_space, dtype=np.float64)
+            if sample_space.shape != (self.nstates, 2):
+                raise ValueError("Expected sample_space to be list of nstates tuples.")
+            mode = self.rng
+            if mode == 'numpy' and self.world > 1:
+                raise ValueError("rng='numpy' replays one serial MT19937 stream and cannot be sharded; use rng='philox'")
+        else:
+            if not hasattr(xrand_gen, '__call__'):
+                raise ValueError("Expected xrand_gen to be None, an integer >= 1,  or a function.")
+            mode = 'callable'
+
+        eng = self._ensure_engine()
+        stream = self._cuda_stream()
+        eng.set_goal(self.goal, self.constraints.goal_buffer)
+        if mode in ('philox', 'numpy'):
+            if tries_limit > 16:
+                raise ValueError("at most 16 sampler tries are supported")
+            eng.set_sampling(sample_space, goal_bias, tries_limit)
+            centers = np.mean(sample_space, axis=1)
+            spans = np.diff(sample_space).flatten()
+            bias_arr = np.asarray(goal_bias, dtype=np.float64)
+
+        # ---- new tree (planner.py:172-173)
+        eng.reset(x0, stream)
+        self.tree = Tree(eng, x0, self._system)
+
+        self.xguide = np.copy(self.goal) if guide is None else np.array(guide, dtype=np.float64)
+
+        if self.printing:
+            print("\n...planning...")
+        self.plan_reached_goal = False
+        self.T = np.inf
+        time_elapsed = 0
+        best_node = -1
+        wave_ctr = 0
+        samples_total = 0
+        stop_request = _waves.STOP_NONE
+        outcome = None
+        exchange = self._get_exchange(eng) if self.world > 1 else None
+        launches0 = eng.launch_count()
+        time_start = self.sys_time()
+
+        while True:
+            W = _waves.wave_size(self.tree.size, self.wave, wave_max=self.wave_max)
+            first, count = _waves.partition(W, self.rank, self.world)
+
+            if mode == 'philox':
+                eng.wave_expand(self.seed, wave_ctr, first, count, None, pruning, stop_request, stream)
+            elif mode == 'numpy':
+                # planner.py:201-211 on the reference's own stream: draw the most tries this wave could
+                # use from a snapshot, let the device pick, then advance the real stream by what was used
+                snap = np.random.get_state()
+                U = np.random.sample(count * tries_limit * (self.nstates + 1)).reshape(-1, self.nstates + 1)
+                cand = centers + spans * (U[:, :self.nstates] - 0.5)
+                pick = np.greater(bias_arr[None, :], U[:, self.nstates:])
+                cand = np.where(pick, self.goal[None, :], cand)
+                used = eng.wave_expand_candidates(count, tries_limit, cand, pruning, stream)
+                np.random.set_state(snap)
+                np.random.sample(used * (self.nstates + 1))
+            else:
+                xs = np.array([np.array(xrand_gen(self), dtype=np.float64) for _ in range(count)]).reshape(count, self.nstates)
+                eng.wave_expand(self.seed, wave_ctr, first, count, xs, pruning, stop_request, stream)
+
+            if exchange is not None:
+                recv = exchange.gather(self._send_view(eng))
+                eng.wave_commit(recv.data_ptr(), self.world, stream)
+            else:
+                eng.wave_commit(None, 1, stream)
+            st = eng.wave_stats()
+            wave_ctr += 1
+            samples_total += st.n_sampled
+            self.tree._set_size(st.tree_size)
+
+            # planner.py:260-283: a strictly faster plan replaces the current one
+            if st.best_node >= 0 and st.best_node != best_node:
+                best_node = st.best_node
+                self.plan_reached_goal = True
+                self.T = (1 + st.best_cost) * self.dt
+                if self.printing:
+                    print("Found plan at elapsed time: {} s".format(np.round(time_elapsed, 6)))
+
+            time_elapsed = self.sys_time() - time_start
+
+            # planner.py:286-311, in the reference's order: kill, reached-goal, out of time/nodes
+            if self.killed:
+                decision = _waves.STOP_KILL
+            elif (self.plan_reached_goal and time_elapsed >= min_time) or \
+                    time_elapsed >= max_time or self.tree.size > self.max_nodes:
+                decision = _waves.STOP_DONE
+            else:
+                decision = _waves.STOP_NONE
+            if self.world > 1:
+                # rank 0's decision rides in the next wave's record header; everyone acts on what
+                # rank 0 decided one wave ago, so all ranks leave the loop after the same wave
+                act = st.flags
+                stop_request = decision if self.rank == 0 else _waves.STOP_NONE
+            else:
+                act = decision
+            if act == _waves.STOP_KILL:
+                outcome = 'killed'
+                break
+            if act == _waves.STOP_DONE:
+                outcome = 'reached' if self.plan_reached_goal else 'timeout'
+                break
+
+        self.stats = dict(waves=wave_ctr, samples=samples_total, nodes=self.tree.size,
+                          elapsed=time_elapsed, gpu_launches=eng.launch_count() - launches0)
+
+        if self.plan_reached_goal:
+            # the plan attributes the reference fills inside its loop (planner.py:276-281)
+            self.node_seq = self.tree.climb(best_node)
+            self.x_seq, self.u_seq = self.tree.trajectory(self.node_seq)
+            self.T = len(self.x_seq) * self.dt
+            self.t_seq = np.arange(len(self.x_seq)) * self.dt
+
+        if outcome == 'reached':
+            if finish_on_goal:                                      # planner.py:294-303
+                budget = float(np.clip(min_time / 2, 0.1, np.inf))
+                max_steps = int(min(200000, max(1, budget * 10000)))
+                xg, ug = eng.steer_force(self.node_seq[-1], self.goal, max_steps, stream)
+                if len(xg) >= max_steps and self.printing:
+                    print("(exact goal-convergence timed-out)")
+                if len(xg) > 0:
+                    xg = [row.copy() for row in xg]; ug = [row.copy() for row in ug]
+                    self.tree.add_node(self.node_seq[-1], self.goal, None, xg, ug)
+                    self.node_seq.append(self.tree.size - 1)
+                    self.x_seq.extend(xg)
+                    self.u_seq.extend(ug)
+                    self.t_seq = np.arange(len(self.x_seq)) * self.dt
+            if self.printing:
+                print("Tree size: {0}\nETA: {1} s".format(self.tree.size, np.round(self.T, 2)))
+            self._prepare_interpolators()
+
+        elif outcome == 'timeout':                                  # planner.py:311-328
+            colmask = np.isinf(self.constraints.goal_buffer)
+            closestID = eng.closest(self.xguide, colmask, stream)
+            self.node_seq = self.tree.climb(closestID)
+            self.x_seq, self.u_seq = self.tree.trajectory(self.node_seq)
+            self.T = len(self.x_seq) * self.dt
+            self.t_seq = np.arange(len(self.x_seq)) * self.dt
+            if self.printing:
+                print("Didn't reach goal.\nTree size: {0}\nETA: {1} s".format(self.tree.size, np.round(self.T, 2)))
+            self._prepare_interpolators()
+
+        if outcome == 'killed' or self.tree.size > self.max_nodes:  # planner.py:330-336
+            if self.printing:
+                print("Plan update terminated abruptly!")
+            self.killed = False
+            return False
+        return True
+
+    def _get_exchange(self, eng):
+        if self._exchange is None:
+            import torch
+            _, nbytes = eng.wave_records()
+            self._exchange = _waves.Exchange(self.comm, nbytes, torch.device('cuda', eng.device))
+        return self._exchange
+
+    def _send_view(self, eng):
+        import torch
+        from ._native import DevicePointer
+        ptr, nbytes = eng.wave_records()
+        return torch.as_tensor(DevicePointer(ptr, nbytes), device=torch.device('cuda', eng.device))
+
+    # ---------------------------------------------------------- interpolators
+    def _prepare_interpolators(self):
+        """planner.py:451-464."""
+        if len(self.x_seq) == 1:
+            self.get_state = lambda t: self.x_seq[0]
+            self.get_effort = lambda t: np.zeros(self.ncontrols)
+        else:
+            self.get_state = scipy.interpolate.interp1d(
+                self.t_seq, np.array(self.x_seq), axis=0, assume_sorted=True,
+                bounds_error=False, fill_value=self.x_seq[-1][:])
+            self.get_effort = scipy.interpolate.interp1d(
+                self.t_seq, np.array(self.u_seq), axis=0, assume_sorted=True,
+                bounds_error=False, fill_value=self.u_seq[-1][:])
+
+    # ---------------------------------------------------------------- setters
+    def set_goal(self, goal):
+        """Modifies the goal state and region (planner.py:468-487)."""
+        if goal is None:
+            self.goal = None
+            return
+        if len(goal) != self.nstates:
+            raise ValueError("The goal state must have same dimensionality as state space.")
+        self.goal = np.array(goal, dtype=np.float64)
+        self.goal_region = [(self.goal[i] - b, self.goal[i] + b) for i, b in enumerate(self.constraints.goal_buffer)]
+        self.plan_reached_goal = False
+
+    def set_runtime(self, min_time=None, max_time=None, max_nodes=None, sys_time=None):
+        """Arguments not given are not modified (planner.py:491-513)."""
+        if min_time is not None:
+            self.min_time = min_time
+        if max_time is not None:
+            self.max_time = max_time
+        if self.min_time > self.max_time:
+            raise ValueError("The min_time must be less than or equal to the max_time.")
+        if max_nodes is not None:
+            self.max_nodes = max_nodes
+        if sys_time is not None:
+            if not hasattr(sys_time, '__call__'):
+                raise ValueError("Expected sys_time to be a function.")
+            self.sys_time = sys_time
+
+    def set_resolution(self, horizon=None, dt=None, FPR=None, error_tol=None):
+        """Arguments not given are not modified (planner.py:517-553)."""
+        if horizon is not None:
+            self.horizon = horizon
+        if dt is not None:
+            self.dt = dt
+        if FPR is not None:
+            self.FPR = FPR
+        if error_tol is not None:
+            if np.shape(error_tol) in [(), (self.nstates,)]:
+                self.error_tol = np.abs(error_tol).astype(np.float64)
+            else:
+                raise ValueError("Shape of error_tol must be scalar or length of state.")
+        if hasattr(self.horizon, '__contains__'):
+            if len(self.horizon) != 2:
+                raise ValueError("Expected horizon to be tuple (min, max) or a single scalar.")
+            if self.horizon[0] < self.dt:
+                raise ValueError("The minimum horizon must be at least as big as dt.")
+            if self.horizon[0] >= self.horizon[1]:
+                raise ValueError("A horizon range tuple must be given as (min, max) where min < max.")
+            self.horizon_iters = 1
+            self.hspan = np.divide(self.horizon, self.dt).astype(np.int64)
+            self.hfactor = int(2)
+        elif self.horizon >= self.dt:
+            self.horizon_iters = int(self.horizon / self.dt)
+            self.hspan = (self.horizon_iters, self.horizon_iters)
+            self.hfactor = 0
+        else:
+            raise ValueError("The horizon must be at least as big as dt.")
+
+    def set_system(self, dynamics=None, lqr=None, constraints=None, erf=None):
+        """Arguments not given are not modified; dynamics and lqr change together (planner.py:557-592)."""
+        if dynamics is not None or lqr is not None:
+            if not hasattr(dynamics, '__call__'):
+                raise ValueError("Expected dynamics to be a function.")
+            if not hasattr(lqr, '__call__'):
+                raise ValueError("Expected lqr to be a function.")
+            self.dynamics = dynamics
+            self.lqr = lqr
+        if constraints is not None:
+            if not isinstance(constraints, Constraints):
+                raise ValueError("Expected constraints to be an instance of the Constraints class.")
+            self.constraints = constraints
+            self.nstates = self.constraints.nstates
+            self.ncontrols = self.constraints.ncontrols
+        if erf is not None:
+            if not hasattr(erf, '__call__'):
+                raise ValueError("Expected erf to be a function.")
+            self.erf = erf
+        self._system = _models.bundle_of(self.dynamics, self.lqr, getattr(self, 'erf', np.subtract),
+                                         self.constraints.is_feasible)
+        if self._system.nstates != self.nstates or self._system.ncontrols != self.ncontrols:
+            raise ValueError("constraints say nstates={}, ncontrols={} but the dynamics model has {} and {}".format(
+                self.nstates, self.ncontrols, self._system.nstates, self._system.ncontrols))
+        self.plan_reached_goal = False
+
+    # -------------------------------------------------------------- kill flag
+    def kill_update(self):
+        """Abruptly terminates update_plan at its next wave boundary (planner.py:596-601); callable from
+        any thread."""
+        self.killed = True
+
+    def unkill(self):
+        """planner.py:605-610."""
+        self.killed = False
+
+    def visualize(self, dx, dy):
+        """planner.py:614-624."""
+        if hasattr(self, 'node_seq'):
+            self.tree.visualize(dx, dy, node_seq=self.node_seq)
+        else:
+            print("There is no plan to visualize!")

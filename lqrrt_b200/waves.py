@@ -1,0 +1,66 @@
+"""
+Host-side wave scheduling: how many samples the next launch expands, which
+slice of them this GPU takes, and how the per-wave records of all GPUs are
+exchanged.  Pure host logic (no CUDA calls) so it is unit-testable on CPU with
+the gloo backend.
+
+The reference expands one sample per loop iteration (lqrrt/planner.py:233-283);
+a wave expands `W` of them against the tree as of wave start (SURVEY.md section 7
+"what wave batching does to the planner").
+"""
+from __future__ import annotations
+
+
+def wave_size(tree_size, fixed=None, wave_min=32, wave_max=8192):
+    """Global samples in the next wave.  `fixed` pins it (1 = the reference's
+    sequential semantics).  Otherwise the wave tracks the tree size, so the tree
+    at most roughly doubles per wave while it is small -- tree depth grows by at
+    most one edge per wave, and a huge first wave would only fan out from the
+    seed -- and saturates at wave_max."""
+    if fixed is not None:
+        return max(1, int(fixed))
+    return int(min(wave_max, max(wave_min, tree_size)))
+
+
+def partition(wave, rank, world):
+    """Contiguous slice [first, first+count) of a wave for `rank`: rank-order
+    concatenation of the slices is sample order, which is what makes the
+    G-GPU tree bit-identical to the 1-GPU tree for the same wave sizes."""
+    base, extra = divmod(int(wave), int(world))
+    count = base + (1 if rank < extra else 0)
+    first = rank * base + min(rank, extra)
+    return first, count
+
+
+def local_capacity(wave_max, world):
+    """Largest slice any rank can receive, rounded to the engine's granule."""
+    per = -(-int(wave_max) // int(world))
+    return (per + 3) & ~3
+
+
+class Exchange(object):
+    """All-gather of the fixed-size record segment every rank packs per wave
+    (csrc/commit.cuh).  One NCCL collective per wave on the current stream;
+    payload = accepted-node records, a few MB at most -- latency-, not
+    bandwidth-bound, so one unsplit collective is the right granularity."""
+
+    def __init__(self, group, segment_bytes, device):
+        import torch
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.segment_bytes = int(segment_bytes)
+        self.recv = torch.empty(self.world * self.segment_bytes, dtype=torch.uint8, device=device)
+
+    def gather(self, send):
+        """send: uint8 tensor of segment_bytes (a zero-copy view of the engine's
+        record buffer).  Returns the (world * segment_bytes) tensor, rank-major."""
+        if send.numel() != self.segment_bytes:
+            raise ValueError("record segment has {} bytes, expected {}".format(send.numel(), self.segment_bytes))
+        self.dist.all_gather_into_tensor(self.recv, send, group=self.group)
+        return self.recv
+
+
+STOP_NONE, STOP_DONE, STOP_KILL = 0, 1, 2
