@@ -190,6 +190,11 @@ int lq_eval_feasible(lq_engine* h, int count, const double* h_x, const double* h
 int lq_launch_count(lq_engine* h, uint64_t* out);
 /* tuning knobs: steer lanes per sample (1, 8, 32; 0 keeps), nearest queries per thread (0 = heuristic) */
 int lq_set_tuning(lq_engine* h, int steer_lanes, int nearest_q);
+/* Per-stage CUDA-event timing of the wave chain on the launching stream (bench.py's roofline leg).
+ * ms[5]: sample, nearest, steer, pack, commit (accumulated);  work[4]: nearest pairs sum(W*N),
+ * nearest algorithmic bytes sum(W*N*n*sizeof(dtype)), samples, waves. */
+int lq_set_profiling(lq_engine* h, int on);
+int lq_profile_read(lq_engine* h, double* ms5, double* work4, int reset);
 
 #ifdef __cplusplus
 }

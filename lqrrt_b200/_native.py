@@ -84,6 +84,8 @@ SYMBOLS = {
     'lq_eval_feasible': (C.c_int, [_P, C.c_int, _D, _D, _U8]),
     'lq_launch_count': (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     'lq_set_tuning': (C.c_int, [_P, C.c_int, C.c_int]),
+    'lq_set_profiling': (C.c_int, [_P, C.c_int]),
+    'lq_profile_read': (C.c_int, [_P, _D, _D, C.c_int]),
 }
 
 _lib = None
@@ -191,6 +193,9 @@ class Engine(object):
             raise NativeError("lq_create failed ({}): {}".format(rc, self.lib.lq_last_error(None).decode()))
         self.h = h
         del keep
+        self.elt = 4 if dtype == 'f32' else 8
+        self.h2d_bytes = 0        # bytes this binding moved host -> device / device -> host
+        self.d2h_bytes = 0
 
     # ------------------------------------------------------------------ utils
     def _ck(self, rc):
@@ -220,6 +225,7 @@ class Engine(object):
     # -------------------------------------------------------------- problem
     def set_goal(self, goal, buffer):
         g = _c64(goal); b = _c64(buffer)
+        self.h2d_bytes += 2 * LQ_MAX_N * self.elt
         self._ck(self.lib.lq_set_goal(self.h, _dp(g), _dp(b)))
 
     def set_sampling(self, sample_space, goal_bias, tries):
@@ -230,10 +236,12 @@ class Engine(object):
 
     def reset(self, x0, stream=None):
         x = _c64(x0)
+        self.h2d_bytes += self.n * self.elt + 8
         self._ck(self.lib.lq_reset(self.h, _dp(x), self._stream(stream)))
 
     def load_nodes(self, state, parent=None, cost=None, stream=None):
         s = _c64(state).reshape(-1, self.n)
+        self.h2d_bytes += len(s) * (self.n * self.elt + 8)
         p = None if parent is None else np.ascontiguousarray(parent, dtype=np.int32)
         c = None if cost is None else np.ascontiguousarray(cost, dtype=np.int32)
         self._ck(self.lib.lq_load_nodes(self.h, len(s), _dp(s), None if p is None else _ip(p),
@@ -261,12 +269,14 @@ class Engine(object):
             hs = _c64(samples).reshape(-1, self.n)
             if len(hs) != count:
                 raise ValueError("samples must be count x n")
+            self.h2d_bytes += hs.size * self.elt
         self._ck(self.lib.lq_wave_expand(self.h, C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), C.c_uint32(int(wave_ctr) & 0xFFFFFFFF),
                                          int(first), int(count), None if hs is None else _dp(hs),
                                          int(bool(use_ignore)), int(flags), self._stream(stream)))
 
     def wave_expand_candidates(self, count, tries, candidates, use_ignore=True, stream=None):
         c = _c64(candidates).reshape(-1, self.n)
+        self.h2d_bytes += c.size * self.elt; self.d2h_bytes += 4
         used = C.c_int(0)
         self._ck(self.lib.lq_wave_expand_candidates(self.h, int(count), int(tries), _dp(c), len(c),
                                                     int(bool(use_ignore)), C.byref(used), self._stream(stream)))
@@ -282,11 +292,13 @@ class Engine(object):
 
     def wave_stats(self):
         st = lq_wave_stats()
+        self.d2h_bytes += C.sizeof(lq_wave_stats)
         self._ck(self.lib.lq_wave_stats_get(self.h, C.byref(st)))
         return st
 
     def closest(self, xguide, colmask, stream=None):
         x = _c64(xguide)
+        self.h2d_bytes += self.n * (self.n + 1) * self.elt; self.d2h_bytes += 4
         mk = np.ascontiguousarray(colmask, dtype=np.uint8)
         out = C.c_int(0)
         self._ck(self.lib.lq_closest(self.h, _dp(x), mk.ctypes.data_as(_U8), C.byref(out), self._stream(stream)))
@@ -315,6 +327,7 @@ class Engine(object):
         cost = np.zeros(count, dtype=np.int32); elen = np.zeros(count, dtype=np.int32)
         ign = np.zeros(count, dtype=np.uint8)
         K = np.zeros((count, self.m, self.n)) if want_K else None
+        self.d2h_bytes += count * (self.n * self.elt + 13 + (self.m * self.n * self.elt if want_K else 0))
         self._ck(self.lib.lq_download_nodes(self.h, int(first), int(count), _dp(state), _ip(parent), _ip(cost), _ip(elen),
                                             ign.ctypes.data_as(_U8), None if K is None else _dp(K), self._stream(stream)))
         return dict(state=state, parent=parent, cost=cost, edge_len=elen, ignore=ign, K=K)
@@ -322,6 +335,7 @@ class Engine(object):
     def download_edges(self, ids, stream=None):
         a = np.ascontiguousarray(ids, dtype=np.int32)
         hx = np.zeros((len(a), self.H, self.n)); hu = np.zeros((len(a), self.H, self.m))
+        self.h2d_bytes += 4 * len(a); self.d2h_bytes += len(a) * self.H * (self.n + self.m) * self.elt
         if len(a):
             self._ck(self.lib.lq_download_edges(self.h, _ip(a), len(a), _dp(hx), _dp(hu), self._stream(stream)))
         return hx, hu
@@ -358,6 +372,15 @@ class Engine(object):
 
     def set_tuning(self, steer_lanes=0, nearest_q=0):
         self._ck(self.lib.lq_set_tuning(self.h, int(steer_lanes), int(nearest_q)))
+
+    def set_profiling(self, on=True):
+        self._ck(self.lib.lq_set_profiling(self.h, int(bool(on))))
+
+    def profile_read(self, reset=False):
+        ms = np.zeros(5); work = np.zeros(4)
+        self._ck(self.lib.lq_profile_read(self.h, _dp(ms), _dp(work), int(bool(reset))))
+        return dict(ms=dict(zip(('sample', 'nearest', 'steer', 'pack', 'commit'), ms.tolist())),
+                    pairs=work[0], nearest_bytes=work[1], samples=work[2], waves=work[3])
 
 
 class ModelEvaluator(object):

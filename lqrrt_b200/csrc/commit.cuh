@@ -116,7 +116,8 @@ template <typename T> struct TreeView {
     int* n_ignored;    // device scalar
     int* n_goal;       // device scalar
     unsigned long long* best;   // (cost << 32 | node), ~0 = none
-    int cap;
+    int cap;           // array stride (node_capacity rounded up to 4)
+    int limit;         // node_capacity: appends beyond it are dropped and flagged
 };
 
 template <typename T>
@@ -149,7 +150,7 @@ __global__ void commit_kernel(TreeView<T> tv, const char* __restrict__ records, 
     }
     if (k >= mine) return;
     const int node = *tv.size + before + k;
-    if (node >= tv.cap) return;
+    if (node >= tv.limit) return;
     const RecView<T> rv = rec_view<T>((void*)(records + (size_t)seg * seg_bytes), Wc, N, M, H);
     const int L = rv.len[k], par = rv.parent[k];
     bool in_goal = true;
@@ -187,13 +188,13 @@ __global__ void commit_finish_kernel(TreeView<T> tv, const char* __restrict__ re
         total += h[HDR_COUNT]; sampled += h[HDR_SAMPLED]; tries += h[HDR_TRIES];
     }
     const int old = *tv.size;
-    const int nsz = min(old + total, tv.cap);
+    const int nsz = min(old + total, tv.limit);
     *tv.size = nsz;
     const unsigned long long b = *tv.best;
     out->v[0] = nsz; out->v[1] = sampled; out->v[2] = nsz - old; out->v[3] = *tv.n_goal;
     out->v[4] = b == ~0ull ? -1 : (int)(b & 0xffffffffu);
     out->v[5] = b == ~0ull ? -1 : (int)(b >> 32);
-    out->v[6] = (old + total > tv.cap) ? 1 : 0;
+    out->v[6] = (old + total > tv.limit) ? 1 : 0;
     out->v[7] = tries;
     out->v[8] = ((const int*)records)[HDR_FLAGS];
     out->v[9] = out->v[10] = out->v[11] = 0;

@@ -49,6 +49,8 @@ struct lq_engine {
     virtual int eval_erf(int count, const double* xg, const double* x, double* e) = 0;
     virtual int eval_feasible(int count, const double* x, const double* u, uint8_t* ok) = 0;
     virtual int set_tuning(int steer_lanes, int nearest_q) = 0;
+    virtual int set_profiling(int on) = 0;
+    virtual int profile_read(double* ms, double* work, int reset) = 0;
 };
 
 namespace lq {
@@ -72,6 +74,7 @@ namespace lq {
         return code;                             \
     } while (0)
 
+static_assert(sizeof(DevStats) == sizeof(lq_wave_stats), "device stats block must mirror lq_wave_stats");
 constexpr int MAX_SPLIT = 128;
 constexpr int NEAR_BLOCK = 128;
 
@@ -174,6 +177,7 @@ struct EngineImpl : lq_engine {
     bool have_goal = false, have_sampling = false;
     int cap = 0, Wc = 0, H = 0, tries_cap = 10;
     int size_ub = 0;                 // host upper bound of the device-side tree size
+    int size_ub_exact = 0;           // tree size as of the last stats read (wave-start size for profiling)
     int steer_lanes = 1, near_q = 0; // tuning (0 = heuristic)
     bool metric_diag = true;
     DiagMetric<T, N> dmet;
@@ -185,8 +189,10 @@ struct EngineImpl : lq_engine {
     DevBuf<uint8_t> t_ignore;
     DevBuf<unsigned long long> t_best;
     TreeView<T> tv;
-    // obstacle tables
+    // obstacle tables and their broad-phase grids
     std::vector<DevBuf<T>*> feas_bufs;
+    std::vector<DevBuf<int>*> grid_bufs;
+    int grid_min_obs = 16;
     // wave working set
     DevBuf<T> w_samples, w_ncost, w_pcost, w_Sp, w_xs, w_us, w_xnew, w_Knew, w_cand, w_goal;
     DevBuf<int> w_nidx, w_pidx, w_len, w_slot, w_tries, w_pick, w_misc;
@@ -199,13 +205,21 @@ struct EngineImpl : lq_engine {
     cudaEvent_t ev_stats = nullptr;
     bool stats_pending = false;
     cudaStream_t last_stream = nullptr;
+    // optional per-stage CUDA-event timing (bench.py roofline): sample | nearest | steer | pack | commit
+    bool prof_on = false, prof_wave_open = false, prof_commit_open = false;
+    cudaEvent_t pev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double prof_ms[5] = {0, 0, 0, 0, 0};
+    double prof_work[4] = {0, 0, 0, 0};    // nearest pairs (W*N), nearest bytes (W*N*n*sizeof T), samples, waves
+    int prof_W = 0;
 
     ~EngineImpl() override {
         cudaSetDevice(device);
         for (auto* b : feas_bufs) delete b;
+        for (auto* b : grid_bufs) delete b;
         if (h_stats) cudaFreeHost(h_stats);
         if (h_misc) cudaFreeHost(h_misc);
         if (ev_stats) cudaEventDestroy(ev_stats);
+        for (auto& e : pev) if (e) cudaEventDestroy(e);
     }
 
     template <typename U>
@@ -233,7 +247,7 @@ struct EngineImpl : lq_engine {
             md.tol[i] = (T)c->error_tol[i];
             md.goal_lo[i] = -Num<T>::inf(); md.goal_hi[i] = Num<T>::inf();
         }
-        cap = (c->node_capacity + 3) & ~3;
+        cap = (c->node_capacity + 1 + 3) & ~3;      // one spare row for the finish_on_goal node (planner.py:299)
         Wc = (c->wave_capacity + 3) & ~3;
         tries_cap = std::max(1, c->tries_capacity);
 
@@ -272,6 +286,7 @@ struct EngineImpl : lq_engine {
             auto* ob = new DevBuf<T>(); feas_bufs.push_back(ob);
             if (int r = upload(*ob, obs)) return r;
             d.obs = ob->p;
+            d.cell_start = nullptr; d.cell_items = nullptr;
             if (s.kind == LQ_FEAS_CIRCLES_CLOUD || s.kind == LQ_FEAS_BOXES_CLOUD) {
                 if (s.n_verts < 1 || !s.verts) LQ_FAIL(LQ_ERR_ARG, "cloud primitive %d needs vertices", pi);
                 std::vector<T> vv((size_t)2 * s.n_verts);
@@ -285,6 +300,8 @@ struct EngineImpl : lq_engine {
                 if (int r = upload(*vb, vv)) return r;
                 d.verts = vb->p;
             }
+            if (s.n_obs >= grid_min_obs)
+                if (int r = build_grid(s, d)) return r;
         }
 
         // tree
@@ -296,7 +313,7 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(t_ignore.alloc(cap)); LQ_CUDA(t_scal.alloc(8)); LQ_CUDA(t_best.alloc(1));
         tv.state = t_state.p; tv.K = t_K.p; tv.parent = t_parent.p; tv.cost = t_cost.p; tv.edge_len = t_elen.p;
         tv.ignore = t_ignore.p; tv.edge_x = t_ex.p; tv.edge_u = t_eu.p;
-        tv.size = t_scal.p; tv.n_ignored = t_scal.p + 1; tv.n_goal = t_scal.p + 2; tv.best = t_best.p; tv.cap = cap;
+        tv.size = t_scal.p; tv.n_ignored = t_scal.p + 1; tv.n_goal = t_scal.p + 2; tv.best = t_best.p; tv.cap = cap; tv.limit = c->node_capacity;
         LQ_CUDA(cudaMemset(t_scal.p, 0, 8 * sizeof(int)));
 
         // wave working set
@@ -351,9 +368,76 @@ struct EngineImpl : lq_engine {
         // heuristic: split the obstacle tables over a warp once they dominate a rollout step
         int obs_work = 0;
         for (int pi = 0; pi < md.feas.n_prims; pi++) obs_work += md.feas.prims[pi].n_obs;
-        steer_lanes = obs_work >= 256 ? 8 : 1;
+        steer_lanes = 1; (void)obs_work;             // the broad-phase grid keeps a check at a few obstacles
         return LQ_OK;
     }
+
+    // Uniform grid over the obstacle table (see FeasPrim).  Zones of influence are axis-aligned boxes:
+    // centre +- (obstacle extent + hull bounding radius + margin); the margin absorbs float rounding of
+    // the cell index on the device.
+    int build_grid(const lq_feas_prim& s, FeasPrim<T>& d) {
+        const int nd = s.kind == LQ_FEAS_SPHERES_POINT ? 3 : 2;
+        const int stride = (s.kind == LQ_FEAS_CIRCLES_POINT || s.kind == LQ_FEAS_CIRCLES_CLOUD) ? 3 : 4;
+        const int O = s.n_obs;
+        std::vector<double> lo((size_t)O * 3, 0.0), hi((size_t)O * 3, 0.0);
+        double blo[3] = {1e300, 1e300, 1e300}, bhi[3] = {-1e300, -1e300, -1e300}, mean_ext = 0;
+        for (int o = 0; o < O; o++) {
+            const double* ob = s.obs + (size_t)o * stride;
+            double ext[3];
+            switch (s.kind) {
+            case LQ_FEAS_CIRCLES_POINT: ext[0] = ext[1] = s.inflate + ob[2]; ext[2] = 0; break;
+            case LQ_FEAS_SPHERES_POINT: ext[0] = ext[1] = ext[2] = s.inflate + ob[3]; break;
+            case LQ_FEAS_CIRCLES_CLOUD: ext[0] = ext[1] = ob[2] + (double)d.bound_r; ext[2] = 0; break;
+            default: ext[0] = ob[2] + (double)d.bound_r; ext[1] = ob[3] + (double)d.bound_r; ext[2] = 0; break;
+            }
+            for (int k = 0; k < nd; k++) {
+                const double e = std::max(0.0, ext[k]) * 1.001 + 1e-3 * (1.0 + std::fabs(ob[k]));
+                lo[o * 3 + k] = ob[k] - e; hi[o * 3 + k] = ob[k] + e;
+                blo[k] = std::min(blo[k], lo[o * 3 + k]); bhi[k] = std::max(bhi[k], hi[o * 3 + k]);
+                mean_ext += e / (nd * O);
+            }
+        }
+        int gn[3] = {1, 1, 1};
+        double cell[3] = {1, 1, 1};
+        for (int k = 0; k < nd; k++) {
+            const double span = std::max(1e-9, bhi[k] - blo[k]);
+            gn[k] = (int)std::min(nd == 3 ? 48.0 : 256.0, std::max(1.0, std::ceil(span / (2.0 * mean_ext))));
+            cell[k] = span / gn[k] * (1.0 + 1e-9);
+        }
+        const size_t ncell = (size_t)gn[0] * gn[1] * gn[2];
+        std::vector<int> count(ncell + 1, 0);
+        auto range = [&](int o, int k, int& a, int& b) {
+            a = std::max(0, std::min(gn[k] - 1, (int)std::floor((lo[o * 3 + k] - blo[k]) / cell[k])));
+            b = std::max(0, std::min(gn[k] - 1, (int)std::floor((hi[o * 3 + k] - blo[k]) / cell[k])));
+        };
+        for (int pass = 0; pass < 2; pass++) {
+            std::vector<int> fill;
+            if (pass == 1) {
+                for (size_t c = 0, run = 0; c <= ncell; c++) { const int n = count[c]; count[c] = (int)run; run += n; }
+                fill.assign(count.begin(), count.end());
+                items_tmp.assign(count[ncell], 0);
+            }
+            for (int o = 0; o < O; o++) {
+                int a[3] = {0, 0, 0}, b[3] = {0, 0, 0};
+                for (int k = 0; k < nd; k++) range(o, k, a[k], b[k]);
+                for (int z = a[2]; z <= b[2]; z++)
+                    for (int y = a[1]; y <= b[1]; y++)
+                        for (int x = a[0]; x <= b[0]; x++) {
+                            const size_t c = ((size_t)z * gn[1] + y) * gn[0] + x;
+                            if (pass == 0) count[c]++; else items_tmp[fill[c]++] = o;
+                        }
+            }
+        }
+        auto* cs = new DevBuf<int>(); grid_bufs.push_back(cs);
+        auto* ci = new DevBuf<int>(); grid_bufs.push_back(ci);
+        if (int r = upload(*cs, count)) return r;
+        if (items_tmp.empty()) items_tmp.push_back(0);
+        if (int r = upload(*ci, items_tmp)) return r;
+        d.cell_start = cs->p; d.cell_items = ci->p;
+        for (int k = 0; k < 3; k++) { d.g0[k] = (T)blo[k]; d.ginv[k] = (T)(1.0 / cell[k]); d.gn[k] = gn[k]; }
+        return LQ_OK;
+    }
+    std::vector<int> items_tmp;
 
     const T* const_metric_ptr() { return const_metric_ptr_impl(md.lqr, 0); }
     template <class L> static auto const_metric_ptr_impl(L& l, int) -> decltype((const T*)l.S) { return l.S; }
@@ -393,7 +477,7 @@ struct EngineImpl : lq_engine {
 
     int load_nodes(int count, const double* state, const int* parent, const int* cost, cudaStream_t st) override {
         LQ_CUDA(cudaSetDevice(device));
-        if (count < 1 || count > cap) LQ_FAIL(LQ_ERR_ARG, "node count %d outside 1..%d", count, cap);
+        if (count < 1 || count > tv.limit) LQ_FAIL(LQ_ERR_ARG, "node count %d outside 1..%d", count, tv.limit);
         std::vector<T> soa((size_t)N * count);
         for (int i = 0; i < count; i++)
             for (int d = 0; d < N; d++) soa[(size_t)d * count + i] = (T)state[(size_t)i * N + d];
@@ -412,7 +496,7 @@ struct EngineImpl : lq_engine {
         init_gain_kernel<T, Sys, Lqr><<<(count + 127) / 128, 128, 0, st>>>(md, t_state.p, t_K.p, cap, count); launches++;
         LQ_CUDA(cudaGetLastError());
         LQ_CUDA(cudaStreamSynchronize(st));     // host staging vectors die here
-        size_ub = count;
+        size_ub = count; size_ub_exact = count;
         memset(h_stats, 0, sizeof(lq_wave_stats));
         h_stats->tree_size = count; h_stats->best_node = -1; h_stats->best_cost = -1;
         stats_pending = false;
@@ -522,13 +606,17 @@ struct EngineImpl : lq_engine {
 
     // ---- one wave -------------------------------------------------------------
     int expand_from_samples(int count, int use_ignore, int flags, cudaStream_t st) {
+        if (prof_on) cudaEventRecord(pev[1], st);
         if (int r = launch_nearest(w_samples.p, Wc, count, use_ignore, w_nidx.p, w_ncost.p, st)) return r;
+        if (prof_on) cudaEventRecord(pev[2], st);
         launch_steer(w_nidx.p, w_samples.p, Wc, count, w_xs.p, w_us.p, w_len.p, w_xnew.p, w_Knew.p, Wc, st);
+        if (prof_on) cudaEventRecord(pev[3], st);
         RecView<T> rv = rec_view<T>(w_rec.p, Wc, N, M, H);
         pack_scan_kernel<1024><<<1, 1024, 0, st>>>(w_len.p, w_tries.p, count, w_slot.p, rv.header, flags); launches++;
         pack_kernel<T><<<(count * 32 + 255) / 256, 256, 0, st>>>(w_len.p, w_slot.p, w_nidx.p, w_xnew.p, w_Knew.p, Wc,
                                                                 w_xs.p, w_us.p, count, rv, Wc, N, M, H);
         launches++;
+        if (prof_on) { cudaEventRecord(pev[4], st); prof_wave_open = true; prof_W = count; }
         LQ_CUDA(cudaGetLastError());
         last_stream = st;
         return LQ_OK;
@@ -548,6 +636,7 @@ struct EngineImpl : lq_engine {
             last_stream = st;
             return LQ_OK;
         }
+        if (prof_on) cudaEventRecord(pev[0], st);
         if (h_samples) {
             std::vector<T> soa((size_t)N * count);
             for (int j = 0; j < count; j++)
@@ -573,6 +662,7 @@ struct EngineImpl : lq_engine {
         if (tries < 1 || n_cand < (long long)count * tries) LQ_FAIL(LQ_ERR_ARG, "need count*tries candidates");
         if (!have_goal) LQ_FAIL(LQ_ERR_STATE, "lq_set_goal has not been called");
         if (w_cand.n < (size_t)N * n_cand) { LQ_CUDA(w_cand.alloc((size_t)N * n_cand)); LQ_CUDA(w_candok.alloc(n_cand)); }
+        if (prof_on) cudaEventRecord(pev[0], st);
         std::vector<T> soa((size_t)N * n_cand);
         for (int j = 0; j < n_cand; j++)
             for (int d = 0; d < N; d++) soa[(size_t)d * n_cand + j] = (T)h_cand[(size_t)j * N + d];
@@ -601,10 +691,12 @@ struct EngineImpl : lq_engine {
         if (n_seg < 1) LQ_FAIL(LQ_ERR_ARG, "n_segments must be >= 1");
         const char* rec = d_records ? (const char*)d_records : w_rec.p;
         const long long warps = (long long)n_seg * Wc;
+        if (prof_on) cudaEventRecord(pev[5], st);
         commit_kernel<T><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(tv, rec, rec_sz, n_seg, Wc, N, M, H,
                                                                                 w_goal.p, w_goal.p + LQ_MAX_N);
         launches++;
         commit_finish_kernel<T><<<1, 1, 0, st>>>(tv, rec, rec_sz, n_seg, w_stats.p); launches++;
+        if (prof_on) { cudaEventRecord(pev[6], st); prof_commit_open = true; }
         LQ_CUDA(cudaGetLastError());
         LQ_CUDA(cudaMemcpyAsync(h_stats, w_stats.p, sizeof(DevStats), cudaMemcpyDeviceToHost, st));
         LQ_CUDA(cudaEventRecord(ev_stats, st));
@@ -615,7 +707,25 @@ struct EngineImpl : lq_engine {
 
     int wave_stats(lq_wave_stats* out) override {
         LQ_CUDA(cudaSetDevice(device));
+        const int size_before = size_ub_exact;
         if (stats_pending) { LQ_CUDA(cudaEventSynchronize(ev_stats)); stats_pending = false; }
+        if (prof_on) {
+            float ms = 0;
+            if (prof_wave_open) {
+                LQ_CUDA(cudaEventSynchronize(pev[4]));
+                for (int k = 0; k < 4; k++) { cudaEventElapsedTime(&ms, pev[k], pev[k + 1]); prof_ms[k] += ms; }
+                prof_work[0] += (double)prof_W * size_before;
+                prof_work[1] += (double)prof_W * size_before * N * sizeof(T);
+                prof_work[2] += prof_W; prof_work[3] += 1;
+                prof_wave_open = false;
+            }
+            if (prof_commit_open) {
+                LQ_CUDA(cudaEventSynchronize(pev[6]));
+                cudaEventElapsedTime(&ms, pev[5], pev[6]); prof_ms[4] += ms;
+                prof_commit_open = false;
+            }
+        }
+        size_ub_exact = h_stats->tree_size;
         size_ub = h_stats->tree_size;
         if (out) *out = *h_stats;
         return LQ_OK;
@@ -674,7 +784,7 @@ struct EngineImpl : lq_engine {
         int sz = 0;
         if (int r = tree_size(&sz)) return r;
         if (parent < 0 || parent >= sz) LQ_FAIL(LQ_ERR_ARG, "The given parent ID, %d, doesn't exist.", parent);   // tree.py:83-84
-        if (sz >= cap) LQ_FAIL(LQ_ERR_STATE, "tree is at node_capacity=%d", cap);
+        if (sz >= cap) LQ_FAIL(LQ_ERR_STATE, "tree storage is full (%d rows)", cap);
         // edges longer than the horizon (force-arrive) keep only their length on the device; the host
         // planner holds the full sequence (planner.py:299-303 extends its own lists)
         const int keep = std::min(len, H);
@@ -814,6 +924,19 @@ struct EngineImpl : lq_engine {
         if (lanes == 1 || lanes == 8 || lanes == 32) steer_lanes = lanes;
         else if (lanes != 0) LQ_FAIL(LQ_ERR_ARG, "steer lanes must be 0 (keep), 1, 8 or 32");
         near_q = nq;
+        return LQ_OK;
+    }
+
+    int set_profiling(int on) override {
+        LQ_CUDA(cudaSetDevice(device));
+        if (on && !pev[0]) for (auto& e : pev) LQ_CUDA(cudaEventCreate(&e));
+        prof_on = on != 0; prof_wave_open = prof_commit_open = false;
+        return LQ_OK;
+    }
+    int profile_read(double* ms, double* work, int reset) override {
+        if (ms) for (int k = 0; k < 5; k++) ms[k] = prof_ms[k];
+        if (work) for (int k = 0; k < 4; k++) work[k] = prof_work[k];
+        if (reset) { for (auto& v : prof_ms) v = 0; for (auto& v : prof_work) v = 0; }
         return LQ_OK;
     }
 };

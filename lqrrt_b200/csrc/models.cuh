@@ -407,16 +407,41 @@ template <typename T> struct FeasPrim {
     int dims[4];
     T inflate;
     T bound_r;            // cloud: max vertex norm (broad phase)
-    const T* obs;         // n_obs x stride (row-major, stride 4)
+    const T* obs;         // n_obs x 4 (row-major)
     const T* verts;       // 2 x n_verts
     T lo[LQ_MAX_N], hi[LQ_MAX_N];
     int nbox;
+    // Uniform-grid broad phase over the obstacle table (host-built, engine.cuh build_grid): cell c lists
+    // every obstacle whose zone of influence (its bounds grown by the hull's bounding radius, plus a
+    // margin) overlaps the cell, so a query only walks the list of the cell it falls in.  Exact: an
+    // obstacle that can be hit from p always has p inside its zone.  cell_start == nullptr => brute force.
+    const int* cell_start;
+    const int* cell_items;
+    T g0[3], ginv[3];
+    int gn[3];
 };
 
 template <typename T> struct FeasSet {
     int n_prims;
     FeasPrim<T> prims[LQ_MAX_PRIMS];
 };
+
+// Candidate obstacle range for a query position: [*b, *e) indexes p.cell_items (or the table itself
+// when there is no grid).  Returns false if the position lies outside every zone of influence.
+template <typename T>
+__device__ __forceinline__ bool feas_candidates(const FeasPrim<T>& p, T px, T py, T pz, int nd, int* b, int* e) {
+    if (!p.cell_start) { *b = 0; *e = p.n_obs; return true; }
+    const T fx = (px - p.g0[0]) * p.ginv[0], fy = (py - p.g0[1]) * p.ginv[1];
+    if (!(fx >= T(0) && fy >= T(0) && fx < (T)p.gn[0] && fy < (T)p.gn[1])) return false;
+    int cell = (int)fy * p.gn[0] + (int)fx;
+    if (nd == 3) {
+        const T fz = (pz - p.g0[2]) * p.ginv[2];
+        if (!(fz >= T(0) && fz < (T)p.gn[2])) return false;
+        cell += (int)fz * p.gn[0] * p.gn[1];
+    }
+    *b = p.cell_start[cell]; *e = p.cell_start[cell + 1];
+    return true;
+}
 
 // lane / lanes: cooperative evaluation by `lanes` threads that all hold the
 // same (x,u); obstacle loops are strided by lane.  Returns this lane's verdict;
@@ -444,28 +469,23 @@ __device__ __forceinline__ bool feasible_eval(const FeasSet<T>& fs, const T* x, 
             if (inside) return false;
             break;
         }
-        case LQ_FEAS_CIRCLES_POINT: {               // demo_boat_novice.py:160-164
-            T px = T(0), py = T(0);
-#pragma unroll
-            for (int i = 0; i < N; i++) { if (i == p.dims[0]) px = x[i]; if (i == p.dims[1]) py = x[i]; }
-            for (int o = lane; o < p.n_obs; o += lanes) {
-                const T dx = px - p.obs[o * 4 + 0], dy = py - p.obs[o * 4 + 1];
-                const T rr = p.obs[o * 4 + 2];      // inflate + r, host-added
-                if (dx * dx + dy * dy <= rr * rr) return false;
-            }
-            break;
-        }
+        case LQ_FEAS_CIRCLES_POINT:                 // demo_boat_novice.py:160-164
         case LQ_FEAS_SPHERES_POINT: {
+            const bool sph = p.kind == LQ_FEAS_SPHERES_POINT;
             T px = T(0), py = T(0), pz = T(0);
 #pragma unroll
             for (int i = 0; i < N; i++) {
                 if (i == p.dims[0]) px = x[i];
                 if (i == p.dims[1]) py = x[i];
-                if (i == p.dims[2]) pz = x[i];
+                if (sph && i == p.dims[2]) pz = x[i];
             }
-            for (int o = lane; o < p.n_obs; o += lanes) {
-                const T dx = px - p.obs[o * 4 + 0], dy = py - p.obs[o * 4 + 1], dz = pz - p.obs[o * 4 + 2];
-                const T rr = p.obs[o * 4 + 3];
+            int b, e;
+            if (!feas_candidates(p, px, py, pz, sph ? 3 : 2, &b, &e)) break;
+            for (int k = b + lane; k < e; k += lanes) {
+                const int o = p.cell_start ? p.cell_items[k] : k;
+                const T dx = px - p.obs[o * 4 + 0], dy = py - p.obs[o * 4 + 1];
+                const T dz = sph ? pz - p.obs[o * 4 + 2] : T(0);
+                const T rr = sph ? p.obs[o * 4 + 3] : p.obs[o * 4 + 2];      // inflate + r, host-added in float64
                 if (dx * dx + dy * dy + dz * dz <= rr * rr) return false;
             }
             break;
@@ -479,24 +499,34 @@ __device__ __forceinline__ bool feasible_eval(const FeasSet<T>& fs, const T* x, 
                 if (i == p.dims[1]) py = x[i];
                 if (i == p.dims[2]) ph = x[i];
             }
+            const bool circ = p.kind == LQ_FEAS_CIRCLES_CLOUD;
+            int b, e;
+            if (p.flags & 1) {                      // demo_car.py:175: an extra vertex at 2 * position
+                const T qx = px + px, qy = py + py;
+                if (feas_candidates(p, qx, qy, T(0), 2, &b, &e)) {
+                    for (int k = b + lane; k < e; k += lanes) {
+                        const int o = p.cell_start ? p.cell_items[k] : k;
+                        const T ex = qx - p.obs[o * 4 + 0], ey = qy - p.obs[o * 4 + 1];
+                        const T a = p.obs[o * 4 + 2], bb = p.obs[o * 4 + 3];
+                        if (circ ? (ex * ex + ey * ey <= a * a) : (abs_t(ex) <= a && abs_t(ey) <= bb)) return false;
+                    }
+                }
+            }
+            if (!feas_candidates(p, px, py, T(0), 2, &b, &e)) break;
             T s, c;
             sincos_t(ph, &s, &c);
-            const bool circ = p.kind == LQ_FEAS_CIRCLES_CLOUD;
-            for (int o = lane; o < p.n_obs; o += lanes) {
+            for (int k = b + lane; k < e; k += lanes) {
+                const int o = p.cell_start ? p.cell_items[k] : k;
                 const T ox = p.obs[o * 4 + 0], oy = p.obs[o * 4 + 1];
-                const T a = p.obs[o * 4 + 2], b = p.obs[o * 4 + 3];
-                if (p.flags & 1) {                  // demo_car.py:175: vertex at 2 * position
-                    const T ex = px + px - ox, ey = py + py - oy;
-                    if (circ ? (ex * ex + ey * ey <= a * a) : (abs_t(ex) <= a && abs_t(ey) <= b)) return false;
-                }
-                // broad phase: hull bounding circle vs obstacle bounding circle (conservative)
+                const T a = p.obs[o * 4 + 2], bb = p.obs[o * 4 + 3];
+                // hull bounding circle vs obstacle bounding circle (conservative)
                 const T dx = px - ox, dy = py - oy;
-                const T reach = (circ ? a : sqrt_t(a * a + b * b)) + p.bound_r;
+                const T reach = (circ ? a : sqrt_t(a * a + bb * bb)) + p.bound_r;
                 if (dx * dx + dy * dy > reach * reach * T(1.0001)) continue;
                 for (int v = 0; v < p.n_verts; v++) {
                     const T bx = p.verts[v], by = p.verts[p.n_verts + v];
                     const T ex = dx + (c * bx - s * by), ey = dy + (s * bx + c * by);
-                    if (circ ? (ex * ex + ey * ey <= a * a) : (abs_t(ex) <= a && abs_t(ey) <= b)) return false;
+                    if (circ ? (ex * ex + ey * ey <= a * a) : (abs_t(ex) <= a && abs_t(ey) <= bb)) return false;
                 }
             }
             break;

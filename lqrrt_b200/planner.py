@@ -11,7 +11,7 @@ commit, include/lqrrt_b200.h) instead of one sample in Python.
 New keyword arguments (all optional, defaults keep reference call sites valid):
   wave      None = adaptive wave size, int = fixed global wave size
             (1 reproduces the reference's sequential semantics)
-  wave_max  cap of the adaptive wave size
+  wave_max  cap of the adaptive wave size;  wave_growth: adaptive W = wave_growth * tree size
   dtype     'f32' (throughput) or 'f64' (reference-parity arithmetic)
   rng       'philox' = counter-based device sampler; 'numpy' = the reference's
             global MT19937 stream, drawn on the host in the reference's order
@@ -44,12 +44,14 @@ class Planner(object):
                  error_tol=0.05, erf=np.subtract,
                  min_time=0.5, max_time=1, max_nodes=1E5,
                  goal0=None, sys_time=time.time, printing=True,
-                 wave=None, wave_max=8192, dtype='f32', rng='philox', seed=0, device=None, comm=None):
+                 wave=None, wave_max=8192, dtype='f32', rng='philox', seed=0, device=None, comm=None,
+                 wave_growth=1.0):
         self._engine = None
         self._engine_key = None
         self._exchange = None
         self.wave = wave
         self.wave_max = int(wave_max)
+        self.wave_growth = float(wave_growth)
         self.dtype = dtype
         if rng not in ('philox', 'numpy'):
             raise ValueError("rng must be 'philox' or 'numpy'")
@@ -199,10 +201,17 @@ class Planner(object):
         outcome = None
         exchange = self._get_exchange(eng) if self.world > 1 else None
         launches0 = eng.launch_count()
+        h2d0, d2h0 = eng.h2d_bytes, eng.d2h_bytes
+        ev0 = ev1 = None
+        if getattr(self, 'profile', False):
+            import torch
+            eng.set_profiling(True)
+            ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
         time_start = self.sys_time()
 
         while True:
-            W = _waves.wave_size(self.tree.size, self.wave, wave_max=self.wave_max)
+            W = _waves.wave_size(self.tree.size, self.wave, wave_max=self.wave_max, growth=self.wave_growth)
             first, count = _waves.partition(W, self.rank, self.world)
 
             if mode == 'philox':
@@ -266,6 +275,9 @@ class Planner(object):
 
         self.stats = dict(waves=wave_ctr, samples=samples_total, nodes=self.tree.size,
                           elapsed=time_elapsed, gpu_launches=eng.launch_count() - launches0)
+        if ev0 is not None:
+            ev1.record(); ev1.synchronize()
+            self.stats['device_ms'] = ev0.elapsed_time(ev1)      # wave loop only, on the launching stream
 
         if self.plan_reached_goal:
             # the plan attributes the reference fills inside its loop (planner.py:276-281)
@@ -303,6 +315,9 @@ class Planner(object):
                 print("Didn't reach goal.\nTree size: {0}\nETA: {1} s".format(self.tree.size, np.round(self.T, 2)))
             self._prepare_interpolators()
 
+        self.stats['gpu_launches'] = eng.launch_count() - launches0
+        self.stats['h2d_bytes'] = eng.h2d_bytes - h2d0
+        self.stats['d2h_bytes'] = eng.d2h_bytes - d2h0
         if outcome == 'killed' or self.tree.size > self.max_nodes:  # planner.py:330-336
             if self.printing:
                 print("Plan update terminated abruptly!")

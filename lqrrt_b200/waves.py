@@ -11,15 +11,16 @@ a wave expands `W` of them against the tree as of wave start (SURVEY.md section 
 from __future__ import annotations
 
 
-def wave_size(tree_size, fixed=None, wave_min=32, wave_max=8192):
+def wave_size(tree_size, fixed=None, wave_min=32, wave_max=8192, growth=1.0):
     """Global samples in the next wave.  `fixed` pins it (1 = the reference's
     sequential semantics).  Otherwise the wave tracks the tree size, so the tree
     at most roughly doubles per wave while it is small -- tree depth grows by at
     most one edge per wave, and a huge first wave would only fan out from the
-    seed -- and saturates at wave_max."""
+    seed -- and saturates at wave_max.  `growth` scales it: W = growth * N; smaller values trade
+    throughput for tree depth per sample."""
     if fixed is not None:
         return max(1, int(fixed))
-    return int(min(wave_max, max(wave_min, tree_size)))
+    return int(min(wave_max, max(wave_min, growth * tree_size)))
 
 
 def partition(wave, rank, world):

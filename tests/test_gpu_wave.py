@@ -1,0 +1,145 @@
+"""
+Wave-level parity (level 3) and shard invariance (level 4): the engine's sample -> nearest -> steer ->
+commit chain against oracle/wave.py, node for node, in float64; and the same wave split into G logical
+shards (the multi-GPU partition, run sequentially on one GPU) must give a bit-identical tree.
+"""
+import numpy as np
+import pytest
+
+from conftest import problem
+from gpu_util import make_engine, tree_arrays
+from oracle.wave import WaveOracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(prob, cap=1 << 30):
+    return WaveOracle(prob.system, prob.goal, prob.goal_buffer, prob.horizon, prob.dt, prob.FPR, prob.error_tol,
+                      node_capacity=cap)
+
+
+@pytest.mark.parametrize('name,W,waves', [('demo_boat_novice', 64, 6), ('demo_car', 48, 4), ('demo_boat_advanced', 128, 4),
+                                          ('c1', 64, 5), ('c2', 32, 3)])
+def test_philox_waves_match_oracle(cuda_device, name, W, waves):
+    prob = problem(name)
+    eng = make_engine(prob, 'f64', node_capacity=4096, wave_capacity=W)
+    eng.set_sampling(prob.sample_space, prob.goal_bias, 10)
+    eng.reset(prob.x0)
+    orc = _oracle(prob); orc.reset(prob.x0)
+    for w in range(waves):
+        eng.wave_expand(99, w, 0, W, None, True)
+        eng.wave_commit(None, 1)
+        st = eng.wave_stats()
+        X, used = orc.sample_wave(99, w, 0, W, prob.sample_space, prob.goal_bias, 10)
+        orc.expand_wave(X)
+        assert st.tree_size == orc.size, (w, st.tree_size, orc.size)
+        assert st.tries_used == int(used.sum())
+        assert st.n_sampled == W
+    t = tree_arrays(eng)
+    assert t['parent'].tolist() == orc.parent
+    assert t['cost'].tolist() == orc.cost
+    tol = 1e-6 if prob.system.lqr.kind == 3 else 1e-9
+    assert np.abs(t['state'] - orc.state).max() <= tol
+    assert np.abs(t['K'] - np.array(orc.K)).max() <= tol * 1e4
+    assert t['ignore'].astype(bool).tolist() == orc.ignore
+    assert (st.best_node, st.best_cost) == ((orc.best_node, orc.best_cost) if orc.best_cost is not None else (-1, -1))
+    hx, hu = eng.download_edges(np.arange(1, orc.size))
+    for i in range(1, orc.size):
+        L = len(orc.x_seq[i])
+        assert t['edge_len'][i] == L
+        assert np.abs(hx[i - 1, :L] - np.array(orc.x_seq[i])).max() <= tol
+        assert np.abs(hu[i - 1, :L] - np.array(orc.u_seq[i])).max() <= tol * 1e4
+        assert np.array_equal(hx[i - 1, L - 1], t['state'][i])          # a node is the end of its edge
+
+
+def test_goal_bookkeeping_matches_oracle(cuda_device):
+    """Enough waves for goal hits: ignore marks along every finished plan, best plan = smallest T,
+    earliest node on ties (planner.py:260-281)."""
+    prob = problem('demo_car')
+    W = 96
+    eng = make_engine(prob, 'f64', node_capacity=8192, wave_capacity=W)
+    eng.set_sampling(prob.sample_space, prob.goal_bias, 10)
+    eng.reset(prob.x0)
+    orc = _oracle(prob); orc.reset(prob.x0)
+    st = None
+    for w in range(14):
+        eng.wave_expand(5, w, 0, W, None, True)
+        eng.wave_commit(None, 1)
+        st = eng.wave_stats()
+        X, _ = orc.sample_wave(5, w, 0, W, prob.sample_space, prob.goal_bias, 10)
+        orc.expand_wave(X)
+        assert st.tree_size == orc.size
+    assert len(orc.goal_nodes) > 0, "test needs goal hits; raise the wave count"
+    t = tree_arrays(eng)
+    assert st.n_goal == len(orc.goal_nodes)
+    assert t['ignore'].astype(bool).tolist() == orc.ignore
+    assert (st.best_node, st.best_cost) == (orc.best_node, orc.best_cost)
+    assert t['parent'].tolist() == orc.parent
+
+
+@pytest.mark.parametrize('dtype', ['f64', 'f32'])
+@pytest.mark.parametrize('G', [2, 3, 8])
+def test_sharded_wave_is_bit_identical(cuda_device, dtype, G):
+    """Level 4: contiguous sample->rank partition + rank-order commit == the unsharded wave, bitwise.
+    G engines stand in for G GPUs; their record segments are concatenated exactly as the allgather would."""
+    import torch
+    from lqrrt_b200 import waves
+    prob = problem('demo_boat_intermediate')
+    W = 200
+    Wc = waves.local_capacity(W, G)
+    ref = make_engine(prob, dtype, node_capacity=4096, wave_capacity=W)
+    ref.set_sampling(prob.sample_space, prob.goal_bias, 10); ref.reset(prob.x0)
+    shards = []
+    for r in range(G):
+        e = make_engine(prob, dtype, node_capacity=4096, wave_capacity=Wc)
+        e.set_sampling(prob.sample_space, prob.goal_bias, 10); e.reset(prob.x0)
+        shards.append(e)
+    _, seg = shards[0].wave_records()
+    recv = torch.empty(G * seg, dtype=torch.uint8, device='cuda')
+    from lqrrt_b200._native import DevicePointer
+    for w in range(5):
+        ref.wave_expand(21, w, 0, W, None, True); ref.wave_commit(None, 1); rs = ref.wave_stats()
+        for r, e in enumerate(shards):
+            first, count = waves.partition(W, r, G)
+            e.wave_expand(21, w, first, count, None, True)
+            ptr, nb = e.wave_records()
+            recv[r * seg:(r + 1) * seg].copy_(torch.as_tensor(DevicePointer(ptr, nb), device='cuda'))
+        torch.cuda.synchronize()
+        for e in shards:
+            e.wave_commit(recv.data_ptr(), G)
+            assert e.wave_stats().tree_size == rs.tree_size
+    a = tree_arrays(ref)
+    for e in shards:
+        b = tree_arrays(e)
+        for k in ('state', 'parent', 'cost', 'edge_len', 'ignore', 'K'):
+            assert np.array_equal(a[k], b[k]), k
+
+
+def test_capacity_truncates_and_flags(cuda_device):
+    prob = problem('demo_boat_novice')
+    eng = make_engine(prob, 'f32', node_capacity=100, wave_capacity=256)
+    eng.set_sampling(prob.sample_space, prob.goal_bias, 10); eng.reset(prob.x0)
+    full = 0
+    for w in range(6):
+        eng.wave_expand(1, w, 0, 256, None, True); eng.wave_commit(None, 1)
+        st = eng.wave_stats(); full |= st.full
+        assert st.tree_size <= 100
+    assert full == 1 and st.tree_size == 100
+
+
+def test_host_supplied_samples_and_empty_wave(cuda_device):
+    prob = problem('demo_boat_novice')
+    eng = make_engine(prob, 'f64', wave_capacity=64)
+    eng.reset(prob.x0)
+    orc = _oracle(prob); orc.reset(prob.x0)
+    rng = np.random.RandomState(0)
+    ss = np.array(prob.sample_space)
+    for w in range(3):
+        X = ss[:, 0] + (ss[:, 1] - ss[:, 0]) * rng.rand(40, 6)
+        eng.wave_expand(0, w, 0, 40, X, True); eng.wave_commit(None, 1)
+        orc.expand_wave(X)
+        assert eng.wave_stats().tree_size == orc.size
+    eng.wave_expand(0, 9, 0, 0, None, True); eng.wave_commit(None, 1)      # a rank with an empty slice
+    st = eng.wave_stats()
+    assert st.n_accepted == 0 and st.tree_size == orc.size
+    assert np.abs(tree_arrays(eng)['state'] - orc.state).max() < 1e-9

@@ -1,0 +1,85 @@
+"""Host mirror of the reference interface: constructor / setter validation and messages
+(planner.py:468-592, constraints.py:39-61) -- no GPU needed until update_plan is called."""
+import numpy as np
+import pytest
+
+import lqrrt_b200 as lqrrt
+from lqrrt_b200 import models, configs
+
+
+def _planner(**kw):
+    prob = configs.demo_boat_novice(0)
+    return prob, prob.make_planner(**kw)
+
+
+def test_package_surface():
+    import lqrrt as alias
+    assert alias.Planner is lqrrt.Planner and alias.Constraints is lqrrt.Constraints
+    assert hasattr(lqrrt, 'Tree')
+
+
+def test_constraints_validation():
+    feas = models.Feasibility()
+    c = lqrrt.Constraints(2, 1, [-1, np.inf], feas)
+    assert c.goal_buffer.dtype == np.float64 and c.goal_buffer[0] == 1.0
+    with pytest.raises(ValueError, match="goal_buffer must have same dimensionality"):
+        c.set_buffers([1, 2, 3])
+    with pytest.raises(ValueError, match="Expected is_feasible to be a function"):
+        c.set_feasibility_function(3)
+
+
+def test_planner_setters_match_reference_rules():
+    prob, p = _planner()
+    assert p.horizon_iters == 20 and p.hfactor == 0 and p.nstates == 6 and p.ncontrols == 3
+    with pytest.raises(ValueError, match="min_time must be less than or equal"):
+        p.set_runtime(min_time=5, max_time=1)
+    p.set_runtime(min_time=1, max_time=5)
+    with pytest.raises(ValueError, match="Expected sys_time to be a function"):
+        p.set_runtime(sys_time=3)
+    with pytest.raises(ValueError, match="horizon must be at least as big as dt"):
+        p.set_resolution(horizon=0.01)
+    p.set_resolution(horizon=2)
+    with pytest.raises(ValueError, match="Shape of error_tol"):
+        p.set_resolution(error_tol=[1, 2])
+    p.set_resolution(horizon=(0.1, 3))
+    assert p.hfactor == 2 and p.horizon_iters == 1 and list(p.hspan) == [1, 30]
+    with pytest.raises(ValueError, match="min < max"):
+        p.set_resolution(horizon=(3, 1))
+    p.set_resolution(horizon=2)
+    with pytest.raises(ValueError, match="goal state must have same dimensionality"):
+        p.set_goal([1, 2])
+    p.set_goal(None)
+    assert p.goal is None
+    p.dt = 0.05                      # plain attribute, as lqrrt_node.py:259 assigns it
+    assert p.dt == 0.05
+    p.kill_update(); assert p.killed
+    p.unkill(); assert not p.killed
+
+
+def test_plain_callables_are_rejected_loudly():
+    """No CPU fallback: arbitrary Python closures cannot run in a kernel."""
+    prob = configs.demo_boat_novice(0)
+    cons = lqrrt.Constraints(6, 3, prob.goal_buffer, lambda x, u: True)
+    with pytest.raises(TypeError, match="no CPU fallback"):
+        lqrrt.Planner(lambda x, u, dt: x, lambda x, u: (np.eye(6), np.zeros((3, 6))), cons, horizon=2, dt=0.1)
+    with pytest.raises(ValueError, match="Expected dynamics to be a function"):
+        lqrrt.Planner(None, prob.system.lqr, cons, horizon=2, dt=0.1)
+
+
+def test_model_blobs_have_the_wire_sizes():
+    for name, n_sys in (('demo_boat_novice', 46), ('demo_car', 9), ('c1', 5), ('c5', 1)):
+        s = configs.BY_NAME[name](0).system
+        assert len(s.dynamics.blob()) == n_sys
+        assert s.erf.mask(s.nstates) in (0, 1, 4)
+    car = configs.demo_car(0).system
+    assert car.is_feasible.prims[0].flags == 1 and car.is_feasible.prims[0].verts.shape[0] == 2
+    nov = configs.demo_boat_novice(0).system
+    assert len(nov.is_feasible.prims[0].obs) < 36        # sentinel slots dropped
+
+
+def test_missing_library_is_an_error(monkeypatch, tmp_path):
+    from lqrrt_b200 import _native
+    monkeypatch.setattr(_native, '_lib', None)
+    monkeypatch.setattr(_native, 'LIB_PATH', str(tmp_path / 'nope.so'))
+    with pytest.raises(_native.NativeError, match="no CPU fallback"):
+        _native.load_library()
