@@ -208,7 +208,8 @@ def run_gpu_arm(args):
 
     for w in range(args.warmup):
         one_plan(9000 + w)
-    planner._engine.profile_read(reset=True)
+    if planner._engine is not None:
+        planner._engine.profile_read(reset=True)
 
     barrier()
     with ClockSampler(local) as clk:

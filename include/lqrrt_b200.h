@@ -188,7 +188,8 @@ int lq_eval_feasible(lq_engine* h, int count, const double* h_x, const double* h
 
 /* number of kernels this engine has launched since creation (bench.py's gpu_launches) */
 int lq_launch_count(lq_engine* h, uint64_t* out);
-/* tuning knobs: steer lanes per sample (1, 8, 32; 0 keeps), nearest queries per thread (0 = heuristic) */
+/* tuning knobs: lanes = steer lanes per sample + 100 * sampler lanes per sample (each 1, 8 or 32; 0 keeps),
+ * nearest_q = nearest queries per thread (0 = heuristic, 1 = small, >1 = large) */
 int lq_set_tuning(lq_engine* h, int steer_lanes, int nearest_q);
 /* Per-stage CUDA-event timing of the wave chain on the launching stream (bench.py's roofline leg).
  * ms[5]: sample, nearest, steer, pack, commit (accumulated);  work[4]: nearest pairs sum(W*N),

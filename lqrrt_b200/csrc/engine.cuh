@@ -178,7 +178,7 @@ struct EngineImpl : lq_engine {
     int cap = 0, Wc = 0, H = 0, tries_cap = 10;
     int size_ub = 0;                 // host upper bound of the device-side tree size
     int size_ub_exact = 0;           // tree size as of the last stats read (wave-start size for profiling)
-    int steer_lanes = 1, near_q = 0; // tuning (0 = heuristic)
+    int steer_lanes = 1, sample_lanes = 1, near_q = 0; // tuning (0 = heuristic)
     bool metric_diag = true;
     DiagMetric<T, N> dmet;
     double Sconst[N * N];
@@ -524,23 +524,31 @@ struct EngineImpl : lq_engine {
             chunk = (chunk + NEAR_BLOCK - 1) / NEAR_BLOCK * NEAR_BLOCK;
             nsplit = (Nub + chunk - 1) / chunk;
         };
+        // the erf masks of the shipped vehicles get compile-time kernels; anything else the generic one
+        const int cmask = md.angle_mask == 0u ? 0 : (md.angle_mask == 4u && N >= 3 ? 4 : (md.angle_mask == 1u ? 1 : -1));
         if (metric_diag) {
             constexpr int QBIG = sizeof(T) == 4 ? 4 : 2;
+            constexpr bool EX = sizeof(T) == 8;
             int nqb, chunk, nsplit;
             plan(QBIG, nqb, chunk, nsplit);
             bool big = (long long)nqb * max_splits >= 148 * 2;
             if (near_q == 1) big = false;
             if (near_q > 1) big = true;
-            if (big) {
-                nearest_diag_kernel<T, N, QBIG, NEAR_BLOCK><<<nqb * nsplit, NEAR_BLOCK, 0, st>>>(
-                    t_state.p, cap, t_ignore.p, tv.size, tv.n_ignored, use_ignore, q, qstride, W, dmet, nqb, chunk,
-                    w_pcost.p, w_pidx.p, Wc);
-            } else {
-                plan(1, nqb, chunk, nsplit);
-                nearest_diag_kernel<T, N, 1, NEAR_BLOCK><<<nqb * nsplit, NEAR_BLOCK, 0, st>>>(
-                    t_state.p, cap, t_ignore.p, tv.size, tv.n_ignored, use_ignore, q, qstride, W, dmet, nqb, chunk,
-                    w_pcost.p, w_pidx.p, Wc);
-            }
+            if (!big) plan(1, nqb, chunk, nsplit);
+#define LQ_NEAR_DIAG(QQ, MM)                                                                              \
+    nearest_diag_kernel<T, N, QQ, NEAR_BLOCK, MM, EX><<<nqb * nsplit, NEAR_BLOCK, 0, st>>>(               \
+        t_state.p, cap, t_ignore.p, tv.size, tv.n_ignored, use_ignore, q, qstride, W, dmet, nqb, chunk, \
+        w_pcost.p, w_pidx.p, Wc)
+#define LQ_NEAR_DIAG_M(QQ)                                  \
+    do {                                                    \
+        if (cmask == 0) LQ_NEAR_DIAG(QQ, 0);                \
+        else if (cmask == 4) LQ_NEAR_DIAG(QQ, (N >= 3 ? 4 : 0)); \
+        else if (cmask == 1) LQ_NEAR_DIAG(QQ, 1);           \
+        else LQ_NEAR_DIAG(QQ, -1);                          \
+    } while (0)
+            if (big) LQ_NEAR_DIAG_M(QBIG); else LQ_NEAR_DIAG_M(1);
+#undef LQ_NEAR_DIAG_M
+#undef LQ_NEAR_DIAG
             nsplit_used = nsplit;
         } else {
             if (qstride != Wc) LQ_FAIL(LQ_ERR_STATE, "dense-metric search needs queries in the engine's wave layout");
@@ -550,9 +558,15 @@ struct EngineImpl : lq_engine {
             }
             int nqb, chunk, nsplit;
             plan(1, nqb, chunk, nsplit);
-            nearest_dense_kernel<T, N, NEAR_BLOCK><<<nqb * nsplit, NEAR_BLOCK, 0, st>>>(
-                t_state.p, cap, t_ignore.p, tv.size, tv.n_ignored, use_ignore, q, qstride, W, w_Sp.p, md.angle_mask,
-                nqb, chunk, w_pcost.p, w_pidx.p, Wc);
+#define LQ_NEAR_DENSE(MM)                                                                                  \
+    nearest_dense_kernel<T, N, NEAR_BLOCK, MM><<<nqb * nsplit, NEAR_BLOCK, 0, st>>>(                       \
+        t_state.p, cap, t_ignore.p, tv.size, tv.n_ignored, use_ignore, q, qstride, W, w_Sp.p, md.angle_mask, \
+        nqb, chunk, w_pcost.p, w_pidx.p, Wc)
+            if (cmask == 0) LQ_NEAR_DENSE(0);
+            else if (cmask == 4) LQ_NEAR_DENSE((N >= 3 ? 4 : 0));
+            else if (cmask == 1) LQ_NEAR_DENSE(1);
+            else LQ_NEAR_DENSE(-1);
+#undef LQ_NEAR_DENSE
             nsplit_used = nsplit;
         }
         launches++;
@@ -576,13 +590,31 @@ struct EngineImpl : lq_engine {
     }
 
     // ---- K2 -------------------------------------------------------------------
+    // Rollouts are latency bound with wildly different trip counts: small CTAs spread a wave over all
+    // 148 SMs, larger ones only pay off once every SM already holds several.
     template <int LANES>
     void launch_steer_l(const int* ids, const T* targets, int tstride, int W, T* xs, T* us, int* len, T* xnew, T* Knew,
                         int ostride, cudaStream_t st) {
-        constexpr int BLOCK = 128;
         const long long threads = (long long)W * LANES;
-        steer_kernel<T, Sys, Lqr, LANES, BLOCK><<<(unsigned)((threads + BLOCK - 1) / BLOCK), BLOCK, 0, st>>>(
-            md, t_state.p, t_K.p, cap, ids, targets, tstride, W, xs, us, len, xnew, Knew, ostride);
+        if (threads >= 148LL * 8 * 128) {
+            steer_kernel<T, Sys, Lqr, LANES, 128><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
+                md, t_state.p, t_K.p, cap, ids, targets, tstride, W, xs, us, len, xnew, Knew, ostride);
+        } else {
+            steer_kernel<T, Sys, Lqr, LANES, 32><<<(unsigned)((threads + 31) / 32), 32, 0, st>>>(
+                md, t_state.p, t_K.p, cap, ids, targets, tstride, W, xs, us, len, xnew, Knew, ostride);
+        }
+        launches++;
+    }
+    template <int LANES>
+    void launch_sample_l(uint64_t seed, uint32_t wave, int first, int count, cudaStream_t st) {
+        const long long threads = (long long)count * LANES;
+        if (threads >= 148LL * 8 * 128) {
+            sample_kernel<T, Sys, Lqr, LANES, 128><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
+                md, sp, seed, wave, first, count, w_samples.p, Wc, w_tries.p);
+        } else {
+            sample_kernel<T, Sys, Lqr, LANES, 32><<<(unsigned)((threads + 31) / 32), 32, 0, st>>>(
+                md, sp, seed, wave, first, count, w_samples.p, Wc, w_tries.p);
+        }
         launches++;
     }
     void launch_steer(const int* ids, const T* targets, int tstride, int W, T* xs, T* us, int* len, T* xnew, T* Knew,
@@ -648,9 +680,9 @@ struct EngineImpl : lq_engine {
             LQ_CUDA(cudaStreamSynchronize(st));
         } else {
             if (!have_sampling) LQ_FAIL(LQ_ERR_STATE, "lq_set_sampling has not been called");
-            sample_kernel<T, Sys, Lqr><<<(count + 127) / 128, 128, 0, st>>>(md, sp, seed, wave, first, count,
-                                                                            w_samples.p, Wc, w_tries.p);
-            launches++;
+            if (sample_lanes >= 32) launch_sample_l<32>(seed, wave, first, count, st);
+            else if (sample_lanes >= 8) launch_sample_l<8>(seed, wave, first, count, st);
+            else launch_sample_l<1>(seed, wave, first, count, st);
         }
         return expand_from_samples(count, use_ignore, flags, st);
     }
@@ -921,8 +953,12 @@ struct EngineImpl : lq_engine {
     }
 
     int set_tuning(int lanes, int nq) override {
-        if (lanes == 1 || lanes == 8 || lanes == 32) steer_lanes = lanes;
-        else if (lanes != 0) LQ_FAIL(LQ_ERR_ARG, "steer lanes must be 0 (keep), 1, 8 or 32");
+        // lanes = steer lanes + 100 * sampler lanes (0 keeps the current value)
+        const int sl = lanes % 100, pl = lanes / 100;
+        if (sl == 1 || sl == 8 || sl == 32) steer_lanes = sl;
+        else if (sl != 0) LQ_FAIL(LQ_ERR_ARG, "steer lanes must be 0 (keep), 1, 8 or 32");
+        if (pl == 1 || pl == 8 || pl == 32) sample_lanes = pl;
+        else if (pl != 0) LQ_FAIL(LQ_ERR_ARG, "sampler lanes must be 0 (keep), 1, 8 or 32");
         near_q = nq;
         return LQ_OK;
     }

@@ -37,7 +37,11 @@ __device__ __forceinline__ T reduce_period(T a) {   // a -> a - 2 pi rint(a / 2 
     return a - Num<T>::two_pi() * rint_t(a * Num<T>::inv_two_pi());
 }
 
-template <typename T, int N, int Q, int BLOCK>
+// MASK >= 0: the erf angle mask is a compile-time constant (the common masks are instantiated, see
+// engine.cuh), so only the wrapped dims pay for the wrap and the others are one FADD + one FFMA.
+// MASK < 0: generic fallback reading met.angle_mask at run time.  EXACT selects the float64 parity
+// formula d*S*d with an rint wrap; otherwise operands are pre-scaled by sqrt(S_ii) while staging.
+template <typename T, int N, int Q, int BLOCK, int MASK, bool EXACT>
 __global__ void __launch_bounds__(BLOCK)
 nearest_diag_kernel(const T* __restrict__ state, int cap, const uint8_t* __restrict__ ignore,
                     const int* __restrict__ d_size, const int* __restrict__ d_nignored, int use_ignore,
@@ -47,6 +51,7 @@ nearest_diag_kernel(const T* __restrict__ state, int cap, const uint8_t* __restr
     constexpr int NP = PadDim<N>::V;
     constexpr int TILE = BLOCK;
     __shared__ __align__(16) T tile[TILE * NP];
+    const uint32_t mask = MASK >= 0 ? (uint32_t)MASK : met.angle_mask;
 
     const int qb = blockIdx.x % nqb;
     const int split = blockIdx.x / nqb;
@@ -67,8 +72,8 @@ nearest_diag_kernel(const T* __restrict__ state, int cap, const uint8_t* __restr
 #pragma unroll
         for (int d = 0; d < N; d++) {
             T v = j < W ? queries[(size_t)d * qstride + j] : T(0);
-            if (!met.exact) {
-                if (met.angle_mask & (1u << d)) v = reduce_period(v);
+            if (!EXACT) {
+                if (mask & (1u << d)) v = reduce_period(v);
                 v *= met.w[d];
             }
             q[k][d] = v;
@@ -83,13 +88,12 @@ nearest_diag_kernel(const T* __restrict__ state, int cap, const uint8_t* __restr
             T v[NP];
 #pragma unroll
             for (int d = 0; d < N; d++) {
-                T a = live ? state[(size_t)d * cap + node] : Num<T>::inf();
-                if (!met.exact) {
-                    if (met.angle_mask & (1u << d)) a = reduce_period(a);
+                T a = live ? state[(size_t)d * cap + node] : T(0);
+                if (!EXACT) {
+                    if (mask & (1u << d)) a = reduce_period(a);
                     a *= met.w[d];
-                    if (!live) a = Num<T>::inf();
                 }
-                v[d] = a;
+                v[d] = live ? a : Num<T>::inf();       // dead rows can never win (inf cost or NaN)
             }
 #pragma unroll
             for (int d = N; d < NP; d++) v[d] = T(0);
@@ -107,18 +111,14 @@ nearest_diag_kernel(const T* __restrict__ state, int cap, const uint8_t* __restr
 #pragma unroll
             for (int k = 0; k < Q; k++) {
                 T c = T(0);
-                if (met.exact) {
 #pragma unroll
-                    for (int d = 0; d < N; d++) {
-                        T e = q[k][d] - v[d];
-                        if (met.angle_mask & (1u << d)) e = reduce_period(e);
+                for (int d = 0; d < N; d++) {
+                    T e = q[k][d] - v[d];
+                    if (EXACT) {
+                        if (mask & (1u << d)) e = reduce_period(e);
                         c += e * met.sdiag[d] * e;
-                    }
-                } else {
-#pragma unroll
-                    for (int d = 0; d < N; d++) {
-                        T e = q[k][d] - v[d];
-                        if (met.angle_mask & (1u << d)) {
+                    } else {
+                        if (mask & (1u << d)) {
                             const T a = abs_t(e);
                             e = min_t(a, met.period[d] - a);
                         }
@@ -142,17 +142,18 @@ nearest_diag_kernel(const T* __restrict__ state, int cap, const uint8_t* __restr
 // Dense per-query metric: cost = d' S d with S symmetrised and packed
 // (diagonal, then doubled upper triangle), NS = N (N + 1) / 2 coefficients per
 // query held in registers.
-template <typename T, int N, int BLOCK>
+template <typename T, int N, int BLOCK, int MASK>
 __global__ void __launch_bounds__(BLOCK)
 nearest_dense_kernel(const T* __restrict__ state, int cap, const uint8_t* __restrict__ ignore,
                      const int* __restrict__ d_size, const int* __restrict__ d_nignored, int use_ignore,
                      const T* __restrict__ queries, int qstride, int W,
-                     const T* __restrict__ Spacked, uint32_t angle_mask, int nqb, int chunk,
+                     const T* __restrict__ Spacked, uint32_t angle_mask_rt, int nqb, int chunk,
                      T* __restrict__ pcost, int* __restrict__ pidx, int pstride) {
     constexpr int NP = PadDim<N>::V;
     constexpr int NS = N * (N + 1) / 2;
     constexpr int TILE = BLOCK;
     __shared__ __align__(16) T tile[TILE * NP];
+    const uint32_t angle_mask = MASK >= 0 ? (uint32_t)MASK : angle_mask_rt;
 
     const int qb = blockIdx.x % nqb;
     const int split = blockIdx.x / nqb;

@@ -37,11 +37,15 @@ __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(
 __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 
-template <typename T, class Sys, class Lqr>
-__global__ void sample_kernel(Model<T, Sys, Lqr> md, SamplerParams<T, Sys::N> sp, uint64_t seed, uint32_t wave,
-                              int first, int count, T* __restrict__ samples, int sstride, int* __restrict__ tries_used) {
+// One sample per group of LANES threads (as steer_kernel): every lane draws the same numbers, the
+// obstacle lists of the feasibility test are split across the lanes.
+template <typename T, class Sys, class Lqr, int LANES, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+sample_kernel(Model<T, Sys, Lqr> md, SamplerParams<T, Sys::N> sp, uint64_t seed, uint32_t wave,
+              int first, int count, T* __restrict__ samples, int sstride, int* __restrict__ tries_used) {
     constexpr int N = Sys::N, M = Sys::M;
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = (blockIdx.x * BLOCK + threadIdx.x) / LANES;
+    const int lane = threadIdx.x % LANES;
     if (j >= count) return;
     const uint32_t g = (uint32_t)(first + j);
     T x[N], u0[M];
@@ -63,11 +67,13 @@ __global__ void sample_kernel(Model<T, Sys, Lqr> md, SamplerParams<T, Sys::N> sp
         const T r = uni[N];                                         // one draw gates every dim, planner.py:205-207
 #pragma unroll
         for (int i = 0; i < N; i++) if (sp.bias[i] > r) x[i] = sp.goal[i];
-        if (feasible_eval<T, N, M>(md.feas, x, u0)) { t++; break; }  // planner.py:208-209
+        if (group_all<LANES>(feasible_eval<T, N, M>(md.feas, x, u0, lane, LANES))) { t++; break; }  // planner.py:208-209
     }
+    if (lane == 0) {
 #pragma unroll
-    for (int i = 0; i < N; i++) samples[(size_t)i * sstride + j] = x[i];
-    if (tries_used) tries_used[j] = t;
+        for (int i = 0; i < N; i++) samples[(size_t)i * sstride + j] = x[i];
+        if (tries_used) tries_used[j] = t;
+    }
 }
 
 // Reference-stream mode, step 1: feasibility of every candidate try.

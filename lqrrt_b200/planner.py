@@ -26,6 +26,7 @@ specs; there is no CPU fallback for arbitrary Python callables.
 """
 from __future__ import annotations
 
+import os
 import time
 
 import numpy as np
@@ -113,6 +114,10 @@ class Planner(object):
                                   dtype=self.dtype, device=self._device())
             self._engine_key = key
             self._exchange = None
+            tune = os.environ.get('LQRRT_TUNING')          # "steer_lanes[,sampler_lanes[,nearest_q]]" for experiments
+            if tune:
+                t = [int(v) for v in tune.split(',')] + [0, 0]
+                self._engine.set_tuning(t[0] + 100 * t[1], t[2])
         return self._engine
 
     @staticmethod
