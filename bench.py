@@ -214,11 +214,13 @@ def run_gpu_arm(args):
     barrier()
     with ClockSampler(local) as clk:
         host_times = []; dev_ms = []; nodes = []; samples = []; waves = []; launches = 0; d2h = 0; h2d = 0
+        phases = np.zeros(3)
         for s in range(args.steps):
             host_s, st = one_plan(s)
             host_times.append(host_s); dev_ms.append(st['device_ms']); nodes.append(st['nodes'] - 1)
             samples.append(st['samples']); waves.append(st['waves']); launches += st['gpu_launches']
             d2h += st['d2h_bytes']; h2d += st['h2d_bytes']
+            phases += [st['host_setup_s'], st['host_loop_s'], st['host_closeout_s']]
         barrier()
     prof = planner._engine.profile_read()
 
@@ -262,7 +264,8 @@ def run_gpu_arm(args):
                        "l2": "tree states (<= 2.4 MB) and obstacle tables are L2-resident by design; every step "
                              "grows a new tree from new samples (no reuse between timed steps)"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
-                    "ms_per_step": tot_host / args.steps * 1e3},
+                    "ms_per_step": tot_host / args.steps * 1e3,
+                    "host_ms_per_step": dict(zip(("setup", "wave_loop", "closeout"), (phases / args.steps * 1e3).round(3).tolist()))},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "nearest_diag_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm if hbm else None, "traffic": None,

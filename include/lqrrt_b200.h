@@ -151,13 +151,16 @@ int lq_wave_expand_candidates(lq_engine* h, int count, int tries, const double* 
 /* `flags` above travels in the record header; after lq_wave_commit every rank reads segment 0's
  * value back in lq_wave_stats.flags -- the host uses it to agree on when to stop without an extra
  * collective (the reference's stop rules are wall-clock based, planner.py:286-311). */
-/* The packed records of the last lq_wave_expand: device pointer + fixed byte size (the allgather payload). */
+/* The packed records of the last lq_wave_expand: device pointer + fixed byte size (the allgather payload).
+ * A record is the node only (state, gain K, parent, edge length); edge trajectories stay on the GPU that
+ * rolled them out and are read back from their owner (lq_download_edges). */
 int lq_wave_records(lq_engine* h, void** d_records, uint64_t* bytes);
 /* Tree.add_node for every accepted record of `n_segments` record buffers laid end to end
  * (segment r = rank r's lq_wave_records), in segment order then record order = global sample order;
- * then goal test / ignores / best plan (planner.py:253-283, tree.py:77-96).  d_records may be the
- * engine's own buffer (single GPU). */
-int lq_wave_commit(lq_engine* h, const void* d_records, int n_segments, void* stream);
+ * then goal test / ignores / best plan (planner.py:253-283, tree.py:77-96).  d_records may be NULL for
+ * the engine's own buffer (single GPU).  `my_segment` is the index of this engine's own segment (its
+ * rank): the edges of those nodes are stored here, every node remembers its owner segment. */
+int lq_wave_commit(lq_engine* h, const void* d_records, int n_segments, int my_segment, void* stream);
 /* Blocks until the last commit finished and returns its counters. */
 int lq_wave_stats_get(lq_engine* h, lq_wave_stats* out);
 
@@ -174,11 +177,17 @@ int lq_append_node(lq_engine* h, int parent, const double* h_state, const double
 /* planner.py:270 for externally chosen ids (tests). */
 int lq_mark_ignore(lq_engine* h, const int32_t* h_ids, int count, void* stream);
 
+/* Tree.climb, tree.py:100-117: node ids from the seed (first) to `node` (last), walked on the device so a
+ * plan read-out does not have to download the whole parent array. */
+int lq_climb(lq_engine* h, int node, int32_t* h_ids, int max_len, int* h_len, void* stream);
+
 /* ---- read-back (Tree.state / pID / lqr / x_seq / u_seq, tree.py:62-70) --- */
 int lq_download_nodes(lq_engine* h, int first, int count, double* h_state, int32_t* h_parent,
-                      int32_t* h_cost, int32_t* h_edge_len, uint8_t* h_ignore, double* h_K, void* stream);
-/* edges of `count` nodes listed in h_ids: h_x count x H x n, h_u count x H x m (rows past the edge length are zero). */
-int lq_download_edges(lq_engine* h, const int32_t* h_ids, int count, double* h_x, double* h_u, void* stream);
+                      int32_t* h_cost, int32_t* h_edge_len, uint8_t* h_ignore, uint8_t* h_owner, double* h_K, void* stream);
+/* edges of `count` nodes listed in h_ids: h_x count x H x n, h_u count x H x m.  Rows past the edge length are
+ * zero, and so is the whole edge of a node owned by another GPU (sum the per-rank answers to assemble a plan).
+ * h_len (may be NULL): the recorded edge lengths (known on every rank). */
+int lq_download_edges(lq_engine* h, const int32_t* h_ids, int count, double* h_x, double* h_u, int32_t* h_len, void* stream);
 
 /* ---- the user callbacks themselves, batched (planner.py:35-59) ------------ */
 int lq_eval_dynamics(lq_engine* h, int count, const double* h_x, const double* h_u, double dt, double* h_xnext);

@@ -70,14 +70,15 @@ SYMBOLS = {
     'lq_wave_expand': (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_int, C.c_int, _D, C.c_int, C.c_int, _P]),
     'lq_wave_expand_candidates': (C.c_int, [_P, C.c_int, C.c_int, _D, C.c_int, C.c_int, C.POINTER(C.c_int), _P]),
     'lq_wave_records': (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64)]),
-    'lq_wave_commit': (C.c_int, [_P, _P, C.c_int, _P]),
+    'lq_wave_commit': (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
     'lq_wave_stats_get': (C.c_int, [_P, C.POINTER(lq_wave_stats)]),
     'lq_closest': (C.c_int, [_P, _D, _U8, C.POINTER(C.c_int), _P]),
     'lq_steer_force': (C.c_int, [_P, C.c_int, _D, C.c_int, _D, _D, C.POINTER(C.c_int), _P]),
     'lq_append_node': (C.c_int, [_P, C.c_int, _D, _D, _D, C.c_int, _P]),
     'lq_mark_ignore': (C.c_int, [_P, _I, C.c_int, _P]),
-    'lq_download_nodes': (C.c_int, [_P, C.c_int, C.c_int, _D, _I, _I, _I, _U8, _D, _P]),
-    'lq_download_edges': (C.c_int, [_P, _I, C.c_int, _D, _D, _P]),
+    'lq_climb': (C.c_int, [_P, C.c_int, _I, C.c_int, C.POINTER(C.c_int), _P]),
+    'lq_download_nodes': (C.c_int, [_P, C.c_int, C.c_int, _D, _I, _I, _I, _U8, _U8, _D, _P]),
+    'lq_download_edges': (C.c_int, [_P, _I, C.c_int, _D, _D, _I, _P]),
     'lq_eval_dynamics': (C.c_int, [_P, C.c_int, _D, _D, C.c_double, _D]),
     'lq_eval_lqr': (C.c_int, [_P, C.c_int, _D, _D, _D, _D]),
     'lq_eval_erf': (C.c_int, [_P, C.c_int, _D, _D, _D]),
@@ -287,8 +288,9 @@ class Engine(object):
         self._ck(self.lib.lq_wave_records(self.h, C.byref(p), C.byref(b)))
         return p.value, b.value
 
-    def wave_commit(self, d_records=None, n_segments=1, stream=None):
-        self._ck(self.lib.lq_wave_commit(self.h, _P(d_records) if d_records else None, int(n_segments), self._stream(stream)))
+    def wave_commit(self, d_records=None, n_segments=1, stream=None, my_segment=0):
+        self._ck(self.lib.lq_wave_commit(self.h, _P(d_records) if d_records else None, int(n_segments),
+                                         int(my_segment), self._stream(stream)))
 
     def wave_stats(self):
         st = lq_wave_stats()
@@ -321,24 +323,32 @@ class Engine(object):
         a = np.ascontiguousarray(ids, dtype=np.int32)
         self._ck(self.lib.lq_mark_ignore(self.h, _ip(a), len(a), self._stream(stream)))
 
+    def climb(self, node, max_len=1 << 16, stream=None):
+        ids = np.zeros(max_len, dtype=np.int32); ln = C.c_int(0)
+        self._ck(self.lib.lq_climb(self.h, int(node), _ip(ids), int(max_len), C.byref(ln), self._stream(stream)))
+        self.d2h_bytes += 4 * ln.value + 4
+        return ids[:ln.value].tolist()
+
     # -------------------------------------------------------------- read-back
     def download_nodes(self, first, count, want_K=False, stream=None):
         state = np.zeros((count, self.n)); parent = np.zeros(count, dtype=np.int32)
         cost = np.zeros(count, dtype=np.int32); elen = np.zeros(count, dtype=np.int32)
-        ign = np.zeros(count, dtype=np.uint8)
+        ign = np.zeros(count, dtype=np.uint8); own = np.zeros(count, dtype=np.uint8)
         K = np.zeros((count, self.m, self.n)) if want_K else None
-        self.d2h_bytes += count * (self.n * self.elt + 13 + (self.m * self.n * self.elt if want_K else 0))
+        self.d2h_bytes += count * (self.n * self.elt + 14 + (self.m * self.n * self.elt if want_K else 0))
         self._ck(self.lib.lq_download_nodes(self.h, int(first), int(count), _dp(state), _ip(parent), _ip(cost), _ip(elen),
-                                            ign.ctypes.data_as(_U8), None if K is None else _dp(K), self._stream(stream)))
-        return dict(state=state, parent=parent, cost=cost, edge_len=elen, ignore=ign, K=K)
+                                            ign.ctypes.data_as(_U8), own.ctypes.data_as(_U8),
+                                            None if K is None else _dp(K), self._stream(stream)))
+        return dict(state=state, parent=parent, cost=cost, edge_len=elen, ignore=ign, owner=own, K=K)
 
     def download_edges(self, ids, stream=None):
         a = np.ascontiguousarray(ids, dtype=np.int32)
         hx = np.zeros((len(a), self.H, self.n)); hu = np.zeros((len(a), self.H, self.m))
         self.h2d_bytes += 4 * len(a); self.d2h_bytes += len(a) * self.H * (self.n + self.m) * self.elt
+        hl = np.zeros(len(a), dtype=np.int32)
         if len(a):
-            self._ck(self.lib.lq_download_edges(self.h, _ip(a), len(a), _dp(hx), _dp(hu), self._stream(stream)))
-        return hx, hu
+            self._ck(self.lib.lq_download_edges(self.h, _ip(a), len(a), _dp(hx), _dp(hu), _ip(hl), self._stream(stream)))
+        return hx, hu, hl
 
     # -------------------------------------------------------------- callbacks
     def eval_dynamics(self, x, u, dt):

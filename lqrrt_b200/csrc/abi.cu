@@ -63,7 +63,7 @@ int lq_wave_expand(lq_engine* h, uint64_t seed, uint32_t wave, int first, int co
 int lq_wave_expand_candidates(lq_engine* h, int count, int tries, const double* c, int nc, int ign, int* used, void* st) {
     LQ_H(h); if (!c) return LQ_ERR_ARG; LQ_TRY(h->wave_expand_candidates(count, tries, c, nc, ign, used, (cudaStream_t)st)) }
 int lq_wave_records(lq_engine* h, void** d, uint64_t* bytes) { LQ_H(h); LQ_TRY(h->wave_records(d, bytes)) }
-int lq_wave_commit(lq_engine* h, const void* rec, int nseg, void* st) { LQ_H(h); LQ_TRY(h->wave_commit(rec, nseg, (cudaStream_t)st)) }
+int lq_wave_commit(lq_engine* h, const void* rec, int nseg, int myseg, void* st) { LQ_H(h); LQ_TRY(h->wave_commit(rec, nseg, myseg, (cudaStream_t)st)) }
 int lq_wave_stats_get(lq_engine* h, lq_wave_stats* out) { LQ_H(h); LQ_TRY(h->wave_stats(out)) }
 int lq_closest(lq_engine* h, const double* xg, const uint8_t* mask, int* id, void* st) {
     LQ_H(h); if (!xg || !id) return LQ_ERR_ARG; LQ_TRY(h->closest(xg, mask, id, (cudaStream_t)st)) }
@@ -72,10 +72,12 @@ int lq_steer_force(lq_engine* h, int node, const double* xt, int ms, double* x, 
 int lq_append_node(lq_engine* h, int parent, const double* s, const double* x, const double* u, int len, void* st) {
     LQ_H(h); if (!s || (len > 0 && (!x || !u))) return LQ_ERR_ARG; LQ_TRY(h->append_node(parent, s, x, u, len, (cudaStream_t)st)) }
 int lq_mark_ignore(lq_engine* h, const int32_t* ids, int count, void* st) { LQ_H(h); LQ_TRY(h->mark_ignore(ids, count, (cudaStream_t)st)) }
-int lq_download_nodes(lq_engine* h, int first, int count, double* s, int32_t* p, int32_t* c, int32_t* el, uint8_t* ig, double* K, void* st) {
-    LQ_H(h); LQ_TRY(h->download_nodes(first, count, s, p, c, el, ig, K, (cudaStream_t)st)) }
-int lq_download_edges(lq_engine* h, const int32_t* ids, int count, double* x, double* u, void* st) {
-    LQ_H(h); if (count > 0 && (!ids || !x || !u)) return LQ_ERR_ARG; LQ_TRY(h->download_edges(ids, count, x, u, (cudaStream_t)st)) }
+int lq_climb(lq_engine* h, int node, int32_t* ids, int max_len, int* len, void* st) {
+    LQ_H(h); if (!ids || !len) return LQ_ERR_ARG; LQ_TRY(h->climb(node, ids, max_len, len, (cudaStream_t)st)) }
+int lq_download_nodes(lq_engine* h, int first, int count, double* s, int32_t* p, int32_t* c, int32_t* el, uint8_t* ig, uint8_t* ow, double* K, void* st) {
+    LQ_H(h); LQ_TRY(h->download_nodes(first, count, s, p, c, el, ig, ow, K, (cudaStream_t)st)) }
+int lq_download_edges(lq_engine* h, const int32_t* ids, int count, double* x, double* u, int32_t* len, void* st) {
+    LQ_H(h); if (count > 0 && (!ids || !x || !u)) return LQ_ERR_ARG; LQ_TRY(h->download_edges(ids, count, x, u, len, (cudaStream_t)st)) }
 int lq_eval_dynamics(lq_engine* h, int count, const double* x, const double* u, double dt, double* xn) {
     LQ_H(h); if (!x || !u || !xn) return LQ_ERR_ARG; LQ_TRY(h->eval_dynamics(count, x, u, dt, xn)) }
 int lq_eval_lqr(lq_engine* h, int count, const double* x, const double* u, double* S, double* K) {

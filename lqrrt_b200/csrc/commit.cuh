@@ -3,10 +3,16 @@
 //
 // pack:   compact the wave's accepted samples (edge length > 0), in sample
 //         order, into a fixed-size record buffer -- the multi-GPU allgather
-//         payload (every rank contributes one such segment per wave).
+//         payload (every rank contributes one such segment per wave).  A record
+//         is the node only (state, gain, parent, edge length: ~100 B at n=6);
+//         the edge trajectory stays on the GPU that rolled it out.
 // commit: append the records of all segments, segment order then record order
 //         (= global sample order), to the SoA tree; goal test, ignore marks
-//         along the new plan, best-plan tracking.
+//         along the new plan, best-plan tracking.  The committing GPU copies the
+//         edges of ITS OWN segment from its rollout scratch into its edge slab
+//         and records the owner of every node, so edges are fetched from their
+//         owner when a plan is read out (tree.py:121-132) instead of crossing
+//         NVLink for every accepted node.
 #pragma once
 #include "steer.cuh"
 
@@ -21,8 +27,6 @@ template <typename T> struct RecView {
     T* K;          // [M*N][Wc]
     int* parent;   // [Wc]
     int* len;      // [Wc]
-    T* ex;         // [Wc][H*N]
-    T* eu;         // [Wc][H*M]
 };
 
 __host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
@@ -33,8 +37,7 @@ __host__ __device__ inline size_t rec_bytes(int Wc, int N, int M, int H) {
     b += align16(sizeof(T) * (size_t)N * Wc);
     b += align16(sizeof(T) * (size_t)M * N * Wc);
     b += align16(sizeof(int) * (size_t)Wc) * 2;
-    b += align16(sizeof(T) * (size_t)Wc * H * N);
-    b += align16(sizeof(T) * (size_t)Wc * H * M);
+    (void)H;
     return b;
 }
 
@@ -46,9 +49,8 @@ __host__ __device__ inline RecView<T> rec_view(void* base, int Wc, int N, int M,
     v.state = (T*)p; p += align16(sizeof(T) * (size_t)N * Wc);
     v.K = (T*)p; p += align16(sizeof(T) * (size_t)M * N * Wc);
     v.parent = (int*)p; p += align16(sizeof(int) * (size_t)Wc);
-    v.len = (int*)p; p += align16(sizeof(int) * (size_t)Wc);
-    v.ex = (T*)p; p += align16(sizeof(T) * (size_t)Wc * H * N);
-    v.eu = (T*)p;
+    v.len = (int*)p;
+    (void)H;
     return v;
 }
 
@@ -82,25 +84,21 @@ pack_scan_kernel(const int* __restrict__ len, const int* __restrict__ tries_used
     if (threadIdx.x == 0) { header[HDR_COUNT] = total; header[HDR_SAMPLED] = count; header[HDR_TRIES] = ttries; header[HDR_FLAGS] = flags; }
 }
 
-// One warp per sample: copy an accepted sample's node record and edge into its slot.
+// One thread per sample: copy an accepted sample's node record into its slot and remember which
+// sample the slot came from (the committing GPU finds the edge in its rollout scratch through it).
 template <typename T>
 __global__ void pack_kernel(const int* __restrict__ len, const int* __restrict__ slot, const int* __restrict__ ids,
-                            const T* __restrict__ xnew, const T* __restrict__ Knew, int ostride,
-                            const T* __restrict__ xseq, const T* __restrict__ useq, int count,
-                            RecView<T> rv, int Wc, int N, int M, int H) {
-    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+                            const T* __restrict__ xnew, const T* __restrict__ Knew, int ostride, int count,
+                            RecView<T> rv, int* __restrict__ sample_of_slot, int Wc, int N, int M) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= count) return;
     const int L = len[j];
     if (L <= 0) return;
     const int s = slot[j];
-    for (int d = lane; d < N; d += 32) rv.state[(size_t)d * Wc + s] = xnew[(size_t)d * ostride + j];
-    for (int k = lane; k < M * N; k += 32) rv.K[(size_t)k * Wc + s] = Knew[(size_t)k * ostride + j];
-    if (lane == 0) { rv.parent[s] = ids[j]; rv.len[s] = L; }
-    const T* sx = xseq + (size_t)j * H * N; T* dx = rv.ex + (size_t)s * H * N;
-    for (int k = lane; k < L * N; k += 32) dx[k] = sx[k];
-    const T* su = useq + (size_t)j * H * M; T* du = rv.eu + (size_t)s * H * M;
-    for (int k = lane; k < L * M; k += 32) du[k] = su[k];
+    for (int d = 0; d < N; d++) rv.state[(size_t)d * Wc + s] = xnew[(size_t)d * ostride + j];
+    for (int k = 0; k < M * N; k++) rv.K[(size_t)k * Wc + s] = Knew[(size_t)k * ostride + j];
+    rv.parent[s] = ids[j]; rv.len[s] = L;
+    sample_of_slot[s] = j;
 }
 
 template <typename T> struct TreeView {
@@ -110,6 +108,7 @@ template <typename T> struct TreeView {
     int* cost;         // [cap] cumulative recorded steps from the seed; T_plan = (1 + cost) dt
     int* edge_len;     // [cap]
     uint8_t* ignore;   // [cap] (word-aligned: marks are set with atomicOr on the containing word)
+    uint8_t* owner;    // [cap] rank (record segment) whose GPU holds the node's edge
     T* edge_x;         // [cap][H*N]
     T* edge_u;         // [cap][H*M]
     int* size;         // device scalar
@@ -137,6 +136,8 @@ __device__ __forceinline__ void mark_path(const TreeView<T>& tv, int node) {
 // One warp per (segment, record).
 template <typename T>
 __global__ void commit_kernel(TreeView<T> tv, const char* __restrict__ records, size_t seg_bytes, int n_seg,
+                              int my_seg, const int* __restrict__ sample_of_slot,
+                              const T* __restrict__ xseq, const T* __restrict__ useq,
                               int Wc, int N, int M, int H,
                               const T* __restrict__ goal_lo, const T* __restrict__ goal_hi) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -161,13 +162,16 @@ __global__ void commit_kernel(TreeView<T> tv, const char* __restrict__ records, 
     }
     in_goal = __all_sync(0xffffffffu, in_goal);
     for (int q = lane; q < M * N; q += 32) tv.K[(size_t)q * tv.cap + node] = rv.K[(size_t)q * Wc + k];
-    const T* sx = rv.ex + (size_t)k * H * N; T* dx = tv.edge_x + (size_t)node * H * N;
-    for (int q = lane; q < L * N; q += 32) dx[q] = sx[q];
-    const T* su = rv.eu + (size_t)k * H * M; T* du = tv.edge_u + (size_t)node * H * M;
-    for (int q = lane; q < L * M; q += 32) du[q] = su[q];
+    if (seg == my_seg) {               // my own rollout: its edge is still in this GPU's scratch
+        const int j = sample_of_slot[k];
+        const T* sx = xseq + (size_t)j * H * N; T* dx = tv.edge_x + (size_t)node * H * N;
+        for (int q = lane; q < L * N; q += 32) dx[q] = sx[q];
+        const T* su = useq + (size_t)j * H * M; T* du = tv.edge_u + (size_t)node * H * M;
+        for (int q = lane; q < L * M; q += 32) du[q] = su[q];
+    }
     if (lane == 0) {
         const int c = tv.cost[par] + L;
-        tv.parent[node] = par; tv.cost[node] = c; tv.edge_len[node] = L;
+        tv.parent[node] = par; tv.cost[node] = c; tv.edge_len[node] = L; tv.owner[node] = (uint8_t)seg;
         if (in_goal) {                                                  // planner.py:260-281
             atomicAdd(tv.n_goal, 1);
             atomicMin(tv.best, ((unsigned long long)(unsigned)c << 32) | (unsigned)node);

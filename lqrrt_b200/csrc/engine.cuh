@@ -35,15 +35,16 @@ struct lq_engine {
     virtual int wave_expand_candidates(int count, int tries, const double* h_cand, int n_cand, int use_ignore,
                                        int* h_consumed, cudaStream_t st) = 0;
     virtual int wave_records(void** d, uint64_t* bytes) = 0;
-    virtual int wave_commit(const void* d_records, int n_seg, cudaStream_t st) = 0;
+    virtual int wave_commit(const void* d_records, int n_seg, int my_seg, cudaStream_t st) = 0;
     virtual int wave_stats(lq_wave_stats* out) = 0;
     virtual int closest(const double* xg, const uint8_t* colmask, int* id, cudaStream_t st) = 0;
     virtual int steer_force(int node, const double* xtar, int max_steps, double* hx, double* hu, int* len, cudaStream_t st) = 0;
     virtual int append_node(int parent, const double* state, const double* hx, const double* hu, int len, cudaStream_t st) = 0;
     virtual int mark_ignore(const int* ids, int count, cudaStream_t st) = 0;
+    virtual int climb(int node, int* ids, int max_len, int* len, cudaStream_t st) = 0;
     virtual int download_nodes(int first, int count, double* state, int* parent, int* cost, int* elen,
-                               uint8_t* ign, double* K, cudaStream_t st) = 0;
-    virtual int download_edges(const int* ids, int count, double* hx, double* hu, cudaStream_t st) = 0;
+                               uint8_t* ign, uint8_t* owner, double* K, cudaStream_t st) = 0;
+    virtual int download_edges(const int* ids, int count, double* hx, double* hu, int* hlen, cudaStream_t st) = 0;
     virtual int eval_dynamics(int count, const double* x, const double* u, double dt, double* xn) = 0;
     virtual int eval_lqr(int count, const double* x, const double* u, double* S, double* K) = 0;
     virtual int eval_erf(int count, const double* xg, const double* x, double* e) = 0;
@@ -136,15 +137,27 @@ __global__ void mark_ignore_kernel(TreeView<T> tv, const int* __restrict__ ids, 
 }
 
 template <typename T>
-__global__ void gather_edges_kernel(TreeView<T> tv, const int* __restrict__ ids, int count, int H, int HN, int HM,
-                                    T* __restrict__ ox, T* __restrict__ ou) {
+__global__ void gather_edges_kernel(TreeView<T> tv, const int* __restrict__ ids, int count, int my_seg, int H, int HN, int HM,
+                                    T* __restrict__ ox, T* __restrict__ ou, int* __restrict__ olen) {
     const int r = blockIdx.x;
     if (r >= count) return;
     const int node = ids[r];
-    const int L = tv.edge_len[node];
-    const int nx = L * (HN / H), nu = L * (HM / H);      // rows past the edge length read back as zero
+    const int L = min(tv.edge_len[node], H);
+    if (threadIdx.x == 0) olen[r] = L;
+    // rows past the edge length, and edges held by another GPU, read back as zero
+    const int mine = my_seg < 0 || tv.owner[node] == my_seg || node == 0;
+    const int nx = mine ? L * (HN / H) : 0, nu = mine ? L * (HM / H) : 0;
     for (int k = threadIdx.x; k < HN; k += blockDim.x) ox[(size_t)r * HN + k] = k < nx ? tv.edge_x[(size_t)node * HN + k] : T(0);
     for (int k = threadIdx.x; k < HM; k += blockDim.x) ou[(size_t)r * HM + k] = k < nu ? tv.edge_u[(size_t)node * HM + k] : T(0);
+}
+
+// Tree.climb (tree.py:100-117) on the device: follow parents from `node` to the seed; ids come out
+// leaf-first, the host reverses them.  One thread: a dependent pointer chase of a few hundred hops.
+template <typename T>
+__global__ void climb_kernel(TreeView<T> tv, int node, int* __restrict__ ids, int max_len, int* __restrict__ len) {
+    int n = 0;
+    while (node >= 0 && n < max_len) { ids[n++] = node; node = tv.parent[node]; }
+    *len = node >= 0 ? -1 : n;          // -1: path longer than the buffer
 }
 
 template <typename T>
@@ -186,7 +199,8 @@ struct EngineImpl : lq_engine {
     // tree: dim-major so that a scan reads each dim as one contiguous stream
     DevBuf<T> t_state, t_K, t_ex, t_eu;
     DevBuf<int> t_parent, t_cost, t_elen, t_scal;
-    DevBuf<uint8_t> t_ignore;
+    DevBuf<uint8_t> t_ignore, t_owner;
+    int last_my_seg = 0;             // segment index this GPU committed as (its rank)
     DevBuf<unsigned long long> t_best;
     TreeView<T> tv;
     // obstacle tables and their broad-phase grids
@@ -195,22 +209,28 @@ struct EngineImpl : lq_engine {
     int grid_min_obs = 16;
     // wave working set
     DevBuf<T> w_samples, w_ncost, w_pcost, w_Sp, w_xs, w_us, w_xnew, w_Knew, w_cand, w_goal;
-    DevBuf<int> w_nidx, w_pidx, w_len, w_slot, w_tries, w_pick, w_misc;
+    DevBuf<int> w_nidx, w_pidx, w_len, w_slot, w_tries, w_pick, w_src, w_misc;
     DevBuf<uint8_t> w_candok;
     DevBuf<char> w_rec;
     DevBuf<DevStats> w_stats;
     size_t rec_sz = 0;
-    lq_wave_stats* h_stats = nullptr;     // pinned
+    // Committed waves whose counters the host has not read yet: a small ring, so the host can enqueue
+    // wave k+1 before it blocks on wave k's counters (the GPU never idles on the host round trip).
+    static constexpr int RING = 4;
+    lq_wave_stats* h_stats = nullptr;     // pinned [RING]
+    lq_wave_stats last_stats;             // what lq_wave_stats_get returns when nothing is pending
     int* h_misc = nullptr;                // pinned
-    cudaEvent_t ev_stats = nullptr;
-    bool stats_pending = false;
+    cudaEvent_t ev_stats[RING] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned q_head = 0, q_tail = 0;      // [q_head, q_tail) = committed, unread
+    int q_add[RING] = {0, 0, 0, 0};       // most nodes that wave can have appended (for the size bound)
     cudaStream_t last_stream = nullptr;
     // optional per-stage CUDA-event timing (bench.py roofline): sample | nearest | steer | pack | commit
-    bool prof_on = false, prof_wave_open = false, prof_commit_open = false;
-    cudaEvent_t pev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool prof_on = false;
+    bool prof_wave_open[RING] = {false, false, false, false}, prof_commit_open[RING] = {false, false, false, false};
+    cudaEvent_t pev[RING][7] = {};
     double prof_ms[5] = {0, 0, 0, 0, 0};
     double prof_work[4] = {0, 0, 0, 0};    // nearest pairs (W*N), nearest bytes (W*N*n*sizeof T), samples, waves
-    int prof_W = 0;
+    int prof_W[RING] = {0, 0, 0, 0};
 
     ~EngineImpl() override {
         cudaSetDevice(device);
@@ -218,8 +238,8 @@ struct EngineImpl : lq_engine {
         for (auto* b : grid_bufs) delete b;
         if (h_stats) cudaFreeHost(h_stats);
         if (h_misc) cudaFreeHost(h_misc);
-        if (ev_stats) cudaEventDestroy(ev_stats);
-        for (auto& e : pev) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_stats) if (e) cudaEventDestroy(e);
+        for (auto& r : pev) for (auto& e : r) if (e) cudaEventDestroy(e);
     }
 
     template <typename U>
@@ -310,9 +330,9 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(t_ex.alloc((size_t)cap * H * N));
         LQ_CUDA(t_eu.alloc((size_t)cap * H * M));
         LQ_CUDA(t_parent.alloc(cap)); LQ_CUDA(t_cost.alloc(cap)); LQ_CUDA(t_elen.alloc(cap));
-        LQ_CUDA(t_ignore.alloc(cap)); LQ_CUDA(t_scal.alloc(8)); LQ_CUDA(t_best.alloc(1));
+        LQ_CUDA(t_ignore.alloc(cap)); LQ_CUDA(t_owner.alloc(cap)); LQ_CUDA(t_scal.alloc(8)); LQ_CUDA(t_best.alloc(1));
         tv.state = t_state.p; tv.K = t_K.p; tv.parent = t_parent.p; tv.cost = t_cost.p; tv.edge_len = t_elen.p;
-        tv.ignore = t_ignore.p; tv.edge_x = t_ex.p; tv.edge_u = t_eu.p;
+        tv.ignore = t_ignore.p; tv.owner = t_owner.p; tv.edge_x = t_ex.p; tv.edge_u = t_eu.p;
         tv.size = t_scal.p; tv.n_ignored = t_scal.p + 1; tv.n_goal = t_scal.p + 2; tv.best = t_best.p; tv.cap = cap; tv.limit = c->node_capacity;
         LQ_CUDA(cudaMemset(t_scal.p, 0, 8 * sizeof(int)));
 
@@ -320,17 +340,18 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(w_samples.alloc((size_t)N * Wc)); LQ_CUDA(w_ncost.alloc(Wc)); LQ_CUDA(w_nidx.alloc(Wc));
         LQ_CUDA(w_pcost.alloc((size_t)MAX_SPLIT * Wc)); LQ_CUDA(w_pidx.alloc((size_t)MAX_SPLIT * Wc));
         LQ_CUDA(w_xs.alloc((size_t)Wc * H * N)); LQ_CUDA(w_us.alloc((size_t)Wc * H * M));
-        LQ_CUDA(w_len.alloc(Wc)); LQ_CUDA(w_slot.alloc(Wc)); LQ_CUDA(w_tries.alloc(Wc)); LQ_CUDA(w_pick.alloc(Wc));
+        LQ_CUDA(w_len.alloc(Wc)); LQ_CUDA(w_slot.alloc(Wc)); LQ_CUDA(w_tries.alloc(Wc)); LQ_CUDA(w_pick.alloc(Wc)); LQ_CUDA(w_src.alloc(Wc));
         LQ_CUDA(w_xnew.alloc((size_t)N * Wc)); LQ_CUDA(w_Knew.alloc((size_t)M * N * Wc));
         LQ_CUDA(w_misc.alloc(8)); LQ_CUDA(w_stats.alloc(1)); LQ_CUDA(w_goal.alloc(2 * LQ_MAX_N));
         rec_sz = rec_bytes<T>(Wc, N, M, H);
         LQ_CUDA(w_rec.alloc(rec_sz));
         LQ_CUDA(cudaMemset(w_rec.p, 0, rec_sz));
         LQ_CUDA(cudaMemset(w_tries.p, 0, Wc * sizeof(int)));
-        LQ_CUDA(cudaMallocHost((void**)&h_stats, sizeof(lq_wave_stats)));
+        LQ_CUDA(cudaMallocHost((void**)&h_stats, RING * sizeof(lq_wave_stats)));
         LQ_CUDA(cudaMallocHost((void**)&h_misc, 8 * sizeof(int)));
-        memset(h_stats, 0, sizeof(lq_wave_stats));
-        LQ_CUDA(cudaEventCreateWithFlags(&ev_stats, cudaEventDisableTiming));
+        memset(h_stats, 0, RING * sizeof(lq_wave_stats));
+        memset(&last_stats, 0, sizeof last_stats);
+        for (auto& e : ev_stats) LQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
         // metric: constant providers are classified once (planner.py:348 evaluates lqr at every sample)
         if (Lqr::CONST_METRIC) {
@@ -368,7 +389,9 @@ struct EngineImpl : lq_engine {
         // heuristic: split the obstacle tables over a warp once they dominate a rollout step
         int obs_work = 0;
         for (int pi = 0; pi < md.feas.n_prims; pi++) obs_work += md.feas.prims[pi].n_obs;
-        steer_lanes = 1; (void)obs_work;             // the broad-phase grid keeps a check at a few obstacles
+        // sub-warp groups of 8 measured best on C4 (profiles/README.md): they split hull vertices / obstacle
+        // lists and cut the divergence of thread-per-sample rollouts; without obstacle tables one lane is enough
+        steer_lanes = sample_lanes = obs_work > 0 ? 8 : 1;
         return LQ_OK;
     }
 
@@ -492,14 +515,16 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(cudaMemcpyAsync(t_cost.p, cst.data(), count * sizeof(int), cudaMemcpyHostToDevice, st));
         LQ_CUDA(cudaMemsetAsync(t_elen.p, 0, count * sizeof(int), st));
         LQ_CUDA(cudaMemsetAsync(t_ignore.p, 0, cap, st));
+        LQ_CUDA(cudaMemsetAsync(t_owner.p, 0, cap, st));
         tree_scalars_kernel<T><<<1, 1, 0, st>>>(tv, count); launches++;
         init_gain_kernel<T, Sys, Lqr><<<(count + 127) / 128, 128, 0, st>>>(md, t_state.p, t_K.p, cap, count); launches++;
         LQ_CUDA(cudaGetLastError());
         LQ_CUDA(cudaStreamSynchronize(st));     // host staging vectors die here
         size_ub = count; size_ub_exact = count;
-        memset(h_stats, 0, sizeof(lq_wave_stats));
-        h_stats->tree_size = count; h_stats->best_node = -1; h_stats->best_cost = -1;
-        stats_pending = false;
+        memset(&last_stats, 0, sizeof last_stats);
+        last_stats.tree_size = count; last_stats.best_node = -1; last_stats.best_cost = -1;
+        q_head = q_tail = 0;
+        for (int k = 0; k < RING; k++) prof_wave_open[k] = prof_commit_open[k] = false;
         return LQ_OK;
     }
 
@@ -638,17 +663,18 @@ struct EngineImpl : lq_engine {
 
     // ---- one wave -------------------------------------------------------------
     int expand_from_samples(int count, int use_ignore, int flags, cudaStream_t st) {
-        if (prof_on) cudaEventRecord(pev[1], st);
+        const int slot = q_tail % RING;
+        if (prof_on) cudaEventRecord(pev[slot][1], st);
         if (int r = launch_nearest(w_samples.p, Wc, count, use_ignore, w_nidx.p, w_ncost.p, st)) return r;
-        if (prof_on) cudaEventRecord(pev[2], st);
+        if (prof_on) cudaEventRecord(pev[slot][2], st);
         launch_steer(w_nidx.p, w_samples.p, Wc, count, w_xs.p, w_us.p, w_len.p, w_xnew.p, w_Knew.p, Wc, st);
-        if (prof_on) cudaEventRecord(pev[3], st);
+        if (prof_on) cudaEventRecord(pev[slot][3], st);
         RecView<T> rv = rec_view<T>(w_rec.p, Wc, N, M, H);
         pack_scan_kernel<1024><<<1, 1024, 0, st>>>(w_len.p, w_tries.p, count, w_slot.p, rv.header, flags); launches++;
-        pack_kernel<T><<<(count * 32 + 255) / 256, 256, 0, st>>>(w_len.p, w_slot.p, w_nidx.p, w_xnew.p, w_Knew.p, Wc,
-                                                                w_xs.p, w_us.p, count, rv, Wc, N, M, H);
+        pack_kernel<T><<<(count + 127) / 128, 128, 0, st>>>(w_len.p, w_slot.p, w_nidx.p, w_xnew.p, w_Knew.p, Wc, count,
+                                                           rv, w_src.p, Wc, N, M);
         launches++;
-        if (prof_on) { cudaEventRecord(pev[4], st); prof_wave_open = true; prof_W = count; }
+        if (prof_on) { cudaEventRecord(pev[slot][4], st); prof_wave_open[slot] = true; prof_W[slot] = count; }
         LQ_CUDA(cudaGetLastError());
         last_stream = st;
         return LQ_OK;
@@ -659,6 +685,7 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(cudaSetDevice(device));
         if (count < 0 || count > Wc) LQ_FAIL(LQ_ERR_ARG, "count=%d outside 0..wave_capacity=%d", count, Wc);
         if (!have_goal) LQ_FAIL(LQ_ERR_STATE, "lq_set_goal has not been called");
+        if (q_tail - q_head >= (unsigned)RING) LQ_FAIL(LQ_ERR_STATE, "%d committed waves are unread: call lq_wave_stats_get", RING);
         if (count == 0) {
             RecView<T> rv = rec_view<T>(w_rec.p, Wc, N, M, H);
             int hdr[REC_HEADER_INTS] = {0};
@@ -668,7 +695,7 @@ struct EngineImpl : lq_engine {
             last_stream = st;
             return LQ_OK;
         }
-        if (prof_on) cudaEventRecord(pev[0], st);
+        if (prof_on) cudaEventRecord(pev[q_tail % RING][0], st);
         if (h_samples) {
             std::vector<T> soa((size_t)N * count);
             for (int j = 0; j < count; j++)
@@ -694,7 +721,8 @@ struct EngineImpl : lq_engine {
         if (tries < 1 || n_cand < (long long)count * tries) LQ_FAIL(LQ_ERR_ARG, "need count*tries candidates");
         if (!have_goal) LQ_FAIL(LQ_ERR_STATE, "lq_set_goal has not been called");
         if (w_cand.n < (size_t)N * n_cand) { LQ_CUDA(w_cand.alloc((size_t)N * n_cand)); LQ_CUDA(w_candok.alloc(n_cand)); }
-        if (prof_on) cudaEventRecord(pev[0], st);
+        if (q_tail - q_head >= (unsigned)RING) LQ_FAIL(LQ_ERR_STATE, "%d committed waves are unread: call lq_wave_stats_get", RING);
+        if (prof_on) cudaEventRecord(pev[q_tail % RING][0], st);
         std::vector<T> soa((size_t)N * n_cand);
         for (int j = 0; j < n_cand; j++)
             for (int d = 0; d < N; d++) soa[(size_t)d * n_cand + j] = (T)h_cand[(size_t)j * N + d];
@@ -718,48 +746,59 @@ struct EngineImpl : lq_engine {
         return LQ_OK;
     }
 
-    int wave_commit(const void* d_records, int n_seg, cudaStream_t st) override {
+    int wave_commit(const void* d_records, int n_seg, int my_seg, cudaStream_t st) override {
         LQ_CUDA(cudaSetDevice(device));
-        if (n_seg < 1) LQ_FAIL(LQ_ERR_ARG, "n_segments must be >= 1");
+        if (n_seg < 1 || n_seg > 255) LQ_FAIL(LQ_ERR_ARG, "n_segments must be in 1..255");
+        if (my_seg < 0 || my_seg >= n_seg) LQ_FAIL(LQ_ERR_ARG, "my_segment must be in 0..n_segments-1");
+        last_my_seg = my_seg;
         const char* rec = d_records ? (const char*)d_records : w_rec.p;
+        if (q_tail - q_head >= (unsigned)RING) LQ_FAIL(LQ_ERR_STATE, "%d committed waves are unread: call lq_wave_stats_get", RING);
+        const int slot = q_tail % RING;
         const long long warps = (long long)n_seg * Wc;
-        if (prof_on) cudaEventRecord(pev[5], st);
-        commit_kernel<T><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(tv, rec, rec_sz, n_seg, Wc, N, M, H,
+        if (prof_on) cudaEventRecord(pev[slot][5], st);
+        commit_kernel<T><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(tv, rec, rec_sz, n_seg, my_seg, w_src.p,
+                                                                                w_xs.p, w_us.p, Wc, N, M, H,
                                                                                 w_goal.p, w_goal.p + LQ_MAX_N);
         launches++;
         commit_finish_kernel<T><<<1, 1, 0, st>>>(tv, rec, rec_sz, n_seg, w_stats.p); launches++;
-        if (prof_on) { cudaEventRecord(pev[6], st); prof_commit_open = true; }
+        if (prof_on) { cudaEventRecord(pev[slot][6], st); prof_commit_open[slot] = true; }
         LQ_CUDA(cudaGetLastError());
-        LQ_CUDA(cudaMemcpyAsync(h_stats, w_stats.p, sizeof(DevStats), cudaMemcpyDeviceToHost, st));
-        LQ_CUDA(cudaEventRecord(ev_stats, st));
-        stats_pending = true;
+        LQ_CUDA(cudaMemcpyAsync(&h_stats[slot], w_stats.p, sizeof(DevStats), cudaMemcpyDeviceToHost, st));
+        LQ_CUDA(cudaEventRecord(ev_stats[slot], st));
+        q_add[slot] = n_seg * Wc;
+        q_tail++;
         size_ub = std::min(cap, size_ub + n_seg * Wc);
         return LQ_OK;
     }
 
     int wave_stats(lq_wave_stats* out) override {
         LQ_CUDA(cudaSetDevice(device));
-        const int size_before = size_ub_exact;
-        if (stats_pending) { LQ_CUDA(cudaEventSynchronize(ev_stats)); stats_pending = false; }
-        if (prof_on) {
-            float ms = 0;
-            if (prof_wave_open) {
-                LQ_CUDA(cudaEventSynchronize(pev[4]));
-                for (int k = 0; k < 4; k++) { cudaEventElapsedTime(&ms, pev[k], pev[k + 1]); prof_ms[k] += ms; }
-                prof_work[0] += (double)prof_W * size_before;
-                prof_work[1] += (double)prof_W * size_before * N * sizeof(T);
-                prof_work[2] += prof_W; prof_work[3] += 1;
-                prof_wave_open = false;
+        if (q_head != q_tail) {                       // oldest committed, unread wave
+            const int slot = q_head % RING;
+            const int size_before = size_ub_exact;
+            LQ_CUDA(cudaEventSynchronize(ev_stats[slot]));
+            if (prof_on) {
+                float ms = 0;
+                if (prof_wave_open[slot]) {
+                    for (int k = 0; k < 4; k++) { cudaEventElapsedTime(&ms, pev[slot][k], pev[slot][k + 1]); prof_ms[k] += ms; }
+                    prof_work[0] += (double)prof_W[slot] * size_before;
+                    prof_work[1] += (double)prof_W[slot] * size_before * N * sizeof(T);
+                    prof_work[2] += prof_W[slot]; prof_work[3] += 1;
+                    prof_wave_open[slot] = false;
+                }
+                if (prof_commit_open[slot]) {
+                    cudaEventElapsedTime(&ms, pev[slot][5], pev[slot][6]); prof_ms[4] += ms;
+                    prof_commit_open[slot] = false;
+                }
             }
-            if (prof_commit_open) {
-                LQ_CUDA(cudaEventSynchronize(pev[6]));
-                cudaEventElapsedTime(&ms, pev[5], pev[6]); prof_ms[4] += ms;
-                prof_commit_open = false;
-            }
+            last_stats = h_stats[slot];
+            q_head++;
+            size_ub_exact = last_stats.tree_size;
+            int ub = last_stats.tree_size;                // exact size + what the waves still in flight may add
+            for (unsigned q = q_head; q != q_tail; q++) ub += q_add[q % RING];
+            size_ub = std::min(cap, ub);
         }
-        size_ub_exact = h_stats->tree_size;
-        size_ub = h_stats->tree_size;
-        if (out) *out = *h_stats;
+        if (out) *out = last_stats;
         return LQ_OK;
     }
 
@@ -833,12 +872,14 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(cudaMemcpy(t_parent.p + sz, &parent, sizeof(int), cudaMemcpyHostToDevice));
         LQ_CUDA(cudaMemcpy(t_cost.p + sz, &c, sizeof(int), cudaMemcpyHostToDevice));
         LQ_CUDA(cudaMemcpy(t_elen.p + sz, &keep, sizeof(int), cudaMemcpyHostToDevice));
+        const uint8_t own = (uint8_t)last_my_seg;
+        LQ_CUDA(cudaMemcpy(t_owner.p + sz, &own, 1, cudaMemcpyHostToDevice));
         // the reference stores lqr=None for this node (planner.py:299); K = lqr(state, 0) keeps it steerable
         init_gain_kernel<T, Sys, Lqr><<<1, 32, 0, st>>>(md, t_state.p + sz, t_K.p + sz, cap, 1); launches++;
         const int nsz = sz + 1;
         LQ_CUDA(cudaMemcpyAsync(tv.size, &nsz, sizeof(int), cudaMemcpyHostToDevice, st));
         LQ_CUDA(cudaStreamSynchronize(st));
-        size_ub = nsz; h_stats->tree_size = nsz;
+        size_ub = nsz; size_ub_exact = nsz; last_stats.tree_size = nsz;
         return LQ_OK;
     }
 
@@ -854,9 +895,31 @@ struct EngineImpl : lq_engine {
         return LQ_OK;
     }
 
+    int climb(int node, int* ids, int max_len, int* len, cudaStream_t st) override {
+        LQ_CUDA(cudaSetDevice(device));
+        int sz = 0;
+        LQ_CUDA(cudaStreamSynchronize(st));
+        LQ_CUDA(cudaMemcpy(&sz, tv.size, sizeof(int), cudaMemcpyDeviceToHost));
+        if (node < 0 || node >= sz) LQ_FAIL(LQ_ERR_ARG, "The given ID, %d, doesn't exist.", node);      // tree.py:109-110
+        if (max_len < 1) LQ_FAIL(LQ_ERR_ARG, "max_len must be >= 1");
+        DevBuf<int> d;
+        LQ_CUDA(d.alloc((size_t)max_len + 1));
+        climb_kernel<T><<<1, 1, 0, st>>>(tv, node, d.p, max_len, d.p + max_len); launches++;
+        LQ_CUDA(cudaGetLastError());
+        LQ_CUDA(cudaStreamSynchronize(st));
+        int L = 0;
+        LQ_CUDA(cudaMemcpy(&L, d.p + max_len, sizeof(int), cudaMemcpyDeviceToHost));
+        if (L < 0) LQ_FAIL(LQ_ERR_STATE, "path from node %d is longer than %d", node, max_len);
+        std::vector<int> tmp(L);
+        LQ_CUDA(cudaMemcpy(tmp.data(), d.p, (size_t)L * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < L; k++) ids[k] = tmp[L - 1 - k];          // seed first, as tree.py:117
+        *len = L;
+        return LQ_OK;
+    }
+
     // ---- read-back --------------------------------------------------------------
-    int download_nodes(int first, int count, double* state, int* parent, int* cost, int* elen, uint8_t* ign, double* K,
-                       cudaStream_t st) override {
+    int download_nodes(int first, int count, double* state, int* parent, int* cost, int* elen, uint8_t* ign,
+                       uint8_t* owner, double* K, cudaStream_t st) override {
         LQ_CUDA(cudaSetDevice(device));
         LQ_CUDA(cudaStreamSynchronize(st));
         int sz = 0;
@@ -881,10 +944,11 @@ struct EngineImpl : lq_engine {
         if (cost) LQ_CUDA(cudaMemcpy(cost, t_cost.p + first, count * sizeof(int), cudaMemcpyDeviceToHost));
         if (elen) LQ_CUDA(cudaMemcpy(elen, t_elen.p + first, count * sizeof(int), cudaMemcpyDeviceToHost));
         if (ign) LQ_CUDA(cudaMemcpy(ign, t_ignore.p + first, count, cudaMemcpyDeviceToHost));
+        if (owner) LQ_CUDA(cudaMemcpy(owner, t_owner.p + first, count, cudaMemcpyDeviceToHost));
         return LQ_OK;
     }
 
-    int download_edges(const int* ids, int count, double* hx, double* hu, cudaStream_t st) override {
+    int download_edges(const int* ids, int count, double* hx, double* hu, int* hlen, cudaStream_t st) override {
         LQ_CUDA(cudaSetDevice(device));
         if (count <= 0) return LQ_OK;
         int sz = 0;
@@ -896,8 +960,9 @@ struct EngineImpl : lq_engine {
         std::vector<int> v(ids, ids + count);
         if (int r = upload(d, v)) return r;
         DevBuf<T> ox, ou;
-        LQ_CUDA(ox.alloc((size_t)count * H * N)); LQ_CUDA(ou.alloc((size_t)count * H * M));
-        gather_edges_kernel<T><<<count, 128, 0, st>>>(tv, d.p, count, H, H * N, H * M, ox.p, ou.p); launches++;
+        DevBuf<int> ol;
+        LQ_CUDA(ox.alloc((size_t)count * H * N)); LQ_CUDA(ou.alloc((size_t)count * H * M)); LQ_CUDA(ol.alloc(count));
+        gather_edges_kernel<T><<<count, 128, 0, st>>>(tv, d.p, count, last_my_seg, H, H * N, H * M, ox.p, ou.p, ol.p); launches++;
         LQ_CUDA(cudaGetLastError());
         std::vector<T> bx((size_t)count * H * N), bu((size_t)count * H * M);
         LQ_CUDA(cudaStreamSynchronize(st));
@@ -905,6 +970,7 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(cudaMemcpy(bu.data(), ou.p, bu.size() * sizeof(T), cudaMemcpyDeviceToHost));
         for (size_t k = 0; k < bx.size(); k++) hx[k] = (double)bx[k];
         for (size_t k = 0; k < bu.size(); k++) hu[k] = (double)bu[k];
+        if (hlen) LQ_CUDA(cudaMemcpy(hlen, ol.p, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost));
         return LQ_OK;
     }
 
@@ -965,8 +1031,9 @@ struct EngineImpl : lq_engine {
 
     int set_profiling(int on) override {
         LQ_CUDA(cudaSetDevice(device));
-        if (on && !pev[0]) for (auto& e : pev) LQ_CUDA(cudaEventCreate(&e));
-        prof_on = on != 0; prof_wave_open = prof_commit_open = false;
+        if (on && !pev[0][0]) for (auto& r : pev) for (auto& e : r) LQ_CUDA(cudaEventCreate(&e));
+        prof_on = on != 0;
+        for (int k = 0; k < RING; k++) prof_wave_open[k] = prof_commit_open[k] = false;
         return LQ_OK;
     }
     int profile_read(double* ms, double* work, int reset) override {

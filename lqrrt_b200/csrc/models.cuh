@@ -515,7 +515,8 @@ __device__ __forceinline__ bool feasible_eval(const FeasSet<T>& fs, const T* x, 
             if (!feas_candidates(p, px, py, T(0), 2, &b, &e)) break;
             T s, c;
             sincos_t(ph, &s, &c);
-            for (int k = b + lane; k < e; k += lanes) {
+            // every lane walks the (short) candidate list; the hull's vertices are what the lanes split
+            for (int k = b; k < e; k++) {
                 const int o = p.cell_start ? p.cell_items[k] : k;
                 const T ox = p.obs[o * 4 + 0], oy = p.obs[o * 4 + 1];
                 const T a = p.obs[o * 4 + 2], bb = p.obs[o * 4 + 3];
@@ -523,7 +524,7 @@ __device__ __forceinline__ bool feasible_eval(const FeasSet<T>& fs, const T* x, 
                 const T dx = px - ox, dy = py - oy;
                 const T reach = (circ ? a : sqrt_t(a * a + bb * bb)) + p.bound_r;
                 if (dx * dx + dy * dy > reach * reach * T(1.0001)) continue;
-                for (int v = 0; v < p.n_verts; v++) {
+                for (int v = lane; v < p.n_verts; v += lanes) {
                     const T bx = p.verts[v], by = p.verts[p.n_verts + v];
                     const T ex = dx + (c * bx - s * by), ey = dy + (s * bx + c * by);
                     if (circ ? (ex * ex + ey * ey <= a * a) : (abs_t(ex) <= a && abs_t(ey) <= bb)) return false;

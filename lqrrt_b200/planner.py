@@ -17,6 +17,7 @@ New keyword arguments (all optional, defaults keep reference call sites valid):
             global MT19937 stream, drawn on the host in the reference's order
   seed      Philox key
   device    CUDA ordinal (default: torch's current device)
+  pipeline  enqueue wave k+1 before reading wave k's counters (device sampler only; default on)
   comm      torch.distributed process group (or True for WORLD): the wave is
             sharded over the ranks and accepted nodes are all-gathered so every
             rank's tree stays identical
@@ -46,8 +47,9 @@ class Planner(object):
                  min_time=0.5, max_time=1, max_nodes=1E5,
                  goal0=None, sys_time=time.time, printing=True,
                  wave=None, wave_max=8192, dtype='f32', rng='philox', seed=0, device=None, comm=None,
-                 wave_growth=1.0):
+                 wave_growth=1.0, pipeline=True):
         self._engine = None
+        self.pipeline = bool(pipeline)
         self._engine_key = None
         self._exchange = None
         self.wave = wave
@@ -177,6 +179,7 @@ class Planner(object):
                 raise ValueError("Expected xrand_gen to be None, an integer >= 1,  or a function.")
             mode = 'callable'
 
+        t_call = time.perf_counter()
         eng = self._ensure_engine()
         stream = self._cuda_stream()
         eng.set_goal(self.goal, self.constraints.goal_buffer)
@@ -190,7 +193,7 @@ class Planner(object):
 
         # ---- new tree (planner.py:172-173)
         eng.reset(x0, stream)
-        self.tree = Tree(eng, x0, self._system)
+        self.tree = Tree(eng, x0, self._system, comm=self.comm, rank=self.rank, world=self.world)
 
         self.xguide = np.copy(self.goal) if guide is None else np.array(guide, dtype=np.float64)
 
@@ -214,11 +217,19 @@ class Planner(object):
             ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
             ev0.record()
         time_start = self.sys_time()
+        t_loop0 = time.perf_counter()
 
-        while True:
-            W = _waves.wave_size(self.tree.size, self.wave, wave_max=self.wave_max, growth=self.wave_growth)
+        # Software pipeline: with the device sampler nothing a wave needs comes from the host, so wave k+1
+        # is enqueued before the host blocks on wave k's counters and the GPU never waits for the round
+        # trip.  Host-fed samplers (the reference's MT19937 stream, user callables that may look at the
+        # tree) stay strictly synchronous, as does wave=1.
+        depth = 1 if (mode == 'philox' and self.pipeline and self.wave != 1) else 0
+        inflight = 0
+        stopping = False
+        known_size = 1
+
+        def launch(W):
             first, count = _waves.partition(W, self.rank, self.world)
-
             if mode == 'philox':
                 eng.wave_expand(self.seed, wave_ctr, first, count, None, pruning, stop_request, stream)
             elif mode == 'numpy':
@@ -235,15 +246,23 @@ class Planner(object):
             else:
                 xs = np.array([np.array(xrand_gen(self), dtype=np.float64) for _ in range(count)]).reshape(count, self.nstates)
                 eng.wave_expand(self.seed, wave_ctr, first, count, xs, pruning, stop_request, stream)
-
             if exchange is not None:
                 recv = exchange.gather(self._send_view(eng))
-                eng.wave_commit(recv.data_ptr(), self.world, stream)
+                eng.wave_commit(recv.data_ptr(), self.world, stream, my_segment=self.rank)
             else:
                 eng.wave_commit(None, 1, stream)
+
+        while True:
+            while inflight <= depth and not stopping:
+                launch(_waves.wave_size(known_size, self.wave, wave_max=self.wave_max, growth=self.wave_growth))
+                wave_ctr += 1
+                inflight += 1
+                if wave_ctr == 1:
+                    break                       # the first wave's size is the only thing known so far
             st = eng.wave_stats()
-            wave_ctr += 1
+            inflight -= 1
             samples_total += st.n_sampled
+            known_size = st.tree_size
             self.tree._set_size(st.tree_size)
 
             # planner.py:260-283: a strictly faster plan replaces the current one
@@ -265,21 +284,25 @@ class Planner(object):
             else:
                 decision = _waves.STOP_NONE
             if self.world > 1:
-                # rank 0's decision rides in the next wave's record header; everyone acts on what
-                # rank 0 decided one wave ago, so all ranks leave the loop after the same wave
+                # rank 0's decision rides in the header of the next wave it launches; every rank acts on
+                # the flag it reads back, so all ranks stop launching after the same wave
                 act = st.flags
-                stop_request = decision if self.rank == 0 else _waves.STOP_NONE
+                if self.rank == 0 and decision != _waves.STOP_NONE:
+                    stop_request = decision
             else:
                 act = decision
-            if act == _waves.STOP_KILL:
-                outcome = 'killed'
+            if act != _waves.STOP_NONE and outcome is None:
+                stopping = True
+                outcome = 'killed' if act == _waves.STOP_KILL else 'done'
+            if stopping and inflight == 0:
                 break
-            if act == _waves.STOP_DONE:
-                outcome = 'reached' if self.plan_reached_goal else 'timeout'
-                break
+        if outcome == 'done':
+            outcome = 'reached' if self.plan_reached_goal else 'timeout'
 
+        t_loop1 = time.perf_counter()
         self.stats = dict(waves=wave_ctr, samples=samples_total, nodes=self.tree.size,
-                          elapsed=time_elapsed, gpu_launches=eng.launch_count() - launches0)
+                          elapsed=time_elapsed, gpu_launches=eng.launch_count() - launches0,
+                          host_setup_s=t_loop0 - t_call, host_loop_s=t_loop1 - t_loop0)
         if ev0 is not None:
             ev1.record(); ev1.synchronize()
             self.stats['device_ms'] = ev0.elapsed_time(ev1)      # wave loop only, on the launching stream
@@ -321,6 +344,7 @@ class Planner(object):
             self._prepare_interpolators()
 
         self.stats['gpu_launches'] = eng.launch_count() - launches0
+        self.stats['host_closeout_s'] = time.perf_counter() - t_loop1
         self.stats['h2d_bytes'] = eng.h2d_bytes - h2d0
         self.stats['d2h_bytes'] = eng.d2h_bytes - d2h0
         if outcome == 'killed' or self.tree.size > self.max_nodes:  # planner.py:330-336
@@ -338,10 +362,13 @@ class Planner(object):
         return self._exchange
 
     def _send_view(self, eng):
-        import torch
-        from ._native import DevicePointer
-        ptr, nbytes = eng.wave_records()
-        return torch.as_tensor(DevicePointer(ptr, nbytes), device=torch.device('cuda', eng.device))
+        """Zero-copy uint8 view of the engine's record buffer (fixed address for the engine's lifetime)."""
+        if getattr(self, '_send_cache', None) is None or self._send_cache[0] is not eng:
+            import torch
+            from ._native import DevicePointer
+            ptr, nbytes = eng.wave_records()
+            self._send_cache = (eng, torch.as_tensor(DevicePointer(ptr, nbytes), device=torch.device('cuda', eng.device)))
+        return self._send_cache[1]
 
     # ---------------------------------------------------------- interpolators
     def _prepare_interpolators(self):

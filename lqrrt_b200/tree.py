@@ -6,7 +6,9 @@ trajectory, visualize).
 The reference keeps an (N x n) float64 ndarray grown by np.vstack plus Python
 lists (tree.py:62-70, 87-93).  Here the arrays belong to the engine
 (structure-of-arrays on the device, csrc/commit.cuh TreeView) and this class
-downloads on demand: node rows incrementally, edges per request.  Reading
+downloads on demand: node rows incrementally, edges per request (with several
+GPUs an edge is held by the rank that rolled it out, so reading edges is a
+collective there: every rank asks for the same nodes).  Reading
 `tree.state[ID]`, `tree.x_seq[ID]`, `tree.pID` etc. therefore works as in the
 reference's demos (demo_car.py:288-295).
 """
@@ -48,9 +50,10 @@ class Tree(object):
     """Bound to an engine by the Planner; ID == insertion order, seed is ID 0
     with pID -1 (tree.py:17-20)."""
 
-    def __init__(self, engine, seed_state, system):
+    def __init__(self, engine, seed_state, system, comm=None, rank=0, world=1):
         self._eng = engine
         self._sys = system
+        self._comm = comm; self._rank = rank; self._world = world
         self.nstates = engine.n
         self.ncontrols = engine.m
         self._seed = np.array(seed_state, dtype=np.float64)
@@ -100,7 +103,6 @@ class Tree(object):
 
     # -- per-node features ------------------------------------------------------
     def _edges(self, ids):
-        self._sync()
         xs = [None] * len(ids); us = [None] * len(ids)
         need = []
         for k, ID in enumerate(ids):
@@ -111,9 +113,21 @@ class Tree(object):
             else:
                 need.append(k)
         if need:
-            hx, hu = self._eng.download_edges([ids[k] for k in need])
+            hx, hu, hl = self._eng.download_edges([ids[k] for k in need])
+            if self._world > 1:
+                # an edge lives on the GPU that rolled it out (csrc/commit.cuh); the other ranks answer
+                # zeros, so the sum over ranks is the edge.  COLLECTIVE: every rank must ask for the same
+                # ids, which holds for the plan read-out in update_plan and for code that all ranks run alike.
+                import torch
+                import torch.distributed as dist
+                dev = torch.device('cuda', self._eng.device) if dist.get_backend(self._comm) == 'nccl' else torch.device('cpu')
+                buf = torch.from_numpy(np.concatenate((hx.reshape(len(need), -1), hu.reshape(len(need), -1)), axis=1)).to(dev)
+                dist.all_reduce(buf, group=self._comm)
+                buf = buf.cpu().numpy()
+                nx = self._eng.H * self.nstates
+                hx = buf[:, :nx].reshape(hx.shape); hu = buf[:, nx:].reshape(hu.shape)
             for j, k in enumerate(need):
-                L = int(self._elen[ids[k]])
+                L = int(hl[j])
                 xs[k] = [hx[j, i].copy() for i in range(L)]
                 us[k] = [hu[j, i].copy() for i in range(L)]
         return xs, us
@@ -144,7 +158,8 @@ class Tree(object):
         """Node IDs from the seed to ID (tree.py:100-117)."""
         if ID >= self.size or ID < 0:
             raise ValueError("The given ID, {}, doesn't exist.".format(ID))
-        self._sync()
+        if self._n_cached < self._size:
+            return self._eng.climb(ID)           # parents are still on the device: walk them there
         path = []
         while ID != -1:
             path.append(int(ID))

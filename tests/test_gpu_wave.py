@@ -43,7 +43,7 @@ def test_philox_waves_match_oracle(cuda_device, name, W, waves):
     assert np.abs(t['K'] - np.array(orc.K)).max() <= tol * 1e4
     assert t['ignore'].astype(bool).tolist() == orc.ignore
     assert (st.best_node, st.best_cost) == ((orc.best_node, orc.best_cost) if orc.best_cost is not None else (-1, -1))
-    hx, hu = eng.download_edges(np.arange(1, orc.size))
+    hx, hu, _ = eng.download_edges(np.arange(1, orc.size))
     for i in range(1, orc.size):
         L = len(orc.x_seq[i])
         assert t['edge_len'][i] == L
@@ -105,14 +105,24 @@ def test_sharded_wave_is_bit_identical(cuda_device, dtype, G):
             ptr, nb = e.wave_records()
             recv[r * seg:(r + 1) * seg].copy_(torch.as_tensor(DevicePointer(ptr, nb), device='cuda'))
         torch.cuda.synchronize()
-        for e in shards:
-            e.wave_commit(recv.data_ptr(), G)
+        for r, e in enumerate(shards):
+            e.wave_commit(recv.data_ptr(), G, my_segment=r)
             assert e.wave_stats().tree_size == rs.tree_size
     a = tree_arrays(ref)
-    for e in shards:
+    n = a['state'].shape[0]
+    ax, au, _ = ref.download_edges(np.arange(n))
+    sx = np.zeros_like(ax); su = np.zeros_like(au)
+    for r, e in enumerate(shards):
         b = tree_arrays(e)
         for k in ('state', 'parent', 'cost', 'edge_len', 'ignore', 'K'):
             assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(b['owner'], tree_arrays(shards[0])['owner'])
+        ex, eu, _ = e.download_edges(np.arange(n))            # zero unless this shard rolled the edge out
+        mine = b['owner'] == r
+        assert np.all(ex[~mine] == 0) and np.array_equal(ex[mine][1:], ax[mine][1:])
+        sx += ex; su += eu
+    assert np.array_equal(sx, ax) and np.array_equal(su, au)   # the shards' answers sum to the full edges
+    assert len(np.unique(tree_arrays(shards[0])['owner'])) == G
 
 
 def test_capacity_truncates_and_flags(cuda_device):
