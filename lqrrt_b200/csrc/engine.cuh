@@ -108,7 +108,7 @@ __global__ void eval_kernel(Model<T, Sys, Lqr> md, int what, int count, const T*
         T x[N], u[M], S[N * N], K[M * N];
         for (int d = 0; d < N; d++) x[d] = a[i * N + d];
         for (int r = 0; r < M; r++) u[r] = b[i * M + r];
-        md.lqr.metric(md.sys, md.dt, x, S);
+        md.lqr.metric(md.sys, md.dt, x, u, S);
         md.lqr.gain(md.sys, md.dt, x, u, K);
         for (int k = 0; k < N * N; k++) o1[(size_t)i * N * N + k] = S[k];
         for (int k = 0; k < M * N; k++) o2[(size_t)i * M * N + k] = K[k];
@@ -207,6 +207,7 @@ struct EngineImpl : lq_engine {
     std::vector<DevBuf<T>*> feas_bufs;
     std::vector<DevBuf<int>*> grid_bufs;
     int grid_min_obs = 16;
+    bool use_hull_grid = true;
     // wave working set
     DevBuf<T> w_samples, w_ncost, w_pcost, w_Sp, w_xs, w_us, w_xnew, w_Knew, w_cand, w_goal;
     DevBuf<int> w_nidx, w_pidx, w_len, w_slot, w_tries, w_pick, w_src, w_misc;
@@ -269,7 +270,7 @@ struct EngineImpl : lq_engine {
         }
         cap = (c->node_capacity + 1 + 3) & ~3;      // one spare row for the finish_on_goal node (planner.py:299)
         Wc = (c->wave_capacity + 3) & ~3;
-        tries_cap = std::max(1, c->tries_capacity);
+        tries_cap = std::min(16, std::max(1, c->tries_capacity));      // the sampler evaluates tries on 16 lanes
 
         // feasibility tables
         if (c->n_prims < 0 || c->n_prims > LQ_MAX_PRIMS) LQ_FAIL(LQ_ERR_ARG, "at most %d feasibility primitives", LQ_MAX_PRIMS);
@@ -307,6 +308,7 @@ struct EngineImpl : lq_engine {
             if (int r = upload(*ob, obs)) return r;
             d.obs = ob->p;
             d.cell_start = nullptr; d.cell_items = nullptr;
+            d.hull_axes = nullptr; d.hull_nx = d.hull_ny = 0;
             if (s.kind == LQ_FEAS_CIRCLES_CLOUD || s.kind == LQ_FEAS_BOXES_CLOUD) {
                 if (s.n_verts < 1 || !s.verts) LQ_FAIL(LQ_ERR_ARG, "cloud primitive %d needs vertices", pi);
                 std::vector<T> vv((size_t)2 * s.n_verts);
@@ -319,6 +321,28 @@ struct EngineImpl : lq_engine {
                 auto* vb = new DevBuf<T>(); feas_bufs.push_back(vb);
                 if (int r = upload(*vb, vv)) return r;
                 d.verts = vb->p;
+                // product-grid hull? (sorted unique x values) x (sorted unique y values) == the vertex set
+                std::vector<double> ux(s.verts, s.verts + s.n_verts), uy(s.verts + s.n_verts, s.verts + 2 * s.n_verts);
+                std::sort(ux.begin(), ux.end()); ux.erase(std::unique(ux.begin(), ux.end()), ux.end());
+                std::sort(uy.begin(), uy.end()); uy.erase(std::unique(uy.begin(), uy.end()), uy.end());
+                if (use_hull_grid && ux.size() * uy.size() == (size_t)s.n_verts && ux.size() + uy.size() < (size_t)s.n_verts) {
+                    std::vector<char> seen((size_t)s.n_verts, 0);
+                    bool full = true;
+                    for (int v = 0; v < s.n_verts && full; v++) {
+                        const size_t i = std::lower_bound(ux.begin(), ux.end(), s.verts[v]) - ux.begin();
+                        const size_t j = std::lower_bound(uy.begin(), uy.end(), s.verts[s.n_verts + v]) - uy.begin();
+                        if (seen[i * uy.size() + j]) full = false;
+                        seen[i * uy.size() + j] = 1;
+                    }
+                    if (full) {
+                        std::vector<T> ax;
+                        for (double v : ux) ax.push_back((T)v);
+                        for (double v : uy) ax.push_back((T)v);
+                        auto* hb = new DevBuf<T>(); feas_bufs.push_back(hb);
+                        if (int r = upload(*hb, ax)) return r;
+                        d.hull_axes = hb->p; d.hull_nx = (int)ux.size(); d.hull_ny = (int)uy.size();
+                    }
+                }
             }
             if (s.n_obs >= grid_min_obs)
                 if (int r = build_grid(s, d)) return r;
@@ -630,14 +654,14 @@ struct EngineImpl : lq_engine {
         }
         launches++;
     }
-    template <int LANES>
-    void launch_sample_l(uint64_t seed, uint32_t wave, int first, int count, cudaStream_t st) {
-        const long long threads = (long long)count * LANES;
+    void launch_sample(uint64_t seed, uint32_t wave, int first, int count, cudaStream_t st) {
+        constexpr int TL = 16;                       // >= tries_capacity
+        const long long threads = (long long)count * TL;
         if (threads >= 148LL * 8 * 128) {
-            sample_kernel<T, Sys, Lqr, LANES, 128><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
+            sample_kernel<T, Sys, Lqr, TL, 128><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
                 md, sp, seed, wave, first, count, w_samples.p, Wc, w_tries.p);
         } else {
-            sample_kernel<T, Sys, Lqr, LANES, 32><<<(unsigned)((threads + 31) / 32), 32, 0, st>>>(
+            sample_kernel<T, Sys, Lqr, TL, 32><<<(unsigned)((threads + 31) / 32), 32, 0, st>>>(
                 md, sp, seed, wave, first, count, w_samples.p, Wc, w_tries.p);
         }
         launches++;
@@ -707,9 +731,7 @@ struct EngineImpl : lq_engine {
             LQ_CUDA(cudaStreamSynchronize(st));
         } else {
             if (!have_sampling) LQ_FAIL(LQ_ERR_STATE, "lq_set_sampling has not been called");
-            if (sample_lanes >= 32) launch_sample_l<32>(seed, wave, first, count, st);
-            else if (sample_lanes >= 8) launch_sample_l<8>(seed, wave, first, count, st);
-            else launch_sample_l<1>(seed, wave, first, count, st);
+            launch_sample(seed, wave, first, count, st);
         }
         return expand_from_samples(count, use_ignore, flags, st);
     }

@@ -70,10 +70,15 @@ template <typename T> struct BoatSys {            // demos/demo_boat_{novice,int
         thruster_clip = p[k++] != 0.0; carlike = p[k++] != 0.0; use_rudder = p[k++] != 0.0;
     }
     static constexpr int NPARAMS = 46;
+    static constexpr int HEADING = 2;     // state dim whose sin/cos the rollout caches
 
     __device__ __forceinline__ void step(const T* x, T* u, T dt, T* xn) const {
         T s, c;
         sincos_t(x[2], &s, &c);
+        step_sc(x, u, dt, xn, s, c);
+    }
+    // (s, c) = sincos(x[HEADING]) supplied by the caller (one evaluation per state in the rollout)
+    __device__ __forceinline__ void step_sc(const T* x, T* u, T dt, T* xn, T s, T c) const {
         const T vx = x[3], vy = x[4], vh = x[5];
         const T D0 = vx >= T(0) ? Dpos[0] : Dneg[0];
         const T D1 = vy >= T(0) ? Dpos[1] : Dneg[1];
@@ -128,9 +133,13 @@ template <typename T> struct CarSys {             // demos/demo_car.py:46-72
         for (int i = 0; i < 2; i++) uhi[i] = (T)p[k++];
         velmax0 = (T)p[k++];
     }
+    static constexpr int HEADING = 2;
     __device__ __forceinline__ void step(const T* x, T* u, T dt, T* xn) const {
         T s, c;
         sincos_t(x[2], &s, &c);
+        step_sc(x, u, dt, xn, s, c);
+    }
+    __device__ __forceinline__ void step_sc(const T* x, T* u, T dt, T* xn, T s, T c) const {
         u[0] = min_t(max_t(u[0], ulo[0]), uhi[0]);
         u[1] = min_t(max_t(u[1], ulo[1]), uhi[1]);
         xn[0] = x[0] + (c * x[3]) * dt;
@@ -151,9 +160,13 @@ template <typename T> struct PendulumSys {        // config C1
     __host__ void unpack(const double* p) {
         ml2 = (T)(p[0] * p[1] * p[1]); mgl = (T)(p[0] * p[3] * p[1]); damping = (T)p[2]; tau_max = (T)p[4];
     }
+    static constexpr int HEADING = 0;
     __device__ __forceinline__ void step(const T* x, T* u, T dt, T* xn) const {
         T s, c;
         sincos_t(x[0], &s, &c);
+        step_sc(x, u, dt, xn, s, c);
+    }
+    __device__ __forceinline__ void step_sc(const T* x, T* u, T dt, T* xn, T s, T) const {
         const T tau = min_t(max_t(u[0], -tau_max), tau_max);
         const T wdot = (tau - damping * x[1] - mgl * s) / ml2;
         xn[0] = x[0] + x[1] * dt;
@@ -165,11 +178,15 @@ template <typename T, int D> struct DoubleIntSys { // config C5
     static constexpr int N = 2 * D, M = D;
     static constexpr int KIND = LQ_SYS_DOUBLE_INTEGRATOR;
     int axes;
-    static constexpr int NPARAMS = 1;
-    __host__ void unpack(const double* p) { axes = (int)p[0]; }
+    T a_max;
+    static constexpr int NPARAMS = 2;
+    __host__ void unpack(const double* p) { axes = (int)p[0]; a_max = (T)p[1]; }
+    static constexpr int HEADING = -1;
+    __device__ __forceinline__ void step_sc(const T* x, T* u, T dt, T* xn, T, T) const { step(x, u, dt, xn); }
     __device__ __forceinline__ void step(const T* x, T* u, T dt, T* xn) const {
 #pragma unroll
         for (int i = 0; i < D; i++) {
+            u[i] = min_t(max_t(u[i], -a_max), a_max);
             xn[i] = x[i] + x[D + i] * dt;
             xn[D + i] = x[D + i] + u[i] * dt;
         }
@@ -194,6 +211,26 @@ __device__ __forceinline__ void erf_eval(uint32_t angle_mask, const T* xgoal, co
     }
 }
 
+// Same, with sin/cos of dim HD of both states supplied by the caller.
+template <typename T, int N, int HD>
+__device__ __forceinline__ void erf_eval_sc(uint32_t angle_mask, const T* xgoal, const T* x, T* e, T sg, T cg, T s, T c) {
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        if (angle_mask & (1u << i)) {
+            if (i == HD) {
+                e[i] = wrap_sc(s, c, sg, cg);
+            } else {
+                T s2, c2, sg2, cg2;
+                sincos_t(x[i], &s2, &c2);
+                sincos_t(xgoal[i], &sg2, &cg2);
+                e[i] = wrap_sc(s2, c2, sg2, cg2);
+            }
+        } else {
+            e[i] = xgoal[i] - x[i];
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------
 // lqr providers (reference a6).  gain(): K (M x N row-major) at (x,u);
 // metric(): S (N x N row-major) at x with u = 0 (planner.py:348).
@@ -212,9 +249,12 @@ template <typename T, class Sys> struct PdRotatedLqr {
         for (int i = 0; i < N * N; i++) S[i] = (T)p[k++];
         return 0;
     }
-    __device__ __forceinline__ void gain(const Sys&, T, const T* x, const T*, T* K) const {
+    __device__ __forceinline__ void gain(const Sys& sys, T dt, const T* x, const T* u, T* K) const {
         T s, c;
         sincos_t(x[2], &s, &c);
+        gain_sc(sys, dt, x, u, K, s, c);
+    }
+    __device__ __forceinline__ void gain_sc(const Sys&, T, const T*, const T*, T* K, T s, T c) const {
         if (M == 3) {                               // K = [kp R(h)^T, kd], demo_boat_novice.py:86-103
 #pragma unroll
             for (int i = 0; i < M; i++) {
@@ -235,7 +275,7 @@ template <typename T, class Sys> struct PdRotatedLqr {
             }
         }
     }
-    __device__ __forceinline__ void metric(const Sys&, T, const T*, T* Sout) const {
+    __device__ __forceinline__ void metric(const Sys&, T, const T*, const T*, T* Sout) const {
 #pragma unroll
         for (int i = 0; i < N * N; i++) Sout[i] = S[i];
     }
@@ -257,7 +297,8 @@ template <typename T, class Sys> struct ConstantLqr {
 #pragma unroll
         for (int i = 0; i < M * N; i++) K[i] = K0[i];
     }
-    __device__ __forceinline__ void metric(const Sys&, T, const T*, T* Sout) const {
+    __device__ __forceinline__ void gain_sc(const Sys& sys, T dt, const T* x, const T* u, T* K, T, T) const { gain(sys, dt, x, u, K); }
+    __device__ __forceinline__ void metric(const Sys&, T, const T*, const T*, T* Sout) const {
 #pragma unroll
         for (int i = 0; i < N * N; i++) Sout[i] = S[i];
     }
@@ -390,11 +431,10 @@ template <typename T, class Sys> struct FdRiccatiLqr {
         T P[N * N];
         solve(sys, dt, x, u, P, K);
     }
-    __device__ void metric(const Sys& sys, T dt, const T* x, T* Sout) const {
-        T K[M * N], u0[M];
-#pragma unroll
-        for (int i = 0; i < M; i++) u0[i] = T(0);
-        solve(sys, dt, x, u0, Sout, K);
+    __device__ void gain_sc(const Sys& sys, T dt, const T* x, const T* u, T* K, T, T) const { gain(sys, dt, x, u, K); }
+    __device__ void metric(const Sys& sys, T dt, const T* x, const T* u, T* Sout) const {
+        T K[M * N];
+        solve(sys, dt, x, u, Sout, K);
     }
 };
 
@@ -419,6 +459,11 @@ template <typename T> struct FeasPrim {
     const int* cell_items;
     T g0[3], ginv[3];
     int gn[3];
+    // Product-grid hull (every demo's vertex cloud is np.mgrid, demo_car.py:77-90): verts = {hx_i} x {hy_j}.
+    // The squared distance from an obstacle centre to its nearest vertex then separates per body axis,
+    // min_i (bx - hx_i)^2 + min_j (by - hy_j)^2, so "any vertex within r" costs nx + ny tests, not nx * ny.
+    const T* hull_axes;   // [nx][ny] values, nullptr when the cloud is not a product grid
+    int hull_nx, hull_ny;
 };
 
 template <typename T> struct FeasSet {
@@ -446,8 +491,10 @@ __device__ __forceinline__ bool feas_candidates(const FeasPrim<T>& p, T px, T py
 // lane / lanes: cooperative evaluation by `lanes` threads that all hold the
 // same (x,u); obstacle loops are strided by lane.  Returns this lane's verdict;
 // the caller combines lanes (AND).  lanes == 1 is the scalar case.
+// hdim >= 0: (hs, hc) = sincos(x[hdim]) is supplied and reused by the hull rotations on that dim.
 template <typename T, int N, int M>
-__device__ __forceinline__ bool feasible_eval(const FeasSet<T>& fs, const T* x, const T* u, int lane = 0, int lanes = 1) {
+__device__ __forceinline__ bool feasible_eval(const FeasSet<T>& fs, const T* x, const T* u, int lane = 0, int lanes = 1,
+                                              int hdim = -1, T hs = T(0), T hc = T(1)) {
     for (int pi = 0; pi < fs.n_prims; pi++) {
         const FeasPrim<T>& p = fs.prims[pi];
         switch (p.kind) {
@@ -513,9 +560,25 @@ __device__ __forceinline__ bool feasible_eval(const FeasSet<T>& fs, const T* x, 
                 }
             }
             if (!feas_candidates(p, px, py, T(0), 2, &b, &e)) break;
-            T s, c;
-            sincos_t(ph, &s, &c);
-            // every lane walks the (short) candidate list; the hull's vertices are what the lanes split
+            T s = hs, c = hc;
+            if (p.dims[2] != hdim) sincos_t(ph, &s, &c);
+            if (circ && p.hull_axes) {
+                // lanes split the candidate list; each candidate is O(nx + ny)
+                for (int k = b + lane; k < e; k += lanes) {
+                    const int o = p.cell_start ? p.cell_items[k] : k;
+                    const T rx = p.obs[o * 4 + 0] - px, ry = p.obs[o * 4 + 1] - py;   // centre relative to the hull origin
+                    const T a = p.obs[o * 4 + 2];
+                    const T reach = a + p.bound_r;
+                    if (rx * rx + ry * ry > reach * reach * T(1.0001)) continue;
+                    const T bx = c * rx + s * ry, by = c * ry - s * rx;                // ... in the body frame
+                    T mx = Num<T>::inf(), my = Num<T>::inf();
+                    for (int i = 0; i < p.hull_nx; i++) { const T d = bx - p.hull_axes[i]; mx = min_t(mx, d * d); }
+                    for (int j = 0; j < p.hull_ny; j++) { const T d = by - p.hull_axes[p.hull_nx + j]; my = min_t(my, d * d); }
+                    if (mx + my <= a * a) return false;
+                }
+                break;
+            }
+            // general cloud: every lane walks the (short) candidate list, the vertices are what the lanes split
             for (int k = b; k < e; k++) {
                 const int o = p.cell_start ? p.cell_items[k] : k;
                 const T ox = p.obs[o * 4 + 0], oy = p.obs[o * 4 + 1];

@@ -234,10 +234,12 @@ __global__ void metric_kernel(Sys sys, Lqr lqr, T dt, const T* __restrict__ quer
     constexpr int N = Sys::N;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= W) return;
-    T x[N], S[N * N];
+    T x[N], S[N * N], u0[Sys::M];
 #pragma unroll
     for (int d = 0; d < N; d++) x[d] = queries[(size_t)d * qstride + j];
-    lqr.metric(sys, dt, x, S);
+#pragma unroll
+    for (int r = 0; r < Sys::M; r++) u0[r] = T(0);            // planner.py:348: lqr(x, zeros)
+    lqr.metric(sys, dt, x, u0, S);
     int s = N;
     for (int a = 0; a < N; a++) {
         Spacked[(size_t)a * qstride + j] = S[a * N + a];

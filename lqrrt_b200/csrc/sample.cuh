@@ -37,22 +37,24 @@ __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(
 __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 
-// One sample per group of LANES threads (as steer_kernel): every lane draws the same numbers, the
-// obstacle lists of the feasibility test are split across the lanes.
-template <typename T, class Sys, class Lqr, int LANES, int BLOCK>
+// One sample per group of TL threads: lane t evaluates try t of the reference's retry loop
+// (planner.py:203-211) -- its own Philox draws, its own feasibility test -- and a group ballot picks the
+// first feasible try (or the last one), exactly what the sequential loop would return.  The latency of a
+// wave's sampling is one try instead of up to `tries` of them.
+template <typename T, class Sys, class Lqr, int TL, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 sample_kernel(Model<T, Sys, Lqr> md, SamplerParams<T, Sys::N> sp, uint64_t seed, uint32_t wave,
               int first, int count, T* __restrict__ samples, int sstride, int* __restrict__ tries_used) {
     constexpr int N = Sys::N, M = Sys::M;
-    const int j = (blockIdx.x * BLOCK + threadIdx.x) / LANES;
-    const int lane = threadIdx.x % LANES;
-    if (j >= count) return;
+    const int j = (blockIdx.x * BLOCK + threadIdx.x) / TL;
+    const int t = threadIdx.x % TL;
+    if (j >= count) return;                                  // whole groups leave together
     const uint32_t g = (uint32_t)(first + j);
     T x[N], u0[M];
 #pragma unroll
     for (int i = 0; i < M; i++) u0[i] = T(0);
-    int t = 0;
-    for (; t < sp.tries; t++) {
+    bool ok = false;
+    if (t < sp.tries) {
         T uni[(N + 4) / 4 * 4];
 #pragma unroll
         for (int b = 0; b < (N + 4) / 4; b++) {
@@ -64,15 +66,17 @@ sample_kernel(Model<T, Sys, Lqr> md, SamplerParams<T, Sys::N> sp, uint64_t seed,
         // xrand = centers + spans * (U - 0.5), planner.py:204 -- un-fused so it matches NumPy bit for bit
 #pragma unroll
         for (int i = 0; i < N; i++) x[i] = add_rn(sp.center[i], mul_rn(sp.span[i], uni[i] - T(0.5)));
-        const T r = uni[N];                                         // one draw gates every dim, planner.py:205-207
+        const T r = uni[N];                                  // one draw gates every dim, planner.py:205-207
 #pragma unroll
         for (int i = 0; i < N; i++) if (sp.bias[i] > r) x[i] = sp.goal[i];
-        if (group_all<LANES>(feasible_eval<T, N, M>(md.feas, x, u0, lane, LANES))) { t++; break; }  // planner.py:208-209
+        ok = feasible_eval<T, N, M>(md.feas, x, u0);          // planner.py:208-209
     }
-    if (lane == 0) {
+    const unsigned votes = cg::tiled_partition<TL>(cg::this_thread_block()).ballot(ok);
+    const int pick = votes ? __ffs(votes) - 1 : sp.tries - 1;   // first feasible try, else the last try
+    if (t == pick) {
 #pragma unroll
         for (int i = 0; i < N; i++) samples[(size_t)i * sstride + j] = x[i];
-        if (tries_used) tries_used[j] = t;
+        if (tries_used) tries_used[j] = votes ? pick + 1 : sp.tries;
     }
 }
 

@@ -62,13 +62,19 @@ steer_kernel(Model<T, Sys, Lqr> md,
 #pragma unroll
     for (int k = 0; k < M * N; k++) K[k] = tK[(size_t)k * cap + id];
 
+    // sin/cos of the heading-like dim are evaluated once per state and shared by erf, dynamics,
+    // the hull rotation in is_feasible and the gain (they were ~half of a step's instructions)
+    constexpr int HD = Sys::HEADING;
+    T sh = T(0), ch = T(1), sg = T(0), cg = T(1);
+    if (HD >= 0) { sincos_t(x[HD < 0 ? 0 : HD], &sh, &ch); sincos_t(xt[HD < 0 ? 0 : HD], &sg, &cg); }
+
     int len = 0, nrec = 0, i = 0;
     T* xrow = xseq + (size_t)j * md.H * N;      // never NULL: the engine supplies scratch
     T* urow = useq + (size_t)j * md.H * M;
 
     while (true) {
         T e[N], u[M], uw[M], xn[N];
-        erf_eval<T, N>(md.angle_mask, xt, x, e);                 // planner.py:386
+        erf_eval_sc<T, N, HD>(md.angle_mask, xt, x, e, sg, cg, sh, ch);   // planner.py:386
 #pragma unroll
         for (int r = 0; r < M; r++) {                            // u = K e, planner.py:387
             T a = T(0);
@@ -76,8 +82,10 @@ steer_kernel(Model<T, Sys, Lqr> md,
             for (int d = 0; d < N; d++) a += K[r * N + d] * e[d];
             u[r] = a; uw[r] = a;
         }
-        md.sys.step(x, uw, md.dt, xn);                           // planner.py:390 (uw = the copy dynamics may clip)
-        const bool ok = group_all<LANES>(feasible_eval<T, N, M>(md.feas, xn, u, lane, LANES));   // planner.py:393
+        md.sys.step_sc(x, uw, md.dt, xn, sh, ch);                // planner.py:390 (uw = the copy dynamics may clip)
+        T sn = T(0), cn = T(1);
+        if (HD >= 0) sincos_t(xn[HD < 0 ? 0 : HD], &sn, &cn);
+        const bool ok = group_all<LANES>(feasible_eval<T, N, M>(md.feas, xn, u, lane, LANES, HD, sn, cn));   // planner.py:393
         if (!ok) { len = fpr_keep(md, nrec); break; }            // planner.py:394-396
         i += 1;                                                  // planner.py:414
         bool conv = true;
@@ -86,6 +94,7 @@ steer_kernel(Model<T, Sys, Lqr> md,
         if (i > md.H || conv) { len = nrec; break; }             // planner.py:428-429
 #pragma unroll
         for (int d = 0; d < N; d++) x[d] = xn[d];
+        sh = sn; ch = cn;
         if (lane == 0) {                                         // planner.py:432-433
 #pragma unroll
             for (int d = 0; d < N; d++) xrow[nrec * N + d] = x[d];
@@ -93,7 +102,7 @@ steer_kernel(Model<T, Sys, Lqr> md,
             for (int r = 0; r < M; r++) urow[nrec * M + r] = u[r];
         }
         nrec += 1;
-        md.lqr.gain(md.sys, md.dt, x, u, K);                     // planner.py:436
+        md.lqr.gain_sc(md.sys, md.dt, x, u, K, sh, ch);          // planner.py:436
     }
 
     if (lane == 0) {

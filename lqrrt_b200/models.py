@@ -160,19 +160,22 @@ class Pendulum2Dynamics(Dynamics):
 
 class DoubleIntegratorDynamics(Dynamics):
     """D-axis double integrator, state [p (D), v (D)], effort [a (D)]
-    (synthetic config C5)."""
+    (synthetic config C5).  `a_max` saturates the applied
+    acceleration inside the dynamics, the way the demos saturate their actuators
+    (demo_car.py:57); inf disables it."""
     kind = SYS_DOUBLE_INTEGRATOR
 
-    def __init__(self, axes=6):
+    def __init__(self, axes=6, a_max=np.inf):
         axes = int(axes)
         if not 1 <= axes <= MAX_M:
             raise ValueError("axes must be in 1..{}".format(MAX_M))
         self.axes = axes
+        self.a_max = float(a_max)
         self.nstates = 2 * axes
         self.ncontrols = axes
 
     def blob(self):
-        return np.array([float(self.axes)])
+        return np.array([float(self.axes), self.a_max])
 
 
 # =============================================================================
@@ -536,16 +539,18 @@ def pendulum2(tau_max=5.0, region=((1.2, -1.0), (1.8, 1.0)), Q=(10.0, 1.0), R=(1
     return System(dyn, lqr, Erf([0]), Feasibility(prims), dt_hint=0.01, name='pendulum2')
 
 
-def double_integrator(axes=6, spheres=(), a_max=1.0, steps=20, eps=1e-3, riccati=True):
-    """Config C5."""
-    dyn = DoubleIntegratorDynamics(axes)
+def double_integrator(axes=6, spheres=(), a_max=1.0, steps=20, eps=1e-3, riccati=True, v_max=3.0):
+    """Config C5: accelerations saturate at a_max inside the dynamics (SURVEY.md's
+    "|u| <= 1 via is_feasible" would reject every rollout whose first LQR effort exceeds 1, i.e. nearly all
+    of them, so the limit is applied where the demos apply theirs); speeds beyond v_max are infeasible."""
+    dyn = DoubleIntegratorDynamics(axes, a_max=a_max)
     n, m = dyn.nstates, dyn.ncontrols
     if riccati:
         lqr = FDRiccatiLqr(np.eye(n), np.eye(m), steps=steps, eps=eps)
     else:
         K = np.hstack((np.eye(m), 1.7 * np.eye(m)))
         lqr = ConstantLqr(np.eye(n), K)
-    prims = [EffortBox([a_max] * m)]
+    prims = [StateBox([-np.inf] * m + [-v_max] * m, [np.inf] * m + [v_max] * m)]
     if len(spheres):
         prims.append(SpheresPoint(spheres, dims=(0, 1, 2)))
     return System(dyn, lqr, Erf(), Feasibility(prims), name='double_integrator{}'.format(n))

@@ -99,7 +99,8 @@ def double_integrator_dynamics(p):
     D = p.axes
 
     def dynamics(x, u, dt):
-        return np.concatenate((x[:D] + x[D:] * dt, x[D:] + np.asarray(u, dtype=np.float64) * dt))
+        a = np.clip(np.asarray(u, dtype=np.float64), -p.a_max, p.a_max)
+        return np.concatenate((x[:D] + x[D:] * dt, x[D:] + a * dt))
     return dynamics
 
 

@@ -67,7 +67,7 @@ def test_plain_callables_are_rejected_loudly():
 
 
 def test_model_blobs_have_the_wire_sizes():
-    for name, n_sys in (('demo_boat_novice', 46), ('demo_car', 9), ('c1', 5), ('c5', 1)):
+    for name, n_sys in (('demo_boat_novice', 46), ('demo_car', 9), ('c1', 5), ('c5', 2)):
         s = configs.BY_NAME[name](0).system
         assert len(s.dynamics.blob()) == n_sys
         assert s.erf.mask(s.nstates) in (0, 1, 4)
