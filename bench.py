@@ -44,6 +44,30 @@ METRIC = "tree_expansions_per_s"
 UNIT = "nodes/s"
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    ncu --set full capture (profiles/ncu_nearest_*.txt); None if there is none."""
+    import glob
+    import re
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', 'ncu_nearest_*.txt'))):
+        vals = []
+        rd = wr = None
+        for line in open(path):
+            m = re.match(r'dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)', line)
+            if m:
+                v = float(m.group(2)) * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(m.group(3), 1)
+                if m.group(1) == 'read':
+                    rd = v
+                else:
+                    wr = v
+                if rd is not None and wr is not None:
+                    vals.append(rd + wr); rd = wr = None
+        if vals:
+            best = float(np.mean(vals))
+    return best
+
+
 def make_problem(name):
     from lqrrt_b200 import configs
     return configs.BY_NAME[name](0)
@@ -54,7 +78,8 @@ def workload_name(prob, name):
         'c4': "C4 demo_boat_advanced 6-DoF boat, 500 circular obstacles, 200 m arena, tree grown to 100k nodes",
         'c3': "C3 demo_boat_novice 6-DoF boat, 50 circular obstacles, tree grown to max_nodes",
         'c2': "C2 demo_car 5-state car, 20 box obstacles, tree grown to max_nodes",
-        'c5': "C5 12-state double integrator, 5000 spheres, FD-Riccati lqr, tree grown to max_nodes",
+        'c5': "C5 12-state double integrator, 5000 spheres, FD-Riccati lqr, tree grown to 1M nodes",
+        'c5k': "C5 12-state double integrator, 5000 spheres, constant LQR gain, tree grown to 1M nodes",
     }.get(name, prob.name)
 
 
@@ -214,13 +239,14 @@ def run_gpu_arm(args):
     barrier()
     with ClockSampler(local) as clk:
         host_times = []; dev_ms = []; nodes = []; samples = []; waves = []; launches = 0; d2h = 0; h2d = 0
-        phases = np.zeros(3)
+        phases = np.zeros(3); reached = 0; depth = []; plan_T = []
         for s in range(args.steps):
             host_s, st = one_plan(s)
             host_times.append(host_s); dev_ms.append(st['device_ms']); nodes.append(st['nodes'] - 1)
             samples.append(st['samples']); waves.append(st['waves']); launches += st['gpu_launches']
             d2h += st['d2h_bytes']; h2d += st['h2d_bytes']
             phases += [st['host_setup_s'], st['host_loop_s'], st['host_closeout_s']]
+            reached += int(planner.plan_reached_goal); depth.append(len(planner.node_seq)); plan_T.append(float(planner.T))
         barrier()
     prof = planner._engine.profile_read()
 
@@ -261,6 +287,11 @@ def run_gpu_arm(args):
                        "wave": "adaptive clamp(N, 32, {})".format(wave_max), "wave_per_gpu_max": wave_max // world,
                        "waves_per_step": float(np.mean(waves)), "samples_per_step": float(np.mean(samples)),
                        "yield": total_nodes / float(np.sum(samples)), "sampler": "philox4x32-10 on device, new seed per step",
+                       "plans_reaching_goal": "{}/{}".format(reached, args.steps), "plan_depth_edges": float(np.mean(depth)),
+                       "plan_duration_s": float(np.mean(plan_T)),
+                       "note": "tree depth grows by at most one edge per wave, so the throughput-maximal wave cap "
+                               "fills 100k nodes before the 283 m-away goal is reached; --wave 512 reaches it "
+                               "(profiles/README.md has both)",
                        "l2": "tree states (<= 2.4 MB) and obstacle tables are L2-resident by design; every step "
                              "grows a new tree from new samples (no reuse between timed steps)"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
@@ -268,14 +299,17 @@ def run_gpu_arm(args):
                     "host_ms_per_step": dict(zip(("setup", "wave_loop", "closeout"), (phases / args.steps * 1e3).round(3).tolist()))},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "nearest_diag_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                         "frac": achieved / hbm if hbm else None, "traffic": None,
+                         "frac": achieved / hbm if hbm else None, "traffic": ncu_traffic(),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes": prof['nearest_bytes'], "kernel_seconds": near_s,
                          "share_of_device_time": (prof['ms']['nearest'] / stage_total) if stage_total else None,
                          "pairs_per_s": pairs_per_s,
+                         "fp32_issue_frac": pairs_per_s * 17.5 / (148 * 128 * 1.965e9),
                          "note": "algorithmic bytes = sum_k W_k*N_k*n*sizeof(dtype) (SURVEY.md 8d); node tiles are reused "
                                  "by every query of a CTA from shared memory and the tree is L2-resident, so frac > 1 is "
-                                 "expected and the binding limit is FP32 issue (pairs_per_s)"},
+                                 "expected and the binding limit is FP32 issue: fp32_issue_frac = pairs_per_s x 17.5 "
+                                 "instructions per pair / (148 SMs x 128 lanes x 1.965 GHz); traffic = measured DRAM bytes "
+                                 "per launch from the committed ncu capture"},
             "stage_ms": prof['ms'],
             "clocks": clk.summary(),
         }

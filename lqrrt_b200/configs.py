@@ -228,4 +228,5 @@ BY_NAME = {
     'demo_boat_advanced': demo_boat_advanced, 'demo_car': demo_car,
     'c1': c1_pendulum, 'c2': c2_car, 'c3': c3_boat_novice, 'c4': c4_boat_advanced,
     'c5': c5_double_integrator,
+    'c5k': lambda seed=0: c5_double_integrator(seed, riccati=False),      # C5 with a constant LQR gain
 }

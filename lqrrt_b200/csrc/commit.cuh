@@ -54,51 +54,61 @@ __host__ __device__ inline RecView<T> rec_view(void* base, int Wc, int N, int M,
     return v;
 }
 
-// Exclusive scan of (len > 0) over the wave -> record slot per sample; one CTA.
-template <int BLOCK>
+// pack: compact the wave's accepted samples (edge length > 0), in sample order.  One kernel: every CTA
+// first counts the accepted samples that precede its own range (the length array is a few KB, L2
+// resident), then scans its range and copies its records; the last CTA's running total is the segment's
+// record count.  Deterministic (no atomics): slot = number of accepted samples with a lower index.
+template <typename T, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
-pack_scan_kernel(const int* __restrict__ len, const int* __restrict__ tries_used, int count,
-                 int* __restrict__ slot, int* __restrict__ header, int flags) {
+pack_kernel(const int* __restrict__ len, const int* __restrict__ tries_used, const int* __restrict__ ids,
+            const T* __restrict__ xnew, const T* __restrict__ Knew, int ostride, int count,
+            RecView<T> rv, int* __restrict__ sample_of_slot, int Wc, int N, int M, int flags) {
     __shared__ int wsum[BLOCK / 32];
-    __shared__ int wtries[BLOCK / 32];
-    const int per = (count + BLOCK - 1) / BLOCK;
-    const int j0 = threadIdx.x * per, j1 = min(j0 + per, count);
-    int local = 0, tries = 0;
-    for (int j = j0; j < j1; j++) { local += len[j] > 0; if (tries_used) tries += tries_used[j]; }
-    int incl = local;
+    __shared__ int wtri[BLOCK / 32];
+    __shared__ int s_before, s_tries;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j0 = blockIdx.x * BLOCK;
+    // accepted samples (and sampler tries) before this CTA's range
+    int before = 0, tries = 0;
+    for (int j = threadIdx.x; j < j0; j += BLOCK) { before += len[j] > 0; tries += tries_used[j]; }
+    // ... plus this CTA's own element, for the block scan below
+    const int j = j0 + threadIdx.x;
+    const int mine = (j < count && len[j] > 0) ? 1 : 0;
+    tries += j < count ? tries_used[j] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        before += __shfl_xor_sync(0xffffffffu, before, o);
+        tries += __shfl_xor_sync(0xffffffffu, tries, o);
+    }
+    int incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int v = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += v;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tries += __shfl_xor_sync(0xffffffffu, tries, o);
-    if (lane == 31) wsum[warp] = incl;
-    if (lane == 0) wtries[warp] = tries;
+    if (lane == 0) { wsum[warp] = before; wtri[warp] = tries; }
     __syncthreads();
-    int woff = 0, total = 0, ttries = 0;
-    for (int w = 0; w < BLOCK / 32; w++) { if (w < warp) woff += wsum[w]; total += wsum[w]; ttries += wtries[w]; }
-    int run = woff + incl - local;
-    for (int j = j0; j < j1; j++) { slot[j] = run; run += len[j] > 0; }
-    if (threadIdx.x == 0) { header[HDR_COUNT] = total; header[HDR_SAMPLED] = count; header[HDR_TRIES] = ttries; header[HDR_FLAGS] = flags; }
-}
-
-// One thread per sample: copy an accepted sample's node record into its slot and remember which
-// sample the slot came from (the committing GPU finds the edge in its rollout scratch through it).
-template <typename T>
-__global__ void pack_kernel(const int* __restrict__ len, const int* __restrict__ slot, const int* __restrict__ ids,
-                            const T* __restrict__ xnew, const T* __restrict__ Knew, int ostride, int count,
-                            RecView<T> rv, int* __restrict__ sample_of_slot, int Wc, int N, int M) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= count) return;
-    const int L = len[j];
-    if (L <= 0) return;
-    const int s = slot[j];
-    for (int d = 0; d < N; d++) rv.state[(size_t)d * Wc + s] = xnew[(size_t)d * ostride + j];
-    for (int k = 0; k < M * N; k++) rv.K[(size_t)k * Wc + s] = Knew[(size_t)k * ostride + j];
-    rv.parent[s] = ids[j]; rv.len[s] = L;
-    sample_of_slot[s] = j;
+    if (threadIdx.x == 0) {
+        int b2 = 0, t2 = 0;
+        for (int w = 0; w < BLOCK / 32; w++) { b2 += wsum[w]; t2 += wtri[w]; }
+        s_before = b2; s_tries = t2;
+    }
+    __syncthreads();
+    if (lane == 31) wsum[warp] = incl;              // per-warp totals of this CTA's own flags
+    __syncthreads();
+    int woff = 0, total = 0;
+    for (int w = 0; w < BLOCK / 32; w++) { if (w < warp) woff += wsum[w]; total += wsum[w]; }
+    const int slot = s_before + woff + incl - mine;
+    if (mine) {
+        for (int d = 0; d < N; d++) rv.state[(size_t)d * Wc + slot] = xnew[(size_t)d * ostride + j];
+        for (int k = 0; k < M * N; k++) rv.K[(size_t)k * Wc + slot] = Knew[(size_t)k * ostride + j];
+        rv.parent[slot] = ids[j]; rv.len[slot] = len[j];
+        sample_of_slot[slot] = j;
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        rv.header[HDR_COUNT] = s_before + total; rv.header[HDR_SAMPLED] = count;
+        rv.header[HDR_TRIES] = s_tries; rv.header[HDR_FLAGS] = flags;
+    }
 }
 
 template <typename T> struct TreeView {
@@ -115,6 +125,7 @@ template <typename T> struct TreeView {
     int* n_ignored;    // device scalar
     int* n_goal;       // device scalar
     unsigned long long* best;   // (cost << 32 | node), ~0 = none
+    unsigned* done;             // CTAs of the running commit that have finished (last one publishes)
     int cap;           // array stride (node_capacity rounded up to 4)
     int limit;         // node_capacity: appends beyond it are dropped and flagged
 };
@@ -133,75 +144,85 @@ __device__ __forceinline__ void mark_path(const TreeView<T>& tv, int node) {
     }
 }
 
-// One warp per (segment, record).
+struct DevStats { int v[12]; };
+
+// One warp per (segment, record); the last CTA to finish publishes the new tree size and the wave's
+// counters (every CTA has read the old size by then).
 template <typename T>
 __global__ void commit_kernel(TreeView<T> tv, const char* __restrict__ records, size_t seg_bytes, int n_seg,
                               int my_seg, const int* __restrict__ sample_of_slot,
                               const T* __restrict__ xseq, const T* __restrict__ useq,
                               int Wc, int N, int M, int H,
-                              const T* __restrict__ goal_lo, const T* __restrict__ goal_hi) {
+                              const T* __restrict__ goal_lo, const T* __restrict__ goal_hi,
+                              DevStats* __restrict__ out) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int seg = w / Wc, k = w % Wc;
-    if (seg >= n_seg) return;
+    const int old_size = *tv.size;
     int before = 0, mine = 0;
-    for (int s = 0; s <= seg; s++) {
-        const int c = ((const int*)(records + (size_t)s * seg_bytes))[HDR_COUNT];
-        if (s < seg) before += c; else mine = c;
-    }
-    if (k >= mine) return;
-    const int node = *tv.size + before + k;
-    if (node >= tv.limit) return;
-    const RecView<T> rv = rec_view<T>((void*)(records + (size_t)seg * seg_bytes), Wc, N, M, H);
-    const int L = rv.len[k], par = rv.parent[k];
-    bool in_goal = true;
-    for (int d = lane; d < N; d += 32) {
-        const T v = rv.state[(size_t)d * Wc + k];
-        tv.state[(size_t)d * tv.cap + node] = v;
-        in_goal = in_goal && (goal_lo[d] < v) && (v < goal_hi[d]);      // planner.py:442-447
-    }
-    in_goal = __all_sync(0xffffffffu, in_goal);
-    for (int q = lane; q < M * N; q += 32) tv.K[(size_t)q * tv.cap + node] = rv.K[(size_t)q * Wc + k];
-    if (seg == my_seg) {               // my own rollout: its edge is still in this GPU's scratch
-        const int j = sample_of_slot[k];
-        const T* sx = xseq + (size_t)j * H * N; T* dx = tv.edge_x + (size_t)node * H * N;
-        for (int q = lane; q < L * N; q += 32) dx[q] = sx[q];
-        const T* su = useq + (size_t)j * H * M; T* du = tv.edge_u + (size_t)node * H * M;
-        for (int q = lane; q < L * M; q += 32) du[q] = su[q];
-    }
-    if (lane == 0) {
-        const int c = tv.cost[par] + L;
-        tv.parent[node] = par; tv.cost[node] = c; tv.edge_len[node] = L; tv.owner[node] = (uint8_t)seg;
-        if (in_goal) {                                                  // planner.py:260-281
-            atomicAdd(tv.n_goal, 1);
-            atomicMin(tv.best, ((unsigned long long)(unsigned)c << 32) | (unsigned)node);
-            mark_path(tv, node);
+    if (seg < n_seg) {
+        for (int s = 0; s <= seg; s++) {
+            const int c = ((const int*)(records + (size_t)s * seg_bytes))[HDR_COUNT];
+            if (s < seg) before += c; else mine = c;
         }
     }
-}
-
-struct DevStats { int v[12]; };
-
-// Single thread: publish the new size and the wave counters.
-template <typename T>
-__global__ void commit_finish_kernel(TreeView<T> tv, const char* __restrict__ records, size_t seg_bytes, int n_seg,
-                                     DevStats* __restrict__ out) {
-    int total = 0, sampled = 0, tries = 0;
-    for (int s = 0; s < n_seg; s++) {
-        const int* h = (const int*)(records + (size_t)s * seg_bytes);
-        total += h[HDR_COUNT]; sampled += h[HDR_SAMPLED]; tries += h[HDR_TRIES];
+    const int node = old_size + before + k;
+    if (seg < n_seg && k < mine && node < tv.limit) {
+        const RecView<T> rv = rec_view<T>((void*)(records + (size_t)seg * seg_bytes), Wc, N, M, H);
+        const int L = rv.len[k], par = rv.parent[k];
+        bool in_goal = true;
+        for (int d = lane; d < N; d += 32) {
+            const T v = rv.state[(size_t)d * Wc + k];
+            tv.state[(size_t)d * tv.cap + node] = v;
+            in_goal = in_goal && (goal_lo[d] < v) && (v < goal_hi[d]);      // planner.py:442-447
+        }
+        in_goal = __all_sync(0xffffffffu, in_goal);
+        for (int q = lane; q < M * N; q += 32) tv.K[(size_t)q * tv.cap + node] = rv.K[(size_t)q * Wc + k];
+        if (seg == my_seg) {               // my own rollout: its edge is still in this GPU's scratch
+            const int j = sample_of_slot[k];
+            const T* sx = xseq + (size_t)j * H * N; T* dx = tv.edge_x + (size_t)node * H * N;
+            for (int q = lane; q < L * N; q += 32) dx[q] = sx[q];
+            const T* su = useq + (size_t)j * H * M; T* du = tv.edge_u + (size_t)node * H * M;
+            for (int q = lane; q < L * M; q += 32) du[q] = su[q];
+        }
+        if (lane == 0) {
+            const int c = tv.cost[par] + L;
+            tv.parent[node] = par; tv.cost[node] = c; tv.edge_len[node] = L; tv.owner[node] = (uint8_t)seg;
+            if (in_goal) {                                                  // planner.py:260-281
+                atomicAdd(tv.n_goal, 1);
+                atomicMin(tv.best, ((unsigned long long)(unsigned)c << 32) | (unsigned)node);
+                mark_path(tv, node);
+            }
+        }
     }
-    const int old = *tv.size;
-    const int nsz = min(old + total, tv.limit);
-    *tv.size = nsz;
-    const unsigned long long b = *tv.best;
-    out->v[0] = nsz; out->v[1] = sampled; out->v[2] = nsz - old; out->v[3] = *tv.n_goal;
-    out->v[4] = b == ~0ull ? -1 : (int)(b & 0xffffffffu);
-    out->v[5] = b == ~0ull ? -1 : (int)(b >> 32);
-    out->v[6] = (old + total > tv.limit) ? 1 : 0;
-    out->v[7] = tries;
-    out->v[8] = ((const int*)records)[HDR_FLAGS];
-    out->v[9] = out->v[10] = out->v[11] = 0;
+    // ---- completion: the last CTA publishes
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(tv.done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        int total = 0, sampled = 0, tries = 0;
+        for (int s = 0; s < n_seg; s++) {
+            const int* h = (const int*)(records + (size_t)s * seg_bytes);
+            total += h[HDR_COUNT]; sampled += h[HDR_SAMPLED]; tries += h[HDR_TRIES];
+        }
+        const int nsz = min(old_size + total, tv.limit);
+        const unsigned long long b = *(volatile unsigned long long*)tv.best;
+        out->v[0] = nsz; out->v[1] = sampled; out->v[2] = nsz - old_size; out->v[3] = *(volatile int*)tv.n_goal;
+        out->v[4] = b == ~0ull ? -1 : (int)(b & 0xffffffffu);
+        out->v[5] = b == ~0ull ? -1 : (int)(b >> 32);
+        out->v[6] = (old_size + total > tv.limit) ? 1 : 0;
+        out->v[7] = tries;
+        out->v[8] = ((const int*)records)[HDR_FLAGS];
+        out->v[9] = out->v[10] = out->v[11] = 0;
+        *tv.done = 0;
+        __threadfence();
+        *tv.size = nsz;
+    }
 }
 
 }  // namespace lq

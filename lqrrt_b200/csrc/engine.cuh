@@ -162,7 +162,7 @@ __global__ void climb_kernel(TreeView<T> tv, int node, int* __restrict__ ids, in
 
 template <typename T>
 __global__ void tree_scalars_kernel(TreeView<T> tv, int size) {
-    *tv.size = size; *tv.n_ignored = 0; *tv.n_goal = 0; *tv.best = ~0ull;
+    *tv.size = size; *tv.n_ignored = 0; *tv.n_goal = 0; *tv.best = ~0ull; *tv.done = 0;
 }
 
 template <typename T> struct DevBuf {
@@ -357,7 +357,8 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(t_ignore.alloc(cap)); LQ_CUDA(t_owner.alloc(cap)); LQ_CUDA(t_scal.alloc(8)); LQ_CUDA(t_best.alloc(1));
         tv.state = t_state.p; tv.K = t_K.p; tv.parent = t_parent.p; tv.cost = t_cost.p; tv.edge_len = t_elen.p;
         tv.ignore = t_ignore.p; tv.owner = t_owner.p; tv.edge_x = t_ex.p; tv.edge_u = t_eu.p;
-        tv.size = t_scal.p; tv.n_ignored = t_scal.p + 1; tv.n_goal = t_scal.p + 2; tv.best = t_best.p; tv.cap = cap; tv.limit = c->node_capacity;
+        tv.size = t_scal.p; tv.n_ignored = t_scal.p + 1; tv.n_goal = t_scal.p + 2; tv.done = (unsigned*)(t_scal.p + 3);
+        tv.best = t_best.p; tv.cap = cap; tv.limit = c->node_capacity;
         LQ_CUDA(cudaMemset(t_scal.p, 0, 8 * sizeof(int)));
 
         // wave working set
@@ -561,7 +562,8 @@ struct EngineImpl : lq_engine {
     }
 
     // ---- K1 -------------------------------------------------------------------
-    int launch_nearest(const T* q, int qstride, int W, int use_ignore, int* idx, T* cost, cudaStream_t st) {
+    // idx == nullptr: leave the per-split partials for the consumer (steer_kernel) and report the split count
+    int launch_nearest(const T* q, int qstride, int W, int use_ignore, int* idx, T* cost, cudaStream_t st, int* nsplit_out = nullptr) {
         const int Nub = std::max(1, size_ub);
         const int max_splits = std::min(MAX_SPLIT, (Nub + NEAR_BLOCK - 1) / NEAR_BLOCK);
         const int target = 148 * 8;
@@ -619,8 +621,11 @@ struct EngineImpl : lq_engine {
             nsplit_used = nsplit;
         }
         launches++;
-        nearest_finalize_kernel<T><<<(W + 127) / 128, 128, 0, st>>>(w_pcost.p, w_pidx.p, Wc, nsplit_used, W, idx, cost);
-        launches++;
+        if (nsplit_out) *nsplit_out = nsplit_used;
+        if (idx) {
+            nearest_finalize_kernel<T><<<(W + 127) / 128, 128, 0, st>>>(w_pcost.p, w_pidx.p, Wc, nsplit_used, W, idx, cost);
+            launches++;
+        }
         LQ_CUDA(cudaGetLastError());
         return LQ_OK;
     }
@@ -642,15 +647,15 @@ struct EngineImpl : lq_engine {
     // Rollouts are latency bound with wildly different trip counts: small CTAs spread a wave over all
     // 148 SMs, larger ones only pay off once every SM already holds several.
     template <int LANES>
-    void launch_steer_l(const int* ids, const T* targets, int tstride, int W, T* xs, T* us, int* len, T* xnew, T* Knew,
-                        int ostride, cudaStream_t st) {
+    void launch_steer_l(const int* ids, NearPartials<T> np, const T* targets, int tstride, int W, T* xs, T* us, int* len,
+                        T* xnew, T* Knew, int ostride, cudaStream_t st) {
         const long long threads = (long long)W * LANES;
         if (threads >= 148LL * 8 * 128) {
             steer_kernel<T, Sys, Lqr, LANES, 128><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
-                md, t_state.p, t_K.p, cap, ids, targets, tstride, W, xs, us, len, xnew, Knew, ostride);
+                md, t_state.p, t_K.p, cap, ids, np, targets, tstride, W, xs, us, len, xnew, Knew, ostride);
         } else {
             steer_kernel<T, Sys, Lqr, LANES, 32><<<(unsigned)((threads + 31) / 32), 32, 0, st>>>(
-                md, t_state.p, t_K.p, cap, ids, targets, tstride, W, xs, us, len, xnew, Knew, ostride);
+                md, t_state.p, t_K.p, cap, ids, np, targets, tstride, W, xs, us, len, xnew, Knew, ostride);
         }
         launches++;
     }
@@ -666,11 +671,11 @@ struct EngineImpl : lq_engine {
         }
         launches++;
     }
-    void launch_steer(const int* ids, const T* targets, int tstride, int W, T* xs, T* us, int* len, T* xnew, T* Knew,
-                      int ostride, cudaStream_t st) {
-        if (steer_lanes >= 32) launch_steer_l<32>(ids, targets, tstride, W, xs, us, len, xnew, Knew, ostride, st);
-        else if (steer_lanes >= 8) launch_steer_l<8>(ids, targets, tstride, W, xs, us, len, xnew, Knew, ostride, st);
-        else launch_steer_l<1>(ids, targets, tstride, W, xs, us, len, xnew, Knew, ostride, st);
+    void launch_steer(const int* ids, NearPartials<T> np, const T* targets, int tstride, int W, T* xs, T* us, int* len,
+                      T* xnew, T* Knew, int ostride, cudaStream_t st) {
+        if (steer_lanes >= 32) launch_steer_l<32>(ids, np, targets, tstride, W, xs, us, len, xnew, Knew, ostride, st);
+        else if (steer_lanes >= 8) launch_steer_l<8>(ids, np, targets, tstride, W, xs, us, len, xnew, Knew, ostride, st);
+        else launch_steer_l<1>(ids, np, targets, tstride, W, xs, us, len, xnew, Knew, ostride, st);
     }
 
     int steer(const int* d_ids, const void* d_t, int W, void* d_x, void* d_u, int* d_len, cudaStream_t st) override {
@@ -680,7 +685,8 @@ struct EngineImpl : lq_engine {
         T* us = d_u ? (T*)d_u : w_us.p;
         if (d_x) LQ_CUDA(cudaMemsetAsync(xs, 0, (size_t)W * H * N * sizeof(T), st));
         if (d_u) LQ_CUDA(cudaMemsetAsync(us, 0, (size_t)W * H * M * sizeof(T), st));
-        launch_steer(d_ids, (const T*)d_t, W, W, xs, us, d_len ? d_len : w_len.p, nullptr, nullptr, 0, st);
+        launch_steer(d_ids, NearPartials<T>{nullptr, nullptr, 0, 0, nullptr}, (const T*)d_t, W, W, xs, us,
+                     d_len ? d_len : w_len.p, nullptr, nullptr, 0, st);
         LQ_CUDA(cudaGetLastError());
         return LQ_OK;
     }
@@ -689,14 +695,15 @@ struct EngineImpl : lq_engine {
     int expand_from_samples(int count, int use_ignore, int flags, cudaStream_t st) {
         const int slot = q_tail % RING;
         if (prof_on) cudaEventRecord(pev[slot][1], st);
-        if (int r = launch_nearest(w_samples.p, Wc, count, use_ignore, w_nidx.p, w_ncost.p, st)) return r;
+        int nsplit = 1;
+        if (int r = launch_nearest(w_samples.p, Wc, count, use_ignore, nullptr, nullptr, st, &nsplit)) return r;
         if (prof_on) cudaEventRecord(pev[slot][2], st);
-        launch_steer(w_nidx.p, w_samples.p, Wc, count, w_xs.p, w_us.p, w_len.p, w_xnew.p, w_Knew.p, Wc, st);
+        launch_steer(nullptr, NearPartials<T>{w_pcost.p, w_pidx.p, Wc, nsplit, w_nidx.p}, w_samples.p, Wc, count,
+                     w_xs.p, w_us.p, w_len.p, w_xnew.p, w_Knew.p, Wc, st);
         if (prof_on) cudaEventRecord(pev[slot][3], st);
         RecView<T> rv = rec_view<T>(w_rec.p, Wc, N, M, H);
-        pack_scan_kernel<1024><<<1, 1024, 0, st>>>(w_len.p, w_tries.p, count, w_slot.p, rv.header, flags); launches++;
-        pack_kernel<T><<<(count + 127) / 128, 128, 0, st>>>(w_len.p, w_slot.p, w_nidx.p, w_xnew.p, w_Knew.p, Wc, count,
-                                                           rv, w_src.p, Wc, N, M);
+        pack_kernel<T, 256><<<(count + 255) / 256, 256, 0, st>>>(w_len.p, w_tries.p, w_nidx.p, w_xnew.p, w_Knew.p, Wc, count,
+                                                                rv, w_src.p, Wc, N, M, flags);
         launches++;
         if (prof_on) { cudaEventRecord(pev[slot][4], st); prof_wave_open[slot] = true; prof_W[slot] = count; }
         LQ_CUDA(cudaGetLastError());
@@ -780,9 +787,8 @@ struct EngineImpl : lq_engine {
         if (prof_on) cudaEventRecord(pev[slot][5], st);
         commit_kernel<T><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(tv, rec, rec_sz, n_seg, my_seg, w_src.p,
                                                                                 w_xs.p, w_us.p, Wc, N, M, H,
-                                                                                w_goal.p, w_goal.p + LQ_MAX_N);
+                                                                                w_goal.p, w_goal.p + LQ_MAX_N, w_stats.p);
         launches++;
-        commit_finish_kernel<T><<<1, 1, 0, st>>>(tv, rec, rec_sz, n_seg, w_stats.p); launches++;
         if (prof_on) { cudaEventRecord(pev[slot][6], st); prof_commit_open[slot] = true; }
         LQ_CUDA(cudaGetLastError());
         LQ_CUDA(cudaMemcpyAsync(&h_stats[slot], w_stats.p, sizeof(DevStats), cudaMemcpyDeviceToHost, st));

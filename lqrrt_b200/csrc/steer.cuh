@@ -42,11 +42,17 @@ __device__ __forceinline__ bool group_all(bool ok) {
 //   xseq [j][H][N], useq [j][H][M]   recorded edge (sample-major)
 //   len  [j]                          kept length after the FPR cut
 //   xnew [N][ostride], Knew [M*N][ostride]   final state and K = lqr(xnew, u_last).K (planner.py:256-257)
+// The node to steer from is either given (ids) or, inside a wave, reduced here from K1's per-split partial
+// minima (pcost/pidx, ascending split order with a strict '<' so the lowest index wins ties, as
+// nearest_finalize_kernel does) and published in ids_out for the pack stage.
+template <typename T>
+struct NearPartials { const T* pcost; const int* pidx; int pstride; int nsplit; int* ids_out; };
+
 template <typename T, class Sys, class Lqr, int LANES, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 steer_kernel(Model<T, Sys, Lqr> md,
              const T* __restrict__ tstate, const T* __restrict__ tK, int cap,
-             const int* __restrict__ ids, const T* __restrict__ targets, int tstride, int W,
+             const int* __restrict__ ids, NearPartials<T> np, const T* __restrict__ targets, int tstride, int W,
              T* __restrict__ xseq, T* __restrict__ useq, int* __restrict__ len_out,
              T* __restrict__ xnew_out, T* __restrict__ Knew_out, int ostride) {
     constexpr int N = Sys::N, M = Sys::M;
@@ -54,7 +60,20 @@ steer_kernel(Model<T, Sys, Lqr> md,
     const int lane = threadIdx.x % LANES;
     if (gid >= W) return;                  // whole groups leave together (BLOCK % LANES == 0)
     const int j = gid;
-    const int id = ids[j];
+    int id;
+    if (np.pidx) {
+        T best = Num<T>::inf();
+        int b = -1;
+        for (int sp = 0; sp < np.nsplit; sp++) {
+            const T c = np.pcost[(size_t)sp * np.pstride + j];
+            const int i2 = np.pidx[(size_t)sp * np.pstride + j];
+            if (i2 >= 0 && (b < 0 || c < best)) { best = c; b = i2; }
+        }
+        id = b < 0 ? 0 : b;
+        if (lane == 0) np.ids_out[j] = id;
+    } else {
+        id = ids[j];
+    }
 
     T x[N], xt[N], K[M * N];
 #pragma unroll
