@@ -216,7 +216,8 @@ def run_gpu_arm(args):
     prob = make_problem(args.config)
     wave_max = args.wave * world if args.scaling == 'weak' else args.wave
     planner = prob.make_planner(dtype=args.dtype, wave=None, wave_max=wave_max, max_nodes=prob.max_nodes,
-                                min_time=1e9, max_time=1e9, comm=comm, device=local)
+                                min_time=1e9, max_time=1e9, comm=comm, device=local,
+                                exchange=os.environ.get('LQRRT_EXCHANGE', 'peer'))
 
     def one_plan(seed):
         planner.seed = seed
@@ -329,7 +330,8 @@ def main():
     ap.add_argument('--config', default='c4')
     ap.add_argument('--dtype', default='f32', choices=['f32', 'f64'])
     ap.add_argument('--wave', type=int, default=8192, help="largest wave per GPU")
-    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
+    ap.add_argument('--scaling', default='strong', choices=['weak', 'strong'],
+                    help="strong: same global wave schedule for every N (bit-identical tree); weak: 8192 samples per GPU per wave")
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()

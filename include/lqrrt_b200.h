@@ -161,6 +161,13 @@ int lq_wave_records(lq_engine* h, void** d_records, uint64_t* bytes);
  * the engine's own buffer (single GPU).  `my_segment` is the index of this engine's own segment (its
  * rank): the edges of those nodes are stored here, every node remembers its owner segment. */
 int lq_wave_commit(lq_engine* h, const void* d_records, int n_segments, int my_segment, void* stream);
+/* Fused pack + exchange over NVLink.  d_peer_bufs[p] is rank p's receive buffer mapped into this process
+ * (peer-mapped symmetric memory, e.g. torch.distributed._symmetric_memory), all of `bytes` >=
+ * 2*world*segment + 2*world*4 bytes and zero-initialised.  After this call lq_wave_expand stores its
+ * records directly into every peer's buffer and raises an arrival flag, and
+ * lq_wave_commit(h, NULL, world, rank, stream) waits for all flags of the wave inside the kernel -- no
+ * collective call per wave.  world <= 1 turns it off. */
+int lq_wave_set_peers(lq_engine* h, int world, int rank, void* const* d_peer_bufs, uint64_t bytes);
 /* Blocks until the last commit finished and returns its counters. */
 int lq_wave_stats_get(lq_engine* h, lq_wave_stats* out);
 

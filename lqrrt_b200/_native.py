@@ -71,6 +71,7 @@ SYMBOLS = {
     'lq_wave_expand_candidates': (C.c_int, [_P, C.c_int, C.c_int, _D, C.c_int, C.c_int, C.POINTER(C.c_int), _P]),
     'lq_wave_records': (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64)]),
     'lq_wave_commit': (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
+    'lq_wave_set_peers': (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), C.c_uint64]),
     'lq_wave_stats_get': (C.c_int, [_P, C.POINTER(lq_wave_stats)]),
     'lq_closest': (C.c_int, [_P, _D, _U8, C.POINTER(C.c_int), _P]),
     'lq_steer_force': (C.c_int, [_P, C.c_int, _D, C.c_int, _D, _D, C.POINTER(C.c_int), _P]),
@@ -291,6 +292,10 @@ class Engine(object):
     def wave_commit(self, d_records=None, n_segments=1, stream=None, my_segment=0):
         self._ck(self.lib.lq_wave_commit(self.h, _P(d_records) if d_records else None, int(n_segments),
                                          int(my_segment), self._stream(stream)))
+
+    def set_peers(self, world, rank, ptrs, nbytes):
+        arr = (_P * max(1, len(ptrs)))(*[_P(int(p)) for p in ptrs])
+        self._ck(self.lib.lq_wave_set_peers(self.h, int(world), int(rank), arr, C.c_uint64(int(nbytes))))
 
     def wave_stats(self):
         st = lq_wave_stats()

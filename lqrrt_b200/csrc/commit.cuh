@@ -58,11 +58,25 @@ __host__ __device__ inline RecView<T> rec_view(void* base, int Wc, int N, int M,
 // first counts the accepted samples that precede its own range (the length array is a few KB, L2
 // resident), then scans its range and copies its records; the last CTA's running total is the segment's
 // record count.  Deterministic (no atomics): slot = number of accepted samples with a lower index.
+// Multi-GPU, fused exchange: instead of packing into a local segment that an NCCL all-gather then copies,
+// the pack kernel stores every record straight into segment `rank` of EVERY peer's receive buffer over
+// NVLink (peer-mapped symmetric memory), and the last CTA publishes the header and raises this rank's
+// arrival flag on every peer.  The commit kernel of each GPU waits for all G flags of the wave.  One
+// kernel does pack + exchange; the collective's launch and rendezvous latency leaves the wave.
+constexpr int MAX_PEERS = 16;
+struct PeerDst {
+    char* seg[MAX_PEERS];          // peer p's receive segment for this rank, current parity
+    unsigned* flag[MAX_PEERS];     // peer p's arrival flag for this rank, current parity
+    int n;                         // 0: single destination `rv` (local segment), no flags
+    unsigned seq;                  // wave sequence number written to the flags
+    unsigned* done;                // local CTA-completion counter
+};
+
 template <typename T, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 pack_kernel(const int* __restrict__ len, const int* __restrict__ tries_used, const int* __restrict__ ids,
             const T* __restrict__ xnew, const T* __restrict__ Knew, int ostride, int count,
-            RecView<T> rv, int* __restrict__ sample_of_slot, int Wc, int N, int M, int flags) {
+            RecView<T> rv, int* __restrict__ sample_of_slot, int Wc, int N, int M, int H, int flags, PeerDst pd) {
     __shared__ int wsum[BLOCK / 32];
     __shared__ int wtri[BLOCK / 32];
     __shared__ int s_before, s_tries;
@@ -99,16 +113,61 @@ pack_kernel(const int* __restrict__ len, const int* __restrict__ tries_used, con
     int woff = 0, total = 0;
     for (int w = 0; w < BLOCK / 32; w++) { if (w < warp) woff += wsum[w]; total += wsum[w]; }
     const int slot = s_before + woff + incl - mine;
+    if (pd.n == 0) {
+        if (mine) {
+            for (int d = 0; d < N; d++) rv.state[(size_t)d * Wc + slot] = xnew[(size_t)d * ostride + j];
+            for (int k = 0; k < M * N; k++) rv.K[(size_t)k * Wc + slot] = Knew[(size_t)k * ostride + j];
+            rv.parent[slot] = ids[j]; rv.len[slot] = len[j];
+            sample_of_slot[slot] = j;
+        }
+        if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+            rv.header[HDR_COUNT] = s_before + total; rv.header[HDR_SAMPLED] = count;
+            rv.header[HDR_TRIES] = s_tries; rv.header[HDR_FLAGS] = flags;
+        }
+        return;
+    }
+    // ---- peer mode
     if (mine) {
-        for (int d = 0; d < N; d++) rv.state[(size_t)d * Wc + slot] = xnew[(size_t)d * ostride + j];
-        for (int k = 0; k < M * N; k++) rv.K[(size_t)k * Wc + slot] = Knew[(size_t)k * ostride + j];
-        rv.parent[slot] = ids[j]; rv.len[slot] = len[j];
+        T st[LQ_MAX_N];
+        for (int d = 0; d < N; d++) st[d] = xnew[(size_t)d * ostride + j];
+        const int par = ids[j], L = len[j];
         sample_of_slot[slot] = j;
+        for (int p = 0; p < pd.n; p++) {
+            const RecView<T> pv = rec_view<T>(pd.seg[p], Wc, N, M, H);
+            for (int d = 0; d < N; d++) pv.state[(size_t)d * Wc + slot] = st[d];
+            for (int k = 0; k < M * N; k++) pv.K[(size_t)k * Wc + slot] = Knew[(size_t)k * ostride + j];
+            pv.parent[slot] = par; pv.len[slot] = L;
+        }
     }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
-        rv.header[HDR_COUNT] = s_before + total; rv.header[HDR_SAMPLED] = count;
-        rv.header[HDR_TRIES] = s_tries; rv.header[HDR_FLAGS] = flags;
+    __shared__ bool last;
+    // the grid's last CTA knows the totals; it parks them for whichever CTA finishes last
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { pd.done[1] = (unsigned)(s_before + total); pd.done[2] = (unsigned)s_tries; }
+    __threadfence_system();                          // my stores are visible system-wide before I count myself done
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(pd.done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence_system();
+        const int cnt = (int)((volatile unsigned*)pd.done)[1], tr = (int)((volatile unsigned*)pd.done)[2];
+        for (int p = 0; p < pd.n; p++) {
+            int* h = (int*)pd.seg[p];
+            h[HDR_COUNT] = cnt; h[HDR_SAMPLED] = count; h[HDR_TRIES] = tr; h[HDR_FLAGS] = flags;
+        }
+        __threadfence_system();
+        for (int p = 0; p < pd.n; p++) *(volatile unsigned*)pd.flag[p] = pd.seq;     // arrival, after the data
+        *pd.done = 0;
     }
+}
+
+// A rank whose slice of the wave is empty still has to announce itself to its peers.
+static __global__ void pack_empty_peer_kernel(PeerDst pd, int flags) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int p = 0; p < pd.n; p++) {
+        int* h = (int*)pd.seg[p];
+        h[HDR_COUNT] = 0; h[HDR_SAMPLED] = 0; h[HDR_TRIES] = 0; h[HDR_FLAGS] = flags;
+    }
+    __threadfence_system();
+    for (int p = 0; p < pd.n; p++) *(volatile unsigned*)pd.flag[p] = pd.seq;
 }
 
 template <typename T> struct TreeView {
@@ -154,7 +213,15 @@ __global__ void commit_kernel(TreeView<T> tv, const char* __restrict__ records, 
                               const T* __restrict__ xseq, const T* __restrict__ useq,
                               int Wc, int N, int M, int H,
                               const T* __restrict__ goal_lo, const T* __restrict__ goal_hi,
-                              DevStats* __restrict__ out) {
+                              DevStats* __restrict__ out, const unsigned* __restrict__ arrive, unsigned seq) {
+    if (arrive) {                        // fused exchange: wait until every peer's records of this wave landed
+        if (threadIdx.x < n_seg) {
+            const volatile unsigned* f = arrive + threadIdx.x;
+            while (*f < seq) __nanosleep(64);
+        }
+        __syncthreads();
+        __threadfence_system();
+    }
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int seg = w / Wc, k = w % Wc;

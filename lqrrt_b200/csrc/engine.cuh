@@ -50,6 +50,7 @@ struct lq_engine {
     virtual int eval_erf(int count, const double* xg, const double* x, double* e) = 0;
     virtual int eval_feasible(int count, const double* x, const double* u, uint8_t* ok) = 0;
     virtual int set_tuning(int steer_lanes, int nearest_q) = 0;
+    virtual int set_peers(int world, int rank, void* const* bufs, uint64_t bytes) = 0;
     virtual int set_profiling(int on) = 0;
     virtual int profile_read(double* ms, double* work, int reset) = 0;
 };
@@ -162,7 +163,7 @@ __global__ void climb_kernel(TreeView<T> tv, int node, int* __restrict__ ids, in
 
 template <typename T>
 __global__ void tree_scalars_kernel(TreeView<T> tv, int size) {
-    *tv.size = size; *tv.n_ignored = 0; *tv.n_goal = 0; *tv.best = ~0ull; *tv.done = 0;
+    *tv.size = size; *tv.n_ignored = 0; *tv.n_goal = 0; *tv.best = ~0ull; *tv.done = 0; tv.done[1] = 0; tv.done[2] = 0; tv.done[3] = 0;
 }
 
 template <typename T> struct DevBuf {
@@ -201,6 +202,11 @@ struct EngineImpl : lq_engine {
     DevBuf<int> t_parent, t_cost, t_elen, t_scal;
     DevBuf<uint8_t> t_ignore, t_owner;
     int last_my_seg = 0;             // segment index this GPU committed as (its rank)
+    // fused exchange over peer-mapped symmetric memory (lq_wave_set_peers); layout of every rank's buffer:
+    // [2 parities][world segments][rec_sz] then [2][world] arrival flags
+    int peer_world = 0, peer_rank = 0;
+    char* peer_buf[MAX_PEERS] = {};
+    unsigned peer_seq = 0;           // waves expanded in peer mode (flags carry it; monotonic for the engine's life)
     DevBuf<unsigned long long> t_best;
     TreeView<T> tv;
     // obstacle tables and their broad-phase grids
@@ -702,12 +708,39 @@ struct EngineImpl : lq_engine {
                      w_xs.p, w_us.p, w_len.p, w_xnew.p, w_Knew.p, Wc, st);
         if (prof_on) cudaEventRecord(pev[slot][3], st);
         RecView<T> rv = rec_view<T>(w_rec.p, Wc, N, M, H);
+        PeerDst pd = next_peer_dst();
         pack_kernel<T, 256><<<(count + 255) / 256, 256, 0, st>>>(w_len.p, w_tries.p, w_nidx.p, w_xnew.p, w_Knew.p, Wc, count,
-                                                                rv, w_src.p, Wc, N, M, flags);
+                                                                rv, w_src.p, Wc, N, M, H, flags, pd);
         launches++;
         if (prof_on) { cudaEventRecord(pev[slot][4], st); prof_wave_open[slot] = true; prof_W[slot] = count; }
         LQ_CUDA(cudaGetLastError());
         last_stream = st;
+        return LQ_OK;
+    }
+
+    size_t peer_flags_offset() const { return (size_t)2 * peer_world * rec_sz; }
+    // destinations of this wave's pack (advances the wave sequence number)
+    PeerDst next_peer_dst() {
+        PeerDst pd;
+        memset(&pd, 0, sizeof pd);
+        if (peer_world <= 1) return pd;
+        peer_seq++;
+        const int par = peer_seq & 1;
+        pd.n = peer_world; pd.seq = peer_seq; pd.done = tv.done + 1;
+        for (int p = 0; p < peer_world; p++) {
+            pd.seg[p] = peer_buf[p] + ((size_t)par * peer_world + peer_rank) * rec_sz;
+            pd.flag[p] = (unsigned*)(peer_buf[p] + peer_flags_offset()) + par * peer_world + peer_rank;
+        }
+        return pd;
+    }
+    int set_peers(int world, int rank, void* const* bufs, uint64_t bytes) override {
+        if (world < 0 || world > MAX_PEERS || (world > 0 && (rank < 0 || rank >= world))) LQ_FAIL(LQ_ERR_ARG, "bad world/rank");
+        if (world > 1) {
+            const uint64_t need = (uint64_t)2 * world * rec_sz + (uint64_t)2 * world * sizeof(unsigned);
+            if (!bufs || bytes < need) LQ_FAIL(LQ_ERR_ARG, "peer buffers must hold %llu bytes", (unsigned long long)need);
+            for (int p = 0; p < world; p++) { if (!bufs[p]) LQ_FAIL(LQ_ERR_ARG, "null peer buffer"); peer_buf[p] = (char*)bufs[p]; }
+        }
+        peer_world = world > 1 ? world : 0; peer_rank = rank; peer_seq = 0;
         return LQ_OK;
     }
 
@@ -717,6 +750,12 @@ struct EngineImpl : lq_engine {
         if (count < 0 || count > Wc) LQ_FAIL(LQ_ERR_ARG, "count=%d outside 0..wave_capacity=%d", count, Wc);
         if (!have_goal) LQ_FAIL(LQ_ERR_STATE, "lq_set_goal has not been called");
         if (q_tail - q_head >= (unsigned)RING) LQ_FAIL(LQ_ERR_STATE, "%d committed waves are unread: call lq_wave_stats_get", RING);
+        if (count == 0 && peer_world > 1) {
+            pack_empty_peer_kernel<<<1, 32, 0, st>>>(next_peer_dst(), flags); launches++;
+            LQ_CUDA(cudaGetLastError());
+            last_stream = st;
+            return LQ_OK;
+        }
         if (count == 0) {
             RecView<T> rv = rec_view<T>(w_rec.p, Wc, N, M, H);
             int hdr[REC_HEADER_INTS] = {0};
@@ -781,13 +820,20 @@ struct EngineImpl : lq_engine {
         if (my_seg < 0 || my_seg >= n_seg) LQ_FAIL(LQ_ERR_ARG, "my_segment must be in 0..n_segments-1");
         last_my_seg = my_seg;
         const char* rec = d_records ? (const char*)d_records : w_rec.p;
+        const unsigned* arrive = nullptr;
+        if (!d_records && peer_world > 1) {             // fused exchange: my own receive buffer, current parity
+            if (n_seg != peer_world || my_seg != peer_rank) LQ_FAIL(LQ_ERR_ARG, "peer mode commits world segments as rank");
+            const int par = peer_seq & 1;
+            rec = peer_buf[peer_rank] + (size_t)par * peer_world * rec_sz;
+            arrive = (const unsigned*)(peer_buf[peer_rank] + peer_flags_offset()) + par * peer_world;
+        }
         if (q_tail - q_head >= (unsigned)RING) LQ_FAIL(LQ_ERR_STATE, "%d committed waves are unread: call lq_wave_stats_get", RING);
         const int slot = q_tail % RING;
         const long long warps = (long long)n_seg * Wc;
         if (prof_on) cudaEventRecord(pev[slot][5], st);
         commit_kernel<T><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(tv, rec, rec_sz, n_seg, my_seg, w_src.p,
                                                                                 w_xs.p, w_us.p, Wc, N, M, H,
-                                                                                w_goal.p, w_goal.p + LQ_MAX_N, w_stats.p);
+                                                                                w_goal.p, w_goal.p + LQ_MAX_N, w_stats.p, arrive, peer_seq);
         launches++;
         if (prof_on) { cudaEventRecord(pev[slot][6], st); prof_commit_open[slot] = true; }
         LQ_CUDA(cudaGetLastError());

@@ -18,6 +18,8 @@ New keyword arguments (all optional, defaults keep reference call sites valid):
   seed      Philox key
   device    CUDA ordinal (default: torch's current device)
   pipeline  enqueue wave k+1 before reading wave k's counters (device sampler only; default on)
+  exchange  'peer' = fused pack + exchange by NVLink peer stores into symmetric memory (default),
+            'nccl' = one all_gather_into_tensor per wave
   comm      torch.distributed process group (or True for WORLD): the wave is
             sharded over the ranks and accepted nodes are all-gathered so every
             rank's tree stays identical
@@ -47,8 +49,11 @@ class Planner(object):
                  min_time=0.5, max_time=1, max_nodes=1E5,
                  goal0=None, sys_time=time.time, printing=True,
                  wave=None, wave_max=8192, dtype='f32', rng='philox', seed=0, device=None, comm=None,
-                 wave_growth=1.0, pipeline=True):
+                 wave_growth=1.0, pipeline=True, exchange='peer'):
         self._engine = None
+        if exchange not in ('peer', 'nccl'):
+            raise ValueError("exchange must be 'peer' or 'nccl'")
+        self.exchange_mode = exchange
         self.pipeline = bool(pipeline)
         self._engine_key = None
         self._exchange = None
@@ -246,11 +251,13 @@ class Planner(object):
             else:
                 xs = np.array([np.array(xrand_gen(self), dtype=np.float64) for _ in range(count)]).reshape(count, self.nstates)
                 eng.wave_expand(self.seed, wave_ctr, first, count, xs, pruning, stop_request, stream)
-            if exchange is not None:
+            if exchange is None:
+                eng.wave_commit(None, 1, stream)
+            elif isinstance(exchange, _waves.PeerExchange):
+                eng.wave_commit(None, self.world, stream, my_segment=self.rank)     # records arrived by peer stores
+            else:
                 recv = exchange.gather(self._send_view(eng))
                 eng.wave_commit(recv.data_ptr(), self.world, stream, my_segment=self.rank)
-            else:
-                eng.wave_commit(None, 1, stream)
 
         while True:
             while inflight <= depth and not stopping:
@@ -358,7 +365,12 @@ class Planner(object):
         if self._exchange is None:
             import torch
             _, nbytes = eng.wave_records()
-            self._exchange = _waves.Exchange(self.comm, nbytes, torch.device('cuda', eng.device))
+            dev = torch.device('cuda', eng.device)
+            if self.exchange_mode == 'peer':
+                self._exchange = _waves.PeerExchange(self.comm, nbytes, dev, eng)
+            else:
+                eng.set_peers(0, 0, [], 0)
+                self._exchange = _waves.Exchange(self.comm, nbytes, dev)
         return self._exchange
 
     def _send_view(self, eng):

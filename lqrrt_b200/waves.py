@@ -64,4 +64,26 @@ class Exchange(object):
         return self.recv
 
 
+class PeerExchange(object):
+    """Fused exchange: every rank's receive buffer lives in peer-mapped symmetric memory; the engine's pack
+    kernel stores records straight into all peers' buffers over NVLink and its commit kernel waits on
+    arrival flags (csrc/commit.cuh).  No collective call per wave; this class only allocates and maps."""
+
+    def __init__(self, group, segment_bytes, device, engine):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.nbytes = 2 * self.world * int(segment_bytes) + 2 * self.world * 4
+        self.nbytes = (self.nbytes + 255) & ~255
+        self.buf = symm.empty(self.nbytes, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                                   # every rank's flags are zero before anyone stores
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        engine.set_peers(self.world, self.rank, self.ptrs, self.nbytes)
+
+
 STOP_NONE, STOP_DONE, STOP_KILL = 0, 1, 2
