@@ -83,7 +83,9 @@ typedef struct lq_config {
     uint32_t angle_mask;           /* erf: bit i set => dim i wraps (demo_boat_novice.py:106-118) */
     int32_t n_prims;
     const lq_feas_prim* prims;
-    int32_t horizon_iters;         /* planner.py:549 */
+    int32_t horizon_iters;         /* planner.py:549; with an adaptive horizon: hspan_hi, the longest edge */
+    int32_t hfactor;               /* planner.py:538-551: 0 = fixed horizon, 2 = adaptive-horizon heuristic */
+    int32_t hspan_lo, hspan_hi;    /* planner.py:546: clip range of horizon_iters in steps */
     double dt;                     /* planner.py:527 */
     double FPR;                    /* planner.py:530; int(FPR*len) is evaluated in float64 on the device */
     double error_tol[LQ_MAX_N];    /* planner.py:532-536 (inf allowed) */
@@ -102,7 +104,8 @@ typedef struct lq_wave_stats {
     int32_t full;                  /* 1 if node_capacity truncated this wave */
     int32_t tries_used;            /* sum over samples of sampler tries */
     int32_t flags;                 /* `flags` rank 0 passed to its lq_wave_expand (host stop protocol) */
-    int32_t reserved[3];
+    int32_t horizon_iters;         /* planner-level horizon after this wave's votes (adaptive horizon, planner.py:421-424) */
+    int32_t reserved[2];
 } lq_wave_stats;
 
 typedef struct lq_engine lq_engine;
@@ -116,6 +119,10 @@ const char* lq_last_error(const lq_engine* h);
 /* ---- problem state ------------------------------------------------------ */
 /* Planner.set_goal, planner.py:468-487: goal and goal region (goal +- buffer, open box). */
 int lq_set_goal(lq_engine* h, const double* h_goal, const double* h_buffer);
+/* Adaptive horizon only (planner.py:418-425): the planner-level horizon_iters the next wave starts from.
+ * Every rollout of a wave starts from this value; its doublings/halving are applied in sample order at
+ * commit (wave = 1 is the reference's sequential behaviour) and reported back in lq_wave_stats. */
+int lq_set_horizon(lq_engine* h, int horizon_iters, void* stream);
 /* default sampler setup, planner.py:178-198: box, goal bias, tries limit. */
 int lq_set_sampling(lq_engine* h, const double* h_lo, const double* h_hi, const double* h_goal_bias, int tries);
 /* Tree.__init__, tree.py:50-73 + planner.py:172-173: new tree seeded at x0, K0 = lqr(x0, 0); clears ignores/best plan. */

@@ -38,7 +38,8 @@ class lq_config(C.Structure):
                 ('n_sys_params', C.c_int32), ('n_lqr_params', C.c_int32),
                 ('sys_params', C.POINTER(C.c_double)), ('lqr_params', C.POINTER(C.c_double)),
                 ('angle_mask', C.c_uint32), ('n_prims', C.c_int32), ('prims', C.POINTER(lq_feas_prim)),
-                ('horizon_iters', C.c_int32), ('dt', C.c_double), ('FPR', C.c_double),
+                ('horizon_iters', C.c_int32), ('hfactor', C.c_int32), ('hspan_lo', C.c_int32), ('hspan_hi', C.c_int32),
+                ('dt', C.c_double), ('FPR', C.c_double),
                 ('error_tol', C.c_double * LQ_MAX_N),
                 ('node_capacity', C.c_int32), ('wave_capacity', C.c_int32), ('tries_capacity', C.c_int32)]
 
@@ -46,8 +47,8 @@ class lq_config(C.Structure):
 class lq_wave_stats(C.Structure):
     _fields_ = [('tree_size', C.c_int32), ('n_sampled', C.c_int32), ('n_accepted', C.c_int32),
                 ('n_goal', C.c_int32), ('best_node', C.c_int32), ('best_cost', C.c_int32),
-                ('full', C.c_int32), ('tries_used', C.c_int32), ('flags', C.c_int32),
-                ('reserved', C.c_int32 * 3)]
+                ('full', C.c_int32), ('tries_used', C.c_int32), ('flags', C.c_int32), ('horizon_iters', C.c_int32),
+                ('reserved', C.c_int32 * 2)]
 
 
 # every symbol include/lqrrt_b200.h declares: (restype, argtypes)
@@ -61,6 +62,7 @@ SYMBOLS = {
     'lq_destroy': (C.c_int, [_P]),
     'lq_last_error': (C.c_char_p, [_P]),
     'lq_set_goal': (C.c_int, [_P, _D, _D]),
+    'lq_set_horizon': (C.c_int, [_P, C.c_int, _P]),
     'lq_set_sampling': (C.c_int, [_P, _D, _D, _D, C.c_int]),
     'lq_reset': (C.c_int, [_P, _D, _P]),
     'lq_load_nodes': (C.c_int, [_P, C.c_int, _D, _I, _I, _P]),
@@ -134,7 +136,7 @@ class Engine(object):
     working set.  Methods map 1:1 onto the C ABI."""
 
     def __init__(self, system, horizon_iters, dt, FPR, error_tol, node_capacity, wave_capacity,
-                 dtype='f32', device=0, tries_capacity=16):
+                 dtype='f32', device=0, tries_capacity=16, hfactor=0, hspan=None):
         self.lib = load_library()
         self.system = system
         self.n = system.nstates; self.m = system.ncontrols
@@ -181,6 +183,8 @@ class Engine(object):
                 arr[i].lo = _dp(lo); arr[i].hi = _dp(hi)
         cfg.n_prims = len(prims); cfg.prims = arr
         cfg.horizon_iters = self.H
+        cfg.hfactor = int(hfactor)
+        cfg.hspan_lo, cfg.hspan_hi = (int(hspan[0]), int(hspan[1])) if hfactor else (self.H, self.H)
         cfg.dt = float(dt); cfg.FPR = float(FPR)
         tol = np.abs(np.asarray(error_tol, dtype=np.float64)) * np.ones(self.n)
         for i in range(self.n):
@@ -229,6 +233,9 @@ class Engine(object):
         g = _c64(goal); b = _c64(buffer)
         self.h2d_bytes += 2 * LQ_MAX_N * self.elt
         self._ck(self.lib.lq_set_goal(self.h, _dp(g), _dp(b)))
+
+    def set_horizon(self, horizon_iters, stream=None):
+        self._ck(self.lib.lq_set_horizon(self.h, int(horizon_iters), self._stream(stream)))
 
     def set_sampling(self, sample_space, goal_bias, tries):
         ss = _c64(sample_space, (self.n, 2))

@@ -48,6 +48,7 @@ const char* lq_last_error(const lq_engine* h) { return h ? h->err.c_str() : g_cr
 #define LQ_TRY(expr) try { return (expr); } catch (const std::exception& ex) { h->err = ex.what(); return LQ_ERR_STATE; }
 
 int lq_set_goal(lq_engine* h, const double* g, const double* b) { LQ_H(h); if (!g || !b) return LQ_ERR_ARG; LQ_TRY(h->set_goal(g, b)) }
+int lq_set_horizon(lq_engine* h, int hz, void* st) { LQ_H(h); LQ_TRY(h->set_horizon(hz, (cudaStream_t)st)) }
 int lq_set_sampling(lq_engine* h, const double* lo, const double* hi, const double* bias, int tries) {
     LQ_H(h); if (!lo || !hi || !bias) return LQ_ERR_ARG; LQ_TRY(h->set_sampling(lo, hi, bias, tries)) }
 int lq_reset(lq_engine* h, const double* x0, void* st) { LQ_H(h); if (!x0) return LQ_ERR_ARG; LQ_TRY(h->reset(x0, (cudaStream_t)st)) }

@@ -27,6 +27,7 @@ template <typename T> struct RecView {
     T* K;          // [M*N][Wc]
     int* parent;   // [Wc]
     int* len;      // [Wc]
+    uint8_t* votes;   // [Wc] per SAMPLE of the segment's slice (not per record): adaptive-horizon votes
 };
 
 __host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
@@ -37,6 +38,7 @@ __host__ __device__ inline size_t rec_bytes(int Wc, int N, int M, int H) {
     b += align16(sizeof(T) * (size_t)N * Wc);
     b += align16(sizeof(T) * (size_t)M * N * Wc);
     b += align16(sizeof(int) * (size_t)Wc) * 2;
+    b += align16((size_t)Wc);
     (void)H;
     return b;
 }
@@ -49,7 +51,8 @@ __host__ __device__ inline RecView<T> rec_view(void* base, int Wc, int N, int M,
     v.state = (T*)p; p += align16(sizeof(T) * (size_t)N * Wc);
     v.K = (T*)p; p += align16(sizeof(T) * (size_t)M * N * Wc);
     v.parent = (int*)p; p += align16(sizeof(int) * (size_t)Wc);
-    v.len = (int*)p;
+    v.len = (int*)p; p += align16(sizeof(int) * (size_t)Wc);
+    v.votes = (uint8_t*)p;
     (void)H;
     return v;
 }
@@ -76,7 +79,8 @@ template <typename T, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 pack_kernel(const int* __restrict__ len, const int* __restrict__ tries_used, const int* __restrict__ ids,
             const T* __restrict__ xnew, const T* __restrict__ Knew, int ostride, int count,
-            RecView<T> rv, int* __restrict__ sample_of_slot, int Wc, int N, int M, int H, int flags, PeerDst pd) {
+            RecView<T> rv, int* __restrict__ sample_of_slot, int Wc, int N, int M, int H, int flags, PeerDst pd,
+            const uint8_t* __restrict__ votes) {
     __shared__ int wsum[BLOCK / 32];
     __shared__ int wtri[BLOCK / 32];
     __shared__ int s_before, s_tries;
@@ -113,6 +117,10 @@ pack_kernel(const int* __restrict__ len, const int* __restrict__ tries_used, con
     int woff = 0, total = 0;
     for (int w = 0; w < BLOCK / 32; w++) { if (w < warp) woff += wsum[w]; total += wsum[w]; }
     const int slot = s_before + woff + incl - mine;
+    if (votes && j < count) {
+        if (pd.n == 0) rv.votes[j] = votes[j];
+        else for (int p = 0; p < pd.n; p++) rec_view<T>(pd.seg[p], Wc, N, M, H).votes[j] = votes[j];
+    }
     if (pd.n == 0) {
         if (mine) {
             for (int d = 0; d < N; d++) rv.state[(size_t)d * Wc + slot] = xnew[(size_t)d * ostride + j];
@@ -213,7 +221,8 @@ __global__ void commit_kernel(TreeView<T> tv, const char* __restrict__ records, 
                               const T* __restrict__ xseq, const T* __restrict__ useq,
                               int Wc, int N, int M, int H,
                               const T* __restrict__ goal_lo, const T* __restrict__ goal_hi,
-                              DevStats* __restrict__ out, const unsigned* __restrict__ arrive, unsigned seq) {
+                              DevStats* __restrict__ out, const unsigned* __restrict__ arrive, unsigned seq,
+                              int* __restrict__ horizon, int hfactor, int hlo, int hhi) {
     if (arrive) {                        // fused exchange: wait until every peer's records of this wave landed
         if (threadIdx.x < n_seg) {
             const volatile unsigned* f = arrive + threadIdx.x;
@@ -285,7 +294,18 @@ __global__ void commit_kernel(TreeView<T> tv, const char* __restrict__ records, 
         out->v[6] = (old_size + total > tv.limit) ? 1 : 0;
         out->v[7] = tries;
         out->v[8] = ((const int*)records)[HDR_FLAGS];
-        out->v[9] = out->v[10] = out->v[11] = 0;
+        int hz = 0;
+        if (hfactor) {                 // planner.py:421-424: the wave's votes, in global sample order
+            hz = *horizon;
+            for (int s = 0; s < n_seg; s++) {
+                const RecView<T> rv = rec_view<T>((void*)(records + (size_t)s * seg_bytes), Wc, N, M, H);
+                const int ns = rv.header[HDR_SAMPLED];
+                for (int q = 0; q < ns; q++) hz = horizon_apply(hz, rv.votes[q], hfactor, hlo, hhi);
+            }
+            *horizon = hz;
+        }
+        out->v[9] = hz;
+        out->v[10] = out->v[11] = 0;
         *tv.done = 0;
         __threadfence();
         *tv.size = nsz;

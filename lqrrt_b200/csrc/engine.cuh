@@ -24,6 +24,7 @@ struct lq_engine {
     int device = 0;
     virtual ~lq_engine() {}
     virtual int set_goal(const double* goal, const double* buf) = 0;
+    virtual int set_horizon(int horizon_iters, cudaStream_t st) = 0;
     virtual int set_sampling(const double* lo, const double* hi, const double* bias, int tries) = 0;
     virtual int reset(const double* x0, cudaStream_t st) = 0;
     virtual int load_nodes(int count, const double* state, const int* parent, const int* cost, cudaStream_t st) = 0;
@@ -217,7 +218,8 @@ struct EngineImpl : lq_engine {
     // wave working set
     DevBuf<T> w_samples, w_ncost, w_pcost, w_Sp, w_xs, w_us, w_xnew, w_Knew, w_cand, w_goal;
     DevBuf<int> w_nidx, w_pidx, w_len, w_slot, w_tries, w_pick, w_src, w_misc;
-    DevBuf<uint8_t> w_candok;
+    DevBuf<uint8_t> w_candok, w_votes;
+    DevBuf<int> w_hor;
     DevBuf<char> w_rec;
     DevBuf<DevStats> w_stats;
     size_t rec_sz = 0;
@@ -270,6 +272,12 @@ struct EngineImpl : lq_engine {
         md.H = H = c->horizon_iters;
         md.dt = (T)c->dt;
         md.FPR = c->FPR;
+        md.hfactor = c->hfactor; md.hlo = c->hspan_lo; md.hhi = c->hspan_hi;
+        if (c->hfactor) {
+            if (c->hfactor < 2 || c->hspan_lo < 1 || c->hspan_hi < c->hspan_lo || c->hspan_hi > c->horizon_iters)
+                LQ_FAIL(LQ_ERR_ARG, "adaptive horizon needs hfactor >= 2 and 1 <= hspan_lo <= hspan_hi <= horizon_iters");
+            if (c->hspan_hi > 127) LQ_FAIL(LQ_ERR_ARG, "adaptive horizon supports at most 127 steps");
+        }
         for (int i = 0; i < N; i++) {
             md.tol[i] = (T)c->error_tol[i];
             md.goal_lo[i] = -Num<T>::inf(); md.goal_hi[i] = Num<T>::inf();
@@ -373,7 +381,10 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(w_xs.alloc((size_t)Wc * H * N)); LQ_CUDA(w_us.alloc((size_t)Wc * H * M));
         LQ_CUDA(w_len.alloc(Wc)); LQ_CUDA(w_slot.alloc(Wc)); LQ_CUDA(w_tries.alloc(Wc)); LQ_CUDA(w_pick.alloc(Wc)); LQ_CUDA(w_src.alloc(Wc));
         LQ_CUDA(w_xnew.alloc((size_t)N * Wc)); LQ_CUDA(w_Knew.alloc((size_t)M * N * Wc));
-        LQ_CUDA(w_misc.alloc(8)); LQ_CUDA(w_stats.alloc(1)); LQ_CUDA(w_goal.alloc(2 * LQ_MAX_N));
+        LQ_CUDA(w_misc.alloc(8)); LQ_CUDA(w_stats.alloc(1)); LQ_CUDA(w_votes.alloc(Wc)); LQ_CUDA(w_hor.alloc(1));
+        { const int h0 = c->hfactor ? c->hspan_lo : c->horizon_iters; LQ_CUDA(cudaMemcpy(w_hor.p, &h0, sizeof(int), cudaMemcpyHostToDevice)); }
+        md.horizon = w_hor.p;
+        LQ_CUDA(cudaMemset(w_votes.p, 0, Wc)); LQ_CUDA(w_goal.alloc(2 * LQ_MAX_N));
         rec_sz = rec_bytes<T>(Wc, N, M, H);
         LQ_CUDA(w_rec.alloc(rec_sz));
         LQ_CUDA(cudaMemset(w_rec.p, 0, rec_sz));
@@ -509,6 +520,15 @@ struct EngineImpl : lq_engine {
         }
         LQ_CUDA(cudaMemcpy(w_goal.p, g.data(), g.size() * sizeof(T), cudaMemcpyHostToDevice));
         have_goal = true;
+        return LQ_OK;
+    }
+
+    int set_horizon(int horizon_iters, cudaStream_t st) override {
+        LQ_CUDA(cudaSetDevice(device));
+        if (!md.hfactor) LQ_FAIL(LQ_ERR_STATE, "the engine was built with a fixed horizon");
+        if (horizon_iters < md.hlo || horizon_iters > md.hhi) LQ_FAIL(LQ_ERR_ARG, "horizon_iters %d outside [%d, %d]", horizon_iters, md.hlo, md.hhi);
+        LQ_CUDA(cudaMemcpyAsync(w_hor.p, &horizon_iters, sizeof(int), cudaMemcpyHostToDevice, st));
+        LQ_CUDA(cudaStreamSynchronize(st));
         return LQ_OK;
     }
 
@@ -656,12 +676,13 @@ struct EngineImpl : lq_engine {
     void launch_steer_l(const int* ids, NearPartials<T> np, const T* targets, int tstride, int W, T* xs, T* us, int* len,
                         T* xnew, T* Knew, int ostride, cudaStream_t st) {
         const long long threads = (long long)W * LANES;
+        uint8_t* votes = md.hfactor ? w_votes.p : nullptr;
         if (threads >= 148LL * 8 * 128) {
             steer_kernel<T, Sys, Lqr, LANES, 128><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
-                md, t_state.p, t_K.p, cap, ids, np, targets, tstride, W, xs, us, len, xnew, Knew, ostride);
+                md, t_state.p, t_K.p, cap, ids, np, targets, tstride, W, xs, us, len, xnew, Knew, ostride, votes);
         } else {
             steer_kernel<T, Sys, Lqr, LANES, 32><<<(unsigned)((threads + 31) / 32), 32, 0, st>>>(
-                md, t_state.p, t_K.p, cap, ids, np, targets, tstride, W, xs, us, len, xnew, Knew, ostride);
+                md, t_state.p, t_K.p, cap, ids, np, targets, tstride, W, xs, us, len, xnew, Knew, ostride, votes);
         }
         launches++;
     }
@@ -710,7 +731,8 @@ struct EngineImpl : lq_engine {
         RecView<T> rv = rec_view<T>(w_rec.p, Wc, N, M, H);
         PeerDst pd = next_peer_dst();
         pack_kernel<T, 256><<<(count + 255) / 256, 256, 0, st>>>(w_len.p, w_tries.p, w_nidx.p, w_xnew.p, w_Knew.p, Wc, count,
-                                                                rv, w_src.p, Wc, N, M, H, flags, pd);
+                                                                rv, w_src.p, Wc, N, M, H, flags, pd,
+                                                                md.hfactor ? w_votes.p : nullptr);
         launches++;
         if (prof_on) { cudaEventRecord(pev[slot][4], st); prof_wave_open[slot] = true; prof_W[slot] = count; }
         LQ_CUDA(cudaGetLastError());
@@ -833,7 +855,8 @@ struct EngineImpl : lq_engine {
         if (prof_on) cudaEventRecord(pev[slot][5], st);
         commit_kernel<T><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(tv, rec, rec_sz, n_seg, my_seg, w_src.p,
                                                                                 w_xs.p, w_us.p, Wc, N, M, H,
-                                                                                w_goal.p, w_goal.p + LQ_MAX_N, w_stats.p, arrive, peer_seq);
+                                                                                w_goal.p, w_goal.p + LQ_MAX_N, w_stats.p, arrive, peer_seq,
+                                                                                w_hor.p, md.hfactor, md.hlo, md.hhi);
         launches++;
         if (prof_on) { cudaEventRecord(pev[slot][6], st); prof_commit_open[slot] = true; }
         LQ_CUDA(cudaGetLastError());

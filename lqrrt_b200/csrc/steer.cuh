@@ -26,7 +26,28 @@ template <typename T, class Sys, class Lqr> struct Model {
     T tol[LQ_MAX_N];             // error_tol (planner.py:532-536)
     T goal_lo[LQ_MAX_N], goal_hi[LQ_MAX_N];   // goal region, open box (planner.py:442-447, 482-486)
     double FPR;                  // int(FPR * len) is evaluated in float64 as Python does (planner.py:394-395)
+    // adaptive-horizon heuristic (planner.py:418-425, 538-547); hfactor == 0: fixed horizon H
+    int hfactor, hlo, hhi;
+    const int* horizon;          // device scalar: planner-level horizon_iters as of wave start
 };
+
+// int(np.clip(h / f, lo, hi)) and int(np.clip(f * h, lo, hi)) of planner.py:421,424 (float64, truncation)
+__host__ __device__ inline int horizon_shrink(int h, int f, int lo, int hi) {
+    double v = (double)h / (double)f;
+    v = v < lo ? lo : (v > hi ? hi : v);
+    return (int)v;
+}
+__host__ __device__ inline int horizon_grow(int h, int f, int lo, int hi) {
+    long long v = (long long)f * h;
+    v = v < lo ? lo : (v > hi ? hi : v);
+    return (int)v;
+}
+// a rollout's effect on the planner-level horizon: low 7 bits = number of doublings, bit 7 = halved
+__host__ __device__ inline int horizon_apply(int h, unsigned vote, int f, int lo, int hi) {
+    for (unsigned k = 0; k < (vote & 0x7fu); k++) h = horizon_grow(h, f, lo, hi);
+    if (vote & 0x80u) h = horizon_shrink(h, f, lo, hi);
+    return h;
+}
 
 template <typename T, class Sys, class Lqr>
 __device__ __forceinline__ int fpr_keep(const Model<T, Sys, Lqr>& md, int len) { return (int)(md.FPR * (double)len); }
@@ -54,7 +75,7 @@ steer_kernel(Model<T, Sys, Lqr> md,
              const T* __restrict__ tstate, const T* __restrict__ tK, int cap,
              const int* __restrict__ ids, NearPartials<T> np, const T* __restrict__ targets, int tstride, int W,
              T* __restrict__ xseq, T* __restrict__ useq, int* __restrict__ len_out,
-             T* __restrict__ xnew_out, T* __restrict__ Knew_out, int ostride) {
+             T* __restrict__ xnew_out, T* __restrict__ Knew_out, int ostride, uint8_t* __restrict__ votes) {
     constexpr int N = Sys::N, M = Sys::M;
     const int gid = (blockIdx.x * BLOCK + threadIdx.x) / LANES;
     const int lane = threadIdx.x % LANES;
@@ -88,6 +109,13 @@ steer_kernel(Model<T, Sys, Lqr> md,
     if (HD >= 0) { sincos_t(x[HD < 0 ? 0 : HD], &sh, &ch); sincos_t(xt[HD < 0 ? 0 : HD], &sg, &cg); }
 
     int len = 0, nrec = 0, i = 0;
+    // every rollout of a wave starts from the same planner-level horizon (frozen at wave start)
+    const bool adaptive = md.hfactor != 0;
+    int hor = adaptive ? *md.horizon : md.H;
+    unsigned vote = 0;
+    T last_emag[N];
+#pragma unroll
+    for (int d = 0; d < N; d++) last_emag[d] = Num<T>::inf();
     T* xrow = xseq + (size_t)j * md.H * N;      // never NULL: the engine supplies scratch
     T* urow = useq + (size_t)j * md.H * M;
 
@@ -110,7 +138,16 @@ steer_kernel(Model<T, Sys, Lqr> md,
         bool conv = true;
 #pragma unroll
         for (int d = 0; d < N; d++) conv = conv && (abs_t(e[d]) <= md.tol[d]);
-        if (i > md.H || conv) { len = nrec; break; }             // planner.py:428-429
+        if (adaptive) {                                          // planner.py:418-425
+            bool stalled = true;
+#pragma unroll
+            for (int d = 0; d < N; d++) stalled = stalled && (abs_t(e[d]) >= last_emag[d]);
+            if (stalled) { len = 0; vote |= 0x80u; break; }      // no error shrank: drop the edge, halve the horizon
+            if (i == hor) { hor = horizon_grow(hor, md.hfactor, md.hlo, md.hhi); vote += 1; }
+#pragma unroll
+            for (int d = 0; d < N; d++) last_emag[d] = abs_t(e[d]);
+        }
+        if (i > hor || conv) { len = nrec; break; }              // planner.py:428-429
 #pragma unroll
         for (int d = 0; d < N; d++) x[d] = xn[d];
         sh = sn; ch = cn;
@@ -126,6 +163,7 @@ steer_kernel(Model<T, Sys, Lqr> md,
 
     if (lane == 0) {
         len_out[j] = len;
+        if (votes) votes[j] = (uint8_t)vote;
         if (xnew_out && len > 0) {
             // The node is the last KEPT state and its gain is lqr(xnew, u_seq[-1]).K (planner.py:256-257).
             // Without an FPR cut, x / K already hold exactly that; after a cut (len < nrec) the

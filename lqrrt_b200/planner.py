@@ -105,20 +105,22 @@ class Planner(object):
         """(Re)build the device engine when anything baked into it changed; `dt` and friends are plain
         attributes in the reference (lqrrt_node.py:259 assigns planner.dt directly), so compare by value."""
         from ._native import Engine
-        if self.hfactor:
-            raise NotImplementedError("adaptive horizon (horizon=(min, max), planner.py:418-425) is not "
-                                      "available on the GPU path yet; pass a scalar horizon")
         # constraints.set_feasibility_function may have swapped the spec since set_system
         self._system = _models.bundle_of(self.dynamics, self.lqr, self.erf, self.constraints.is_feasible)
         tol = np.abs(np.asarray(self.error_tol, dtype=np.float64)) * np.ones(self.nstates)
-        key = (id(self._system), int(self.horizon_iters), float(self.dt), float(self.FPR), tuple(tol.tolist()),
+        # with the adaptive heuristic horizon_iters is run-time state (planner.py:421,424) and the longest edge
+        # is hspan[1]; with a fixed horizon it is baked in
+        H = int(self.hspan[1]) if self.hfactor else int(self.horizon_iters)
+        key = (id(self._system), H, int(self.hfactor), int(self.hspan[0]), int(self.hspan[1]), float(self.dt),
+               float(self.FPR), tuple(tol.tolist()),
                int(self.max_nodes) + 1, self._wave_capacity(), self.dtype, self._device())
         if self._engine is None or key != self._engine_key:
             if self._engine is not None:
                 self._engine.close()
-            self._engine = Engine(self._system, self.horizon_iters, self.dt, self.FPR, tol,
+            self._engine = Engine(self._system, H, self.dt, self.FPR, tol,
                                   node_capacity=int(self.max_nodes) + 1, wave_capacity=self._wave_capacity(),
-                                  dtype=self.dtype, device=self._device())
+                                  dtype=self.dtype, device=self._device(), hfactor=int(self.hfactor),
+                                  hspan=(int(self.hspan[0]), int(self.hspan[1])))
             self._engine_key = key
             self._exchange = None
             tune = os.environ.get('LQRRT_TUNING')          # "steer_lanes[,sampler_lanes[,nearest_q]]" for experiments
@@ -196,6 +198,10 @@ class Planner(object):
             spans = np.diff(sample_space).flatten()
             bias_arr = np.asarray(goal_bias, dtype=np.float64)
 
+        if self.hfactor:
+            # planner-level state carried across steers and plans (planner.py:421,424,545)
+            eng.set_horizon(int(np.clip(self.horizon_iters, self.hspan[0], self.hspan[1])), stream)
+
         # ---- new tree (planner.py:172-173)
         eng.reset(x0, stream)
         self.tree = Tree(eng, x0, self._system, comm=self.comm, rank=self.rank, world=self.world)
@@ -271,6 +277,8 @@ class Planner(object):
             samples_total += st.n_sampled
             known_size = st.tree_size
             self.tree._set_size(st.tree_size)
+            if self.hfactor:
+                self.horizon_iters = int(st.horizon_iters)
 
             # planner.py:260-283: a strictly faster plan replaces the current one
             if st.best_node >= 0 and st.best_node != best_node:

@@ -33,7 +33,14 @@ class WaveOracle(object):
         self.feas_batch = make_is_feasible_batch(system.is_feasible)
         self.angle_dims = tuple(system.erf.angle_dims)
         self.dt = dt; self.FPR = FPR
-        self.H = int(horizon / dt)
+        if hasattr(horizon, '__contains__'):          # adaptive-horizon heuristic, planner.py:538-547
+            self.hspan = np.divide(horizon, dt).astype(np.int64)
+            self.hfactor = 2
+            self.horizon_iters = 1
+            self.H = int(self.hspan[1])
+        else:
+            self.H = int(horizon / dt)
+            self.hspan = (self.H, self.H); self.hfactor = 0; self.horizon_iters = self.H
         self.error_tol = np.abs(error_tol).astype(np.float64) * np.ones(self.n)
         self.goal = np.array(goal, dtype=np.float64)
         gb = np.abs(goal_buffer).astype(np.float64)
@@ -119,10 +126,16 @@ class WaveOracle(object):
             best[j] = c[ids[j]]
         return ids, best
 
-    # -- 3. steer (planner.py:354-438, fixed horizon) -------------------------
-    def steer(self, ID, xtar):
+    # -- 3. steer (planner.py:354-438) ----------------------------------------
+    def steer(self, ID, xtar, votes=None):
+        """Every rollout of a wave starts from the planner-level horizon as of wave start; with the adaptive
+        heuristic (planner.py:418-425) its doublings / halving are returned through `votes` as
+        (n_doublings, halved) and applied in sample order by commit."""
         K = np.copy(self.K[ID]); x = np.copy(self.state[ID])
         xs = []; us = []; i = 0
+        hor = self.horizon_iters
+        last_emag = np.inf
+        doubles = 0; halved = False
         while True:
             e = self.erf(np.copy(xtar), np.copy(x))
             u = K.dot(e)
@@ -132,11 +145,28 @@ class WaveOracle(object):
                 xs = xs[:keep]; us = us[:keep]
                 break
             i += 1
-            if i > self.H or np.all(np.abs(e) <= self.error_tol):
+            emag = np.abs(e)
+            if self.hfactor:
+                if np.all(emag >= last_emag):
+                    xs = []; us = []; halved = True
+                    break
+                if i == hor:
+                    hor = int(np.clip(self.hfactor * hor, self.hspan[0], self.hspan[1])); doubles += 1
+                last_emag = emag
+            if i > hor or np.all(emag <= self.error_tol):
                 break
             xs.append(x); us.append(u)
             K = np.array(self.lqr(x, u)[1], dtype=np.float64)
+        if votes is not None:
+            votes.append((doubles, halved))
         return xs, us
+
+    def apply_votes(self, votes):
+        for doubles, halved in votes:
+            for _ in range(doubles):
+                self.horizon_iters = int(np.clip(self.hfactor * self.horizon_iters, self.hspan[0], self.hspan[1]))
+            if halved:
+                self.horizon_iters = int(np.clip(self.horizon_iters / self.hfactor, self.hspan[0], self.hspan[1]))
 
     def in_goal(self, x):
         return bool(np.all((self.goal_lo < x) & (x < self.goal_hi)))
@@ -171,8 +201,12 @@ class WaveOracle(object):
 
     def expand_wave(self, X, use_ignore=True):
         ids, _ = self.nearest(X, use_ignore)
-        edges = [self.steer(int(i), x) for i, x in zip(ids, X)]
-        return self.commit(ids, edges), ids, edges
+        votes = []
+        edges = [self.steer(int(i), x, votes) for i, x in zip(ids, X)]
+        added = self.commit(ids, edges)
+        if self.hfactor:
+            self.apply_votes(votes)
+        return added, ids, edges
 
     def climb(self, ID):
         path = []

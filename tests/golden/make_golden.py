@@ -84,5 +84,31 @@ def main():
         print(name, 'size', tree.size, 'T', planner.T, 'steer lens', sl.tolist()[:10], '->', os.path.getsize(path), 'bytes')
 
 
+def adaptive():
+    """Adaptive-horizon heuristic (planner.py:418-425): boat_novice with horizon=(0.1, 3) as the ROS
+    behaviours use it (behaviors/params.py:31), two consecutive plans so the carried-over horizon_iters matters."""
+    ref = ref_shim.import_reference()
+    ns = ref_shim.load_demo_model('demo_boat_novice', 0)
+    cons = ref.Constraints(nstates=6, ncontrols=3, goal_buffer=ns['goal_buffer'], is_feasible=ns['is_feasible'])
+    clock = ref_shim.FrameClock()
+    planner = ref.Planner(ns['dynamics'], ns['lqr'], cons, horizon=(0.1, 3), dt=0.1, FPR=0.5, error_tol=ns['error_tol'],
+                          erf=ns['erf'], min_time=300, max_time=300, max_nodes=1E5, goal0=ns['goal'], sys_time=clock,
+                          printing=False)
+    out = {}
+    for k in range(2):
+        clock.t = -1
+        planner.update_plan(ns['x0'], ns['sample_space'], goal_bias=ns['goal_bias'], xrand_gen=10)
+        out['state%d' % k] = planner.tree.state
+        out['pID%d' % k] = np.array(planner.tree.pID)
+        out['edge_len%d' % k] = np.array([len(e) for e in planner.tree.x_seq])
+        out['horizon_iters%d' % k] = planner.horizon_iters
+        out['T%d' % k] = planner.T
+    path = os.path.join(HERE, 'adaptive_boat_novice.npz')
+    np.savez_compressed(path, **out)
+    print('adaptive', [out['state%d' % k].shape for k in range(2)], [int(out['horizon_iters%d' % k]) for k in range(2)],
+          'max edge', [int(out['edge_len%d' % k].max()) for k in range(2)])
+
+
 if __name__ == '__main__':
     main()
+    adaptive()

@@ -162,3 +162,53 @@ def test_riccati_provider_plans_pendulum(cuda_device):
     assert planner.tree.size > 50
     xs = np.array(planner.x_seq)
     assert np.all(np.abs(np.diff(xs[:, 0])) < 0.2)
+
+
+def test_adaptive_horizon_wave1_reproduces_reference(cuda_device):
+    """The adaptive-horizon heuristic (planner.py:418-425) through the engine, two consecutive plans with
+    the carried-over horizon_iters, against the unmodified reference's trees."""
+    g = load_golden('adaptive_boat_novice')
+    prob = problem('demo_boat_novice')
+    planner = prob.make_planner(dtype='f64', wave=1, rng='numpy', horizon=(0.1, 3), min_time=300, max_time=300,
+                                sys_time=WaveClock())
+    assert planner.hfactor == 2 and planner.horizon_iters == 1
+    np.random.seed(0)
+    np.random.rand(setup_draws('demo_boat_novice'))
+    for k in range(2):
+        planner.sys_time.t = -1
+        planner.update_plan(prob.x0, prob.sample_space, goal_bias=prob.goal_bias, xrand_gen=10)
+        tree = planner.tree
+        assert tree.size == len(g['state%d' % k])
+        assert tree.pID == g['pID%d' % k].tolist()
+        assert [len(e) for e in tree.x_seq] == g['edge_len%d' % k].tolist()
+        assert np.abs(tree.state - g['state%d' % k]).max() <= 1e-9
+        assert planner.horizon_iters == int(g['horizon_iters%d' % k])
+        assert planner.T == pytest.approx(float(g['T%d' % k]), abs=1e-12)
+
+
+def test_adaptive_horizon_waves_match_oracle(cuda_device):
+    """W = 48: every rollout starts from the wave-start horizon, votes applied in sample order at commit."""
+    from gpu_util import make_engine, tree_arrays
+    from lqrrt_b200._native import Engine
+    from oracle.wave import WaveOracle
+    prob = problem('demo_boat_novice')
+    eng = Engine(prob.system, 30, 0.1, 0.5, prob.error_tol, node_capacity=4096, wave_capacity=48, dtype='f64',
+                 device=0, hfactor=2, hspan=(1, 30))
+    eng.set_goal(prob.goal, prob.goal_buffer)
+    eng.set_sampling(prob.sample_space, prob.goal_bias, 10)
+    eng.set_horizon(1)
+    eng.reset(prob.x0)
+    orc = WaveOracle(prob.system, prob.goal, prob.goal_buffer, (0.1, 3), 0.1, 0.5, prob.error_tol)
+    orc.reset(prob.x0)
+    hist = []
+    for w in range(8):
+        eng.wave_expand(3, w, 0, 48, None, True); eng.wave_commit(None, 1)
+        st = eng.wave_stats()
+        X, _ = orc.sample_wave(3, w, 0, 48, prob.sample_space, prob.goal_bias, 10)
+        orc.expand_wave(X)
+        assert (st.tree_size, st.horizon_iters) == (orc.size, orc.horizon_iters), w
+        hist.append(st.horizon_iters)
+    t = tree_arrays(eng)
+    assert t['parent'].tolist() == orc.parent and np.abs(t['state'] - orc.state).max() <= 1e-9
+    assert t['edge_len'][1:].tolist() == [len(e) for e in orc.x_seq[1:]]
+    assert max(hist) == 30 and max(t['edge_len']) > 20

@@ -77,3 +77,25 @@ def test_hot_path_functions(name):
             assert np.array_equal(np.array(xs), g['hot_steer_x'][j, :L])
             assert np.array_equal(np.array(us), g['hot_steer_u'][j, :L])
     assert g['hot_steer_len'].max() > 0
+
+
+def test_adaptive_horizon_two_plans_bit_exact():
+    """planner.py:418-425, 538-547: horizon=(0.1, 3) as the ROS behaviours use it; horizon_iters is carried
+    from the first plan into the second."""
+    g = load_golden('adaptive_boat_novice')
+    prob = problem('demo_boat_novice')
+    dyn, lqr, erf, feas = om.make_callbacks(prob.system, prob.dt)
+    clock = IterationClock()
+    sp = SeqPlanner(dyn, lqr, 6, 3, prob.goal_buffer, feas, (0.1, 3), 0.1, 0.5, prob.error_tol, erf,
+                    min_time=300, max_time=300, goal0=prob.goal, sys_time=clock)
+    np.random.seed(0)
+    np.random.rand(setup_draws('demo_boat_novice'))
+    for k in range(2):
+        clock.t = -1
+        sp.update_plan(prob.x0, prob.sample_space, goal_bias=prob.goal_bias, xrand_gen=10)
+        assert np.array_equal(sp.tree.state, g['state%d' % k])
+        assert sp.tree.pID == g['pID%d' % k].tolist()
+        assert [len(e) for e in sp.tree.x_seq] == g['edge_len%d' % k].tolist()
+        assert sp.horizon_iters == int(g['horizon_iters%d' % k])
+        assert sp.T == float(g['T%d' % k])
+    assert g['edge_len0'].max() > 20          # edges longer than the fixed-horizon demos' 20 steps occur

@@ -70,3 +70,23 @@ def test_partition_and_wave_size():
             assert max(c for _, c in parts) <= waves.local_capacity(W, G)
     assert waves.wave_size(1) == 32 and waves.wave_size(500) == 500 and waves.wave_size(10 ** 6) == 8192
     assert waves.wave_size(10 ** 6, fixed=1) == 1
+
+
+def test_wave1_equals_sequential_with_adaptive_horizon():
+    prob = problem('demo_boat_novice')
+    K = 250
+    dyn, lqr, erf, feas = om.make_callbacks(prob.system, prob.dt)
+    sp = SeqPlanner(dyn, lqr, 6, 3, prob.goal_buffer, feas, (0.1, 3), 0.1, 0.5, prob.error_tol, erf,
+                    min_time=K, max_time=K, goal0=prob.goal, sys_time=IterationClock())
+    trace = []
+    np.random.seed(9)
+    sp.update_plan(prob.x0, prob.sample_space, goal_bias=prob.goal_bias, xrand_gen=10, trace=trace)
+    orc = WaveOracle(prob.system, prob.goal, prob.goal_buffer, (0.1, 3), 0.1, 0.5, prob.error_tol)
+    orc.reset(prob.x0)
+    seen = set()
+    for xrand, near, L in trace:
+        added, ids, edges = orc.expand_wave(xrand[None, :])
+        assert int(ids[0]) == near and len(edges[0][0]) == L
+        seen.add(orc.horizon_iters)
+    assert orc.horizon_iters == sp.horizon_iters and max(seen) == 30      # one rollout can double 1 -> 30
+    assert np.array_equal(orc.state, sp.tree.state) and orc.parent == sp.tree.pID
