@@ -433,7 +433,7 @@ struct EngineImpl : lq_engine {
         for (int pi = 0; pi < md.feas.n_prims; pi++) obs_work += md.feas.prims[pi].n_obs;
         // sub-warp groups of 8 measured best on C4 (profiles/README.md): they split hull vertices / obstacle
         // lists and cut the divergence of thread-per-sample rollouts; without obstacle tables one lane is enough
-        steer_lanes = sample_lanes = obs_work > 0 ? 8 : 1;
+        steer_lanes = sample_lanes = (obs_work > 0 || Lqr::COOP) ? 8 : 1;
         return LQ_OK;
     }
 
@@ -630,7 +630,13 @@ struct EngineImpl : lq_engine {
         } else {
             if (qstride != Wc) LQ_FAIL(LQ_ERR_STATE, "dense-metric search needs queries in the engine's wave layout");
             if (!Lqr::CONST_METRIC) {
-                metric_kernel<T, Sys, Lqr><<<(W + 63) / 64, 64, 0, st>>>(md.sys, md.lqr, md.dt, q, qstride, W, w_Sp.p);
+                if (Lqr::COOP) {
+                    constexpr int ML = 8;
+                    metric_coop_kernel<T, Sys, Lqr, ML><<<(unsigned)(((long long)W * ML + 31) / 32), 32,
+                                                          (32 / ML) * Lqr::COOP_SCALARS * sizeof(T), st>>>(md, q, qstride, W, w_Sp.p);
+                } else {
+                    metric_kernel<T, Sys, Lqr><<<(W + 63) / 64, 64, 0, st>>>(md.sys, md.lqr, md.dt, q, qstride, W, w_Sp.p);
+                }
                 launches++;
             }
             int nqb, chunk, nsplit;
@@ -677,11 +683,13 @@ struct EngineImpl : lq_engine {
                         T* xnew, T* Knew, int ostride, cudaStream_t st) {
         const long long threads = (long long)W * LANES;
         uint8_t* votes = md.hfactor ? w_votes.p : nullptr;
-        if (threads >= 148LL * 8 * 128) {
+        // cooperative providers keep their matrices in a per-group slice of shared memory: one warp per CTA
+        const size_t coop32 = (size_t)(32 / LANES) * Lqr::COOP_SCALARS * sizeof(T);
+        if (threads >= 148LL * 8 * 128 && !(Lqr::COOP && LANES > 1)) {
             steer_kernel<T, Sys, Lqr, LANES, 128><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
                 md, t_state.p, t_K.p, cap, ids, np, targets, tstride, W, xs, us, len, xnew, Knew, ostride, votes);
         } else {
-            steer_kernel<T, Sys, Lqr, LANES, 32><<<(unsigned)((threads + 31) / 32), 32, 0, st>>>(
+            steer_kernel<T, Sys, Lqr, LANES, 32><<<(unsigned)((threads + 31) / 32), 32, LANES > 1 ? coop32 : 0, st>>>(
                 md, t_state.p, t_K.p, cap, ids, np, targets, tstride, W, xs, us, len, xnew, Knew, ostride, votes);
         }
         launches++;

@@ -249,6 +249,8 @@ template <typename T, class Sys> struct PdRotatedLqr {
     static constexpr int N = Sys::N, M = Sys::M;
     static constexpr int KIND = LQ_LQR_PD_ROTATED;
     static constexpr bool CONST_METRIC = true;
+    static constexpr bool COOP = false;
+    static constexpr int COOP_SCALARS = 0;
     T kp[M * M], kd[M * M], S[N * N];
     __host__ int unpack(const double* p, int count) {
         if (count != 2 * M * M + N * N) return -1;
@@ -295,6 +297,8 @@ template <typename T, class Sys> struct ConstantLqr {
     static constexpr int N = Sys::N, M = Sys::M;
     static constexpr int KIND = LQ_LQR_CONSTANT;
     static constexpr bool CONST_METRIC = true;
+    static constexpr bool COOP = false;
+    static constexpr int COOP_SCALARS = 0;
     T S[N * N], K0[M * N];
     __host__ int unpack(const double* p, int count) {
         if (count != N * N + M * N) return -1;
@@ -322,6 +326,12 @@ template <typename T, class Sys> struct FdRiccatiLqr {
     static constexpr int N = Sys::N, M = Sys::M;
     static constexpr int KIND = LQ_LQR_FD_RICCATI;
     static constexpr bool CONST_METRIC = false;
+    // Cooperative form: the L lanes that share one sample keep the matrices of the sweep in a slice of
+    // shared memory and split every product by output element; finite-difference columns are split the
+    // same way.  Each output is accumulated in ascending k exactly as in solve(), so both forms agree.
+    static constexpr bool COOP = true;
+    // A, B, P, BtP, G, Rhs/K, AmBK, AtP
+    static constexpr int COOP_SCALARS = N * N + N * M + N * N + M * N + M * M + M * N + N * N + N * N;
     T Q[N * N], R[M * M];
     T eps;
     int steps;
@@ -437,6 +447,148 @@ template <typename T, class Sys> struct FdRiccatiLqr {
                 }
         }
     }
+    // All `lanes` threads of the group call this with identical (x, u); on return sm holds P (offset
+    // P_OFF) and K (offset K_OFF).  sync() must order shared-memory accesses within the group.
+    static constexpr int A_OFF = 0, B_OFF = A_OFF + N * N, P_OFF = B_OFF + N * M, BTP_OFF = P_OFF + N * N,
+                         G_OFF = BTP_OFF + M * N, K_OFF = G_OFF + M * M, AMBK_OFF = K_OFF + M * N,
+                         ATP_OFF = AMBK_OFF + N * N;
+    template <class Sync>
+    __device__ void solve_coop(const Sys& sys, T dt, const T* x, const T* u, T* sm, int lane, int lanes, Sync sync) const {
+        T* A = sm + A_OFF; T* Bm = sm + B_OFF; T* P = sm + P_OFF; T* BtP = sm + BTP_OFF;
+        T* G = sm + G_OFF; T* K = sm + K_OFF; T* AmBK = sm + AMBK_OFF; T* AtP = sm + ATP_OFF;
+        const T inv2e = T(1) / (T(2) * eps);
+        sync();                                        // previous users of the slice are done
+        for (int j = lane; j < N + M; j += lanes) {    // finite-difference columns of [A | B]
+            T xp[N], xm[N], up[M], um[M], fp[N], fm[N];
+#pragma unroll
+            for (int i = 0; i < N; i++) { xp[i] = x[i]; xm[i] = x[i]; }
+#pragma unroll
+            for (int i = 0; i < M; i++) { up[i] = u[i]; um[i] = u[i]; }
+#pragma unroll
+            for (int i = 0; i < N; i++) if (i == j) { xp[i] += eps; xm[i] -= eps; }
+#pragma unroll
+            for (int i = 0; i < M; i++) if (N + i == j) { up[i] += eps; um[i] -= eps; }
+            sys.step(xp, up, dt, fp);
+            sys.step(xm, um, dt, fm);
+            if (j < N) {
+#pragma unroll
+                for (int i = 0; i < N; i++) A[i * N + j] = (fp[i] - fm[i]) * inv2e;
+            } else {
+#pragma unroll
+                for (int i = 0; i < N; i++) Bm[i * M + (j - N)] = (fp[i] - fm[i]) * inv2e;
+            }
+        }
+        for (int e = lane; e < N * N; e += lanes) P[e] = Q[e];
+        sync();
+        for (int it = 0; it < steps; it++) {
+            for (int e = lane; e < M * N + N * N; e += lanes) {
+                if (e < M * N) {                       // BtP = B' P
+                    const int i = e / N, j = e % N;
+                    T a = T(0);
+                    for (int k = 0; k < N; k++) a += Bm[k * M + i] * P[k * N + j];
+                    BtP[e] = a;
+                } else {                               // AtP = A' P
+                    const int q = e - M * N, i = q / N, j = q % N;
+                    T a = T(0);
+                    for (int k = 0; k < N; k++) a += A[k * N + i] * P[k * N + j];
+                    AtP[q] = a;
+                }
+            }
+            sync();
+            for (int e = lane; e < M * M + M * N; e += lanes) {
+                if (e < M * M) {                       // G = R + B'P B
+                    const int i = e / M, j = e % M;
+                    T a = R[e];
+                    for (int k = 0; k < N; k++) a += BtP[i * N + k] * Bm[k * M + j];
+                    G[e] = a;
+                } else {                               // Rhs = B'P A (stored where K will be)
+                    const int q = e - M * M, i = q / N, j = q % N;
+                    T a = T(0);
+                    for (int k = 0; k < N; k++) a += BtP[i * N + k] * A[k * N + j];
+                    K[q] = a;
+                }
+            }
+            sync();
+            {   // K = G^-1 Rhs: every lane factors its own copy of the M x M system (identical pivots) and
+                // carries the right-hand-side columns it owns through it.  Fully unrolled with predicated
+                // row swaps so Gl / mult / rhs stay in registers (no dynamically indexed local arrays).
+                T Gl[M * M], mult[M * M];
+                int perm[M];
+#pragma unroll
+                for (int e = 0; e < M * M; e++) { Gl[e] = G[e]; mult[e] = T(0); }
+#pragma unroll
+                for (int col = 0; col < M; col++) {
+                    int piv = col;
+                    T big = abs_t(Gl[col * M + col]);
+#pragma unroll
+                    for (int r = col + 1; r < M; r++) {
+                        const T v = abs_t(Gl[r * M + col]);
+                        if (v > big) { big = v; piv = r; }
+                    }
+                    perm[col] = piv;
+#pragma unroll
+                    for (int r = col + 1; r < M; r++) {
+                        if (r == piv) {
+#pragma unroll
+                            for (int j = 0; j < M; j++) { const T t = Gl[col * M + j]; Gl[col * M + j] = Gl[r * M + j]; Gl[r * M + j] = t; }
+                        }
+                    }
+                    const T inv = T(1) / Gl[col * M + col];
+#pragma unroll
+                    for (int r = col + 1; r < M; r++) {
+                        const T f = Gl[r * M + col] * inv;
+                        mult[r * M + col] = f;
+#pragma unroll
+                        for (int j = col; j < M; j++) Gl[r * M + j] -= f * Gl[col * M + j];
+                    }
+                }
+                for (int j = lane; j < N; j += lanes) {
+                    T rhs[M];
+#pragma unroll
+                    for (int r = 0; r < M; r++) rhs[r] = K[r * N + j];
+#pragma unroll
+                    for (int col = 0; col < M; col++) {
+#pragma unroll
+                        for (int r = col + 1; r < M; r++)
+                            if (r == perm[col]) { const T t = rhs[col]; rhs[col] = rhs[r]; rhs[r] = t; }
+#pragma unroll
+                        for (int r = col + 1; r < M; r++) rhs[r] -= mult[r * M + col] * rhs[col];
+                    }
+#pragma unroll
+                    for (int r = M - 1; r >= 0; r--) {
+                        T a = rhs[r];
+#pragma unroll
+                        for (int k = r + 1; k < M; k++) a -= Gl[r * M + k] * rhs[k];
+                        rhs[r] = a * (T(1) / Gl[r * M + r]);
+                    }
+#pragma unroll
+                    for (int r = 0; r < M; r++) K[r * N + j] = rhs[r];
+                }
+            }
+            sync();
+            for (int e = lane; e < N * N; e += lanes) {   // A - B K
+                const int i = e / N, j = e % N;
+                T a = A[e];
+                for (int k = 0; k < M; k++) a -= Bm[i * M + k] * K[k * N + j];
+                AmBK[e] = a;
+            }
+            sync();
+            for (int e = lane; e < N * N; e += lanes) {   // P = Q + A'P (A - B K)
+                const int i = e / N, j = e % N;
+                T a = Q[e];
+                for (int k = 0; k < N; k++) a += AtP[i * N + k] * AmBK[k * N + j];
+                P[e] = a;
+            }
+            sync();
+        }
+    }
+    template <class Sync>
+    __device__ void gain_coop(const Sys& sys, T dt, const T* x, const T* u, T* K, T* sm, int lane, int lanes, Sync sync) const {
+        solve_coop(sys, dt, x, u, sm, lane, lanes, sync);
+#pragma unroll
+        for (int e = 0; e < M * N; e++) K[e] = sm[K_OFF + e];
+    }
+
     __device__ void gain(const Sys& sys, T dt, const T* x, const T* u, T* K) const {
         T P[N * N];
         solve(sys, dt, x, u, P, K);

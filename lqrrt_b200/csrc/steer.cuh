@@ -52,6 +52,25 @@ __host__ __device__ inline int horizon_apply(int h, unsigned vote, int f, int lo
 template <typename T, class Sys, class Lqr>
 __device__ __forceinline__ int fpr_keep(const Model<T, Sys, Lqr>& md, int len) { return (int)(md.FPR * (double)len); }
 
+// Shared-memory ordering inside the group of LANES threads that share one sample.
+template <int LANES>
+struct GroupSync {
+    __device__ __forceinline__ void operator()() const {
+        if (LANES > 1) cg::tiled_partition<LANES>(cg::this_thread_block()).sync();
+    }
+};
+
+// K = lqr(x, u).K, cooperatively when the provider supports it (FD-Jacobian + Riccati) and the group has lanes.
+template <typename T, class Sys, class Lqr, int LANES>
+__device__ __forceinline__ void group_gain(const Model<T, Sys, Lqr>& md, const T* x, const T* u, T* K, T s, T c,
+                                           T* coop, int lane) {
+    if constexpr (Lqr::COOP && LANES > 1) {
+        md.lqr.gain_coop(md.sys, md.dt, x, u, K, coop, lane, LANES, GroupSync<LANES>());
+    } else {
+        md.lqr.gain_sc(md.sys, md.dt, x, u, K, s, c);
+    }
+}
+
 template <int LANES>
 __device__ __forceinline__ bool group_all(bool ok) {
     if (LANES == 1) return ok;
@@ -77,6 +96,8 @@ steer_kernel(Model<T, Sys, Lqr> md,
              T* __restrict__ xseq, T* __restrict__ useq, int* __restrict__ len_out,
              T* __restrict__ xnew_out, T* __restrict__ Knew_out, int ostride, uint8_t* __restrict__ votes) {
     constexpr int N = Sys::N, M = Sys::M;
+    extern __shared__ __align__(16) unsigned char coop_raw[];
+    T* coop = reinterpret_cast<T*>(coop_raw) + (size_t)(threadIdx.x / LANES) * Lqr::COOP_SCALARS;
     const int gid = (blockIdx.x * BLOCK + threadIdx.x) / LANES;
     const int lane = threadIdx.x % LANES;
     if (gid >= W) return;                  // whole groups leave together (BLOCK % LANES == 0)
@@ -158,28 +179,65 @@ steer_kernel(Model<T, Sys, Lqr> md,
             for (int r = 0; r < M; r++) urow[nrec * M + r] = u[r];
         }
         nrec += 1;
-        md.lqr.gain_sc(md.sys, md.dt, x, u, K, sh, ch);          // planner.py:436
+        group_gain<T, Sys, Lqr, LANES>(md, x, u, K, sh, ch, coop, lane);   // planner.py:436
     }
 
+    // The node is the last KEPT state and its gain is lqr(xnew, u_seq[-1]).K (planner.py:256-257).  Without an
+    // FPR cut, x / K already hold exactly that; after a cut (0 < len < nrec) the kept tail is re-read from
+    // the group's own edge rows (written by lane 0) and the gain recomputed by the whole group.
+    if (xnew_out && len > 0 && len < nrec) {
+        GroupSync<LANES>()();
+        T uk[M];
+#pragma unroll
+        for (int d = 0; d < N; d++) x[d] = xrow[(len - 1) * N + d];
+#pragma unroll
+        for (int r = 0; r < M; r++) uk[r] = urow[(len - 1) * M + r];
+        T s2 = T(0), c2 = T(1);
+        if (HD >= 0) sincos_t(x[HD < 0 ? 0 : HD], &s2, &c2);
+        group_gain<T, Sys, Lqr, LANES>(md, x, uk, K, s2, c2, coop, lane);
+    }
     if (lane == 0) {
         len_out[j] = len;
         if (votes) votes[j] = (uint8_t)vote;
         if (xnew_out && len > 0) {
-            // The node is the last KEPT state and its gain is lqr(xnew, u_seq[-1]).K (planner.py:256-257).
-            // Without an FPR cut, x / K already hold exactly that; after a cut (len < nrec) the
-            // kept tail is re-read from this thread's own edge rows and the gain recomputed.
-            if (len < nrec) {
-                T uk[M];
-#pragma unroll
-                for (int d = 0; d < N; d++) x[d] = xrow[(len - 1) * N + d];
-#pragma unroll
-                for (int r = 0; r < M; r++) uk[r] = urow[(len - 1) * M + r];
-                md.lqr.gain(md.sys, md.dt, x, uk, K);
-            }
 #pragma unroll
             for (int d = 0; d < N; d++) xnew_out[(size_t)d * ostride + j] = x[d];
 #pragma unroll
             for (int k = 0; k < M * N; k++) Knew_out[(size_t)k * ostride + j] = K[k];
+        }
+    }
+}
+
+// Per-query metric S = lqr(x, 0).S for cooperative providers: LANES threads per query share one sweep
+// (the thread-per-query metric_kernel in nearest.cuh serves the others).  Packed like metric_kernel.
+template <typename T, class Sys, class Lqr, int LANES>
+__global__ void __launch_bounds__(32)
+metric_coop_kernel(Model<T, Sys, Lqr> md, const T* __restrict__ queries, int qstride, int W, T* __restrict__ Spacked) {
+    constexpr int N = Sys::N, M = Sys::M;
+    extern __shared__ __align__(16) unsigned char coop_raw[];
+    T* coop = reinterpret_cast<T*>(coop_raw) + (size_t)(threadIdx.x / LANES) * Lqr::COOP_SCALARS;
+    const int j = (blockIdx.x * 32 + threadIdx.x) / LANES;
+    const int lane = threadIdx.x % LANES;
+    if (j >= W) return;
+    T x[N], u0[M];
+#pragma unroll
+    for (int d = 0; d < N; d++) x[d] = queries[(size_t)d * qstride + j];
+#pragma unroll
+    for (int r = 0; r < M; r++) u0[r] = T(0);                    // planner.py:348: lqr(x, zeros)
+    if constexpr (Lqr::COOP) {
+        md.lqr.solve_coop(md.sys, md.dt, x, u0, coop, lane, LANES, GroupSync<LANES>());
+        const T* S = coop + Lqr::P_OFF;
+        constexpr int NS = N * (N + 1) / 2;
+        for (int e = lane; e < NS; e += LANES) {                 // packed index e -> (a, b)
+            int a = 0, b = 0;
+            if (e < N) { a = b = e; }
+            else {
+                int s = N;
+                for (int aa = 0; aa < N; aa++)
+                    for (int bb = aa + 1; bb < N; bb++, s++)
+                        if (s == e) { a = aa; b = bb; }
+            }
+            Spacked[(size_t)e * qstride + j] = a == b ? S[a * N + a] : S[a * N + b] + S[b * N + a];
         }
     }
 }
