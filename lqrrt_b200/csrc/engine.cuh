@@ -433,7 +433,8 @@ struct EngineImpl : lq_engine {
         for (int pi = 0; pi < md.feas.n_prims; pi++) obs_work += md.feas.prims[pi].n_obs;
         // sub-warp groups of 8 measured best on C4 (profiles/README.md): they split hull vertices / obstacle
         // lists and cut the divergence of thread-per-sample rollouts; without obstacle tables one lane is enough
-        steer_lanes = sample_lanes = (obs_work > 0 || Lqr::COOP) ? 8 : 1;
+        steer_lanes = sample_lanes = obs_work > 0 ? 8 : 1;
+        if (Lqr::COOP) steer_lanes = 32;       // a warp per sample shares the Riccati sweep (measured 1.7x over 8 lanes on C5)
         return LQ_OK;
     }
 

@@ -415,12 +415,36 @@ class System(object):
         return self._eval
 
 
-def bundle_of(dynamics, lqr, erf, is_feasible):
+_RECOGNISED = {}       # (id(dynamics), id(lqr), id(erf), id(is_feasible)) -> verified System
+
+
+def bundle_of(dynamics, lqr, erf, is_feasible, nstates=None, ncontrols=None):
     """Resolve the four Planner arguments to one System, or raise.
 
-    There is no host fallback: arbitrary Python closures cannot run inside a
-    kernel, so anything that is not a device spec is an error."""
+    Device specs are used as they are.  Plain Python callables (the unchanged reference demos) go through
+    `recognize.recognise`: parameters are read from the functions' globals and the resulting device model
+    is accepted only if it reproduces the user's own functions on a few hundred probes.  There is no host
+    fallback: anything that cannot be verified on the device is an error."""
     specs = (dynamics, lqr, is_feasible)
+    if not any(isinstance(s, _Spec) for s in specs) and all(hasattr(s, '__call__') for s in specs) \
+            and nstates is not None:
+        key = (id(dynamics), id(lqr), id(erf), id(is_feasible))
+        if key not in _RECOGNISED:
+            from . import recognize
+            from ._native import NativeError
+            try:
+                _RECOGNISED[key] = recognize.recognise(dynamics, lqr, erf, is_feasible, int(nstates), int(ncontrols))
+            except recognize.NotRecognised as e:
+                raise TypeError(
+                    "lqrrt_b200 runs the planner on the GPU and needs device model specs (lqrrt_b200.models); the "
+                    "plain Python callables given could not be matched to a compiled model: {}. There is no CPU "
+                    "fallback.".format(e))
+            except NativeError as e:
+                raise TypeError(
+                    "plain Python callables can only be accepted after the device model has been verified "
+                    "against them on the GPU, and the engine is not available ({}). There is no CPU fallback."
+                    .format(e))
+        return _RECOGNISED[key]
     for s, nm in zip(specs, ('dynamics', 'lqr', 'is_feasible')):
         if not isinstance(s, _Spec):
             raise TypeError(

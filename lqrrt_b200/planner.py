@@ -106,7 +106,8 @@ class Planner(object):
         attributes in the reference (lqrrt_node.py:259 assigns planner.dt directly), so compare by value."""
         from ._native import Engine
         # constraints.set_feasibility_function may have swapped the spec since set_system
-        self._system = _models.bundle_of(self.dynamics, self.lqr, self.erf, self.constraints.is_feasible)
+        self._system = _models.bundle_of(self.dynamics, self.lqr, self.erf, self.constraints.is_feasible,
+                                         self.nstates, self.ncontrols)
         tol = np.abs(np.asarray(self.error_tol, dtype=np.float64)) * np.ones(self.nstates)
         # with the adaptive heuristic horizon_iters is run-time state (planner.py:421,424) and the longest edge
         # is hspan[1]; with a fixed horizon it is baked in
@@ -481,7 +482,7 @@ class Planner(object):
                 raise ValueError("Expected erf to be a function.")
             self.erf = erf
         self._system = _models.bundle_of(self.dynamics, self.lqr, getattr(self, 'erf', np.subtract),
-                                         self.constraints.is_feasible)
+                                         self.constraints.is_feasible, self.nstates, self.ncontrols)
         if self._system.nstates != self.nstates or self._system.ncontrols != self.ncontrols:
             raise ValueError("constraints say nstates={}, ncontrols={} but the dynamics model has {} and {}".format(
                 self.nstates, self.ncontrols, self._system.nstates, self._system.ncontrols))
