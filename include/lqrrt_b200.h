@@ -56,7 +56,10 @@ enum { LQ_FEAS_STATE_BOX = 1,        /* demo_boat_advanced.py:211-213 */
        LQ_FEAS_CIRCLES_POINT = 4,    /* demo_boat_novice.py:160-164 */
        LQ_FEAS_CIRCLES_CLOUD = 5,    /* demo_boat_intermediate.py:198-210, demo_car.py:168-180 */
        LQ_FEAS_BOXES_CLOUD = 6,      /* config C2 boxes */
-       LQ_FEAS_SPHERES_POINT = 7     /* config C5 spheres */ };
+       LQ_FEAS_SPHERES_POINT = 7,    /* config C5 spheres */
+       LQ_FEAS_OGRID_CLOUD = 8       /* demos/lqrrt_ros/nodes/lqrrt_node.py:719-745: hull vertices vs an occupancy grid;
+                                        obs = grid rows x cols (row-major, n_obs = rows), lo = {cols, cells per metre,
+                                        origin x, origin y, threshold} */ };
 
 typedef struct lq_feas_prim {
     int32_t kind;
@@ -211,7 +214,7 @@ int lq_eval_feasible(lq_engine* h, int count, const double* h_x, const double* h
 
 /* number of kernels this engine has launched since creation (bench.py's gpu_launches) */
 int lq_launch_count(lq_engine* h, uint64_t* out);
-/* tuning knobs: lanes = steer lanes per sample + 100 * sampler lanes per sample (each 1, 8 or 32; 0 keeps),
+/* tuning knobs: steer_lanes = threads sharing one rollout (1, 8 or 32; 0 keeps the heuristic),
  * nearest_q = nearest queries per thread (0 = heuristic, 1 = small, >1 = large) */
 int lq_set_tuning(lq_engine* h, int steer_lanes, int nearest_q);
 /* Per-stage CUDA-event timing of the wave chain on the launching stream (bench.py's roofline leg).

@@ -174,7 +174,10 @@ class Engine(object):
             if p.verts is not None:
                 v = _c64(p.verts); keep.append(v)
                 arr[i].n_verts = v.shape[1]; arr[i].verts = _dp(v)
-            if p.lo is not None:
+            if p.kind == M.FEAS_OGRID_CLOUD:
+                lo = _c64(p.lo); hi = _c64(p.hi); keep += [lo, hi]
+                arr[i].lo = _dp(lo); arr[i].hi = _dp(hi)
+            elif p.lo is not None:
                 want = self.m if p.kind == M.FEAS_EFFORT_BOX else self.n
                 lo = _c64(p.lo); hi = _c64(p.hi)
                 if len(lo) != want or len(hi) != want:

@@ -193,7 +193,7 @@ struct EngineImpl : lq_engine {
     int cap = 0, Wc = 0, H = 0, tries_cap = 10;
     int size_ub = 0;                 // host upper bound of the device-side tree size
     int size_ub_exact = 0;           // tree size as of the last stats read (wave-start size for profiling)
-    int steer_lanes = 1, sample_lanes = 1, near_q = 0; // tuning (0 = heuristic)
+    int steer_lanes = 1, near_q = 0; // tuning (0 = heuristic)
     bool metric_diag = true;
     DiagMetric<T, N> dmet;
     double Sconst[N * N];
@@ -217,7 +217,7 @@ struct EngineImpl : lq_engine {
     bool use_hull_grid = true;
     // wave working set
     DevBuf<T> w_samples, w_ncost, w_pcost, w_Sp, w_xs, w_us, w_xnew, w_Knew, w_cand, w_goal;
-    DevBuf<int> w_nidx, w_pidx, w_len, w_slot, w_tries, w_pick, w_src, w_misc;
+    DevBuf<int> w_nidx, w_pidx, w_len, w_tries, w_pick, w_src, w_misc;
     DevBuf<uint8_t> w_candok, w_votes;
     DevBuf<int> w_hor;
     DevBuf<char> w_rec;
@@ -302,6 +302,22 @@ struct EngineImpl : lq_engine {
                 for (int k = 0; k < d.nbox; k++) { d.lo[k] = (T)s.lo[k]; d.hi[k] = (T)s.hi[k]; }
                 continue;
             }
+            if (s.kind == LQ_FEAS_OGRID_CLOUD) {
+                if (!s.lo || !s.obs || !s.verts || s.n_obs < 1 || s.n_verts < 1 || s.lo[0] < 1) LQ_FAIL(LQ_ERR_ARG, "occupancy-grid primitive %d needs grid, vertices and {cols, cpm, ox, oy, threshold}", pi);
+                for (int k = 0; k < 3; k++)
+                    if (s.dims[k] < 0 || s.dims[k] >= N) LQ_FAIL(LQ_ERR_ARG, "primitive %d: state dim %d out of range", pi, s.dims[k]);
+                const size_t cells = (size_t)s.n_obs * (size_t)s.lo[0];
+                std::vector<T> grid(cells), vv((size_t)2 * s.n_verts);
+                for (size_t k = 0; k < cells; k++) grid[k] = (T)s.obs[k];
+                for (int k = 0; k < 2 * s.n_verts; k++) vv[k] = (T)s.verts[k];
+                auto* gb = new DevBuf<T>(); feas_bufs.push_back(gb);
+                auto* vb = new DevBuf<T>(); feas_bufs.push_back(vb);
+                if (int r = upload(*gb, grid)) return r;
+                if (int r = upload(*vb, vv)) return r;
+                d.obs = gb->p; d.verts = vb->p; d.cell_start = nullptr; d.cell_items = nullptr; d.hull_axes = nullptr;
+                for (int k = 0; k < 5; k++) d.lo[k] = (T)s.lo[k];
+                continue;
+            }
             int stride;
             switch (s.kind) {
             case LQ_FEAS_CIRCLES_POINT: case LQ_FEAS_CIRCLES_CLOUD: stride = 3; break;
@@ -379,7 +395,7 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(w_samples.alloc((size_t)N * Wc)); LQ_CUDA(w_ncost.alloc(Wc)); LQ_CUDA(w_nidx.alloc(Wc));
         LQ_CUDA(w_pcost.alloc((size_t)MAX_SPLIT * Wc)); LQ_CUDA(w_pidx.alloc((size_t)MAX_SPLIT * Wc));
         LQ_CUDA(w_xs.alloc((size_t)Wc * H * N)); LQ_CUDA(w_us.alloc((size_t)Wc * H * M));
-        LQ_CUDA(w_len.alloc(Wc)); LQ_CUDA(w_slot.alloc(Wc)); LQ_CUDA(w_tries.alloc(Wc)); LQ_CUDA(w_pick.alloc(Wc)); LQ_CUDA(w_src.alloc(Wc));
+        LQ_CUDA(w_len.alloc(Wc)); LQ_CUDA(w_tries.alloc(Wc)); LQ_CUDA(w_pick.alloc(Wc)); LQ_CUDA(w_src.alloc(Wc));
         LQ_CUDA(w_xnew.alloc((size_t)N * Wc)); LQ_CUDA(w_Knew.alloc((size_t)M * N * Wc));
         LQ_CUDA(w_misc.alloc(8)); LQ_CUDA(w_stats.alloc(1)); LQ_CUDA(w_votes.alloc(Wc)); LQ_CUDA(w_hor.alloc(1));
         { const int h0 = c->hfactor ? c->hspan_lo : c->horizon_iters; LQ_CUDA(cudaMemcpy(w_hor.p, &h0, sizeof(int), cudaMemcpyHostToDevice)); }
@@ -433,7 +449,7 @@ struct EngineImpl : lq_engine {
         for (int pi = 0; pi < md.feas.n_prims; pi++) obs_work += md.feas.prims[pi].n_obs;
         // sub-warp groups of 8 measured best on C4 (profiles/README.md): they split hull vertices / obstacle
         // lists and cut the divergence of thread-per-sample rollouts; without obstacle tables one lane is enough
-        steer_lanes = sample_lanes = obs_work > 0 ? 8 : 1;
+        steer_lanes = obs_work > 0 ? 8 : 1;
         if (Lqr::COOP) steer_lanes = 32;       // a warp per sample shares the Riccati sweep (measured 1.7x over 8 lanes on C5)
         return LQ_OK;
     }
@@ -1125,12 +1141,8 @@ struct EngineImpl : lq_engine {
     }
 
     int set_tuning(int lanes, int nq) override {
-        // lanes = steer lanes + 100 * sampler lanes (0 keeps the current value)
-        const int sl = lanes % 100, pl = lanes / 100;
-        if (sl == 1 || sl == 8 || sl == 32) steer_lanes = sl;
-        else if (sl != 0) LQ_FAIL(LQ_ERR_ARG, "steer lanes must be 0 (keep), 1, 8 or 32");
-        if (pl == 1 || pl == 8 || pl == 32) sample_lanes = pl;
-        else if (pl != 0) LQ_FAIL(LQ_ERR_ARG, "sampler lanes must be 0 (keep), 1, 8 or 32");
+        if (lanes == 1 || lanes == 8 || lanes == 32) steer_lanes = lanes;
+        else if (lanes != 0) LQ_FAIL(LQ_ERR_ARG, "steer lanes must be 0 (keep), 1, 8 or 32");
         near_q = nq;
         return LQ_OK;
     }

@@ -757,6 +757,29 @@ __device__ __forceinline__ bool feasible_eval(const FeasSet<T>& fs, const T* x, 
             }
             break;
         }
+        case LQ_FEAS_OGRID_CLOUD: {                 // demos/lqrrt_ros/nodes/lqrrt_node.py:730-745
+            T px = T(0), py = T(0), ph = T(0);
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                if (i == p.dims[0]) px = x[i];
+                if (i == p.dims[1]) py = x[i];
+                if (i == p.dims[2]) ph = x[i];
+            }
+            T s = hs, c = hc;
+            if (p.dims[2] != hdim) sincos_t(ph, &s, &c);
+            const long long rows = p.n_obs, cols = (long long)p.lo[0];
+            const T cpm = p.lo[1], ox = p.lo[2], oy = p.lo[3], thr = p.lo[4];
+            for (int v = lane; v < p.n_verts; v += lanes) {
+                const T bx = p.verts[v], by = p.verts[p.n_verts + v];
+                const T wx = px + (c * bx - s * by), wy = py + (s * bx + c * by);
+                long long ix = (long long)(cpm * (wx - ox)), iy = (long long)(cpm * (wy - oy));   // astype(int64): toward zero
+                if (ix < 0) ix += cols;             // NumPy wraps negative indices once ...
+                if (iy < 0) iy += rows;
+                if (ix < 0 || ix >= cols || iy < 0 || iy >= rows) return false;                   // ... IndexError => infeasible
+                if (!(p.obs[iy * cols + ix] < thr)) return false;
+            }
+            break;
+        }
         default: break;
         }
     }

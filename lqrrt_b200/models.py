@@ -37,6 +37,7 @@ FEAS_CIRCLES_POINT = 4
 FEAS_CIRCLES_CLOUD = 5
 FEAS_BOXES_CLOUD = 6
 FEAS_SPHERES_POINT = 7
+FEAS_OGRID_CLOUD = 8
 
 MAX_N = 12
 MAX_M = 6
@@ -366,6 +367,29 @@ class SpheresPoint(_Prim):
         self.inflate = float(inflate)
         self.obs = _live(obs, 4, self.inflate)
         self.dims = (int(dims[0]), int(dims[1]), int(dims[2]), 0)
+
+
+class OccupancyGrid(_Prim):
+    """Hull vertex cloud vs an occupancy grid, the ROS node's is_feasible
+    (demos/lqrrt_ros/nodes/lqrrt_node.py:719-745): every vertex is mapped to a cell by truncating
+    cpm * (vertex - origin) toward zero; infeasible if any cell value is >= threshold or any index is
+    past the grid's end.  Negative indices wrap around as NumPy's do (and are out of range below -size),
+    which is what the reference does, deliberately or not."""
+    kind = FEAS_OGRID_CLOUD
+
+    def __init__(self, grid, cpm, origin, threshold, verts, dims=(0, 1, 2)):
+        g = np.ascontiguousarray(np.array(grid, dtype=np.float64))
+        if g.ndim != 2:
+            raise ValueError("grid must be rows x cols")
+        self.grid_shape = g.shape
+        self.obs = g.reshape(g.shape[0], g.shape[1])
+        self.verts = _f64(verts)
+        if self.verts.ndim != 2 or self.verts.shape[0] != 2:
+            raise ValueError("verts must be 2 x V")
+        self.cpm = float(cpm); self.origin = _f64(origin, (2,)); self.threshold = float(threshold)
+        self.dims = (int(dims[0]), int(dims[1]), int(dims[2]), 0)
+        self.lo = np.array([float(g.shape[1]), self.cpm, self.origin[0], self.origin[1], self.threshold])
+        self.hi = np.zeros(5)
 
 
 class Feasibility(_Spec):

@@ -124,10 +124,10 @@ class Planner(object):
                                   hspan=(int(self.hspan[0]), int(self.hspan[1])))
             self._engine_key = key
             self._exchange = None
-            tune = os.environ.get('LQRRT_TUNING')          # "steer_lanes[,sampler_lanes[,nearest_q]]" for experiments
+            tune = os.environ.get('LQRRT_TUNING')          # "steer_lanes[,nearest_q]" for experiments
             if tune:
-                t = [int(v) for v in tune.split(',')] + [0, 0]
-                self._engine.set_tuning(t[0] + 100 * t[1], t[2])
+                t = [int(v) for v in tune.split(',')] + [0]
+                self._engine.set_tuning(t[0], t[1])
         return self._engine
 
     @staticmethod

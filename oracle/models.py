@@ -252,6 +252,17 @@ def _prim_ok(p, x, u):
             if np.any((np.abs(verts[:, 0] - ob[0]) <= ob[2]) & (np.abs(verts[:, 1] - ob[1]) <= ob[3])):
                 return False
         return True
+    if k == M.FEAS_OGRID_CLOUD:        # lqrrt_node.py:730-745
+        dx, dy, dh = p.dims[0], p.dims[1], p.dims[2]
+        c, s = np.cos(x[dh]), np.sin(x[dh])
+        R = np.array([[c, -s], [s, c]])
+        points = np.array([x[dx], x[dy]]) + R.dot(p.verts).T
+        ind = (p.cpm * (points - p.origin)).astype(np.int64)
+        try:
+            vals = p.obs[ind[:, 1], ind[:, 0]]
+        except IndexError:
+            return False
+        return bool(np.all(vals < p.threshold))
     if k == M.FEAS_SPHERES_POINT:
         pos = np.array([x[p.dims[0]], x[p.dims[1]], x[p.dims[2]]])
         for ob in p.obs:
@@ -309,6 +320,8 @@ def make_is_feasible_batch(spec):
                         else:
                             hit = np.any((np.abs(vx - ob[0]) <= ob[2]) & (np.abs(vy - ob[1]) <= ob[3]), axis=1)
                         ok &= ~hit
+            elif k == M.FEAS_OGRID_CLOUD:
+                ok &= np.array([_prim_ok(p, x, u) for x, u in zip(X, U)], dtype=bool)
             else:
                 raise ValueError("unknown feasibility primitive")
         return ok

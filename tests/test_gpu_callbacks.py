@@ -102,3 +102,32 @@ def test_feasibility_full_size_fields(cuda_device, dtype):
         flips = int((got != want).sum())
         assert flips <= (0 if dtype == 'f64' else 4), flips
         assert 0.05 < want.mean() < 0.95
+
+
+@pytest.mark.parametrize('dtype', ['f64', 'f32'])
+def test_occupancy_grid_primitive(cuda_device, dtype):
+    """The ROS node's is_feasible (lqrrt_node.py:719-745): hull vertices truncated to cell indices, hit if any
+    cell >= threshold, IndexError (index past the end) => infeasible, negative indices wrap as in NumPy."""
+    from lqrrt_b200 import models, configs
+    from oracle.models import make_is_feasible
+    rng = np.random.RandomState(4)
+    grid = (rng.rand(120, 160) < 0.002) * 100.0
+    grid[40:60, 50:52] = 100.0
+    base = configs.demo_boat_novice(0)
+    vps = models.vertex_cloud(models.BOAT_LENGTH, models.BOAT_WIDTH, 0.15, 0.4)
+    og = models.OccupancyGrid(grid, cpm=2.5, origin=[-5.0, -8.0], threshold=90, verts=vps)
+    system = models.System(base.system.dynamics, base.system.lqr, models.Erf([2]), models.Feasibility([og]))
+    prob = configs.Problem('ogrid', system, base.x0, base.goal, base.goal_buffer, base.error_tol, base.sample_space,
+                           base.goal_bias, base.horizon, base.dt, base.FPR)
+    eng = make_engine(prob, dtype)
+    X = np.zeros((3000, 6))
+    X[:, 0] = rng.uniform(-12, 66, 3000); X[:, 1] = rng.uniform(-14, 46, 3000); X[:, 2] = rng.uniform(-4, 4, 3000)
+    U = np.zeros((3000, 3))
+    feas = make_is_feasible(system.is_feasible)
+    want = np.array([feas(x, u) for x, u in zip(X, U)])
+    got = eng.eval_feasible(X, U)
+    flips = int((got != want).sum())
+    assert flips <= (0 if dtype == 'f64' else 3), flips
+    assert 0.05 < want.mean() < 0.9
+    outside = (X[:, 0] > 62) | (X[:, 1] > 43)                     # past the grid's end: IndexError => infeasible
+    assert not got[outside].any()

@@ -212,3 +212,23 @@ def test_adaptive_horizon_waves_match_oracle(cuda_device):
     assert t['parent'].tolist() == orc.parent and np.abs(t['state'] - orc.state).max() <= 1e-9
     assert t['edge_len'][1:].tolist() == [len(e) for e in orc.x_seq[1:]]
     assert max(hist) == 30 and max(t['edge_len']) > 20
+
+
+def test_replanning_pattern(cuda_device):
+    """The ROS node's tree-chaining use (lqrrt_node.py:389-500): the same planner is asked for a new tree
+    every cycle with a ~fixed time budget (specific_time), seeded from a state along the previous plan, and
+    can be killed from another thread."""
+    import time
+    prob = problem('demo_boat_novice')
+    planner = prob.make_planner(dtype='f32', wave_max=512, min_time=5, max_time=5, max_nodes=400000)
+    x0 = prob.x0.copy()
+    sizes = []
+    for cycle in range(4):
+        t0 = time.time()
+        ok = planner.update_plan(x0, prob.sample_space, goal_bias=prob.goal_bias, specific_time=0.1)
+        dt = time.time() - t0
+        assert ok and 0.1 <= dt < 1.5, (ok, dt, planner.tree.size)
+        assert np.allclose(planner.get_state(0.0), x0, atol=1e-5)
+        sizes.append(planner.tree.size)
+        x0 = np.array(planner.get_state(min(1.0, planner.T)), dtype=np.float64)     # next seed lies on the current plan
+    assert min(sizes) > 100 and planner.tree.size <= planner.max_nodes + 1
