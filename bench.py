@@ -148,6 +148,37 @@ def cpu_growth(name, seed, budget_s):
     return sp.tree.size - 1, sp.iterations, dt
 
 
+def cpu_frozen_tree(name, state, parent, sizes=((1000, 20), (10000, 8), (100000, 3))):
+    """BASELINE.md protocol B: inject the first N nodes of a GPU-grown tree into the sequential CPU port and
+    time whole loop iterations (sample -> _costs_to_go -> selection -> _steer) at that fixed tree size."""
+    from oracle import models as om
+    from oracle.seqplanner import SeqPlanner, SeqTree, costs_to_go, default_sampler
+    prob = make_problem(name)
+    dyn, lqr, erf, feas = om.make_callbacks(prob.system, prob.dt)
+    sp = SeqPlanner(dyn, lqr, prob.nstates, prob.ncontrols, prob.goal_buffer, feas, prob.horizon, prob.dt,
+                    prob.FPR, prob.error_tol, erf, goal0=prob.goal)
+    np.random.seed(0)
+    gen = default_sampler(prob.sample_space, prob.goal_bias, sp.goal, feas, prob.ncontrols, 10)
+    out = []
+    zero = np.zeros(prob.ncontrols)
+    for N, iters in sizes:
+        if N > len(state):
+            continue
+        tree = SeqTree(state[0], lqr(state[0], zero))
+        tree.state = np.array(state[:N], dtype=np.float64)
+        tree.pID = list(parent[:N]); tree.size = N
+        tree.lqr = [lqr(x, zero) for x in tree.state]
+        sp.tree = tree
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            xr = gen(None)
+            c = costs_to_go(sp.lqr, sp.erf_v, sp.ncontrols, tree.state, xr)
+            sp.steer(int(np.argsort(c)[0]), xr)
+        dt = (time.perf_counter() - t0) / iters
+        out.append({"tree_size": N, "ms_per_iteration": dt * 1e3, "iterations_per_s": 1.0 / dt})
+    return out
+
+
 def _cpu_worker(args):
     os.environ['OMP_NUM_THREADS'] = '1'
     os.environ['OPENBLAS_NUM_THREADS'] = '1'
@@ -280,6 +311,11 @@ def run_gpu_arm(args):
             cpu = {"value": n_add / secs, "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": "{:.0f} s of sequential growth from an empty tree on the same obstacle field "
                              "({} iterations, {} nodes)".format(secs, iters, n_add)}
+            if args.cpu_frozen:
+                tr = planner.tree
+                cpu["frozen_tree"] = cpu_frozen_tree(args.config, tr.state, tr.pID)
+                cpu["frozen_tree_note"] = "one loop iteration of the CPU port on the first N nodes of the GPU-grown tree " \
+                                          "(BASELINE.md protocol B); a GPU wave at that size expands thousands of samples"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": tot_dev / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
@@ -334,6 +370,7 @@ def main():
                     help="strong: same global wave schedule for every N (bit-identical tree); weak: 8192 samples per GPU per wave")
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--cpu-frozen', action='store_true', help="also time the CPU port on frozen trees of 1e3/1e4/1e5 nodes")
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)

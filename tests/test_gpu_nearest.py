@@ -34,7 +34,8 @@ def _oracle_for(prob):
     return WaveOracle(prob.system, prob.goal, prob.goal_buffer, prob.horizon, prob.dt, prob.FPR, prob.error_tol)
 
 
-@pytest.mark.parametrize('dtype,N,W', [('f64', 3000, 300), ('f32', 20000, 1500), ('f32', 777, 5), ('f64', 1, 3)])
+@pytest.mark.parametrize('dtype,N,W', [('f64', 3000, 300), ('f32', 20000, 1500), ('f32', 777, 5), ('f64', 1, 3),
+                                       ('f32', 30001, 1), ('f64', 129, 257)])
 def test_nearest_random_tree(cuda_device, dtype, N, W):
     """Random node cloud with headings spread over several turns (wrap matters), ragged sizes."""
     prob = problem('demo_boat_novice')

@@ -18,10 +18,19 @@ def _oracle(prob, cap=1 << 30):
                       node_capacity=cap)
 
 
+def _named_problem(name):
+    from lqrrt_b200 import configs
+    if name == 'c5-riccati-6':        # 6-state double integrator, FD-Riccati provider (cooperative sweep, warp per sample)
+        return configs.c5_double_integrator(0, count=300, axes=3, riccati=True)
+    if name == 'c5-const-12':         # 12 states: the widest compiled model, dense search path not needed (S = I)
+        return configs.c5_double_integrator(0, count=500, axes=6, riccati=False)
+    return problem(name)
+
+
 @pytest.mark.parametrize('name,W,waves', [('demo_boat_novice', 64, 6), ('demo_car', 48, 4), ('demo_boat_advanced', 128, 4),
-                                          ('c1', 64, 5), ('c2', 32, 3)])
+                                          ('c1', 64, 5), ('c2', 32, 3), ('c5-riccati-6', 24, 3), ('c5-const-12', 61, 4)])
 def test_philox_waves_match_oracle(cuda_device, name, W, waves):
-    prob = problem(name)
+    prob = _named_problem(name)
     eng = make_engine(prob, 'f64', node_capacity=4096, wave_capacity=W)
     eng.set_sampling(prob.sample_space, prob.goal_bias, 10)
     eng.reset(prob.x0)
