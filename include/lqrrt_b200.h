@@ -217,6 +217,17 @@ int lq_launch_count(lq_engine* h, uint64_t* out);
 /* tuning knobs: steer_lanes = threads sharing one rollout (1, 8 or 32; 0 keeps the heuristic),
  * nearest_q = nearest queries per thread (0 = heuristic, 1 = small, >1 = large) */
 int lq_set_tuning(lq_engine* h, int steer_lanes, int nearest_q);
+/* Engine options.  Every setting produces the same tree, bit for bit; they select how the work is issued.
+ *   LQ_OPT_NEAREST_KERNEL  float32 diagonal-metric scan (planner.py:340-350): LQ_NEAREST_SCALAR = one FADD + one
+ *                          FFMA per (query, node, dim) and a per-pair compare/select; LQ_NEAREST_PACKED = the same
+ *                          arithmetic on the FP32x2 pipe (two queries per instruction) with a two-level argmin.
+ *                          float64 engines and dense metrics ignore it.
+ *   LQ_OPT_SAMPLE_PREFETCH 1: the device sampler (planner.py:201-211) of a wave is issued on a side stream into
+ *                          the second sample buffer, so it overlaps the previous wave's scan and rollouts. */
+enum { LQ_OPT_NEAREST_KERNEL = 1, LQ_OPT_SAMPLE_PREFETCH = 2 };
+enum { LQ_NEAREST_SCALAR = 0, LQ_NEAREST_PACKED = 1 };
+int lq_set_option(lq_engine* h, int option, int value);
+int lq_get_option(lq_engine* h, int option, int* value);
 /* Per-stage CUDA-event timing of the wave chain on the launching stream (bench.py's roofline leg).
  * ms[5]: sample, nearest, steer, pack, commit (accumulated);  work[4]: nearest pairs sum(W*N),
  * nearest algorithmic bytes sum(W*N*n*sizeof(dtype)), samples, waves. */

@@ -19,6 +19,8 @@ LIB_PATH = os.path.join(_HERE, 'liblqrrt_b200.so')
 LQ_ABI_VERSION = 1
 LQ_MAX_N = 12
 LQ_F32, LQ_F64 = 0, 1
+LQ_OPT_NEAREST_KERNEL, LQ_OPT_SAMPLE_PREFETCH = 1, 2
+NEAREST_KERNELS = {'scalar': 0, 'packed': 1}
 
 
 class NativeError(RuntimeError):
@@ -88,6 +90,8 @@ SYMBOLS = {
     'lq_eval_feasible': (C.c_int, [_P, C.c_int, _D, _D, _U8]),
     'lq_launch_count': (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     'lq_set_tuning': (C.c_int, [_P, C.c_int, C.c_int]),
+    'lq_set_option': (C.c_int, [_P, C.c_int, C.c_int]),
+    'lq_get_option': (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
     'lq_set_profiling': (C.c_int, [_P, C.c_int]),
     'lq_profile_read': (C.c_int, [_P, _D, _D, C.c_int]),
 }
@@ -397,6 +401,14 @@ class Engine(object):
 
     def set_tuning(self, steer_lanes=0, nearest_q=0):
         self._ck(self.lib.lq_set_tuning(self.h, int(steer_lanes), int(nearest_q)))
+
+    def set_option(self, option, value):
+        self._ck(self.lib.lq_set_option(self.h, int(option), int(value)))
+
+    def get_option(self, option):
+        out = C.c_int(0)
+        self._ck(self.lib.lq_get_option(self.h, int(option), C.byref(out)))
+        return out.value
 
     def set_profiling(self, on=True):
         self._ck(self.lib.lq_set_profiling(self.h, int(bool(on))))

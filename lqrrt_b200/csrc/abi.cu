@@ -89,6 +89,8 @@ int lq_eval_feasible(lq_engine* h, int count, const double* x, const double* u, 
     LQ_H(h); if (!x || !u || !ok) return LQ_ERR_ARG; LQ_TRY(h->eval_feasible(count, x, u, ok)) }
 int lq_launch_count(lq_engine* h, uint64_t* out) { LQ_H(h); if (!out) return LQ_ERR_ARG; *out = h->launches; return LQ_OK; }
 int lq_set_tuning(lq_engine* h, int steer_lanes, int nearest_q) { LQ_H(h); LQ_TRY(h->set_tuning(steer_lanes, nearest_q)) }
+int lq_set_option(lq_engine* h, int opt, int v) { LQ_H(h); LQ_TRY(h->set_option(opt, v)) }
+int lq_get_option(lq_engine* h, int opt, int* v) { LQ_H(h); if (!v) return LQ_ERR_ARG; LQ_TRY(h->get_option(opt, v)) }
 int lq_wave_set_peers(lq_engine* h, int world, int rank, void* const* bufs, uint64_t bytes) { LQ_H(h); LQ_TRY(h->set_peers(world, rank, bufs, bytes)) }
 int lq_set_profiling(lq_engine* h, int on) { LQ_H(h); LQ_TRY(h->set_profiling(on)) }
 int lq_profile_read(lq_engine* h, double* ms, double* work, int reset) { LQ_H(h); LQ_TRY(h->profile_read(ms, work, reset)) }

@@ -52,6 +52,8 @@ struct lq_engine {
     virtual int eval_feasible(int count, const double* x, const double* u, uint8_t* ok) = 0;
     virtual int set_tuning(int steer_lanes, int nearest_q) = 0;
     virtual int set_peers(int world, int rank, void* const* bufs, uint64_t bytes) = 0;
+    virtual int set_option(int option, int value) = 0;
+    virtual int get_option(int option, int* value) = 0;
     virtual int set_profiling(int on) = 0;
     virtual int profile_read(double* ms, double* work, int reset) = 0;
 };
@@ -194,6 +196,15 @@ struct EngineImpl : lq_engine {
     int size_ub = 0;                 // host upper bound of the device-side tree size
     int size_ub_exact = 0;           // tree size as of the last stats read (wave-start size for profiling)
     int steer_lanes = 1, near_q = 0; // tuning (0 = heuristic)
+    int near_kernel = LQ_NEAREST_SCALAR;   // lq_set_option(LQ_OPT_NEAREST_KERNEL)
+    // lq_set_option(LQ_OPT_SAMPLE_PREFETCH): sampler of the next wave on a side stream, double-buffered
+    bool prefetch_on = false;
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_sampled[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+    bool consumed_valid[2] = {false, false};
+    int sample_parity = 0;
+    T* cur_samples = nullptr;
+    int* cur_tries = nullptr;
     bool metric_diag = true;
     DiagMetric<T, N> dmet;
     double Sconst[N * N];
@@ -249,6 +260,9 @@ struct EngineImpl : lq_engine {
         if (h_misc) cudaFreeHost(h_misc);
         for (auto& e : ev_stats) if (e) cudaEventDestroy(e);
         for (auto& r : pev) for (auto& e : r) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_sampled) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_consumed) if (e) cudaEventDestroy(e);
+        if (aux) cudaStreamDestroy(aux);
     }
 
     template <typename U>
@@ -392,10 +406,13 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(cudaMemset(t_scal.p, 0, 8 * sizeof(int)));
 
         // wave working set
-        LQ_CUDA(w_samples.alloc((size_t)N * Wc)); LQ_CUDA(w_ncost.alloc(Wc)); LQ_CUDA(w_nidx.alloc(Wc));
+        // samples / sampler tries are double-buffered: with LQ_OPT_SAMPLE_PREFETCH the next wave's sampler
+        // runs on a side stream while this wave's scan and rollouts still read theirs
+        LQ_CUDA(w_samples.alloc((size_t)2 * N * Wc)); LQ_CUDA(w_ncost.alloc(Wc)); LQ_CUDA(w_nidx.alloc(Wc));
+        cur_samples = w_samples.p;
         LQ_CUDA(w_pcost.alloc((size_t)MAX_SPLIT * Wc)); LQ_CUDA(w_pidx.alloc((size_t)MAX_SPLIT * Wc));
         LQ_CUDA(w_xs.alloc((size_t)Wc * H * N)); LQ_CUDA(w_us.alloc((size_t)Wc * H * M));
-        LQ_CUDA(w_len.alloc(Wc)); LQ_CUDA(w_tries.alloc(Wc)); LQ_CUDA(w_pick.alloc(Wc)); LQ_CUDA(w_src.alloc(Wc));
+        LQ_CUDA(w_len.alloc(Wc)); LQ_CUDA(w_tries.alloc((size_t)2 * Wc)); LQ_CUDA(w_pick.alloc(Wc)); LQ_CUDA(w_src.alloc(Wc));
         LQ_CUDA(w_xnew.alloc((size_t)N * Wc)); LQ_CUDA(w_Knew.alloc((size_t)M * N * Wc));
         LQ_CUDA(w_misc.alloc(8)); LQ_CUDA(w_stats.alloc(1)); LQ_CUDA(w_votes.alloc(Wc)); LQ_CUDA(w_hor.alloc(1));
         { const int h0 = c->hfactor ? c->hspan_lo : c->horizon_iters; LQ_CUDA(cudaMemcpy(w_hor.p, &h0, sizeof(int), cudaMemcpyHostToDevice)); }
@@ -404,7 +421,8 @@ struct EngineImpl : lq_engine {
         rec_sz = rec_bytes<T>(Wc, N, M, H);
         LQ_CUDA(w_rec.alloc(rec_sz));
         LQ_CUDA(cudaMemset(w_rec.p, 0, rec_sz));
-        LQ_CUDA(cudaMemset(w_tries.p, 0, Wc * sizeof(int)));
+        LQ_CUDA(cudaMemset(w_tries.p, 0, (size_t)2 * Wc * sizeof(int)));
+        cur_tries = w_tries.p;
         LQ_CUDA(cudaMallocHost((void**)&h_stats, RING * sizeof(lq_wave_stats)));
         LQ_CUDA(cudaMallocHost((void**)&h_misc, 8 * sizeof(int)));
         memset(h_stats, 0, RING * sizeof(lq_wave_stats));
@@ -640,7 +658,22 @@ struct EngineImpl : lq_engine {
         else if (cmask == 1) LQ_NEAR_DIAG(QQ, 1);           \
         else LQ_NEAR_DIAG(QQ, -1);                          \
     } while (0)
-            if (big) LQ_NEAR_DIAG_M(QBIG); else LQ_NEAR_DIAG_M(1);
+#define LQ_NEAR_PK(MM)                                                                                    \
+    nearest_diag_pk_kernel<N, 4, NEAR_BLOCK, MM, 8><<<nqb * nsplit, NEAR_BLOCK, 0, st>>>(                   \
+        t_state.p, cap, t_ignore.p, tv.size, tv.n_ignored, use_ignore, q, qstride, W, dmet, nqb, chunk,   \
+        w_pcost.p, w_pidx.p, Wc)
+            bool packed = false;
+            if constexpr (sizeof(T) == 4) {          // FP32x2 issue + two-level argmin: same results, fewer issue slots
+                if (big && near_kernel == LQ_NEAREST_PACKED) {
+                    packed = true;
+                    if (cmask == 0) LQ_NEAR_PK(0);
+                    else if (cmask == 4) LQ_NEAR_PK((N >= 3 ? 4 : 0));
+                    else if (cmask == 1) LQ_NEAR_PK(1);
+                    else LQ_NEAR_PK(-1);
+                }
+            }
+            if (!packed) { if (big) LQ_NEAR_DIAG_M(QBIG); else LQ_NEAR_DIAG_M(1); }
+#undef LQ_NEAR_PK
 #undef LQ_NEAR_DIAG_M
 #undef LQ_NEAR_DIAG
             nsplit_used = nsplit;
@@ -716,10 +749,10 @@ struct EngineImpl : lq_engine {
         const long long threads = (long long)count * TL;
         if (threads >= 148LL * 8 * 128) {
             sample_kernel<T, Sys, Lqr, TL, 128><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
-                md, sp, seed, wave, first, count, w_samples.p, Wc, w_tries.p);
+                md, sp, seed, wave, first, count, cur_samples, Wc, cur_tries);
         } else {
             sample_kernel<T, Sys, Lqr, TL, 32><<<(unsigned)((threads + 31) / 32), 32, 0, st>>>(
-                md, sp, seed, wave, first, count, w_samples.p, Wc, w_tries.p);
+                md, sp, seed, wave, first, count, cur_samples, Wc, cur_tries);
         }
         launches++;
     }
@@ -748,14 +781,14 @@ struct EngineImpl : lq_engine {
         const int slot = q_tail % RING;
         if (prof_on) cudaEventRecord(pev[slot][1], st);
         int nsplit = 1;
-        if (int r = launch_nearest(w_samples.p, Wc, count, use_ignore, nullptr, nullptr, st, &nsplit)) return r;
+        if (int r = launch_nearest(cur_samples, Wc, count, use_ignore, nullptr, nullptr, st, &nsplit)) return r;
         if (prof_on) cudaEventRecord(pev[slot][2], st);
-        launch_steer(nullptr, NearPartials<T>{w_pcost.p, w_pidx.p, Wc, nsplit, w_nidx.p}, w_samples.p, Wc, count,
+        launch_steer(nullptr, NearPartials<T>{w_pcost.p, w_pidx.p, Wc, nsplit, w_nidx.p}, cur_samples, Wc, count,
                      w_xs.p, w_us.p, w_len.p, w_xnew.p, w_Knew.p, Wc, st);
         if (prof_on) cudaEventRecord(pev[slot][3], st);
         RecView<T> rv = rec_view<T>(w_rec.p, Wc, N, M, H);
         PeerDst pd = next_peer_dst();
-        pack_kernel<T, 256><<<(count + 255) / 256, 256, 0, st>>>(w_len.p, w_tries.p, w_nidx.p, w_xnew.p, w_Knew.p, Wc, count,
+        pack_kernel<T, 256><<<(count + 255) / 256, 256, 0, st>>>(w_len.p, cur_tries, w_nidx.p, w_xnew.p, w_Knew.p, Wc, count,
                                                                 rv, w_src.p, Wc, N, M, H, flags, pd,
                                                                 md.hfactor ? w_votes.p : nullptr);
         launches++;
@@ -813,6 +846,7 @@ struct EngineImpl : lq_engine {
             return LQ_OK;
         }
         if (prof_on) cudaEventRecord(pev[q_tail % RING][0], st);
+        cur_samples = w_samples.p; cur_tries = w_tries.p;
         if (h_samples) {
             std::vector<T> soa((size_t)N * count);
             for (int j = 0; j < count; j++)
@@ -824,6 +858,22 @@ struct EngineImpl : lq_engine {
             LQ_CUDA(cudaStreamSynchronize(st));
         } else {
             if (!have_sampling) LQ_FAIL(LQ_ERR_STATE, "lq_set_sampling has not been called");
+            if (prefetch_on) {
+                // The sampler reads nothing of the tree (planner.py:201-211), and the host enqueues wave k+1
+                // while wave k is still running: issue it on the side stream into the other buffer, so it
+                // overlaps wave k's scan / rollouts instead of heading wave k+1's dependent chain.
+                if (int r = prefetch_setup()) return r;
+                const int par = sample_parity; sample_parity ^= 1;
+                cur_samples = w_samples.p + (size_t)par * N * Wc; cur_tries = w_tries.p + (size_t)par * Wc;
+                if (consumed_valid[par]) LQ_CUDA(cudaStreamWaitEvent(aux, ev_consumed[par], 0));   // its last reader (pack, two waves ago)
+                launch_sample(seed, wave, first, count, aux);
+                LQ_CUDA(cudaEventRecord(ev_sampled[par], aux));
+                LQ_CUDA(cudaStreamWaitEvent(st, ev_sampled[par], 0));
+                const int r = expand_from_samples(count, use_ignore, flags, st);
+                LQ_CUDA(cudaEventRecord(ev_consumed[par], st));
+                consumed_valid[par] = true;
+                return r;
+            }
             launch_sample(seed, wave, first, count, st);
         }
         return expand_from_samples(count, use_ignore, flags, st);
@@ -848,6 +898,7 @@ struct EngineImpl : lq_engine {
                                                           w_samples.p, Wc, w_pick.p, w_misc.p);
         launches++;
         LQ_CUDA(cudaMemsetAsync(w_tries.p, 0, count * sizeof(int), st));
+        cur_samples = w_samples.p; cur_tries = w_tries.p;
         LQ_CUDA(cudaMemcpyAsync(h_misc, w_misc.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         if (int r = expand_from_samples(count, use_ignore, 0, st)) return r;
         LQ_CUDA(cudaStreamSynchronize(st));
@@ -1145,6 +1196,32 @@ struct EngineImpl : lq_engine {
         else if (lanes != 0) LQ_FAIL(LQ_ERR_ARG, "steer lanes must be 0 (keep), 1, 8 or 32");
         near_q = nq;
         return LQ_OK;
+    }
+
+    int prefetch_setup() {
+        if (aux) return LQ_OK;
+        LQ_CUDA(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+        for (auto& e : ev_sampled) LQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : ev_consumed) LQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        return LQ_OK;
+    }
+    int set_option(int option, int value) override {
+        LQ_CUDA(cudaSetDevice(device));
+        switch (option) {
+        case LQ_OPT_NEAREST_KERNEL:
+            if (value != LQ_NEAREST_SCALAR && value != LQ_NEAREST_PACKED) LQ_FAIL(LQ_ERR_ARG, "unknown nearest kernel %d", value);
+            near_kernel = value; return LQ_OK;
+        case LQ_OPT_SAMPLE_PREFETCH:
+            prefetch_on = value != 0; return LQ_OK;
+        default: LQ_FAIL(LQ_ERR_ARG, "unknown option %d", option);
+        }
+    }
+    int get_option(int option, int* value) override {
+        switch (option) {
+        case LQ_OPT_NEAREST_KERNEL: *value = near_kernel; return LQ_OK;
+        case LQ_OPT_SAMPLE_PREFETCH: *value = prefetch_on ? 1 : 0; return LQ_OK;
+        default: LQ_FAIL(LQ_ERR_ARG, "unknown option %d", option);
+        }
     }
 
     int set_profiling(int on) override {

@@ -139,6 +139,149 @@ nearest_diag_kernel(const T* __restrict__ state, int cap, const uint8_t* __restr
     }
 }
 
+// ---- float32 scan on the packed FP32x2 pipe --------------------------------------------------------
+// Same arithmetic as nearest_diag_kernel<float, ..., EXACT = false>, bit for bit (every operation is a
+// round-to-nearest FADD / FFMA / FMUL on the same operands in the same order), issued differently:
+//   * two queries share one instruction: Blackwell's add.f32x2 / fma.rn.f32x2 (FADD2 / FFMA2) work on a
+//     64-bit register pair, so the 2n operations of a (query, node) pair cost n issue slots; the node
+//     tile is staged pre-duplicated (v, v) so a broadcast LDS.128 delivers two aligned operand pairs;
+//   * wrapped dims stay scalar (|e| is a free operand modifier there);
+//   * the running argmin is two-level: inside a sub-block of SB nodes only the minimum cost is tracked
+//     (one FMNMX per pair instead of compare + two selects), the (cost, sub-block) record is updated once
+//     per sub-block with a strict '<' (earliest sub-block wins ties), and the winning sub-block is
+//     re-evaluated once at the end to recover the first node whose cost equals the minimum -- the same
+//     lowest-index tie-break as the one-level scan.
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+
+template <int N, int MASK>
+__device__ __forceinline__ float2 pair_cost(const float2 (&q)[N], const float2* __restrict__ v, uint32_t mask,
+                                            const float (&period)[N]) {
+    // v[d] = (-node_d, -node_d) (staged negated: q - v == q + (-v) exactly); q[d] = (query A_d, query B_d)
+    float2 c = f2(0.f, 0.f);
+    bool first = true;
+#pragma unroll
+    for (int d = 0; d < N; d++) {
+        const float2 vd = v[d];
+        if (mask & (1u << d)) {
+            float ea = q[d].x + vd.x, eb = q[d].y + vd.x;
+            const float aa = fabsf(ea), ab = fabsf(eb);
+            ea = fminf(aa, period[d] - aa); eb = fminf(ab, period[d] - ab);
+            c.x = fmaf(ea, ea, c.x); c.y = fmaf(eb, eb, c.y);      // fma(e, e, 0) == e * e exactly
+        } else {
+            const float2 e = __fadd2_rn(q[d], vd);
+            c = first ? __fmul2_rn(e, e) : __ffma2_rn(e, e, c);
+        }
+        first = false;
+    }
+    return c;
+}
+
+template <int N, int Q, int BLOCK, int MASK, int SB>
+__global__ void __launch_bounds__(BLOCK)
+nearest_diag_pk_kernel(const float* __restrict__ state, int cap, const uint8_t* __restrict__ ignore,
+                       const int* __restrict__ d_size, const int* __restrict__ d_nignored, int use_ignore,
+                       const float* __restrict__ queries, int qstride, int W,
+                       DiagMetric<float, N> met, int nqb, int chunk,
+                       float* __restrict__ pcost, int* __restrict__ pidx, int pstride) {
+    static_assert(Q % 2 == 0 && BLOCK % SB == 0, "queries are processed in pairs, tiles in whole sub-blocks");
+    constexpr int NE = (N + 1) / 2 * 2;      // dims per node row, even: one LDS.128 = two (v, v) pairs
+    constexpr int TILE = BLOCK;
+    constexpr int QP = Q / 2;
+    __shared__ __align__(16) float2 tile[TILE * NE];
+    const uint32_t mask = MASK >= 0 ? (uint32_t)MASK : met.angle_mask;
+
+    const int qb = blockIdx.x % nqb;
+    const int split = blockIdx.x / nqb;
+    const int size = *d_size;
+    const bool mask_on = use_ignore && (*d_nignored < size);
+    const int n0 = split * chunk;
+    const int n1 = min(n0 + chunk, size);
+
+    float2 q[QP][N];
+    float best[Q];
+    int bsb[Q];
+    const int qbase = qb * (BLOCK * Q) + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < Q; k++) {
+        const int j = qbase + k * BLOCK;
+        best[k] = INFINITY;
+        bsb[k] = -1;
+#pragma unroll
+        for (int d = 0; d < N; d++) {
+            float v = j < W ? queries[(size_t)d * qstride + j] : 0.f;
+            if (mask & (1u << d)) v = reduce_period(v);
+            v *= met.w[d];
+            if (k & 1) q[k / 2][d].y = v; else q[k / 2][d].x = v;
+        }
+    }
+
+    auto staged = [&](int node, float (&v)[N]) -> bool {       // the node row exactly as the scan sees it
+        const bool live = node < n1 && !(mask_on && ignore[node]);
+#pragma unroll
+        for (int d = 0; d < N; d++) {
+            float a = live ? state[(size_t)d * cap + node] : 0.f;
+            if (mask & (1u << d)) a = reduce_period(a);
+            a *= met.w[d];
+            v[d] = live ? a : INFINITY;
+        }
+        return live;
+    };
+
+    for (int base = n0; base < n1; base += TILE) {
+        __syncthreads();
+        {
+            float v[N];
+            staged(base + threadIdx.x, v);
+#pragma unroll
+            for (int d = 0; d < NE; d++) tile[threadIdx.x * NE + d] = d < N ? f2(-v[d], -v[d]) : f2(0.f, 0.f);
+        }
+        __syncthreads();
+        const int cnt = min(TILE, n1 - base);                    // rows past cnt are staged as +inf
+        for (int s = 0; s < cnt; s += SB) {
+            float2 m[QP];
+#pragma unroll
+            for (int kp = 0; kp < QP; kp++) m[kp] = f2(INFINITY, INFINITY);
+#pragma unroll
+            for (int i = 0; i < SB; i++) {
+                float2 v[NE];
+#pragma unroll
+                for (int d = 0; d < NE; d++) v[d] = tile[(s + i) * NE + d];    // same address in every lane: broadcast
+#pragma unroll
+                for (int kp = 0; kp < QP; kp++) {
+                    const float2 c = pair_cost<N, MASK>(q[kp], v, mask, met.period);
+                    m[kp].x = fminf(m[kp].x, c.x); m[kp].y = fminf(m[kp].y, c.y);
+                }
+            }
+#pragma unroll
+            for (int kp = 0; kp < QP; kp++) {
+                if (m[kp].x < best[2 * kp]) { best[2 * kp] = m[kp].x; bsb[2 * kp] = base + s; }
+                if (m[kp].y < best[2 * kp + 1]) { best[2 * kp + 1] = m[kp].y; bsb[2 * kp + 1] = base + s; }
+            }
+        }
+    }
+    // resolve the node inside the winning sub-block: first row whose cost equals the minimum
+#pragma unroll
+    for (int k = 0; k < Q; k++) {
+        const int j = qbase + k * BLOCK;
+        int bidx = -1;
+        if (bsb[k] >= 0) {
+            for (int i = 0; i < SB && bidx < 0; i++) {
+                float v[N];
+                float2 v2[NE];
+                staged(bsb[k] + i, v);
+#pragma unroll
+                for (int d = 0; d < NE; d++) v2[d] = d < N ? f2(-v[d], -v[d]) : f2(0.f, 0.f);
+                const float2 c = pair_cost<N, MASK>(q[k / 2], v2, mask, met.period);
+                if (((k & 1) ? c.y : c.x) == best[k]) bidx = bsb[k] + i;
+            }
+        }
+        if (j < W) {
+            pcost[(size_t)split * pstride + j] = best[k];
+            pidx[(size_t)split * pstride + j] = bidx;
+        }
+    }
+}
+
 // Dense per-query metric: cost = d' S d with S symmetrised and packed
 // (diagonal, then doubled upper triangle), NS = N (N + 1) / 2 coefficients per
 // query held in registers.

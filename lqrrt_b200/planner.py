@@ -20,6 +20,10 @@ New keyword arguments (all optional, defaults keep reference call sites valid):
   pipeline  enqueue wave k+1 before reading wave k's counters (device sampler only; default on)
   exchange  'peer' = fused pack + exchange by NVLink peer stores into symmetric memory (default),
             'nccl' = one all_gather_into_tensor per wave
+  nearest_kernel  'scalar' | 'packed' (FP32x2 issue + two-level argmin; float32 diagonal metrics only);
+            None = $LQRRT_NEAREST or DEFAULT_NEAREST_KERNEL.  Same tree either way.
+  prefetch  issue each wave's device sampler on a side stream so it overlaps the previous wave
+            (needs pipeline); None = $LQRRT_PREFETCH or DEFAULT_PREFETCH.  Same tree either way.
   comm      torch.distributed process group (or True for WORLD): the wave is
             sharded over the ranks and accepted nodes are all-gathered so every
             rank's tree stays identical
@@ -41,6 +45,11 @@ from .constraints import Constraints
 from .tree import Tree
 
 
+# Issue-level options of the engine (include/lqrrt_b200.h lq_set_option); results do not depend on them.
+DEFAULT_NEAREST_KERNEL = 'scalar'
+DEFAULT_PREFETCH = False
+
+
 class Planner(object):
 
     def __init__(self, dynamics, lqr, constraints,
@@ -49,8 +58,17 @@ class Planner(object):
                  min_time=0.5, max_time=1, max_nodes=1E5,
                  goal0=None, sys_time=time.time, printing=True,
                  wave=None, wave_max=8192, dtype='f32', rng='philox', seed=0, device=None, comm=None,
-                 wave_growth=1.0, pipeline=True, exchange='peer'):
+                 wave_growth=1.0, pipeline=True, exchange='peer', nearest_kernel=None, prefetch=None):
         self._engine = None
+        if nearest_kernel is None:
+            nearest_kernel = os.environ.get('LQRRT_NEAREST') or DEFAULT_NEAREST_KERNEL
+        if nearest_kernel not in ('scalar', 'packed'):
+            raise ValueError("nearest_kernel must be 'scalar' or 'packed'")
+        self.nearest_kernel = nearest_kernel
+        if prefetch is None:
+            env = os.environ.get('LQRRT_PREFETCH')
+            prefetch = DEFAULT_PREFETCH if env in (None, '') else env not in ('0', 'false', 'off')
+        self.prefetch = bool(prefetch)
         if exchange not in ('peer', 'nccl'):
             raise ValueError("exchange must be 'peer' or 'nccl'")
         self.exchange_mode = exchange
@@ -128,6 +146,9 @@ class Planner(object):
             if tune:
                 t = [int(v) for v in tune.split(',')] + [0]
                 self._engine.set_tuning(t[0], t[1])
+        from ._native import LQ_OPT_NEAREST_KERNEL, LQ_OPT_SAMPLE_PREFETCH, NEAREST_KERNELS
+        self._engine.set_option(LQ_OPT_NEAREST_KERNEL, NEAREST_KERNELS[self.nearest_kernel])
+        self._engine.set_option(LQ_OPT_SAMPLE_PREFETCH, int(self.prefetch and self.pipeline))
         return self._engine
 
     @staticmethod

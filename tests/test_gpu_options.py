@@ -1,0 +1,110 @@
+"""
+Engine options (include/lqrrt_b200.h lq_set_option) change how the work is issued, never the result:
+
+* LQ_OPT_NEAREST_KERNEL = packed: the float32 diagonal-metric scan on the FP32x2 pipe with a two-level
+  argmin must return bit-identical (index, cost) to the scalar scan -- same lowest-index tie-break
+  (planner.py:247 np.argmin), same ignore handling (planner.py:240-245), ragged sizes included;
+* LQ_OPT_SAMPLE_PREFETCH: the sampler on a side stream must grow the same tree, bit for bit.
+"""
+import numpy as np
+import pytest
+
+from conftest import problem
+from gpu_util import make_engine, nearest
+
+pytestmark = pytest.mark.gpu
+
+OPT_NEAREST, OPT_PREFETCH = 1, 2
+SCALAR, PACKED = 0, 1
+
+
+def _both(eng, Q, use_ignore=False):
+    eng.set_tuning(0, 4)                         # large-wave launch shape (Q = 4 queries per thread) for any W
+    eng.set_option(OPT_NEAREST, SCALAR)
+    a = nearest(eng, Q, use_ignore)
+    eng.set_option(OPT_NEAREST, PACKED)
+    assert eng.get_option(OPT_NEAREST) == PACKED
+    b = nearest(eng, Q, use_ignore)
+    return a, b
+
+
+def _cloud(prob, rng, count, turns=15.0):
+    ss = np.array(prob.sample_space)
+    pts = ss[:, 0] + (ss[:, 1] - ss[:, 0]) * rng.rand(count, len(ss))
+    return pts
+
+
+@pytest.mark.parametrize('name,N,W', [('demo_boat_novice', 20000, 1500), ('demo_boat_novice', 777, 5),
+                                      ('demo_boat_novice', 1, 3), ('demo_boat_novice', 30001, 513),
+                                      ('demo_boat_novice', 129, 1027), ('demo_boat_novice', 8, 512),
+                                      ('demo_car', 9001, 700), ('c5k', 5003, 600), ('c4', 100000, 2048)])
+def test_packed_scan_is_bit_identical(cuda_device, name, N, W):
+    prob = problem(name)
+    rng = np.random.RandomState(N + W)
+    nodes = _cloud(prob, rng, N); Q = _cloud(prob, rng, W)
+    if name != 'c5k':
+        nodes[:, 2] = 15 * (rng.rand(N) - 0.5)           # headings over several turns: the wrap matters
+        Q[:, 2] = 15 * (rng.rand(W) - 0.5)
+    eng = make_engine(prob, 'f32', node_capacity=N + 8, wave_capacity=W + 3)
+    eng.load_nodes(nodes)
+    (i0, c0), (i1, c1) = _both(eng, Q)
+    assert np.array_equal(i0, i1)
+    assert np.array_equal(c0.view(np.int64), c1.view(np.int64))
+
+
+def test_packed_scan_ties_and_ignores(cuda_device):
+    prob = problem('demo_boat_novice')
+    rng = np.random.RandomState(5)
+    # many exact duplicates, spread over sub-blocks, tiles and splits: the lowest index must win
+    nodes = np.zeros((5000, 6)); nodes[:, 0] = np.arange(5000) % 11; nodes[:, 1] = (np.arange(5000) // 11) % 3
+    Q = np.zeros((600, 6)); Q[:, 0] = rng.randint(0, 11, 600); Q[:, 1] = rng.randint(0, 3, 600)
+    eng = make_engine(prob, 'f32', node_capacity=5008, wave_capacity=640)
+    eng.load_nodes(nodes)
+    (i0, c0), (i1, c1) = _both(eng, Q)
+    assert np.array_equal(i0, i1) and np.all(c1 == 0)
+    assert np.array_equal(i1, Q[:, 0].astype(int) + 11 * Q[:, 1].astype(int))
+    # ignore the winners (planner.py:240-245): both scans must fall to the same runner-ups
+    eng.mark_ignore(np.unique(i0))
+    (j0, d0), (j1, d1) = _both(eng, Q, use_ignore=True)
+    assert np.array_equal(j0, j1) and np.array_equal(d0.view(np.int64), d1.view(np.int64))
+    assert not np.isin(j1, np.unique(i0)).any()
+    # everything ignored: plain argmin again
+    eng.mark_ignore(np.arange(5000))
+    (k0, _), (k1, _) = _both(eng, Q, use_ignore=True)
+    assert np.array_equal(k0, i0) and np.array_equal(k1, i0)
+
+
+def _grow(prob, **kw):
+    planner = prob.make_planner(dtype='f32', seed=3, max_nodes=20000, min_time=1e9, max_time=1e9, **kw)
+    ok = planner.update_plan(prob.x0, prob.sample_space, goal_bias=prob.goal_bias, xrand_gen=10)
+    tree = planner.tree
+    return ok, tree.size, np.array(tree.state), list(tree.pID), planner.stats['waves'], planner.T
+
+
+@pytest.mark.parametrize('name', ['c3', 'c4'])
+def test_options_grow_the_same_tree(cuda_device, name):
+    prob = problem(name)
+    base = _grow(prob, nearest_kernel='scalar', prefetch=False)
+    for kw in (dict(nearest_kernel='packed', prefetch=False), dict(nearest_kernel='scalar', prefetch=True),
+               dict(nearest_kernel='packed', prefetch=True)):
+        got = _grow(prob, **kw)
+        assert got[0] == base[0] and got[1] == base[1] and got[4] == base[4], kw
+        assert got[3] == base[3], kw
+        assert np.array_equal(got[2].view(np.int64), base[2].view(np.int64)), kw
+        assert got[5] == base[5]
+
+
+def test_prefetch_across_plans_and_wave_sizes(cuda_device):
+    """Replanning pattern (lqrrt_node.py:389-500): the double-buffered sampler must survive resets, odd wave
+    counts and fixed small waves."""
+    prob = problem('c3')
+    out = []
+    for pf in (False, True):
+        planner = prob.make_planner(dtype='f32', seed=11, max_nodes=3000, min_time=1e9, max_time=1e9, prefetch=pf,
+                                    wave=96)
+        sizes = []
+        for rep in range(3):
+            planner.update_plan(prob.x0 + 0.01 * rep, prob.sample_space, goal_bias=prob.goal_bias, xrand_gen=10)
+            sizes.append((planner.tree.size, planner.stats['waves'], np.array(planner.tree.state).tobytes()))
+        out.append(sizes)
+    assert out[0] == out[1]
