@@ -113,6 +113,18 @@ typedef struct lq_wave_stats {
 
 typedef struct lq_engine lq_engine;
 
+/* ---- user-compiled dynamics ----------------------
+ * The reference takes `dynamics` as a Python closure (planner.py:35-37); a kernel cannot call Python, so a
+ * vehicle that is not one of the compiled models above is supplied as CUDA source for one explicit step
+ * (lqrrt_b200/plugin.py UserDynamics).  That source is compiled by nvcc against this engine's own headers
+ * into a small shared library whose factory builds the same lq_engine (same kernels, same C ABI) around
+ * the user's model; the library registers it here and lq_create dispatches any sys_kind >=
+ * LQ_SYS_PLUGIN_BASE to the factory registered for (sys_kind, dtype, lqr_kind).  The factory returns NULL
+ * and fills err / *rc on failure; it must not throw. */
+#define LQ_SYS_PLUGIN_BASE 1000
+typedef lq_engine* (*lq_plugin_factory)(const lq_config* cfg, char* err, int err_len, int* rc);
+int lq_register_plugin(int sys_kind, int dtype, int lqr_kind, lq_plugin_factory make);
+
 /* ---- lifetime ----------------------------------------------------------- */
 int lq_abi_version(void);
 int lq_create(const lq_config* cfg, lq_engine** out);       /* replaces Planner.__init__/set_system/set_resolution, planner.py:85-100,517-592 */

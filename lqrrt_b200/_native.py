@@ -61,6 +61,7 @@ _U8 = C.POINTER(C.c_uint8)
 SYMBOLS = {
     'lq_abi_version': (C.c_int, []),
     'lq_create': (C.c_int, [C.POINTER(lq_config), C.POINTER(_P)]),
+    'lq_register_plugin': (C.c_int, [C.c_int, C.c_int, C.c_int, _P]),
     'lq_destroy': (C.c_int, [_P]),
     'lq_last_error': (C.c_char_p, [_P]),
     'lq_set_goal': (C.c_int, [_P, _D, _D]),
@@ -200,6 +201,9 @@ class Engine(object):
         cfg.wave_capacity = self.wave_capacity
         cfg.tries_capacity = int(tries_capacity)
 
+        prepare = getattr(system.dynamics, 'prepare', None)
+        if prepare is not None:         # user-compiled dynamics (plugin.py): build + register its factory first
+            prepare(self.lib, dtype, system.lqr.kind)
         h = _P()
         rc = self.lib.lq_create(C.byref(cfg), C.byref(h))
         if rc != 0:

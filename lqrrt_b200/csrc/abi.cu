@@ -1,7 +1,16 @@
 // extern "C" surface of include/lqrrt_b200.h: argument checks, model dispatch, no exceptions across the boundary.
 #include "inst.cuh"
 
+#include <map>
+#include <mutex>
+#include <tuple>
+
 static thread_local std::string g_create_err = "";
+static std::mutex g_plugin_mu;
+static std::map<std::tuple<int, int, int>, lq_plugin_factory>& plugin_registry() {
+    static std::map<std::tuple<int, int, int>, lq_plugin_factory> r;
+    return r;
+}
 
 extern "C" {
 
@@ -24,6 +33,21 @@ int lq_create(const lq_config* cfg, lq_engine** out) {
     int rc = LQ_ERR_UNSUPPORTED;
     std::string err = "lq_create: unknown dynamics kind";
     lq_engine* e = nullptr;
+    if (cfg->sys_kind >= LQ_SYS_PLUGIN_BASE) {          // user-compiled dynamics: the plugin library's own factory
+        lq_plugin_factory make = nullptr;
+        {
+            std::lock_guard<std::mutex> g(g_plugin_mu);
+            auto it = plugin_registry().find(std::make_tuple(cfg->sys_kind, cfg->dtype, cfg->lqr_kind));
+            if (it != plugin_registry().end()) make = it->second;
+        }
+        if (!make) { g_create_err = "lq_create: no plugin registered for this (sys_kind, dtype, lqr_kind)"; return LQ_ERR_UNSUPPORTED; }
+        char buf[512] = {0};
+        rc = LQ_ERR_STATE;
+        e = make(cfg, buf, (int)sizeof buf, &rc);
+        if (!e) { g_create_err = std::string("lq_create (plugin): ") + buf; return rc == LQ_OK ? LQ_ERR_STATE : rc; }
+        *out = e;
+        return LQ_OK;
+    }
     try {
         switch (cfg->sys_kind) {
         case LQ_SYS_BOAT: e = f64 ? lq::make_boat_f64(cfg, err, &rc) : lq::make_boat_f32(cfg, err, &rc); break;
@@ -37,6 +61,13 @@ int lq_create(const lq_config* cfg, lq_engine** out) {
     }
     if (!e) { g_create_err = err; return rc; }
     *out = e;
+    return LQ_OK;
+}
+
+int lq_register_plugin(int sys_kind, int dtype, int lqr_kind, lq_plugin_factory make) {
+    if (sys_kind < LQ_SYS_PLUGIN_BASE || !make || (dtype != LQ_F32 && dtype != LQ_F64)) return LQ_ERR_ARG;
+    std::lock_guard<std::mutex> g(g_plugin_mu);
+    plugin_registry()[std::make_tuple(sys_kind, dtype, lqr_kind)] = make;
     return LQ_OK;
 }
 

@@ -75,7 +75,7 @@ def test_packed_scan_ties_and_ignores(cuda_device):
 
 
 def _grow(prob, **kw):
-    planner = prob.make_planner(dtype='f32', seed=3, max_nodes=20000, min_time=1e9, max_time=1e9, **kw)
+    planner = prob.make_planner(dtype='f32', seed=3, max_nodes=20000, min_time=60, max_time=60, **kw)
     ok = planner.update_plan(prob.x0, prob.sample_space, goal_bias=prob.goal_bias, xrand_gen=10)
     tree = planner.tree
     return ok, tree.size, np.array(tree.state), list(tree.pID), planner.stats['waves'], planner.T
@@ -100,7 +100,7 @@ def test_prefetch_across_plans_and_wave_sizes(cuda_device):
     prob = problem('c3')
     out = []
     for pf in (False, True):
-        planner = prob.make_planner(dtype='f32', seed=11, max_nodes=3000, min_time=1e9, max_time=1e9, prefetch=pf,
+        planner = prob.make_planner(dtype='f32', seed=11, max_nodes=3000, min_time=60, max_time=60, prefetch=pf,
                                     wave=96)
         sizes = []
         for rep in range(3):
