@@ -16,5 +16,5 @@ echo "== full gpu suite"; timeout 600 python -m pytest tests -m gpu -x -q --time
 echo "== ncu launch list (packed + prefetch)"
 LQRRT_NEAREST=packed LQRRT_PREFETCH=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_r1_packed.csv python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/ncu_bench.log 2>&1
 echo "== ncu full capture of the packed scan"
-LQRRT_NEAREST=packed timeout 300 ncu --set full --clock-control none --import-source on -k regex:nearest_diag_pk -s 45 -c 1 -o gpurun_out/ncu_nearest_pk_r1 -f python bench.py --steps 1 --warmup 0 --no-cpu > gpurun_out/ncu_full.log 2>&1
+LQRRT_NEAREST=packed timeout 300 ncu --set full --clock-control none --import-source on -k regex:nearest_diag_pk -s 30 -c 1 -o gpurun_out/ncu_nearest_pk_r1 -f python bench.py --steps 1 --warmup 0 --no-cpu > gpurun_out/ncu_full.log 2>&1
 date
