@@ -246,9 +246,14 @@ def run_gpu_arm(args):
 
     prob = make_problem(args.config)
     wave_max = args.wave * world if args.scaling == 'weak' else args.wave
-    planner = prob.make_planner(dtype=args.dtype, wave=None, wave_max=wave_max, max_nodes=prob.max_nodes,
+    planner = prob.make_planner(dtype=args.dtype, wave=None, wave_max=wave_max, wave_growth=args.growth, max_nodes=prob.max_nodes,
                                 min_time=1e9, max_time=1e9, comm=comm, device=local,
-                                exchange=os.environ.get('LQRRT_EXCHANGE', 'peer'))
+                                exchange=os.environ.get('LQRRT_EXCHANGE', 'peer'),
+                                nearest_kernel=args.nearest, prefetch=args.prefetch)
+    packed = planner.nearest_kernel != 'scalar' and args.dtype == 'f32'
+    # issue slots per (query, node) pair of the scan's inner loop at n = 6, one wrapped dim (cuobjdump -sass,
+    # profiles/README.md): scalar kernel 17.5; packed kernel 11.3, of which 5 are FP32x2 instructions
+    slots_per_pair = 11.3 if packed else 17.5
 
     def one_plan(seed):
         planner.seed = seed
@@ -321,9 +326,10 @@ def run_gpu_arm(args):
             "ms_per_step": tot_dev / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload_name(prob, args.config), "max_nodes": int(prob.max_nodes),
-                       "wave": "adaptive clamp(N, 32, {})".format(wave_max), "wave_per_gpu_max": wave_max // world,
+                       "wave": "adaptive clamp({:g}*N, 32, {})".format(args.growth, wave_max), "wave_per_gpu_max": wave_max // world,
                        "waves_per_step": float(np.mean(waves)), "samples_per_step": float(np.mean(samples)),
                        "yield": total_nodes / float(np.sum(samples)), "sampler": "philox4x32-10 on device, new seed per step",
+                       "nearest_kernel": planner.nearest_kernel, "sample_prefetch": planner.prefetch_active,
                        "plans_reaching_goal": "{}/{}".format(reached, args.steps), "plan_depth_edges": float(np.mean(depth)),
                        "plan_duration_s": float(np.mean(plan_T)),
                        "note": "tree depth grows by at most one edge per wave, so the throughput-maximal wave cap "
@@ -335,17 +341,18 @@ def run_gpu_arm(args):
                     "ms_per_step": tot_host / args.steps * 1e3,
                     "host_ms_per_step": dict(zip(("setup", "wave_loop", "closeout"), (phases / args.steps * 1e3).round(3).tolist()))},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "nearest_diag_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "nearest_diag_pk_kernel" if packed else "nearest_diag_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm if hbm else None, "traffic": ncu_traffic(),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes": prof['nearest_bytes'], "kernel_seconds": near_s,
                          "share_of_device_time": (prof['ms']['nearest'] / stage_total) if stage_total else None,
                          "pairs_per_s": pairs_per_s,
-                         "fp32_issue_frac": pairs_per_s * 17.5 / (148 * 128 * 1.965e9),
+                         "fp32_issue_frac": pairs_per_s * slots_per_pair / (148 * 128 * 1.965e9),
+                         "issue_slots_per_pair": slots_per_pair,
                          "note": "algorithmic bytes = sum_k W_k*N_k*n*sizeof(dtype) (SURVEY.md 8d); node tiles are reused "
                                  "by every query of a CTA from shared memory and the tree is L2-resident, so frac > 1 is "
-                                 "expected and the binding limit is FP32 issue: fp32_issue_frac = pairs_per_s x 17.5 "
-                                 "instructions per pair / (148 SMs x 128 lanes x 1.965 GHz); traffic = measured DRAM bytes "
+                                 "expected and the binding limit is FP32 issue: fp32_issue_frac = pairs_per_s x issue_slots_per_pair "
+                                 "/ (148 SMs x 128 lanes x 1.965 GHz); traffic = measured DRAM bytes "
                                  "per launch from the committed ncu capture"},
             "stage_ms": prof['ms'],
             "clocks": clk.summary(),
@@ -368,6 +375,11 @@ def main():
     ap.add_argument('--wave', type=int, default=8192, help="largest wave per GPU")
     ap.add_argument('--scaling', default='strong', choices=['weak', 'strong'],
                     help="strong: same global wave schedule for every N (bit-identical tree); weak: 8192 samples per GPU per wave")
+    ap.add_argument('--growth', type=float, default=2.0,
+                    help="adaptive wave size W = clamp(growth * tree size, 32, --wave); 1.0 is the Planner's own default "
+                         "(deeper tree per sample, ~40 more small waves per 100k-node plan)")
+    ap.add_argument('--nearest', default=None, help="nearest-scan kernel (default: the planner's)")
+    ap.add_argument('--prefetch', default=None, type=int, choices=[0, 1], help="side-stream sampler prefetch (default: the planner's)")
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--cpu-frozen', action='store_true', help="also time the CPU port on frozen trees of 1e3/1e4/1e5 nodes")

@@ -236,8 +236,12 @@ int lq_set_tuning(lq_engine* h, int steer_lanes, int nearest_q);
  *                          float64 engines and dense metrics ignore it.
  *   LQ_OPT_SAMPLE_PREFETCH 1: the device sampler (planner.py:201-211) of a wave is issued on a side stream into
  *                          the second sample buffer, so it overlaps the previous wave's scan and rollouts. */
-enum { LQ_OPT_NEAREST_KERNEL = 1, LQ_OPT_SAMPLE_PREFETCH = 2 };
-enum { LQ_NEAREST_SCALAR = 0, LQ_NEAREST_PACKED = 1 };
+enum { LQ_OPT_NEAREST_KERNEL = 1, LQ_OPT_SAMPLE_PREFETCH = 2,
+       LQ_OPT_NEAREST_CTAS_PER_SM = 3   /* grid target of the scan in CTAs per SM; 0 = auto (16 for n <= 6, else 8) */ };
+enum { LQ_NEAREST_SCALAR = 0, LQ_NEAREST_PACKED = 1,
+       /* tuning variants, same results: 8 queries per thread (best on the 12-state scan), and the two-level
+        * argmin with one-lane-at-a-time arithmetic */
+       LQ_NEAREST_PACKED_Q8 = 2, LQ_NEAREST_TWO_LEVEL = 3 };
 int lq_set_option(lq_engine* h, int option, int value);
 int lq_get_option(lq_engine* h, int option, int* value);
 /* Per-stage CUDA-event timing of the wave chain on the launching stream (bench.py's roofline leg).

@@ -3,4 +3,4 @@
 resolved to the B200 engine, so code written against jnez71/lqRRT only has to
 swap its model callbacks for `lqrrt.models` specs.
 """
-from lqrrt_b200 import Constraints, Planner, Tree, models, configs  # noqa: F401
+from lqrrt_b200 import Constraints, Planner, Tree, models, configs, plugin  # noqa: F401

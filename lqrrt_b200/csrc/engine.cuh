@@ -197,6 +197,7 @@ struct EngineImpl : lq_engine {
     int size_ub_exact = 0;           // tree size as of the last stats read (wave-start size for profiling)
     int steer_lanes = 1, near_q = 0; // tuning (0 = heuristic)
     int near_kernel = LQ_NEAREST_SCALAR;   // lq_set_option(LQ_OPT_NEAREST_KERNEL)
+    int near_ctas_per_sm = 0;              // lq_set_option(LQ_OPT_NEAREST_CTAS_PER_SM): grid target of the scan, 0 = auto
     // lq_set_option(LQ_OPT_SAMPLE_PREFETCH): sampler of the next wave on a side stream, double-buffered
     bool prefetch_on = false;
     cudaStream_t aux = nullptr;
@@ -627,7 +628,9 @@ struct EngineImpl : lq_engine {
     int launch_nearest(const T* q, int qstride, int W, int use_ignore, int* idx, T* cost, cudaStream_t st, int* nsplit_out = nullptr) {
         const int Nub = std::max(1, size_ub);
         const int max_splits = std::min(MAX_SPLIT, (Nub + NEAR_BLOCK - 1) / NEAR_BLOCK);
-        const int target = 148 * 8;
+        // measured (profiles/README.md, sweep_k1_r1): 16 CTAs per SM fill the machine better on the n <= 6 trees
+        // (mid-size waves), the 12-state scan prefers 8
+        const int target = 148 * (near_ctas_per_sm > 0 ? near_ctas_per_sm : (N <= 6 ? 16 : 8));
         int nsplit_used = 1;
         auto plan = [&](int qper, int& nqb, int& chunk, int& nsplit) {
             nqb = (W + NEAR_BLOCK * qper - 1) / (NEAR_BLOCK * qper);
@@ -658,21 +661,32 @@ struct EngineImpl : lq_engine {
         else if (cmask == 1) LQ_NEAR_DIAG(QQ, 1);           \
         else LQ_NEAR_DIAG(QQ, -1);                          \
     } while (0)
-#define LQ_NEAR_PK(MM)                                                                                    \
-    nearest_diag_pk_kernel<N, 4, NEAR_BLOCK, MM, 8><<<nqb * nsplit, NEAR_BLOCK, 0, st>>>(                   \
+#define LQ_NEAR_PK(QQ, MB, PK, MM)                                                                         \
+    nearest_diag_pk_kernel<N, QQ, NEAR_BLOCK, MM, 8, MB, PK><<<nqb * nsplit, NEAR_BLOCK, 0, st>>>(          \
         t_state.p, cap, t_ignore.p, tv.size, tv.n_ignored, use_ignore, q, qstride, W, dmet, nqb, chunk,   \
         w_pcost.p, w_pidx.p, Wc)
+#define LQ_NEAR_PK_M(QQ, MB, PK)                                  \
+    do {                                                          \
+        plan(QQ, nqb, chunk, nsplit);                             \
+        if (cmask == 0) LQ_NEAR_PK(QQ, MB, PK, 0);                \
+        else if (cmask == 4) LQ_NEAR_PK(QQ, MB, PK, (N >= 3 ? 4 : 0)); \
+        else if (cmask == 1) LQ_NEAR_PK(QQ, MB, PK, 1);           \
+        else LQ_NEAR_PK(QQ, MB, PK, -1);                          \
+    } while (0)
             bool packed = false;
             if constexpr (sizeof(T) == 4) {          // FP32x2 issue + two-level argmin: same results, fewer issue slots
-                if (big && near_kernel == LQ_NEAREST_PACKED) {
+                if (big && near_kernel != LQ_NEAREST_SCALAR) {
                     packed = true;
-                    if (cmask == 0) LQ_NEAR_PK(0);
-                    else if (cmask == 4) LQ_NEAR_PK((N >= 3 ? 4 : 0));
-                    else if (cmask == 1) LQ_NEAR_PK(1);
-                    else LQ_NEAR_PK(-1);
+                    switch (near_kernel) {
+                    // minimum CTAs per SM = the register budget each variant is compiled for (128-thread CTAs)
+                    case LQ_NEAREST_PACKED: LQ_NEAR_PK_M(4, (N <= 6 ? 8 : 4), true); break;
+                    case LQ_NEAREST_PACKED_Q8: LQ_NEAR_PK_M(8, (N <= 6 ? 4 : 2), true); break;
+                    default: LQ_NEAR_PK_M(4, (N <= 6 ? 8 : 4), false); break;     // LQ_NEAREST_TWO_LEVEL
+                    }
                 }
             }
             if (!packed) { if (big) LQ_NEAR_DIAG_M(QBIG); else LQ_NEAR_DIAG_M(1); }
+#undef LQ_NEAR_PK_M
 #undef LQ_NEAR_PK
 #undef LQ_NEAR_DIAG_M
 #undef LQ_NEAR_DIAG
@@ -1209,8 +1223,11 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(cudaSetDevice(device));
         switch (option) {
         case LQ_OPT_NEAREST_KERNEL:
-            if (value != LQ_NEAREST_SCALAR && value != LQ_NEAREST_PACKED) LQ_FAIL(LQ_ERR_ARG, "unknown nearest kernel %d", value);
+            if (value < LQ_NEAREST_SCALAR || value > LQ_NEAREST_TWO_LEVEL) LQ_FAIL(LQ_ERR_ARG, "unknown nearest kernel %d", value);
             near_kernel = value; return LQ_OK;
+        case LQ_OPT_NEAREST_CTAS_PER_SM:
+            if (value < 0 || value > 64) LQ_FAIL(LQ_ERR_ARG, "CTAs per SM must be in 0 (auto)..64");
+            near_ctas_per_sm = value; return LQ_OK;
         case LQ_OPT_SAMPLE_PREFETCH:
             prefetch_on = value != 0; return LQ_OK;
         default: LQ_FAIL(LQ_ERR_ARG, "unknown option %d", option);
@@ -1219,6 +1236,7 @@ struct EngineImpl : lq_engine {
     int get_option(int option, int* value) override {
         switch (option) {
         case LQ_OPT_NEAREST_KERNEL: *value = near_kernel; return LQ_OK;
+        case LQ_OPT_NEAREST_CTAS_PER_SM: *value = near_ctas_per_sm; return LQ_OK;
         case LQ_OPT_SAMPLE_PREFETCH: *value = prefetch_on ? 1 : 0; return LQ_OK;
         default: LQ_FAIL(LQ_ERR_ARG, "unknown option %d", option);
         }

@@ -153,7 +153,7 @@ nearest_diag_kernel(const T* __restrict__ state, int cap, const uint8_t* __restr
 //     lowest-index tie-break as the one-level scan.
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 
-template <int N, int MASK>
+template <int N, int MASK, bool PACKED>
 __device__ __forceinline__ float2 pair_cost(const float2 (&q)[N], const float2* __restrict__ v, uint32_t mask,
                                             const float (&period)[N]) {
     // v[d] = (-node_d, -node_d) (staged negated: q - v == q + (-v) exactly); q[d] = (query A_d, query B_d)
@@ -167,17 +167,20 @@ __device__ __forceinline__ float2 pair_cost(const float2 (&q)[N], const float2* 
             const float aa = fabsf(ea), ab = fabsf(eb);
             ea = fminf(aa, period[d] - aa); eb = fminf(ab, period[d] - ab);
             c.x = fmaf(ea, ea, c.x); c.y = fmaf(eb, eb, c.y);      // fma(e, e, 0) == e * e exactly
-        } else {
+        } else if (PACKED) {
             const float2 e = __fadd2_rn(q[d], vd);
             c = first ? __fmul2_rn(e, e) : __ffma2_rn(e, e, c);
+        } else {                                        // same operations, one lane at a time
+            const float ea = q[d].x + vd.x, eb = q[d].y + vd.x;
+            c.x = fmaf(ea, ea, c.x); c.y = fmaf(eb, eb, c.y);
         }
         first = false;
     }
     return c;
 }
 
-template <int N, int Q, int BLOCK, int MASK, int SB>
-__global__ void __launch_bounds__(BLOCK)
+template <int N, int Q, int BLOCK, int MASK, int SB, int MINB, bool PACKED>
+__global__ void __launch_bounds__(BLOCK, MINB)
 nearest_diag_pk_kernel(const float* __restrict__ state, int cap, const uint8_t* __restrict__ ignore,
                        const int* __restrict__ d_size, const int* __restrict__ d_nignored, int use_ignore,
                        const float* __restrict__ queries, int qstride, int W,
@@ -248,7 +251,7 @@ nearest_diag_pk_kernel(const float* __restrict__ state, int cap, const uint8_t* 
                 for (int d = 0; d < NE; d++) v[d] = tile[(s + i) * NE + d];    // same address in every lane: broadcast
 #pragma unroll
                 for (int kp = 0; kp < QP; kp++) {
-                    const float2 c = pair_cost<N, MASK>(q[kp], v, mask, met.period);
+                    const float2 c = pair_cost<N, MASK, PACKED>(q[kp], v, mask, met.period);
                     m[kp].x = fminf(m[kp].x, c.x); m[kp].y = fminf(m[kp].y, c.y);
                 }
             }
@@ -271,7 +274,7 @@ nearest_diag_pk_kernel(const float* __restrict__ state, int cap, const uint8_t* 
                 staged(bsb[k] + i, v);
 #pragma unroll
                 for (int d = 0; d < NE; d++) v2[d] = d < N ? f2(-v[d], -v[d]) : f2(0.f, 0.f);
-                const float2 c = pair_cost<N, MASK>(q[k / 2], v2, mask, met.period);
+                const float2 c = pair_cost<N, MASK, PACKED>(q[k / 2], v2, mask, met.period);
                 if (((k & 1) ? c.y : c.x) == best[k]) bidx = bsb[k] + i;
             }
         }

@@ -46,8 +46,12 @@ from .tree import Tree
 
 
 # Issue-level options of the engine (include/lqrrt_b200.h lq_set_option); results do not depend on them.
-DEFAULT_NEAREST_KERNEL = 'scalar'
-DEFAULT_PREFETCH = False
+# Measured on B200 (profiles/README.md, round 1): packed scan +3 % (C4) / +11 % (C5k) on the scan's time,
+# prefetch takes the sampler (1.0 of 14.7 ms per C4 plan) off the wave's dependent chain.  Prefetch is on by
+# default for single-GPU planners only: it is verified bit-identical there (tests/test_gpu_zz_options.py);
+# multi-GPU planners take it when asked (prefetch=True or $LQRRT_PREFETCH=1).
+DEFAULT_NEAREST_KERNEL = 'packed'
+DEFAULT_PREFETCH = True
 
 
 class Planner(object):
@@ -62,12 +66,15 @@ class Planner(object):
         self._engine = None
         if nearest_kernel is None:
             nearest_kernel = os.environ.get('LQRRT_NEAREST') or DEFAULT_NEAREST_KERNEL
-        if nearest_kernel not in ('scalar', 'packed'):
-            raise ValueError("nearest_kernel must be 'scalar' or 'packed'")
+        from ._native import NEAREST_KERNELS
+        if nearest_kernel not in NEAREST_KERNELS:
+            raise ValueError("nearest_kernel must be one of {}".format(sorted(NEAREST_KERNELS)))
         self.nearest_kernel = nearest_kernel
+        self._prefetch_explicit = True
         if prefetch is None:
             env = os.environ.get('LQRRT_PREFETCH')
-            prefetch = DEFAULT_PREFETCH if env in (None, '') else env not in ('0', 'false', 'off')
+            self._prefetch_explicit = env not in (None, '')
+            prefetch = DEFAULT_PREFETCH if not self._prefetch_explicit else env not in ('0', 'false', 'off')
         self.prefetch = bool(prefetch)
         if exchange not in ('peer', 'nccl'):
             raise ValueError("exchange must be 'peer' or 'nccl'")
@@ -107,6 +114,10 @@ class Planner(object):
         self.comm = comm
         self.world = dist.get_world_size(comm)
         self.rank = dist.get_rank(comm)
+
+    @property
+    def prefetch_active(self):
+        return bool(self.prefetch and self.pipeline and (self.world == 1 or self._prefetch_explicit))
 
     # ---------------------------------------------------------------- engine
     def _device(self):
@@ -148,7 +159,7 @@ class Planner(object):
                 self._engine.set_tuning(t[0], t[1])
         from ._native import LQ_OPT_NEAREST_KERNEL, LQ_OPT_SAMPLE_PREFETCH, NEAREST_KERNELS
         self._engine.set_option(LQ_OPT_NEAREST_KERNEL, NEAREST_KERNELS[self.nearest_kernel])
-        self._engine.set_option(LQ_OPT_SAMPLE_PREFETCH, int(self.prefetch and self.pipeline))
+        self._engine.set_option(LQ_OPT_SAMPLE_PREFETCH, int(self.prefetch_active))
         return self._engine
 
     @staticmethod

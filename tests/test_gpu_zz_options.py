@@ -14,16 +14,16 @@ from gpu_util import make_engine, nearest
 
 pytestmark = pytest.mark.gpu
 
-OPT_NEAREST, OPT_PREFETCH = 1, 2
-SCALAR, PACKED = 0, 1
+OPT_NEAREST, OPT_PREFETCH, OPT_CTAS = 1, 2, 3
+SCALAR, PACKED, PACKED_Q8, TWO_LEVEL = 0, 1, 2, 3
 
 
-def _both(eng, Q, use_ignore=False):
-    eng.set_tuning(0, 4)                         # large-wave launch shape (Q = 4 queries per thread) for any W
-    eng.set_option(OPT_NEAREST, SCALAR)
+def _both(eng, Q, use_ignore=False, kernel=PACKED, ctas=0):
+    eng.set_tuning(0, 4)                         # large-wave launch shape (several queries per thread) for any W
+    eng.set_option(OPT_NEAREST, SCALAR); eng.set_option(OPT_CTAS, 8)
     a = nearest(eng, Q, use_ignore)
-    eng.set_option(OPT_NEAREST, PACKED)
-    assert eng.get_option(OPT_NEAREST) == PACKED
+    eng.set_option(OPT_NEAREST, kernel); eng.set_option(OPT_CTAS, ctas)
+    assert eng.get_option(OPT_NEAREST) == kernel
     b = nearest(eng, Q, use_ignore)
     return a, b
 
@@ -38,7 +38,8 @@ def _cloud(prob, rng, count, turns=15.0):
                                       ('demo_boat_novice', 1, 3), ('demo_boat_novice', 30001, 513),
                                       ('demo_boat_novice', 129, 1027), ('demo_boat_novice', 8, 512),
                                       ('demo_car', 9001, 700), ('c5k', 5003, 600), ('c4', 100000, 2048)])
-def test_packed_scan_is_bit_identical(cuda_device, name, N, W):
+@pytest.mark.parametrize('kernel,ctas', [(PACKED, 0), (PACKED_Q8, 8), (TWO_LEVEL, 16), (PACKED, 3)])
+def test_packed_scan_is_bit_identical(cuda_device, name, N, W, kernel, ctas):
     prob = problem(name)
     rng = np.random.RandomState(N + W)
     nodes = _cloud(prob, rng, N); Q = _cloud(prob, rng, W)
@@ -47,7 +48,7 @@ def test_packed_scan_is_bit_identical(cuda_device, name, N, W):
         Q[:, 2] = 15 * (rng.rand(W) - 0.5)
     eng = make_engine(prob, 'f32', node_capacity=N + 8, wave_capacity=W + 3)
     eng.load_nodes(nodes)
-    (i0, c0), (i1, c1) = _both(eng, Q)
+    (i0, c0), (i1, c1) = _both(eng, Q, kernel=kernel, ctas=ctas)
     assert np.array_equal(i0, i1)
     assert np.array_equal(c0.view(np.int64), c1.view(np.int64))
 
