@@ -251,9 +251,19 @@ def run_gpu_arm(args):
                                 exchange=os.environ.get('LQRRT_EXCHANGE', 'peer'),
                                 nearest_kernel=args.nearest, prefetch=args.prefetch)
     packed = planner.nearest_kernel != 'scalar' and args.dtype == 'f32'
-    # issue slots per (query, node) pair of the scan's inner loop at n = 6, one wrapped dim (cuobjdump -sass,
-    # profiles/README.md): scalar kernel 17.5; packed kernel 11.3, of which 5 are FP32x2 instructions
-    slots_per_pair = 11.3 if packed else 17.5
+    # Issue slots and FMA-pipe cycles per (query, node) pair of the scan's inner loop, n dims of which w wrap
+    # (cuobjdump -sass of csrc/nearest.cuh, checked against ncu's instruction counts in profiles/README.md):
+    #   scalar: FADD+FFMA per dim, 4 per wrapped dim, compare + 2 selects, LDS/loop 0.5      -> 17.5 at n=6, w=1
+    #   packed: FADD2+FFMA2 per dim per TWO pairs, wrapped dims scalar, FMNMX + 3/8 per pair,
+    #           LDS.128 n/8 per pair                                                          -> 11.3 at n=6, w=1
+    #   FMA pipe: FFMA2/FADD2 hold it 2 cycles, so both forms cost 2(n-w) + 3w cycles per pair -> 13
+    n_dims = prob.nstates
+    n_wrap = bin(prob.system.erf.mask(n_dims)).count('1')
+    if packed:
+        slots_per_pair = (n_dims - n_wrap) + 4 * n_wrap + 1.4 + (n_dims + 1) // 2 * 2 / 8.0 + 0.2
+    else:
+        slots_per_pair = 2 * (n_dims - n_wrap) + 4 * n_wrap + 3.5
+    pipe_cycles_per_pair = 2 * (n_dims - n_wrap) + 3 * n_wrap
 
     def one_plan(seed):
         planner.seed = seed
@@ -349,10 +359,14 @@ def run_gpu_arm(args):
                          "pairs_per_s": pairs_per_s,
                          "fp32_issue_frac": pairs_per_s * slots_per_pair / (148 * 128 * 1.965e9),
                          "issue_slots_per_pair": slots_per_pair,
+                         "fma_pipe_frac": pairs_per_s * pipe_cycles_per_pair / (148 * 128 * 1.965e9),
+                         "fma_pipe_cycles_per_pair": pipe_cycles_per_pair,
                          "note": "algorithmic bytes = sum_k W_k*N_k*n*sizeof(dtype) (SURVEY.md 8d); node tiles are reused "
                                  "by every query of a CTA from shared memory and the tree is L2-resident, so frac > 1 is "
-                                 "expected and the binding limit is FP32 issue: fp32_issue_frac = pairs_per_s x issue_slots_per_pair "
-                                 "/ (148 SMs x 128 lanes x 1.965 GHz); traffic = measured DRAM bytes "
+                                 "expected and the binding limit is the FP32 pipe: fp32_issue_frac = pairs_per_s x issue_slots_per_pair "
+                                 "/ (148 SMs x 128 lanes x 1.965 GHz) bounds the scalar kernel (ncu: 90 % of issue slots), "
+                                 "fma_pipe_frac = pairs_per_s x fma_pipe_cycles_per_pair / the same denominator bounds the packed "
+                                 "kernel (ncu: FMA pipe 67.6 % of cycles, math-pipe-throttle the top stall); traffic = measured DRAM bytes "
                                  "per launch from the committed ncu capture"},
             "stage_ms": prof['ms'],
             "clocks": clk.summary(),

@@ -1,6 +1,7 @@
 """Turns what a gpurun call left in gpurun_out/ into the tracked summaries under profiles/.
 
     python profiles/summarize.py r1            # reads gpurun_out/{launches_r1.csv, prof_*_r1.ncu-rep, bench_r1_*.json}
+    python profiles/summarize.py r1b k1        # launches_r1b.csv + gpurun_out/ncu_k1_r1.ncu-rep -> ncu_nearest_r1b.txt (+ stall table)
 """
 import collections
 import csv
@@ -14,13 +15,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, 'profiles')
 SRC = os.path.join(ROOT, 'gpurun_out')
 
+STALLS = ['math_pipe_throttle', 'not_selected', 'wait', 'short_scoreboard', 'dispatch_stall', 'long_scoreboard', 'barrier',
+          'branch_resolving', 'mio_throttle', 'lg_throttle', 'no_instruction']
+
 KEYS = ['Kernel Name', 'Grid Size', 'Block Size', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'lts__t_bytes.sum', 'l1tex__t_bytes.sum',
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_alu.sum',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
         'smsp__thread_inst_executed_per_inst_executed.ratio', 'launch__registers_per_thread',
-        'launch__waves_per_multiprocessor', 'sm__cycles_elapsed.max', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active']
+        'launch__waves_per_multiprocessor', 'sm__cycles_elapsed.max', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'smsp__warps_active.avg.per_cycle_active',
+        'smsp__warps_eligible.avg.per_cycle_active', 'launch__occupancy_limit_registers',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']
 
 
 def launches(tag):
@@ -50,8 +58,8 @@ def launches(tag):
             f.write("%-28s %6d %12.1f %6.1f%% %10.1f %10.1f\n" % (k, v[0], v[1] / 1e3, 100 * v[1] / tot, v[1] / v[0] / 1e3, v[2] / 1e3))
 
 
-def full(tag, which):
-    rep = os.path.join(SRC, 'prof_%s_%s.ncu-rep' % (which, tag))
+def full(tag, which, rep=None):
+    rep = rep or os.path.join(SRC, 'prof_%s_%s.ncu-rep' % (which, tag))
     if not os.path.isfile(rep):
         return
     raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
@@ -65,6 +73,10 @@ def full(tag, which):
                 if k in hdr:
                     i = hdr.index(k)
                     f.write("%-72s %s %s\n" % (k, r[i][:120], units[i]))
+            for st in STALLS:          # warp-cycles stalled per issued instruction, by reason
+                k = 'smsp__average_warps_issue_stalled_%s_per_issue_active.ratio' % st
+                if k in hdr:
+                    f.write("%-72s %s\n" % ('stall/issue ' + st, r[hdr.index(k)]))
 
 
 def bench(tag):
@@ -80,7 +92,10 @@ def bench(tag):
 if __name__ == '__main__':
     tag = sys.argv[1] if len(sys.argv) > 1 else 'r1'
     launches(tag)
-    for which in ('nearest', 'steer'):
-        full(tag, which)
-    bench(tag)
+    if len(sys.argv) > 2 and sys.argv[2] == 'k1':
+        full(tag, 'nearest', os.path.join(SRC, 'ncu_k1_r1.ncu-rep'))
+    else:
+        for which in ('nearest', 'steer'):
+            full(tag, which)
+        bench(tag)
     print(sorted(os.listdir(OUT)))
