@@ -83,3 +83,61 @@ def test_missing_library_is_an_error(monkeypatch, tmp_path):
     monkeypatch.setattr(_native, 'LIB_PATH', str(tmp_path / 'nope.so'))
     with pytest.raises(_native.NativeError, match="no CPU fallback"):
         _native.load_library()
+
+
+def test_engine_option_arguments(monkeypatch):
+    """Issue-level options (lq_set_option): validated on the host, results never depend on them."""
+    from lqrrt_b200 import planner as pl
+    monkeypatch.delenv('LQRRT_NEAREST', raising=False)
+    monkeypatch.delenv('LQRRT_PREFETCH', raising=False)
+    prob, p = _planner()
+    assert p.nearest_kernel == pl.DEFAULT_NEAREST_KERNEL and p.prefetch == pl.DEFAULT_PREFETCH
+    assert p.prefetch_active == (pl.DEFAULT_PREFETCH and p.world == 1)
+    with pytest.raises(ValueError, match="nearest_kernel must be one of"):
+        _planner(nearest_kernel='fastest')
+    _, q = _planner(nearest_kernel='scalar', prefetch=False)
+    assert q.nearest_kernel == 'scalar' and not q.prefetch_active
+    _, r = _planner(prefetch=True, pipeline=False)          # nothing to overlap with without the pipelined loop
+    assert not r.prefetch_active
+    monkeypatch.setenv('LQRRT_NEAREST', 'two_level')
+    monkeypatch.setenv('LQRRT_PREFETCH', '0')
+    _, e = _planner()
+    assert e.nearest_kernel == 'two_level' and not e.prefetch
+    # a multi-GPU planner takes the prefetch only when asked (planner.py DEFAULT_PREFETCH note)
+    monkeypatch.delenv('LQRRT_PREFETCH', raising=False)
+    _, m = _planner()
+    m.world = 2
+    assert not m.prefetch_active
+    _, m2 = _planner(prefetch=True)
+    m2.world = 2
+    assert m2.prefetch_active
+
+
+def test_bench_cli_defaults():
+    """The driver runs `python bench.py` bare: N = 1, the C4 workload, growth-2 waves, the planner's own kernels."""
+    import importlib.util
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(root, 'bench.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    argv, sys.argv = sys.argv, ['bench.py']
+    try:
+        import argparse
+        captured = {}
+        orig = argparse.ArgumentParser.parse_args
+
+        def grab(self, *a, **k):
+            ns = orig(self, *a, **k)
+            captured['ns'] = ns
+            raise SystemExit(0)
+        argparse.ArgumentParser.parse_args = grab
+        with pytest.raises(SystemExit):
+            mod.main()
+    finally:
+        argparse.ArgumentParser.parse_args = orig
+        sys.argv = argv
+    ns = captured['ns']
+    assert (ns.gpus, ns.config, ns.impl, ns.wave, ns.growth, ns.nearest, ns.prefetch) == (1, 'c4', 'ours', 8192, 2.0, None, None)
+    assert ns.steps >= 1 and ns.warmup >= 3
