@@ -241,7 +241,10 @@ enum { LQ_OPT_NEAREST_KERNEL = 1, LQ_OPT_SAMPLE_PREFETCH = 2,
 enum { LQ_NEAREST_SCALAR = 0, LQ_NEAREST_PACKED = 1,
        /* tuning variants, same results: 8 queries per thread (best on the 12-state scan), and the two-level
         * argmin with one-lane-at-a-time arithmetic */
-       LQ_NEAREST_PACKED_Q8 = 2, LQ_NEAREST_TWO_LEVEL = 3 };
+       LQ_NEAREST_PACKED_Q8 = 2, LQ_NEAREST_TWO_LEVEL = 3,
+       /* experimental (not measured yet): partial-distance filter -- the cost of the leading position dims is a
+        * floating-point lower bound of the full cost, pairs that cannot win skip the other dims; same results */
+       LQ_NEAREST_PREFIX = 4 };
 int lq_set_option(lq_engine* h, int option, int value);
 int lq_get_option(lq_engine* h, int option, int* value);
 /* Per-stage CUDA-event timing of the wave chain on the launching stream (bench.py's roofline leg).

@@ -21,7 +21,7 @@ LQ_MAX_N = 12
 LQ_F32, LQ_F64 = 0, 1
 LQ_OPT_NEAREST_KERNEL, LQ_OPT_SAMPLE_PREFETCH = 1, 2
 LQ_OPT_NEAREST_CTAS_PER_SM = 3
-NEAREST_KERNELS = {'scalar': 0, 'packed': 1, 'packed_q8': 2, 'two_level': 3}
+NEAREST_KERNELS = {'scalar': 0, 'packed': 1, 'packed_q8': 2, 'two_level': 3, 'prefix': 4}
 
 
 class NativeError(RuntimeError):

@@ -681,6 +681,21 @@ struct EngineImpl : lq_engine {
                     // minimum CTAs per SM = the register budget each variant is compiled for (128-thread CTAs)
                     case LQ_NEAREST_PACKED: LQ_NEAR_PK_M(4, (N <= 6 ? 8 : 4), true); break;
                     case LQ_NEAREST_PACKED_Q8: LQ_NEAR_PK_M(8, (N <= 6 ? 4 : 2), true); break;
+                    case LQ_NEAREST_PREFIX:                // experimental partial-distance filter on the leading (position) dims
+                        if constexpr (N >= 3) {
+                            constexpr int PFX = N >= 12 ? 3 : 2;          // leading position dims used as the bound
+                            if ((md.angle_mask & ((1u << PFX) - 1u)) == 0u && (cmask == 0 || cmask == 4)) {
+                                plan(4, nqb, chunk, nsplit);
+#define LQ_NEAR_PFX(MM)                                                                                   \
+    nearest_diag_prefix_kernel<N, 4, NEAR_BLOCK, MM, PFX><<<nqb * nsplit, NEAR_BLOCK, 0, st>>>(             \
+        t_state.p, cap, t_ignore.p, tv.size, tv.n_ignored, use_ignore, q, qstride, W, dmet, nqb, chunk,   \
+        w_pcost.p, w_pidx.p, Wc)
+                                if (cmask == 0) LQ_NEAR_PFX(0); else LQ_NEAR_PFX((N >= 3 ? 4 : 0));
+#undef LQ_NEAR_PFX
+                                break;
+                            }
+                        }
+                        LQ_NEAR_PK_M(4, (N <= 6 ? 8 : 4), true); break;      // not applicable: the packed scan
                     default: LQ_NEAR_PK_M(4, (N <= 6 ? 8 : 4), false); break;     // LQ_NEAREST_TWO_LEVEL
                     }
                 }
@@ -1223,7 +1238,7 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(cudaSetDevice(device));
         switch (option) {
         case LQ_OPT_NEAREST_KERNEL:
-            if (value < LQ_NEAREST_SCALAR || value > LQ_NEAREST_TWO_LEVEL) LQ_FAIL(LQ_ERR_ARG, "unknown nearest kernel %d", value);
+            if (value < LQ_NEAREST_SCALAR || value > LQ_NEAREST_PREFIX) LQ_FAIL(LQ_ERR_ARG, "unknown nearest kernel %d", value);
             near_kernel = value; return LQ_OK;
         case LQ_OPT_NEAREST_CTAS_PER_SM:
             if (value < 0 || value > 64) LQ_FAIL(LQ_ERR_ARG, "CTAs per SM must be in 0 (auto)..64");

@@ -37,6 +37,12 @@ __device__ __forceinline__ T reduce_period(T a) {   // a -> a - 2 pi rint(a / 2 
     return a - Num<T>::two_pi() * rint_t(a * Num<T>::inv_two_pi());
 }
 
+// Pre-scaling by sqrt(S_ii) is a rounded multiply of its own (never contracted into the later subtraction as
+// an FMA): every float32 variant of the scan then evaluates round(q w) - round(v w) and they stay bit-identical
+// to each other for any weights, not only for the demos' S = I.
+__device__ __forceinline__ float prescale(float a, float w) { return __fmul_rn(a, w); }
+__device__ __forceinline__ double prescale(double a, double w) { return __dmul_rn(a, w); }
+
 // MASK >= 0: the erf angle mask is a compile-time constant (the common masks are instantiated, see
 // engine.cuh), so only the wrapped dims pay for the wrap and the others are one FADD + one FFMA.
 // MASK < 0: generic fallback reading met.angle_mask at run time.  EXACT selects the float64 parity
@@ -74,7 +80,7 @@ nearest_diag_kernel(const T* __restrict__ state, int cap, const uint8_t* __restr
             T v = j < W ? queries[(size_t)d * qstride + j] : T(0);
             if (!EXACT) {
                 if (mask & (1u << d)) v = reduce_period(v);
-                v *= met.w[d];
+                v = prescale(v, met.w[d]);
             }
             q[k][d] = v;
         }
@@ -91,7 +97,7 @@ nearest_diag_kernel(const T* __restrict__ state, int cap, const uint8_t* __restr
                 T a = live ? state[(size_t)d * cap + node] : T(0);
                 if (!EXACT) {
                     if (mask & (1u << d)) a = reduce_period(a);
-                    a *= met.w[d];
+                    a = prescale(a, met.w[d]);
                 }
                 v[d] = live ? a : Num<T>::inf();       // dead rows can never win (inf cost or NaN)
             }
@@ -213,7 +219,7 @@ nearest_diag_pk_kernel(const float* __restrict__ state, int cap, const uint8_t* 
         for (int d = 0; d < N; d++) {
             float v = j < W ? queries[(size_t)d * qstride + j] : 0.f;
             if (mask & (1u << d)) v = reduce_period(v);
-            v *= met.w[d];
+            v = prescale(v, met.w[d]);
             if (k & 1) q[k / 2][d].y = v; else q[k / 2][d].x = v;
         }
     }
@@ -224,7 +230,7 @@ nearest_diag_pk_kernel(const float* __restrict__ state, int cap, const uint8_t* 
         for (int d = 0; d < N; d++) {
             float a = live ? state[(size_t)d * cap + node] : 0.f;
             if (mask & (1u << d)) a = reduce_period(a);
-            a *= met.w[d];
+            a = prescale(a, met.w[d]);
             v[d] = live ? a : INFINITY;
         }
         return live;
@@ -281,6 +287,105 @@ nearest_diag_pk_kernel(const float* __restrict__ state, int cap, const uint8_t* 
         if (j < W) {
             pcost[(size_t)split * pstride + j] = best[k];
             pidx[(size_t)split * pstride + j] = bidx;
+        }
+    }
+}
+
+// ---- float32 scan with a partial-distance filter (experimental, LQ_NEAREST_PREFIX) ---------------------
+// The cost chain c = fma(e_d, e_d, c), d = 0..N-1, only grows: every term is >= 0 and rounding is monotone,
+// so the value after the first PREFIX dims (the positions) is a rigorous lower bound of the full cost IN
+// FLOATING POINT.  A pair whose prefix is not below the query's running best cannot win and skips the other
+// N - PREFIX dims; a pair that passes continues the same chain, so costs, argmin and the lowest-index
+// tie-break are bit-identical to nearest_diag_kernel.  With nodes in insertion order the expected number of
+// passes per (query, chunk of m nodes) is O(log m) (tools/filter_study.py: 0.7 % of pairs on a C4 tree), but
+// a warp pays for the long path whenever one of its lanes takes it -- whether that wins is a measurement
+// for round 2.  Leading dims must not be wrapped (the engine checks the mask).
+template <int N, int Q, int BLOCK, int MASK, int PREFIX>
+__global__ void __launch_bounds__(BLOCK)
+nearest_diag_prefix_kernel(const float* __restrict__ state, int cap, const uint8_t* __restrict__ ignore,
+                           const int* __restrict__ d_size, const int* __restrict__ d_nignored, int use_ignore,
+                           const float* __restrict__ queries, int qstride, int W,
+                           DiagMetric<float, N> met, int nqb, int chunk,
+                           float* __restrict__ pcost, int* __restrict__ pidx, int pstride) {
+    static_assert(PREFIX >= 1 && PREFIX < N, "the prefix is a proper, non-empty part of the state");
+    constexpr int NP = PadDim<N>::V;
+    constexpr int TILE = BLOCK;
+    __shared__ __align__(16) float tile[TILE * NP];
+    const uint32_t mask = MASK >= 0 ? (uint32_t)MASK : met.angle_mask;
+
+    const int qb = blockIdx.x % nqb;
+    const int split = blockIdx.x / nqb;
+    const int size = *d_size;
+    const bool mask_on = use_ignore && (*d_nignored < size);
+    const int n0 = split * chunk;
+    const int n1 = min(n0 + chunk, size);
+
+    float q[Q][N];
+    float best[Q];
+    int bidx[Q];
+    const int qbase = qb * (BLOCK * Q) + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < Q; k++) {
+        const int j = qbase + k * BLOCK;
+        best[k] = INFINITY;
+        bidx[k] = -1;
+#pragma unroll
+        for (int d = 0; d < N; d++) {
+            float v = j < W ? queries[(size_t)d * qstride + j] : 0.f;
+            if (mask & (1u << d)) v = reduce_period(v);
+            q[k][d] = prescale(v, met.w[d]);
+        }
+    }
+
+    for (int base = n0; base < n1; base += TILE) {
+        __syncthreads();
+        {
+            const int node = base + threadIdx.x;
+            const bool live = node < n1 && !(mask_on && ignore[node]);
+#pragma unroll
+            for (int d = 0; d < NP; d++) {
+                float a = (live && d < N) ? state[(size_t)d * cap + node] : 0.f;
+                if (d < N && (mask & (1u << d))) a = reduce_period(a);
+                if (d < N) a = prescale(a, met.w[d]);
+                tile[threadIdx.x * NP + d] = d < N ? (live ? a : INFINITY) : 0.f;
+            }
+        }
+        __syncthreads();
+        const int cnt = min(TILE, n1 - base);
+#pragma unroll 2
+        for (int i = 0; i < cnt; i++) {
+            float v[NP];
+#pragma unroll
+            for (int d = 0; d < NP; d++) v[d] = tile[i * NP + d];
+#pragma unroll
+            for (int k = 0; k < Q; k++) {
+                float c = 0.f;
+#pragma unroll
+                for (int d = 0; d < PREFIX; d++) {
+                    const float e = q[k][d] - v[d];
+                    c = fmaf(e, e, c);
+                }
+                if (c < best[k]) {                          // otherwise the full cost is >= best as well
+#pragma unroll
+                    for (int d = PREFIX; d < N; d++) {
+                        float e = q[k][d] - v[d];
+                        if (mask & (1u << d)) {
+                            const float a = fabsf(e);
+                            e = fminf(a, met.period[d] - a);
+                        }
+                        c = fmaf(e, e, c);
+                    }
+                    if (c < best[k]) { best[k] = c; bidx[k] = base + i; }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < Q; k++) {
+        const int j = qbase + k * BLOCK;
+        if (j < W) {
+            pcost[(size_t)split * pstride + j] = best[k];
+            pidx[(size_t)split * pstride + j] = bidx[k];
         }
     }
 }
