@@ -297,7 +297,7 @@ nearest_diag_pk_kernel(const float* __restrict__ state, int cap, const uint8_t* 
 // FLOATING POINT.  A pair whose prefix is not below the query's running best cannot win and skips the other
 // N - PREFIX dims; a pair that passes continues the same chain, so costs, argmin and the lowest-index
 // tie-break are bit-identical to nearest_diag_kernel.  With nodes in insertion order the expected number of
-// passes per (query, chunk of m nodes) is O(log m) (tools/filter_study.py: 0.7 % of pairs on a C4 tree), but
+// passes per (query, chunk of m nodes) is O(log m) (tests/studies/filter_study.py: 0.7 % of pairs on a C4 tree), but
 // a warp pays for the long path whenever one of its lanes takes it -- whether that wins is a measurement
 // for round 2.  Leading dims must not be wrapped (the engine checks the mask).
 template <int N, int Q, int BLOCK, int MASK, int PREFIX>

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """
-CPU study for round 2 (no GPU needed): how often would a partial-distance filter in the nearest scan have
+CPU study for round 2 (no GPU needed; lives under tests/ because it drives the wave ORACLE, which only test
+infrastructure may import): how often would a partial-distance filter in the nearest scan have
 to fall back to the full evaluation?
 
 The exact scan accumulates  c = sum_d (w_d (q_d - v_d))^2  in dim order; every prefix of that sum is a
@@ -18,7 +19,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from lqrrt_b200 import configs          # noqa: E402
 from oracle.wave import WaveOracle      # noqa: E402

@@ -5,7 +5,7 @@
 //
 // Exact cost (csrc/nearest.cuh, float32 diagonal metric, pre-scaled operands):
 //     c(q, v) = sum_d e_d^2,  e_d = q_d - v_d,  wrapped dims: e_d = min(|e_d|, P_d - |e_d|)
-// Bound (numerics in tools/tf32_bound_study.py): with features
+// Bound (numerics in tests/studies/tf32_bound_study.py): with features
 //     F(x) = [ x_d - centre_d  (unwrapped dims) ...,  w cos(x_h), w sin(x_h)  (wrapped dims) ]
 //     LB(q, v) = |F(q)|^2 + |F(v)|^2 - 2 F(q).F(v)  <=  c(q, v)      (chord: 2 - 2 cos(dh) <= dh^2)
 // F(q).F(v) is a K = 8 GEMM: one mma.sync m16n8k8 TF32 per 16 queries x 8 nodes, evaluated as 3xTF32
