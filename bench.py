@@ -8,25 +8,31 @@ Workload (config.workload): BASELINE.json configs[3], "demo_boat_advanced.py 6-D
 obstacles, 100k-node tree"  -- the configuration the metric's 1/2/4/8-GPU
 scaling is quoted on and the north_star's ">= 1e6 expansions/s on the 6-DoF boat" target.  One STEP =
 one whole plan: a new tree grown from the seed until it holds max_nodes nodes, through the public
-`Planner.update_plan` call (sample -> nearest -> steer -> commit waves).  Every step uses a new Philox
-seed (different samples, same obstacle field), so nothing is cached between steps; the tree (2.4 MB of
-states) is L2-resident by design, which `config.l2` states.
+`Planner.update_plan` call (the device-scheduled wave pipeline, lq_plan_run).  Every step uses a new
+Philox seed (different samples, same obstacle field), so nothing is cached between steps; the tree
+(2.4 MB of states) is L2-resident by design, which `config.l2` states.
 
-  value   nodes added / device time of the wave loop (CUDA events on the launching stream; samples are
-          generated on the device, so every input is HBM-resident), max over ranks
+  value   nodes added / device time of the wave pipeline (CUDA events on the pipeline's own chain stream;
+          samples are generated on the device, so every input is HBM-resident), max over ranks
   e2e     the same plans timed on the host clock around the whole update_plan call: host-side problem
           inputs (seed state, goal, sample box) copied in, per-wave counters read back, and the plan
           (node chain + edges) downloaded and interpolators built -- bytes counted from those copies
-  roofline  the nearest-neighbour scan (K1): algorithmic bytes sum_k W_k * N_k * n * 4
-          over its CUDA-event time inside the same timed steps, against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline  the sequential NumPy oracle port of the reference loop, one core, a bounded wall budget
-          on the same obstacle field (the unmodified reference is Python and cannot travel to the box;
-          the port is pinned bit-for-bit to it by tests/test_oracle_*.py)
+  roofline  the nearest-neighbour scan (K1).  It is bound by the FP32 pipe, not by HBM (the tree is L2-resident
+          and every staged tile serves 512 queries): `achieved` = algorithmic flops (3n per (query, node) pair,
+          SURVEY.md 8d secondary bound) over the scan kernels' CUDA-event time, `peak` = SMs x 128 lanes x 2 x the
+          SM clock sampled during the run; the HBM view the contract also asks for (algorithmic bytes
+          sum_k W_k N_k n 4 over the same time, against MEASURED_PEAKS.json) is kept as `hbm_effective_*`
+  plan    a second leg outside the timed region: the same field planned with the goal-reaching wave policy
+          (small waves: tree depth grows one edge per wave) until the first plan to the goal 283 m away
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref, copied from /root/reference by build()) on one host core
+          for a bounded wall budget on the same obstacle field; falls back to the oracle port (bit-pinned to the
+          reference by tests/test_oracle_*.py) where oracle/_ref did not travel, `kind` says which
 
---impl reference times that CPU port (the reference's algorithm on the host cores: one independent
-replica per core, different seeds, nodes/s summed) and prints the same JSON shape.
+--impl reference times that CPU implementation on all host cores (one independent replica per core, different
+seeds, nodes/s summed) and prints the same JSON shape.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -45,11 +51,12 @@ UNIT = "nodes/s"
 
 
 def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    ncu --set full capture (profiles/ncu_nearest_*.txt); None if there is none."""
+    """(bytes, file): dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, parsed from
+    the newest committed ncu --set full capture (profiles/ncu_nearest_*.txt) -- a constant of that capture, not
+    something this run measured; (None, None) if there is none."""
     import glob
     import re
-    best = None
+    best = (None, None)
     for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', 'ncu_nearest_*.txt'))):
         vals = []
         rd = wr = None
@@ -64,7 +71,7 @@ def ncu_traffic():
                 if rd is not None and wr is not None:
                     vals.append(rd + wr); rd = wr = None
         if vals:
-            best = float(np.mean(vals))
+            best = (float(np.mean(vals)), os.path.relpath(path, ROOT))
     return best
 
 
@@ -78,6 +85,7 @@ def workload_name(prob, name):
         'c4': "C4 demo_boat_advanced 6-DoF boat, 500 circular obstacles, 200 m arena, tree grown to 100k nodes",
         'c3': "C3 demo_boat_novice 6-DoF boat, 50 circular obstacles, tree grown to max_nodes",
         'c2': "C2 demo_car 5-state car, 20 box obstacles, tree grown to max_nodes",
+        'c1': "C1 2-state pendulum swing-up, FD-Riccati lqr, 1 forbidden region, tree grown to max_nodes",
         'c5': "C5 12-state double integrator, 5000 spheres, FD-Riccati lqr, tree grown to 1M nodes",
         'c5k': "C5 12-state double integrator, 5000 spheres, constant LQR gain, tree grown to 1M nodes",
     }.get(name, prob.name)
@@ -106,7 +114,7 @@ class ClockSampler(object):
                     self.rows.append(parts)
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.1)
 
     def __enter__(self):
         self.th.start()
@@ -129,14 +137,39 @@ class ClockSampler(object):
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU side: the sequential oracle port
+# CPU side: the unmodified reference (oracle/_ref) or, where it did not travel, the oracle port
 # ---------------------------------------------------------------------------------------------
+REF_DEMO = {'c4': 'demo_boat_advanced', 'c3': 'demo_boat_novice'}
+
+
+def reference_available(name):
+    from oracle import build_ref
+    return name in REF_DEMO and build_ref.available()
+
+
 def cpu_growth(name, seed, budget_s):
-    """Sequential reference-algorithm growth from an empty tree for a wall budget; returns
-    (nodes added, iterations, seconds)."""
+    """Sequential growth from an empty tree for a wall budget on the config's obstacle field; returns
+    (nodes added, iterations or None, seconds, kind, reached, T)."""
+    prob = make_problem(name)
+    if reference_available(name):
+        # the reference's own Planner and the demo's own dynamics / lqr / erf / is_feasible; only the obstacle
+        # table, goal and sample box are the benchmark's (the demo file's module globals, set from the outside)
+        from oracle import build_ref
+        ref = build_ref.load()
+        ns = build_ref.demo_model(REF_DEMO[name], 0)
+        ns['obs'] = np.array(prob.obs, dtype=np.float64)
+        cons = ref.Constraints(nstates=prob.nstates, ncontrols=prob.ncontrols, goal_buffer=prob.goal_buffer,
+                               is_feasible=ns['is_feasible'])
+        planner = ref.Planner(ns['dynamics'], ns['lqr'], cons, horizon=prob.horizon, dt=prob.dt, FPR=prob.FPR,
+                              error_tol=prob.error_tol, erf=ns['erf'], min_time=budget_s, max_time=budget_s,
+                              max_nodes=prob.max_nodes, goal0=prob.goal, printing=False)
+        np.random.seed(seed)
+        t0 = time.perf_counter()
+        planner.update_plan(prob.x0, prob.sample_space, goal_bias=prob.goal_bias, xrand_gen=10)
+        dt = time.perf_counter() - t0
+        return planner.tree.size - 1, None, dt, 'reference', bool(planner.plan_reached_goal), float(planner.T)
     from oracle import models as om
     from oracle.seqplanner import SeqPlanner
-    prob = make_problem(name)
     dyn, lqr, erf, feas = om.make_callbacks(prob.system, prob.dt)
     sp = SeqPlanner(dyn, lqr, prob.nstates, prob.ncontrols, prob.goal_buffer, feas, prob.horizon, prob.dt,
                     prob.FPR, prob.error_tol, erf, min_time=budget_s, max_time=budget_s, max_nodes=prob.max_nodes,
@@ -145,7 +178,7 @@ def cpu_growth(name, seed, budget_s):
     t0 = time.perf_counter()
     sp.update_plan(prob.x0, prob.sample_space, goal_bias=prob.goal_bias, xrand_gen=10)
     dt = time.perf_counter() - t0
-    return sp.tree.size - 1, sp.iterations, dt
+    return sp.tree.size - 1, sp.iterations, dt, 'port', bool(sp.plan_reached_goal), float(sp.T)
 
 
 def cpu_frozen_tree(name, state, parent, sizes=((1000, 20), (10000, 8), (100000, 3))):
@@ -186,8 +219,8 @@ def _cpu_worker(args):
 
 
 def run_reference_arm(args):
-    """The reference's own CPU algorithm on the host cores (oracle port; the Python reference cannot be
-    shipped to the GPU box).  One independent replica per usable core, nodes/s summed."""
+    """The reference's own CPU implementation on the host cores: one independent replica per usable core (the
+    reference is single-threaded), nodes/s summed."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -198,6 +231,7 @@ def run_reference_arm(args):
     budget = float(args.cpu_seconds)
     steps = max(1, args.steps)
     per = []
+    kind = 'port'
     ctx = mp.get_context('fork')
     t_all = time.perf_counter()
     with ctx.Pool(cores) as pool:
@@ -206,16 +240,20 @@ def run_reference_arm(args):
                 res = pool.map(_cpu_worker, [(args.config, 1000 + c, min(1.0, budget)) for c in range(cores)])
                 continue
             res = pool.map(_cpu_worker, [(args.config, 100 * s + c, budget) for c in range(cores)])
+            kind = res[0][3]
             per.append((sum(r[0] / r[2] for r in res), sum(r[0] for r in res), max(r[2] for r in res)))
     value = float(np.mean([p[0] for p in per]))
     ms = float(np.mean([p[2] for p in per])) * 1e3
+    what = "unmodified reference (oracle/_ref: lqrrt.Planner + the demo's own model functions)" if kind == 'reference' \
+        else "oracle port of the reference loop (oracle/_ref absent on this box)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(prob, args.config), "note": "sequential expand loop (one sample per iteration), "
-                   "trees stay at N~1e2-1e3 within the budget; the reference cannot reach 100k nodes (BASELINE.md section 2)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+        "config": {"workload": workload_name(prob, args.config), "implementation": what,
+                   "note": "sequential expand loop (one sample per iteration); trees stay at N~1e2-1e3 within the budget, "
+                           "the reference cannot reach 100k nodes (BASELINE.md section 2)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": "{} independent replicas x {:.0f} s of sequential growth from an empty tree, summed".format(cores, budget)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_all,
@@ -226,6 +264,46 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+def tree_digest(tree):
+    """sha1 over node states (float64 as downloaded), parents and cumulative costs: equal digests = the same tree,
+    node for node and bit for bit.  The wave schedule does not depend on the number of GPUs, so the driver's
+    1/2/4/8-GPU runs must all print the same digest."""
+    h = hashlib.sha1()
+    h.update(np.ascontiguousarray(tree.state).tobytes())
+    h.update(np.asarray(tree.pID, dtype=np.int32).tobytes())
+    h.update(np.ascontiguousarray(tree.cost).astype(np.int32).tobytes())
+    return h.hexdigest()[:16]
+
+
+def goal_leg(prob, args, comm, local, plans):
+    """Plans that actually reach the goal: the same obstacle field with the goal-reaching wave policy (waves of at most
+    `--plan-wave` samples -- depth grows one edge per wave and the goal is >= 130 edges away), stopping at the first
+    plan found (min_time = 0).  Outside the timed region of `value`."""
+    planner = prob.make_planner(dtype=args.dtype, wave=None, wave_max=args.plan_wave, wave_growth=1.0, max_nodes=prob.max_nodes,
+                                min_time=0.0, max_time=10.0, comm=comm, device=local,
+                                exchange=os.environ.get('LQRRT_EXCHANGE', 'peer'))
+    ms = []; T = []; nodes = []; waves = []; reached = 0
+    for s in range(plans + 1):
+        planner.seed = 5000 + s
+        t0 = time.perf_counter()
+        planner.update_plan(prob.x0, prob.sample_space, goal_bias=prob.goal_bias)
+        dt = time.perf_counter() - t0
+        if s == 0:
+            continue                       # warm-up (engine construction)
+        if planner.plan_reached_goal:
+            reached += 1
+            ms.append(dt * 1e3); T.append(float(planner.T)); nodes.append(planner.tree.size); waves.append(planner.stats['waves'])
+    out = {"policy": "adaptive clamp(N, 32, {}) waves, stop at the first plan (min_time 0)".format(args.plan_wave),
+           "plans_reaching_goal": "{}/{}".format(reached, plans)}
+    if reached:
+        out.update({"time_to_first_plan_ms": float(np.mean(ms)), "time_to_first_plan_ms_max": float(np.max(ms)),
+                    "plan_duration_s": float(np.mean(T)), "tree_size_at_plan": float(np.mean(nodes)),
+                    "waves_to_plan": float(np.mean(waves))})
+    if planner._engine is not None:
+        planner._engine.close()
+    return out
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -249,21 +327,15 @@ def run_gpu_arm(args):
     planner = prob.make_planner(dtype=args.dtype, wave=None, wave_max=wave_max, wave_growth=args.growth, max_nodes=prob.max_nodes,
                                 min_time=1e9, max_time=1e9, comm=comm, device=local,
                                 exchange=os.environ.get('LQRRT_EXCHANGE', 'peer'),
-                                nearest_kernel=args.nearest, prefetch=args.prefetch)
+                                nearest_kernel=args.nearest, prefetch=args.prefetch, schedule=args.schedule)
     packed = planner.nearest_kernel != 'scalar' and args.dtype == 'f32'
-    # Issue slots and FMA-pipe cycles per (query, node) pair of the scan's inner loop, n dims of which w wrap
-    # (cuobjdump -sass of csrc/nearest.cuh, checked against ncu's instruction counts in profiles/README.md):
-    #   scalar: FADD+FFMA per dim, 4 per wrapped dim, compare + 2 selects, LDS/loop 0.5      -> 17.5 at n=6, w=1
-    #   packed: FADD2+FFMA2 per dim per TWO pairs, wrapped dims scalar, FMNMX + 3/8 per pair,
-    #           LDS.128 n/8 per pair                                                          -> 11.3 at n=6, w=1
-    #   FMA pipe: FFMA2/FADD2 hold it 2 cycles, so both forms cost 2(n-w) + 3w cycles per pair -> 13
+    # FMA-pipe cycles per (query, node) pair of the scan's inner loop, n dims of which w wrap (cuobjdump -sass of
+    # csrc/nearest.cuh, checked against ncu's instruction counts in profiles/README.md): FFMA2/FADD2 hold the pipe 2
+    # cycles, so the packed and the scalar form both cost 2(n-w) + 3w cycles per pair -> 13 at n = 6, w = 1
     n_dims = prob.nstates
     n_wrap = bin(prob.system.erf.mask(n_dims)).count('1')
-    if packed:
-        slots_per_pair = (n_dims - n_wrap) + 4 * n_wrap + 1.4 + (n_dims + 1) // 2 * 2 / 8.0 + 0.2
-    else:
-        slots_per_pair = 2 * (n_dims - n_wrap) + 4 * n_wrap + 3.5
     pipe_cycles_per_pair = 2 * (n_dims - n_wrap) + 3 * n_wrap
+    flops_per_pair = 3 * n_dims                       # n sub, n mul, n add for a diagonal metric
 
     def one_plan(seed):
         planner.seed = seed
@@ -296,6 +368,8 @@ def run_gpu_arm(args):
             reached += int(planner.plan_reached_goal); depth.append(len(planner.node_seq)); plan_T.append(float(planner.T))
         barrier()
     prof = planner._engine.profile_read()
+    digest = tree_digest(planner.tree)
+    schedule_used = planner.stats.get('schedule')
 
     tot_dev = float(np.sum(dev_ms)) / 1e3
     tot_host = float(np.sum(host_times))
@@ -303,9 +377,18 @@ def run_gpu_arm(args):
         t = torch.tensor([tot_dev, tot_host], dtype=torch.float64, device='cuda')
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         tot_dev, tot_host = float(t[0]), float(t[1])
+        # every rank must hold the same tree
+        dg = [None] * world
+        dist.all_gather_object(dg, digest)
+        if len(set(dg)) != 1:
+            raise SystemExit("ranks disagree on the tree: {}".format(dg))
     total_nodes = float(np.sum(nodes))
     value = total_nodes / tot_dev
     e2e = total_nodes / tot_host
+
+    plan = None
+    if args.plan_leg and args.config in ('c4', 'c3', 'demo_boat_novice'):
+        plan = goal_leg(prob, args, comm, local, args.plan_leg)
 
     if rank == 0:
         peaks = {}
@@ -314,18 +397,22 @@ def run_gpu_arm(args):
         except Exception:
             pass
         hbm = float(peaks.get('hbm_gbs', 6650.0))
-        near_s = prof['ms']['nearest'] / 1e3
-        elt = 4 if args.dtype == 'f32' else 8
-        achieved = prof['nearest_bytes'] / near_s / 1e9 if near_s > 0 else 0.0
-        stage_total = sum(prof['ms'].values())
-        # secondary bound: FP32 issue rate.  ~16 issue slots per (query, node) pair for n=6 (csrc/nearest.cuh)
+        clocks = clk.summary()
+        sm_hz = (clocks.get('sm_mhz') or float(peaks.get('sm_max_mhz', 1965.0))) * 1e6
+        fp32_peak = 148 * 128 * 2 * sm_hz / 1e12                 # TFLOP/s of the FP32 pipes at the clock of this run
+        near_s = (prof['ms']['nearest_old'] + prof['ms']['nearest_delta']) / 1e3
         pairs_per_s = prof['pairs'] / near_s if near_s > 0 else 0.0
+        achieved = pairs_per_s * flops_per_pair / 1e12
+        hbm_eff = prof['nearest_bytes'] / near_s / 1e9 if near_s > 0 else 0.0
+        stage_total = sum(prof['ms'].values())
+        traffic, traffic_file = ncu_traffic()
         cpu = None
         if not args.no_cpu:
-            n_add, iters, secs = cpu_growth(args.config, 0, float(args.cpu_seconds))
-            cpu = {"value": n_add / secs, "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": "{:.0f} s of sequential growth from an empty tree on the same obstacle field "
-                             "({} iterations, {} nodes)".format(secs, iters, n_add)}
+            n_add, iters, secs, kind, cpu_reached, cpu_T = cpu_growth(args.config, 0, float(args.cpu_seconds))
+            cpu = {"value": n_add / secs, "unit": UNIT, "cores": 1, "kind": kind,
+                   "sample": "{:.0f} s of sequential growth from an empty tree on the same obstacle field ({} nodes{})".format(
+                       secs, n_add, "" if iters is None else ", {} iterations".format(iters)),
+                   "reached_goal": cpu_reached, "plan_duration_s": cpu_T if np.isfinite(cpu_T) else None}
             if args.cpu_frozen:
                 tr = planner.tree
                 cpu["frozen_tree"] = cpu_frozen_tree(args.config, tr.state, tr.pID)
@@ -334,43 +421,49 @@ def run_gpu_arm(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": tot_dev / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
-            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "tree_digest": digest,
             "config": {"workload": workload_name(prob, args.config), "max_nodes": int(prob.max_nodes),
-                       "wave": "adaptive clamp({:g}*N, 32, {})".format(args.growth, wave_max), "wave_per_gpu_max": wave_max // world,
+                       "wave": "adaptive clamp({:g}*N, 32, {}), wave k sized from the tree wave k-1 started with".format(args.growth, wave_max),
+                       "wave_per_gpu_max": wave_max // world, "schedule": schedule_used,
                        "waves_per_step": float(np.mean(waves)), "samples_per_step": float(np.mean(samples)),
                        "yield": total_nodes / float(np.sum(samples)), "sampler": "philox4x32-10 on device, new seed per step",
-                       "nearest_kernel": planner.nearest_kernel, "sample_prefetch": planner.prefetch_active,
+                       "nearest_kernel": planner.nearest_kernel,
                        "plans_reaching_goal": "{}/{}".format(reached, args.steps), "plan_depth_edges": float(np.mean(depth)),
                        "plan_duration_s": float(np.mean(plan_T)),
-                       "note": "tree depth grows by at most one edge per wave, so the throughput-maximal wave cap "
-                               "fills 100k nodes before the 283 m-away goal is reached; --wave 512 reaches it "
-                               "(profiles/README.md has both)",
+                       "note": "throughput workload: the tree is filled to max_nodes with the largest waves; tree depth grows by "
+                               "at most one edge per wave, so it fills before the 283 m-away goal is reached -- the `plan` "
+                               "object times the goal-reaching policy on the same field",
                        "l2": "tree states (<= 2.4 MB) and obstacle tables are L2-resident by design; every step "
                              "grows a new tree from new samples (no reuse between timed steps)"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
                     "ms_per_step": tot_host / args.steps * 1e3,
                     "host_ms_per_step": dict(zip(("setup", "wave_loop", "closeout"), (phases / args.steps * 1e3).round(3).tolist()))},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "nearest_diag_pk_kernel" if packed else "nearest_diag_kernel", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                         "frac": achieved / hbm if hbm else None, "traffic": ncu_traffic(),
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                         "algorithmic_bytes": prof['nearest_bytes'], "kernel_seconds": near_s,
-                         "share_of_device_time": (prof['ms']['nearest'] / stage_total) if stage_total else None,
-                         "pairs_per_s": pairs_per_s,
-                         "fp32_issue_frac": pairs_per_s * slots_per_pair / (148 * 128 * 1.965e9),
-                         "issue_slots_per_pair": slots_per_pair,
-                         "fma_pipe_frac": pairs_per_s * pipe_cycles_per_pair / (148 * 128 * 1.965e9),
+            "roofline": {"bound": "fp32_pipe", "kernel": "nearest_diag_pk_kernel" if packed else "nearest_diag_kernel",
+                         "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
+                         "peak_source": "148 SMs x 128 FP32 lanes x 2 x SM clock sampled during this run ({:.0f} MHz)".format(sm_hz / 1e6),
+                         "flops_per_pair": flops_per_pair, "pairs_per_s": pairs_per_s, "kernel_seconds": near_s,
+                         "share_of_device_time": (near_s * 1e3 / stage_total) if stage_total else None,
+                         "fma_pipe_frac": pairs_per_s * pipe_cycles_per_pair / (148 * 128 * sm_hz),
                          "fma_pipe_cycles_per_pair": pipe_cycles_per_pair,
-                         "note": "algorithmic bytes = sum_k W_k*N_k*n*sizeof(dtype) (SURVEY.md 8d); node tiles are reused "
-                                 "by every query of a CTA from shared memory and the tree is L2-resident, so frac > 1 is "
-                                 "expected and the binding limit is the FP32 pipe: fp32_issue_frac = pairs_per_s x issue_slots_per_pair "
-                                 "/ (148 SMs x 128 lanes x 1.965 GHz) bounds the scalar kernel (ncu: 90 % of issue slots), "
-                                 "fma_pipe_frac = pairs_per_s x fma_pipe_cycles_per_pair / the same denominator bounds the packed "
-                                 "kernel (ncu: FMA pipe 67.6 % of cycles, math-pipe-throttle the top stall); traffic = measured DRAM bytes "
-                                 "per launch from the committed ncu capture"},
+                         "hbm_effective_gbs": hbm_eff, "hbm_peak_gbs": hbm, "hbm_effective_frac": hbm_eff / hbm if hbm else None,
+                         "hbm_peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                         "algorithmic_bytes": prof['nearest_bytes'],
+                         "traffic": traffic, "traffic_source": "constant from {} (ncu --set full of one launch), not measured by this run".format(traffic_file) if traffic_file else None,
+                         "note": "the scan's tree is L2-resident and every staged node tile serves 512 queries, so HBM does not bound it "
+                                 "(hbm_effective_frac = algorithmic bytes sum_k W_k*N_k*n*sizeof(dtype) over the kernel time against the HBM peak is > 1 "
+                                 "by construction; measured DRAM traffic is `traffic` per launch).  The binding unit is the FP32 pipe: frac = "
+                                 "3n flops per (query, node) pair over the pipe peak; fma_pipe_frac counts the cycles the packed FADD2/FFMA2 "
+                                 "instructions hold the pipe (ncu: 67.6 % of cycles on a saturated launch).  Kernel time = CUDA events around "
+                                 "the scan launches on the streams they run on; the old-tree scan shares the GPU with the previous wave's "
+                                 "rollouts and commit, which is the point of it."},
             "stage_ms": prof['ms'],
-            "clocks": clk.summary(),
+            "stage_note": "per-stage CUDA-event sums over the timed steps; nearest_old and sample run on the scan stream concurrently with "
+                          "the previous wave's nearest_delta -> steer -> commit chain, so the stages do not add up to the step time",
+            "clocks": clocks,
         }
+        if plan is not None:
+            line["plan"] = plan
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
@@ -391,9 +484,12 @@ def main():
                     help="strong: same global wave schedule for every N (bit-identical tree); weak: 8192 samples per GPU per wave")
     ap.add_argument('--growth', type=float, default=2.0,
                     help="adaptive wave size W = clamp(growth * tree size, 32, --wave); 1.0 is the Planner's own default "
-                         "(deeper tree per sample, ~40 more small waves per 100k-node plan)")
+                         "(deeper tree per sample, more small waves per 100k-node plan)")
     ap.add_argument('--nearest', default=None, help="nearest-scan kernel (default: the planner's)")
-    ap.add_argument('--prefetch', default=None, type=int, choices=[0, 1], help="side-stream sampler prefetch (default: the planner's)")
+    ap.add_argument('--prefetch', default=None, type=int, choices=[0, 1], help="side-stream sampler prefetch of the host-scheduled loop")
+    ap.add_argument('--schedule', default=None, choices=['device', 'host'], help="wave scheduling (default: the planner's, 'device')")
+    ap.add_argument('--plan-leg', type=int, default=10, help="goal-reaching plans timed after the throughput steps (0 = skip)")
+    ap.add_argument('--plan-wave', type=int, default=512, help="wave cap of the goal-reaching policy")
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--cpu-frozen', action='store_true', help="also time the CPU port on frozen trees of 1e3/1e4/1e5 nodes")

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LQ_ABI_VERSION 1
+#define LQ_ABI_VERSION 2
 #define LQ_MAX_N 12          /* states   */
 #define LQ_MAX_M 6           /* controls */
 #define LQ_MAX_PRIMS 8
@@ -160,8 +160,9 @@ int lq_steer(lq_engine* h, const int32_t* d_ids, const void* d_targets, int W,
 
 /* One wave of the expand loop, planner.py:233-283, for samples [first, first+count) of a global
  * wave of `wave_size` samples: sample (planner.py:201-211; Philox stream keyed by seed/wave_ctr/sample,
- * or h_samples: count x n float64 when non-NULL, or h_candidates below) -> nearest -> steer ->
- * pack accepted records, in sample order, into the engine's send buffer.  Nothing is appended yet. */
+ * or h_samples: count x n float64 when non-NULL, or h_candidates below) -> nearest -> steer, whose
+ * epilogue writes every sample's result (edge length; parent, state and gain if a node came out) into the
+ * engine's exchange segment -- or straight into every peer's, see lq_wave_set_peers.  Nothing is appended yet. */
 int lq_wave_expand(lq_engine* h, uint64_t seed, uint32_t wave_ctr, int first, int count,
                    const double* h_samples, int use_ignore, int flags, void* stream);
 /* Reference-stream sampling (planner.py:201-211 on NumPy's MT19937): h_candidates holds
@@ -173,25 +174,67 @@ int lq_wave_expand_candidates(lq_engine* h, int count, int tries, const double* 
 /* `flags` above travels in the record header; after lq_wave_commit every rank reads segment 0's
  * value back in lq_wave_stats.flags -- the host uses it to agree on when to stop without an extra
  * collective (the reference's stop rules are wall-clock based, planner.py:286-311). */
-/* The packed records of the last lq_wave_expand: device pointer + fixed byte size (the allgather payload).
- * A record is the node only (state, gain K, parent, edge length); edge trajectories stay on the GPU that
- * rolled them out and are read back from their owner (lq_download_edges). */
+/* The exchange segment of the last lq_wave_expand: device pointer + fixed byte size (the allgather payload):
+ * a small header, one meta word per sample of the slice and one record row (state, gain K) + parent per
+ * sample that produced a node -- uncompacted, lq_wave_commit derives the node ids.  Edge trajectories stay on
+ * the GPU that rolled them out and are read back from their owner (lq_download_edges). */
 int lq_wave_records(lq_engine* h, void** d_records, uint64_t* bytes);
-/* Tree.add_node for every accepted record of `n_segments` record buffers laid end to end
- * (segment r = rank r's lq_wave_records), in segment order then record order = global sample order;
+/* Tree.add_node for every accepted sample of `n_segments` exchange segments laid end to end
+ * (segment r = rank r's lq_wave_records), in segment order then sample order = global sample order;
  * then goal test / ignores / best plan (planner.py:253-283, tree.py:77-96).  d_records may be NULL for
  * the engine's own buffer (single GPU).  `my_segment` is the index of this engine's own segment (its
  * rank): the edges of those nodes are stored here, every node remembers its owner segment. */
 int lq_wave_commit(lq_engine* h, const void* d_records, int n_segments, int my_segment, void* stream);
-/* Fused pack + exchange over NVLink.  d_peer_bufs[p] is rank p's receive buffer mapped into this process
+/* Fused rollout + exchange over NVLink.  d_peer_bufs[p] is rank p's receive buffer mapped into this process
  * (peer-mapped symmetric memory, e.g. torch.distributed._symmetric_memory), all of `bytes` >=
- * 2*world*segment + 2*world*4 bytes and zero-initialised.  After this call lq_wave_expand stores its
- * records directly into every peer's buffer and raises an arrival flag, and
+ * 2*world*segment + 2*world*4 bytes and zero-initialised.  After this call the rollout kernel stores its
+ * results directly into every peer's buffer (16-byte stores) and its last CTA raises an arrival flag, and
  * lq_wave_commit(h, NULL, world, rank, stream) waits for all flags of the wave inside the kernel -- no
  * collective call per wave.  world <= 1 turns it off. */
 int lq_wave_set_peers(lq_engine* h, int world, int rank, void* const* d_peer_bufs, uint64_t bytes);
 /* Blocks until the last commit finished and returns its counters. */
 int lq_wave_stats_get(lq_engine* h, lq_wave_stats* out);
+
+/* ---- the whole expand loop of one plan, scheduled on the device ------------------------------------------
+ * Planner.update_plan's `while True:` (planner.py:233-311) as one call: waves of Philox samples are sized on the
+ * device (W = clamp(int(growth * N), wave_min, wave_max), or wave_fixed), enqueued `depth` waves ahead of the
+ * counters the host has seen, and the scan of the part of the tree a wave cannot have changed runs on a side
+ * stream under the previous wave's rollouts and commit.  Wave k is sized from the tree size wave k-1 started
+ * with (waves 0 and 1 from the initial tree); the nodes it appends are exactly those of the stepwise calls
+ * lq_wave_expand / lq_wave_commit with the same sizes.
+ *   on_wave   called on the caller's thread once per committed wave, in order, with that wave's counters;
+ *             returns 0 to go on, 1 to stop (planner.py:293/311: done) or 2 (planner.py:289: killed).  The
+ *             request reaches the device through mapped host memory; `flags` of the counters tell when it
+ *             took effect (a few waves later) -- on several GPUs rank 0's request is the one that counts and
+ *             every rank stops after the same wave.  May be NULL (runs until the tree is full).
+ *   world, rank   > 1 GPUs: lq_wave_set_peers must have been called; every rank calls lq_plan_run with
+ *             the same arguments. */
+typedef int (*lq_wave_callback)(void* user, const lq_wave_stats* wave);
+typedef struct lq_plan_args {
+    uint64_t seed;                 /* Philox key */
+    uint32_t wave_ctr0;            /* Philox wave counter of the first wave (keeps counting across plans) */
+    int32_t wave_fixed;            /* > 0: every wave has this many samples */
+    int32_t wave_min, wave_max;    /* adaptive wave size bounds */
+    double growth;
+    int32_t use_ignore;            /* pruning (planner.py:239-245) */
+    int32_t world, rank;
+    int32_t depth;                 /* waves in flight ahead of the host (0 = default) */
+    lq_wave_callback on_wave;
+    void* user;
+} lq_plan_args;
+typedef struct lq_plan_summary {
+    int32_t waves;                 /* waves whose counters were delivered (incl. the no-op tail after a stop) */
+    int32_t waves_enqueued;
+    int32_t stop_code;             /* 0: ran out of capacity only; else the stop request / full flag seen by the device */
+    int32_t reserved;
+    int64_t samples;
+    double device_ms;              /* CUDA-event time of the wave pipeline on its own stream */
+    lq_wave_stats last;
+} lq_plan_summary;
+int lq_plan_run(lq_engine* h, const lq_plan_args* args, lq_plan_summary* out, void* stream);
+/* The host word the rollout kernels poll for a stop request (mapped pinned memory): another thread may set it to
+ * 1 (done) or 2 (kill) at any time, e.g. Planner.kill_update (planner.py:596-601); lq_plan_run clears it on entry. */
+int lq_stop_word(lq_engine* h, int32_t** out);
 
 /* closest-to-guide, planner.py:313-318: argmin_i d_i' Sg d_i, Sg = lqr(xguide,0).S with the
  * columns of dims where h_colmask[i] != 0 zeroed. */
@@ -237,7 +280,11 @@ int lq_set_tuning(lq_engine* h, int steer_lanes, int nearest_q);
  *   LQ_OPT_SAMPLE_PREFETCH 1: the device sampler (planner.py:201-211) of a wave is issued on a side stream into
  *                          the second sample buffer, so it overlaps the previous wave's scan and rollouts. */
 enum { LQ_OPT_NEAREST_KERNEL = 1, LQ_OPT_SAMPLE_PREFETCH = 2,
-       LQ_OPT_NEAREST_CTAS_PER_SM = 3   /* grid target of the scan in CTAs per SM; 0 = auto (16 for n <= 6, else 8) */ };
+       LQ_OPT_NEAREST_CTAS_PER_SM = 3,  /* grid target of the scan in CTAs per SM; 0 = auto (16 for n <= 6, else 8) */
+       LQ_OPT_SPECULATIVE_SCAN = 4,     /* lq_plan_run: 1 (default) = old-tree scan of wave k+1 on a side stream under wave k */
+       LQ_OPT_FORCE_RESCAN = 5,         /* tests: every query takes the rollout kernel's own rescan path */
+       LQ_OPT_STAGE_TABLES = 6,         /* 1 (default) = obstacle tables staged in shared memory by the rollout kernels */
+       LQ_OPT_STEER_BLOCK = 7           /* CTA size of the wave rollout kernel: 0 = auto, 32, 128 */ };
 enum { LQ_NEAREST_SCALAR = 0, LQ_NEAREST_PACKED = 1,
        /* tuning variants, same results: 8 queries per thread (best on the 12-state scan), and the two-level
         * argmin with one-lane-at-a-time arithmetic */
@@ -248,7 +295,8 @@ enum { LQ_NEAREST_SCALAR = 0, LQ_NEAREST_PACKED = 1,
 int lq_set_option(lq_engine* h, int option, int value);
 int lq_get_option(lq_engine* h, int option, int* value);
 /* Per-stage CUDA-event timing of the wave chain on the launching stream (bench.py's roofline leg).
- * ms[5]: sample, nearest, steer, pack, commit (accumulated);  work[4]: nearest pairs sum(W*N),
+ * ms[5]: sample, nearest (old-tree scan, side stream), nearest (delta / whole-tree scan), steer, commit (accumulated);
+ * work[4]: nearest pairs sum(W*N),
  * nearest algorithmic bytes sum(W*N*n*sizeof(dtype)), samples, waves. */
 int lq_set_profiling(lq_engine* h, int on);
 int lq_profile_read(lq_engine* h, double* ms5, double* work4, int reset);

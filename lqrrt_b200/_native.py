@@ -16,11 +16,12 @@ from . import models as M
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'liblqrrt_b200.so')
 
-LQ_ABI_VERSION = 1
+LQ_ABI_VERSION = 2
 LQ_MAX_N = 12
 LQ_F32, LQ_F64 = 0, 1
 LQ_OPT_NEAREST_KERNEL, LQ_OPT_SAMPLE_PREFETCH = 1, 2
 LQ_OPT_NEAREST_CTAS_PER_SM = 3
+LQ_OPT_SPECULATIVE_SCAN, LQ_OPT_FORCE_RESCAN, LQ_OPT_STAGE_TABLES, LQ_OPT_STEER_BLOCK = 4, 5, 6, 7
 NEAREST_KERNELS = {'scalar': 0, 'packed': 1, 'packed_q8': 2, 'two_level': 3, 'prefix': 4}
 
 
@@ -54,6 +55,21 @@ class lq_wave_stats(C.Structure):
                 ('reserved', C.c_int32 * 2)]
 
 
+WAVE_CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(lq_wave_stats))
+
+
+class lq_plan_args(C.Structure):
+    _fields_ = [('seed', C.c_uint64), ('wave_ctr0', C.c_uint32), ('wave_fixed', C.c_int32),
+                ('wave_min', C.c_int32), ('wave_max', C.c_int32), ('growth', C.c_double),
+                ('use_ignore', C.c_int32), ('world', C.c_int32), ('rank', C.c_int32), ('depth', C.c_int32),
+                ('on_wave', WAVE_CALLBACK), ('user', C.c_void_p)]
+
+
+class lq_plan_summary(C.Structure):
+    _fields_ = [('waves', C.c_int32), ('waves_enqueued', C.c_int32), ('stop_code', C.c_int32), ('reserved', C.c_int32),
+                ('samples', C.c_int64), ('device_ms', C.c_double), ('last', lq_wave_stats)]
+
+
 # every symbol include/lqrrt_b200.h declares: (restype, argtypes)
 _P = C.c_void_p
 _D = C.POINTER(C.c_double)
@@ -79,6 +95,8 @@ SYMBOLS = {
     'lq_wave_commit': (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
     'lq_wave_set_peers': (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P), C.c_uint64]),
     'lq_wave_stats_get': (C.c_int, [_P, C.POINTER(lq_wave_stats)]),
+    'lq_plan_run': (C.c_int, [_P, C.POINTER(lq_plan_args), C.POINTER(lq_plan_summary), _P]),
+    'lq_stop_word': (C.c_int, [_P, C.POINTER(C.POINTER(C.c_int32))]),
     'lq_closest': (C.c_int, [_P, _D, _U8, C.POINTER(C.c_int), _P]),
     'lq_steer_force': (C.c_int, [_P, C.c_int, _D, C.c_int, _D, _D, C.POINTER(C.c_int), _P]),
     'lq_append_node': (C.c_int, [_P, C.c_int, _D, _D, _D, C.c_int, _P]),
@@ -322,6 +340,40 @@ class Engine(object):
         self._ck(self.lib.lq_wave_stats_get(self.h, C.byref(st)))
         return st
 
+    def plan_run(self, seed, wave_ctr0, wave_fixed, wave_min, wave_max, growth, use_ignore, on_wave=None,
+                 world=1, rank=0, depth=0, stream=None):
+        """The whole expand loop of one plan on the device-scheduled pipeline (lq_plan_run).  `on_wave(stats)`
+        is called once per committed wave and returns 0 / 1 (done) / 2 (kill).  Returns the summary struct."""
+        err = []
+
+        def _cb(_user, st_ptr):
+            try:
+                return int(on_wave(st_ptr.contents)) if on_wave is not None else 0
+            except BaseException as e:          # never unwind through the C frame: stop the plan, re-raise after
+                err.append(e)
+                return 2
+        cb = WAVE_CALLBACK(_cb)
+        a = lq_plan_args()
+        a.seed = int(seed) & 0xFFFFFFFFFFFFFFFF; a.wave_ctr0 = int(wave_ctr0) & 0xFFFFFFFF
+        a.wave_fixed = int(wave_fixed or 0); a.wave_min = int(wave_min); a.wave_max = int(wave_max)
+        a.growth = float(growth); a.use_ignore = int(bool(use_ignore)); a.world = int(world); a.rank = int(rank)
+        a.depth = int(depth); a.on_wave = cb; a.user = None
+        out = lq_plan_summary()
+        rc = self.lib.lq_plan_run(self.h, C.byref(a), C.byref(out), self._stream(stream))
+        if err:
+            raise err[0]
+        self._ck(rc)
+        self.d2h_bytes += out.waves * 64
+        return out
+
+    def request_stop(self, code):
+        """Write the stop word the rollout kernels poll (callable from any thread; 1 = done, 2 = kill)."""
+        if getattr(self, '_stop_ptr', None) is None:
+            p = C.POINTER(C.c_int32)()
+            self._ck(self.lib.lq_stop_word(self.h, C.byref(p)))
+            self._stop_ptr = p
+        self._stop_ptr[0] = int(code)
+
     def closest(self, xguide, colmask, stream=None):
         x = _c64(xguide)
         self.h2d_bytes += self.n * (self.n + 1) * self.elt; self.d2h_bytes += 4
@@ -421,7 +473,7 @@ class Engine(object):
     def profile_read(self, reset=False):
         ms = np.zeros(5); work = np.zeros(4)
         self._ck(self.lib.lq_profile_read(self.h, _dp(ms), _dp(work), int(bool(reset))))
-        return dict(ms=dict(zip(('sample', 'nearest', 'steer', 'pack', 'commit'), ms.tolist())),
+        return dict(ms=dict(zip(('sample', 'nearest_old', 'nearest_delta', 'steer', 'commit'), ms.tolist())),
                     pairs=work[0], nearest_bytes=work[1], samples=work[2], waves=work[3])
 
 

@@ -97,6 +97,8 @@ int lq_wave_expand_candidates(lq_engine* h, int count, int tries, const double* 
 int lq_wave_records(lq_engine* h, void** d, uint64_t* bytes) { LQ_H(h); LQ_TRY(h->wave_records(d, bytes)) }
 int lq_wave_commit(lq_engine* h, const void* rec, int nseg, int myseg, void* st) { LQ_H(h); LQ_TRY(h->wave_commit(rec, nseg, myseg, (cudaStream_t)st)) }
 int lq_wave_stats_get(lq_engine* h, lq_wave_stats* out) { LQ_H(h); LQ_TRY(h->wave_stats(out)) }
+int lq_plan_run(lq_engine* h, const lq_plan_args* a, lq_plan_summary* out, void* st) { LQ_H(h); if (!a || !out) return LQ_ERR_ARG; LQ_TRY(h->plan_run(a, out, (cudaStream_t)st)) }
+int lq_stop_word(lq_engine* h, int32_t** out) { LQ_H(h); if (!out) return LQ_ERR_ARG; LQ_TRY(h->stop_word(out)) }
 int lq_closest(lq_engine* h, const double* xg, const uint8_t* mask, int* id, void* st) {
     LQ_H(h); if (!xg || !id) return LQ_ERR_ARG; LQ_TRY(h->closest(xg, mask, id, (cudaStream_t)st)) }
 int lq_steer_force(lq_engine* h, int node, const double* xt, int ms, double* x, double* u, int* len, void* st) {

@@ -1,201 +1,20 @@
 // K4: Tree.add_node for a whole wave + the post-add bookkeeping
-// (reference lqrrt/tree.py:77-96, lqrrt/planner.py:253-283).
+// (reference lqrrt/tree.py:77-96, lqrrt/planner.py:253-283), and the device side of the loop control
+// (planner.py:286-311): sizing the next waves and stopping.
 //
-// pack:   compact the wave's accepted samples (edge length > 0), in sample
-//         order, into a fixed-size record buffer -- the multi-GPU allgather
-//         payload (every rank contributes one such segment per wave).  A record
-//         is the node only (state, gain, parent, edge length: ~100 B at n=6);
-//         the edge trajectory stays on the GPU that rolled it out.
-// commit: append the records of all segments, segment order then record order
-//         (= global sample order), to the SoA tree; goal test, ignore marks
-//         along the new plan, best-plan tracking.  The committing GPU copies the
-//         edges of ITS OWN segment from its rollout scratch into its edge slab
-//         and records the owner of every node, so edges are fetched from their
-//         owner when a plan is read out (tree.py:121-132) instead of crossing
-//         NVLink for every accepted node.
+// Input: the exchange segments of all ranks (wave.cuh) -- per sample a meta word, and for samples that produced a
+// node its parent and record row -- as written by the rollout kernels of the G replicas.  Every replica
+// runs the same commit over the same segments: the nodes of a wave are appended in global sample order
+// (segment = rank order, then sample order), so all replicas, and the 1-GPU run with the same wave sizes,
+// hold bit-identical trees.  Node ids come from a prefix count over the meta words (no separate pack
+// kernel, no atomics: slot = accepted samples with a lower global index).  The committing GPU copies the
+// edges of ITS OWN segment from its rollout scratch into its edge slab and records the owner of every
+// node, so edges are fetched from their owner when a plan is read out (tree.py:121-132) instead of
+// crossing NVLink for every accepted node.
 #pragma once
 #include "steer.cuh"
 
 namespace lq {
-
-constexpr int REC_HEADER_INTS = 32;
-enum { HDR_COUNT = 0, HDR_SAMPLED = 1, HDR_TRIES = 2, HDR_FLAGS = 3 };
-
-template <typename T> struct RecView {
-    int* header;
-    T* state;      // [N][Wc]
-    T* K;          // [M*N][Wc]
-    int* parent;   // [Wc]
-    int* len;      // [Wc]
-    uint8_t* votes;   // [Wc] per SAMPLE of the segment's slice (not per record): adaptive-horizon votes
-};
-
-__host__ __device__ inline size_t align16(size_t b) { return (b + 15) & ~(size_t)15; }
-
-template <typename T>
-__host__ __device__ inline size_t rec_bytes(int Wc, int N, int M, int H) {
-    size_t b = REC_HEADER_INTS * sizeof(int);
-    b += align16(sizeof(T) * (size_t)N * Wc);
-    b += align16(sizeof(T) * (size_t)M * N * Wc);
-    b += align16(sizeof(int) * (size_t)Wc) * 2;
-    b += align16((size_t)Wc);
-    (void)H;
-    return b;
-}
-
-template <typename T>
-__host__ __device__ inline RecView<T> rec_view(void* base, int Wc, int N, int M, int H) {
-    RecView<T> v;
-    char* p = (char*)base;
-    v.header = (int*)p; p += REC_HEADER_INTS * sizeof(int);
-    v.state = (T*)p; p += align16(sizeof(T) * (size_t)N * Wc);
-    v.K = (T*)p; p += align16(sizeof(T) * (size_t)M * N * Wc);
-    v.parent = (int*)p; p += align16(sizeof(int) * (size_t)Wc);
-    v.len = (int*)p; p += align16(sizeof(int) * (size_t)Wc);
-    v.votes = (uint8_t*)p;
-    (void)H;
-    return v;
-}
-
-// pack: compact the wave's accepted samples (edge length > 0), in sample order.  One kernel: every CTA
-// first counts the accepted samples that precede its own range (the length array is a few KB, L2
-// resident), then scans its range and copies its records; the last CTA's running total is the segment's
-// record count.  Deterministic (no atomics): slot = number of accepted samples with a lower index.
-// Multi-GPU, fused exchange: instead of packing into a local segment that an NCCL all-gather then copies,
-// the pack kernel stores every record straight into segment `rank` of EVERY peer's receive buffer over
-// NVLink (peer-mapped symmetric memory), and the last CTA publishes the header and raises this rank's
-// arrival flag on every peer.  The commit kernel of each GPU waits for all G flags of the wave.  One
-// kernel does pack + exchange; the collective's launch and rendezvous latency leaves the wave.
-constexpr int MAX_PEERS = 16;
-struct PeerDst {
-    char* seg[MAX_PEERS];          // peer p's receive segment for this rank, current parity
-    unsigned* flag[MAX_PEERS];     // peer p's arrival flag for this rank, current parity
-    int n;                         // 0: single destination `rv` (local segment), no flags
-    unsigned seq;                  // wave sequence number written to the flags
-    unsigned* done;                // local CTA-completion counter
-};
-
-template <typename T, int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
-pack_kernel(const int* __restrict__ len, const int* __restrict__ tries_used, const int* __restrict__ ids,
-            const T* __restrict__ xnew, const T* __restrict__ Knew, int ostride, int count,
-            RecView<T> rv, int* __restrict__ sample_of_slot, int Wc, int N, int M, int H, int flags, PeerDst pd,
-            const uint8_t* __restrict__ votes) {
-    __shared__ int wsum[BLOCK / 32];
-    __shared__ int wtri[BLOCK / 32];
-    __shared__ int s_before, s_tries;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int j0 = blockIdx.x * BLOCK;
-    // accepted samples (and sampler tries) before this CTA's range
-    int before = 0, tries = 0;
-    for (int j = threadIdx.x; j < j0; j += BLOCK) { before += len[j] > 0; tries += tries_used[j]; }
-    // ... plus this CTA's own element, for the block scan below
-    const int j = j0 + threadIdx.x;
-    const int mine = (j < count && len[j] > 0) ? 1 : 0;
-    tries += j < count ? tries_used[j] : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        before += __shfl_xor_sync(0xffffffffu, before, o);
-        tries += __shfl_xor_sync(0xffffffffu, tries, o);
-    }
-    int incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 0) { wsum[warp] = before; wtri[warp] = tries; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int b2 = 0, t2 = 0;
-        for (int w = 0; w < BLOCK / 32; w++) { b2 += wsum[w]; t2 += wtri[w]; }
-        s_before = b2; s_tries = t2;
-    }
-    __syncthreads();
-    if (lane == 31) wsum[warp] = incl;              // per-warp totals of this CTA's own flags
-    __syncthreads();
-    int woff = 0, total = 0;
-    for (int w = 0; w < BLOCK / 32; w++) { if (w < warp) woff += wsum[w]; total += wsum[w]; }
-    const int slot = s_before + woff + incl - mine;
-    if (votes && j < count) {
-        if (pd.n == 0) rv.votes[j] = votes[j];
-        else for (int p = 0; p < pd.n; p++) rec_view<T>(pd.seg[p], Wc, N, M, H).votes[j] = votes[j];
-    }
-    if (pd.n == 0) {
-        if (mine) {
-            for (int d = 0; d < N; d++) rv.state[(size_t)d * Wc + slot] = xnew[(size_t)d * ostride + j];
-            for (int k = 0; k < M * N; k++) rv.K[(size_t)k * Wc + slot] = Knew[(size_t)k * ostride + j];
-            rv.parent[slot] = ids[j]; rv.len[slot] = len[j];
-            sample_of_slot[slot] = j;
-        }
-        if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
-            rv.header[HDR_COUNT] = s_before + total; rv.header[HDR_SAMPLED] = count;
-            rv.header[HDR_TRIES] = s_tries; rv.header[HDR_FLAGS] = flags;
-        }
-        return;
-    }
-    // ---- peer mode
-    if (mine) {
-        T st[LQ_MAX_N];
-        for (int d = 0; d < N; d++) st[d] = xnew[(size_t)d * ostride + j];
-        const int par = ids[j], L = len[j];
-        sample_of_slot[slot] = j;
-        for (int p = 0; p < pd.n; p++) {
-            const RecView<T> pv = rec_view<T>(pd.seg[p], Wc, N, M, H);
-            for (int d = 0; d < N; d++) pv.state[(size_t)d * Wc + slot] = st[d];
-            for (int k = 0; k < M * N; k++) pv.K[(size_t)k * Wc + slot] = Knew[(size_t)k * ostride + j];
-            pv.parent[slot] = par; pv.len[slot] = L;
-        }
-    }
-    __shared__ bool last;
-    // the grid's last CTA knows the totals; it parks them for whichever CTA finishes last
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) { pd.done[1] = (unsigned)(s_before + total); pd.done[2] = (unsigned)s_tries; }
-    __threadfence_system();                          // my stores are visible system-wide before I count myself done
-    __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(pd.done, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (last && threadIdx.x == 0) {
-        __threadfence_system();
-        const int cnt = (int)((volatile unsigned*)pd.done)[1], tr = (int)((volatile unsigned*)pd.done)[2];
-        for (int p = 0; p < pd.n; p++) {
-            int* h = (int*)pd.seg[p];
-            h[HDR_COUNT] = cnt; h[HDR_SAMPLED] = count; h[HDR_TRIES] = tr; h[HDR_FLAGS] = flags;
-        }
-        __threadfence_system();
-        for (int p = 0; p < pd.n; p++) *(volatile unsigned*)pd.flag[p] = pd.seq;     // arrival, after the data
-        *pd.done = 0;
-    }
-}
-
-// A rank whose slice of the wave is empty still has to announce itself to its peers.
-static __global__ void pack_empty_peer_kernel(PeerDst pd, int flags) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    for (int p = 0; p < pd.n; p++) {
-        int* h = (int*)pd.seg[p];
-        h[HDR_COUNT] = 0; h[HDR_SAMPLED] = 0; h[HDR_TRIES] = 0; h[HDR_FLAGS] = flags;
-    }
-    __threadfence_system();
-    for (int p = 0; p < pd.n; p++) *(volatile unsigned*)pd.flag[p] = pd.seq;
-}
-
-template <typename T> struct TreeView {
-    T* state;          // [N][cap]
-    T* K;              // [M*N][cap]
-    int* parent;       // [cap]
-    int* cost;         // [cap] cumulative recorded steps from the seed; T_plan = (1 + cost) dt
-    int* edge_len;     // [cap]
-    uint8_t* ignore;   // [cap] (word-aligned: marks are set with atomicOr on the containing word)
-    uint8_t* owner;    // [cap] rank (record segment) whose GPU holds the node's edge
-    T* edge_x;         // [cap][H*N]
-    T* edge_u;         // [cap][H*M]
-    int* size;         // device scalar
-    int* n_ignored;    // device scalar
-    int* n_goal;       // device scalar
-    unsigned long long* best;   // (cost << 32 | node), ~0 = none
-    unsigned* done;             // CTAs of the running commit that have finished (last one publishes)
-    int cap;           // array stride (node_capacity rounded up to 4)
-    int limit;         // node_capacity: appends beyond it are dropped and flagged
-};
 
 template <typename T>
 __device__ __forceinline__ void mark_path(const TreeView<T>& tv, int node) {
@@ -211,59 +30,153 @@ __device__ __forceinline__ void mark_path(const TreeView<T>& tv, int node) {
     }
 }
 
-struct DevStats { int v[12]; };
+// Stepwise driver: the host sizes the wave itself (lq_wave_expand).
+static __global__ void ctl_set_kernel(WaveCtl* ctl, int slot, int W, int first, int count, int n_old) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ctl->ring[slot].W = W; ctl->ring[slot].first = first; ctl->ring[slot].count = count; ctl->ring[slot].n_old = n_old;
+    ctl->stopped = 0;
+}
 
-// One warp per (segment, record); the last CTA to finish publishes the new tree size and the wave's
-// counters (every CTA has read the old size by then).
+// Device-scheduled driver, plan start: waves 0 and 1 are sized from the tree as loaded (planner.py:172).
+static __global__ void ctl_start_kernel(WaveCtl* ctl, const int* d_size, WavePolicy pol) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int n = *d_size;
+    const int W = policy_wave(pol, n);
+    for (int k = 0; k < CTL_RING; k++) {
+        WaveSlot s{0, 0, 0, n};
+        if (k < 2) { s.W = W; policy_slice(W, pol.rank, pol.world, &s.first, &s.count); }
+        ctl->ring[k] = s;
+    }
+    ctl->stopped = 0; ctl->acc[0] = ctl->acc[1] = ctl->acc[2] = 0; ctl->done_steer = 0; ctl->done_commit = 0;
+}
+
+constexpr int COMMIT_BLOCK = 128;
+constexpr int COMMIT_SLOTS = 32;                          // sample slots per CTA: its 4 warps share their accepted records
+constexpr unsigned PEER_SPIN_LIMIT_NS = 4000000000u;      // 4 s: a peer that never arrives is an error, not a hang
+
+// One CTA per 32 consecutive global sample slots.  Every warp derives the node ids of those slots (prefix count of
+// the accepted samples before them: one pass over the meta words, 4 KB per 1024 samples, L2 resident); the records
+// are then dealt out to the CTA's four warps, all 32 lanes of a warp copy one record.  The last CTA to finish
+// publishes the new tree size, the wave's counters and the control slots of the waves to come (every CTA has
+// read the old size by then).
 template <typename T>
-__global__ void commit_kernel(TreeView<T> tv, const char* __restrict__ records, size_t seg_bytes, int n_seg,
-                              int my_seg, const int* __restrict__ sample_of_slot,
-                              const T* __restrict__ xseq, const T* __restrict__ useq,
-                              int Wc, int N, int M, int H,
-                              const T* __restrict__ goal_lo, const T* __restrict__ goal_hi,
-                              DevStats* __restrict__ out, const unsigned* __restrict__ arrive, unsigned seq,
-                              int* __restrict__ horizon, int hfactor, int hlo, int hhi) {
-    if (arrive) {                        // fused exchange: wait until every peer's records of this wave landed
+__global__ void __launch_bounds__(COMMIT_BLOCK)
+commit_x_kernel(TreeView<T> tv, WaveCtl* __restrict__ ctl, int wave_k,
+                const char* segs, size_t seg_stride, int n_seg, int my_seg,
+                const T* __restrict__ xseq, const T* __restrict__ useq, int Wc, int N, int M, int H,
+                const T* __restrict__ goal_lo, const T* __restrict__ goal_hi,
+                WavePolicy pol, DevStats* __restrict__ out, unsigned out_seq,
+                const unsigned* __restrict__ arrive, unsigned seq,
+                int* __restrict__ horizon, int hfactor, int hlo, int hhi) {
+    __shared__ int s_part[COMMIT_BLOCK / 32];
+    __shared__ int s_err;
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_err = 0;
+    if (arrive) {                        // fused exchange: wait until every peer's results of this wave landed
+        __syncthreads();
         if (threadIdx.x < n_seg) {
             const volatile unsigned* f = arrive + threadIdx.x;
-            while (*f < seq) __nanosleep(64);
+            unsigned long long t0 = 0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while ((int)(*f - seq) < 0) {
+                __nanosleep(32);
+                unsigned long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > (unsigned long long)PEER_SPIN_LIMIT_NS) { s_err = 1; break; }
+            }
         }
         __syncthreads();
         __threadfence_system();
     }
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    const int seg = w / Wc, k = w % Wc;
     const int old_size = *tv.size;
-    int before = 0, mine = 0;
-    if (seg < n_seg) {
-        for (int s = 0; s <= seg; s++) {
-            const int c = ((const int*)(records + (size_t)s * seg_bytes))[HDR_COUNT];
-            if (s < seg) before += c; else mine = c;
+    const int rw = rec_words<T>(N, M);
+
+    // global slot g -> (segment, sample); segments hold HDR_SAMPLED samples each.  The CTA's threads split the
+    // metas that precede its 32 slots; lane `lane` of every warp owns slot g0 + lane.
+    const int g0 = blockIdx.x * COMMIT_SLOTS;
+    const int g = g0 + lane;
+    int seg = -1, idx = 0, off = 0, before = 0;
+    unsigned meta = 0;
+    for (int s = 0; s < n_seg; s++) {
+        const char* base = segs + (size_t)s * seg_stride;
+        const int c = min(max(((const int*)base)[HDR_SAMPLED], 0), Wc);
+        const SegView<T> sv = seg_view<T>((void*)base, Wc, N, M);
+        const int upto = min(c, g0 - off);                      // this segment's samples that precede the CTA's slots
+        for (int i = threadIdx.x; i < upto; i += COMMIT_BLOCK) before += meta_len(sv.meta[i]) > 0 ? 1 : 0;
+        if (g >= off && g < off + c) { seg = s; idx = g - off; meta = sv.meta[idx]; }
+        off += c;
+    }
+    const int total_slots = off;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    if (lane == 0) s_part[warp] = before;
+    __syncthreads();
+    before = 0;
+    for (int w = 0; w < COMMIT_BLOCK / 32; w++) before += s_part[w];
+    const bool mine = seg >= 0 && meta_len(meta) > 0;
+    const unsigned acc_mask = __ballot_sync(0xffffffffu, mine);
+    const int rank_in_cta = __popc(acc_mask & ((1u << lane) - 1u));
+    const int node_mine = old_size + before + rank_in_cta;
+    if (warp == 0) {                     // the CTA's contribution to the wave totals (once, not per warp)
+        int tsum = seg >= 0 ? meta_tries(meta) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tsum += __shfl_xor_sync(0xffffffffu, tsum, o);
+        if (lane == 0) {
+            if (tsum) atomicAdd(&ctl->acc[1], tsum);
+            if (acc_mask) atomicAdd(&ctl->acc[0], __popc(acc_mask));
         }
     }
-    const int node = old_size + before + k;
-    if (seg < n_seg && k < mine && node < tv.limit) {
-        const RecView<T> rv = rec_view<T>((void*)(records + (size_t)seg * seg_bytes), Wc, N, M, H);
-        const int L = rv.len[k], par = rv.parent[k];
+
+    // ---- append: record r of the CTA goes to warp r % 4; all 32 lanes copy one record
+    unsigned todo = __ballot_sync(0xffffffffu, mine && node_mine < tv.limit && (rank_in_cta % (COMMIT_BLOCK / 32)) == warp);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int node = __shfl_sync(0xffffffffu, node_mine, src);
+        const int sg = __shfl_sync(0xffffffffu, seg, src);
+        const int k = __shfl_sync(0xffffffffu, idx, src);
+        const int L = meta_len(__shfl_sync(0xffffffffu, meta, src));
+        const SegView<T> sv = seg_view<T>((void*)(segs + (size_t)sg * seg_stride), Wc, N, M);
+        const T* row = sv.rec + (size_t)k * rw;
+        // issue every load of the record before the first dependent store: one round trip instead of one per chunk
+        const int par = sv.parent[k];
+        const int nrec = N + M * N;
+        T rv[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) { const int q = lane + 32 * c; rv[c] = q < nrec ? row[q] : T(0); }
+        const bool own = sg == my_seg;     // my own rollout: its edge is still in this GPU's scratch
+        const T* sx = xseq + (size_t)k * H * N; const T* su = useq + (size_t)k * H * M;
+        const int nx = own ? L * N : 0, nu = own ? L * M : 0;
+        T ex[4], eu[2];
+#pragma unroll
+        for (int c = 0; c < 4; c++) { const int q = lane + 32 * c; ex[c] = q < nx ? sx[q] : T(0); }
+#pragma unroll
+        for (int c = 0; c < 2; c++) { const int q = lane + 32 * c; eu[c] = q < nu ? su[q] : T(0); }
+        const int pc = tv.cost[par];
         bool in_goal = true;
-        for (int d = lane; d < N; d += 32) {
-            const T v = rv.state[(size_t)d * Wc + k];
-            tv.state[(size_t)d * tv.cap + node] = v;
-            in_goal = in_goal && (goal_lo[d] < v) && (v < goal_hi[d]);      // planner.py:442-447
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const int q = lane + 32 * c;
+            if (q < N) {
+                tv.state[(size_t)q * tv.cap + node] = rv[c];
+                in_goal = in_goal && (goal_lo[q] < rv[c]) && (rv[c] < goal_hi[q]);      // planner.py:442-447
+            } else if (q < nrec) {
+                tv.K[(size_t)(q - N) * tv.cap + node] = rv[c];
+            }
         }
+        for (int q = lane + 96; q < nrec; q += 32) tv.K[(size_t)(q - N) * tv.cap + node] = row[q];       // wide models
         in_goal = __all_sync(0xffffffffu, in_goal);
-        for (int q = lane; q < M * N; q += 32) tv.K[(size_t)q * tv.cap + node] = rv.K[(size_t)q * Wc + k];
-        if (seg == my_seg) {               // my own rollout: its edge is still in this GPU's scratch
-            const int j = sample_of_slot[k];
-            const T* sx = xseq + (size_t)j * H * N; T* dx = tv.edge_x + (size_t)node * H * N;
-            for (int q = lane; q < L * N; q += 32) dx[q] = sx[q];
-            const T* su = useq + (size_t)j * H * M; T* du = tv.edge_u + (size_t)node * H * M;
-            for (int q = lane; q < L * M; q += 32) du[q] = su[q];
-        }
+        T* dx = tv.edge_x + (size_t)node * H * N; T* du = tv.edge_u + (size_t)node * H * M;
+#pragma unroll
+        for (int c = 0; c < 4; c++) { const int q = lane + 32 * c; if (q < nx) dx[q] = ex[c]; }
+#pragma unroll
+        for (int c = 0; c < 2; c++) { const int q = lane + 32 * c; if (q < nu) du[q] = eu[c]; }
+        for (int q = lane + 128; q < nx; q += 32) dx[q] = sx[q];                                         // long edges
+        for (int q = lane + 64; q < nu; q += 32) du[q] = su[q];
         if (lane == 0) {
-            const int c = tv.cost[par] + L;
-            tv.parent[node] = par; tv.cost[node] = c; tv.edge_len[node] = L; tv.owner[node] = (uint8_t)seg;
+            const int c = pc + L;
+            tv.parent[node] = par; tv.cost[node] = c; tv.edge_len[node] = L; tv.owner[node] = (uint8_t)sg;
             if (in_goal) {                                                  // planner.py:260-281
                 atomicAdd(tv.n_goal, 1);
                 atomicMin(tv.best, ((unsigned long long)(unsigned)c << 32) | (unsigned)node);
@@ -271,44 +184,64 @@ __global__ void commit_kernel(TreeView<T> tv, const char* __restrict__ records, 
             }
         }
     }
+
     // ---- completion: the last CTA publishes
-    __shared__ bool last;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        last = atomicAdd(tv.done, 1u) == gridDim.x - 1;
+        if (s_err) atomicExch(&ctl->acc[2], 1);
+        s_last = atomicAdd(&ctl->done_commit, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (last && threadIdx.x == 0) {
+    if (s_last && threadIdx.x == 0) {
         __threadfence();
-        int total = 0, sampled = 0, tries = 0;
-        for (int s = 0; s < n_seg; s++) {
-            const int* h = (const int*)(records + (size_t)s * seg_bytes);
-            total += h[HDR_COUNT]; sampled += h[HDR_SAMPLED]; tries += h[HDR_TRIES];
-        }
+        const int total = *(volatile int*)&ctl->acc[0], tries = *(volatile int*)&ctl->acc[1];
+        const int err = *(volatile int*)&ctl->acc[2];
+        const int flags = ((const int*)segs)[HDR_FLAGS];          // rank 0's stop request rides in segment 0
         const int nsz = min(old_size + total, tv.limit);
         const unsigned long long b = *(volatile unsigned long long*)tv.best;
-        out->v[0] = nsz; out->v[1] = sampled; out->v[2] = nsz - old_size; out->v[3] = *(volatile int*)tv.n_goal;
-        out->v[4] = b == ~0ull ? -1 : (int)(b & 0xffffffffu);
-        out->v[5] = b == ~0ull ? -1 : (int)(b >> 32);
-        out->v[6] = (old_size + total > tv.limit) ? 1 : 0;
-        out->v[7] = tries;
-        out->v[8] = ((const int*)records)[HDR_FLAGS];
         int hz = 0;
         if (hfactor) {                 // planner.py:421-424: the wave's votes, in global sample order
             hz = *horizon;
             for (int s = 0; s < n_seg; s++) {
-                const RecView<T> rv = rec_view<T>((void*)(records + (size_t)s * seg_bytes), Wc, N, M, H);
-                const int ns = rv.header[HDR_SAMPLED];
-                for (int q = 0; q < ns; q++) hz = horizon_apply(hz, rv.votes[q], hfactor, hlo, hhi);
+                const char* base = segs + (size_t)s * seg_stride;
+                const SegView<T> sv = seg_view<T>((void*)base, Wc, N, M);
+                const int ns = min(max(sv.hdr[HDR_SAMPLED], 0), Wc);
+                for (int q = 0; q < ns; q++) hz = horizon_apply(hz, meta_vote(sv.meta[q]), hfactor, hlo, hhi);
             }
             *horizon = hz;
         }
-        out->v[9] = hz;
-        out->v[10] = out->v[11] = 0;
-        *tv.done = 0;
+        // loop control (planner.py:289-311): a stop request or a full tree ends the plan; otherwise size the
+        // wave after next from the size the next wave starts with
+        int stopped = ctl->stopped;
+        if (flags) stopped = flags;
+        else if (nsz >= tv.limit && !stopped) stopped = 1;
+        if (pol.device_schedule) {
+            WaveSlot nxt{0, 0, 0, nsz};
+            if (!stopped) {
+                nxt.W = policy_wave(pol, nsz);
+                policy_slice(nxt.W, pol.rank, pol.world, &nxt.first, &nxt.count);
+            } else {
+                WaveSlot& s1 = ctl->ring[(wave_k + 1) % CTL_RING];    // the wave already sampling becomes a no-op too
+                s1.W = 0; s1.count = 0;
+            }
+            ctl->ring[(wave_k + 2) % CTL_RING] = nxt;
+            ctl->stopped = stopped;
+        }
+        ctl->acc[0] = 0; ctl->acc[1] = 0; ctl->acc[2] = 0; ctl->done_commit = 0;
         __threadfence();
         *tv.size = nsz;
+        // counters for the host (mapped host memory or a device block the host copies)
+        out->v[0] = nsz; out->v[1] = total_slots; out->v[2] = nsz - old_size; out->v[3] = *(volatile int*)tv.n_goal;
+        out->v[4] = b == ~0ull ? -1 : (int)(b & 0xffffffffu);
+        out->v[5] = b == ~0ull ? -1 : (int)(b >> 32);
+        out->v[6] = (old_size + total > tv.limit) ? 1 : 0;
+        out->v[7] = tries;
+        out->v[8] = pol.device_schedule ? stopped : flags;
+        out->v[9] = hz;
+        out->v[10] = err; out->v[11] = 0;
+        __threadfence_system();
+        *(volatile unsigned*)&out->seq = out_seq;
     }
 }
 

@@ -38,6 +38,8 @@ struct lq_engine {
     virtual int wave_records(void** d, uint64_t* bytes) = 0;
     virtual int wave_commit(const void* d_records, int n_seg, int my_seg, cudaStream_t st) = 0;
     virtual int wave_stats(lq_wave_stats* out) = 0;
+    virtual int plan_run(const lq_plan_args* a, lq_plan_summary* out, cudaStream_t st) = 0;
+    virtual int stop_word(int** out) = 0;
     virtual int closest(const double* xg, const uint8_t* colmask, int* id, cudaStream_t st) = 0;
     virtual int steer_force(int node, const double* xtar, int max_steps, double* hx, double* hu, int* len, cudaStream_t st) = 0;
     virtual int append_node(int parent, const double* state, const double* hx, const double* hu, int len, cudaStream_t st) = 0;
@@ -79,8 +81,13 @@ namespace lq {
         return code;                             \
     } while (0)
 
-static_assert(sizeof(DevStats) == sizeof(lq_wave_stats), "device stats block must mirror lq_wave_stats");
-constexpr int MAX_SPLIT = 128;
+static_assert(sizeof(lq_wave_stats) == 12 * sizeof(int), "device stats block must mirror lq_wave_stats");
+// partial-minimum slots per query: the old-tree scan writes [0, MAX_SPLIT_OLD), the delta scan (or the one full
+// scan of a stepwise wave) [MAX_SPLIT_OLD, MAX_SLOTS)
+constexpr int MAX_SPLIT_OLD = 192;
+constexpr int MAX_SPLIT_NEW = 128;
+constexpr int MAX_SLOTS = MAX_SPLIT_OLD + MAX_SPLIT_NEW;
+constexpr int MAX_SPLIT = MAX_SPLIT_NEW;
 constexpr int NEAR_BLOCK = 128;
 
 // ---- small utility kernels --------------------------------------------------
@@ -149,7 +156,7 @@ __global__ void gather_edges_kernel(TreeView<T> tv, const int* __restrict__ ids,
     const int L = min(tv.edge_len[node], H);
     if (threadIdx.x == 0) olen[r] = L;
     // rows past the edge length, and edges held by another GPU, read back as zero
-    const int mine = my_seg < 0 || tv.owner[node] == my_seg || node == 0;
+    const int mine = my_seg < 0 || tv.owner[node] == my_seg || node == 0 || (tv.owner[node] == 255 && my_seg == 0);
     const int nx = mine ? L * (HN / H) : 0, nu = mine ? L * (HM / H) : 0;
     for (int k = threadIdx.x; k < HN; k += blockDim.x) ox[(size_t)r * HN + k] = k < nx ? tv.edge_x[(size_t)node * HN + k] : T(0);
     for (int k = threadIdx.x; k < HM; k += blockDim.x) ou[(size_t)r * HM + k] = k < nu ? tv.edge_u[(size_t)node * HM + k] : T(0);
@@ -165,8 +172,10 @@ __global__ void climb_kernel(TreeView<T> tv, int node, int* __restrict__ ids, in
 }
 
 template <typename T>
-__global__ void tree_scalars_kernel(TreeView<T> tv, int size) {
-    *tv.size = size; *tv.n_ignored = 0; *tv.n_goal = 0; *tv.best = ~0ull; *tv.done = 0; tv.done[1] = 0; tv.done[2] = 0; tv.done[3] = 0;
+__global__ void tree_scalars_kernel(TreeView<T> tv, int size, WaveCtl* ctl) {
+    *tv.size = size; *tv.n_ignored = 0; *tv.n_goal = 0; *tv.best = ~0ull;
+    ctl->stopped = 0; ctl->acc[0] = ctl->acc[1] = ctl->acc[2] = 0; ctl->done_steer = 0; ctl->done_commit = 0;
+    for (int k = 0; k < CTL_RING; k++) ctl->ring[k] = WaveSlot{0, 0, 0, size};
 }
 
 template <typename T> struct DevBuf {
@@ -196,19 +205,23 @@ struct EngineImpl : lq_engine {
     int size_ub = 0;                 // host upper bound of the device-side tree size
     int size_ub_exact = 0;           // tree size as of the last stats read (wave-start size for profiling)
     int steer_lanes = 1, near_q = 0; // tuning (0 = heuristic)
+    int steer_block = 0;             // CTA size of the wave rollout kernel (0 = heuristic)
     int near_kernel = LQ_NEAREST_SCALAR;   // lq_set_option(LQ_OPT_NEAREST_KERNEL)
     int near_ctas_per_sm = 0;              // lq_set_option(LQ_OPT_NEAREST_CTAS_PER_SM): grid target of the scan, 0 = auto
-    // lq_set_option(LQ_OPT_SAMPLE_PREFETCH): sampler of the next wave on a side stream, double-buffered
+    int force_rescan = 0;                  // lq_set_option(LQ_OPT_FORCE_RESCAN): tests -- every query takes the rescan path
+    int spec_scan = 1;                     // lq_set_option(LQ_OPT_SPECULATIVE_SCAN): old-tree scan on the side stream
+    int stage_tables_on = 1;               // lq_set_option(LQ_OPT_STAGE_TABLES)
+    // lq_set_option(LQ_OPT_SAMPLE_PREFETCH): sampler of the next wave on a side stream (stepwise driver)
     bool prefetch_on = false;
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_sampled[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
     bool consumed_valid[2] = {false, false};
     int sample_parity = 0;
-    T* cur_samples = nullptr;
-    int* cur_tries = nullptr;
+    int cur_parity = 0;              // sample / partials / segment parity of the wave being expanded
     bool metric_diag = true;
     DiagMetric<T, N> dmet;
     double Sconst[N * N];
+    StagePlan stage_plan;
 
     // tree: dim-major so that a scan reads each dim as one contiguous stream
     DevBuf<T> t_state, t_K, t_ex, t_eu;
@@ -216,7 +229,7 @@ struct EngineImpl : lq_engine {
     DevBuf<uint8_t> t_ignore, t_owner;
     int last_my_seg = 0;             // segment index this GPU committed as (its rank)
     // fused exchange over peer-mapped symmetric memory (lq_wave_set_peers); layout of every rank's buffer:
-    // [2 parities][world segments][rec_sz] then [2][world] arrival flags
+    // [2 parities][world segments][seg_sz] then [2][world] arrival flags
     int peer_world = 0, peer_rank = 0;
     char* peer_buf[MAX_PEERS] = {};
     unsigned peer_seq = 0;           // waves expanded in peer mode (flags carry it; monotonic for the engine's life)
@@ -227,43 +240,60 @@ struct EngineImpl : lq_engine {
     std::vector<DevBuf<int>*> grid_bufs;
     int grid_min_obs = 16;
     bool use_hull_grid = true;
-    // wave working set
-    DevBuf<T> w_samples, w_ncost, w_pcost, w_Sp, w_xs, w_us, w_xnew, w_Knew, w_cand, w_goal;
-    DevBuf<int> w_nidx, w_pidx, w_len, w_tries, w_pick, w_src, w_misc;
-    DevBuf<uint8_t> w_candok, w_votes;
+    // wave working set (double-buffered by wave parity where two waves overlap)
+    DevBuf<T> w_samples, w_pcost, w_Sp, w_xs, w_us, w_cand, w_goal;
+    DevBuf<int> w_pidx, w_len, w_tries, w_pick, w_misc, w_nidx;
+    DevBuf<T> w_ncost;
+    DevBuf<uint8_t> w_candok;
     DevBuf<int> w_hor;
-    DevBuf<char> w_rec;
-    DevBuf<DevStats> w_stats;
-    size_t rec_sz = 0;
-    // Committed waves whose counters the host has not read yet: a small ring, so the host can enqueue
-    // wave k+1 before it blocks on wave k's counters (the GPU never idles on the host round trip).
-    static constexpr int RING = 4;
-    lq_wave_stats* h_stats = nullptr;     // pinned [RING]
+    DevBuf<char> w_seg;                   // [2 parities] this engine's own exchange segment
+    DevBuf<WaveCtl> w_ctl;
+    size_t seg_sz = 0;
+    // Per-wave counters come back through mapped pinned host memory: the publishing CTA of a commit writes the
+    // block and then its sequence number, the host polls the number (no copy, no event on the way).
+    static constexpr int RING = 8;
+    DevStats* h_ring = nullptr;           // pinned + mapped [RING]
+    DevStats* d_ring = nullptr;           // the device's view of it
+    int* h_stop = nullptr;                // pinned + mapped: the host's stop request, read by the rollout kernel
+    int* d_stop = nullptr;
     lq_wave_stats last_stats;             // what lq_wave_stats_get returns when nothing is pending
     int* h_misc = nullptr;                // pinned
-    cudaEvent_t ev_stats[RING] = {nullptr, nullptr, nullptr, nullptr};
-    unsigned q_head = 0, q_tail = 0;      // [q_head, q_tail) = committed, unread
-    int q_add[RING] = {0, 0, 0, 0};       // most nodes that wave can have appended (for the size bound)
+    unsigned q_head = 0, q_tail = 0;      // [q_head, q_tail) = committed, unread (stepwise driver)
+    unsigned stat_seq = 0;                // sequence number of the last commit launched
+    unsigned q_seq[RING] = {};
+    int q_add[RING] = {};                 // most nodes that wave can have appended (for the size bound)
+    cudaStream_t q_stream[RING] = {};
     cudaStream_t last_stream = nullptr;
-    // optional per-stage CUDA-event timing (bench.py roofline): sample | nearest | steer | pack | commit
+    // the device-scheduled driver's own streams: rollout chain (high priority) and scan / sampler (low priority)
+    cudaStream_t s_chain = nullptr, s_scan = nullptr;
+    static constexpr int EVR = 8;
+    cudaEvent_t ev_commit[EVR] = {}, ev_scan[EVR] = {}, ev_in = nullptr, ev_begin = nullptr, ev_end = nullptr;
+    // optional per-stage CUDA-event timing (bench.py roofline): sample | nearest (old-tree + delta) | steer | commit
     bool prof_on = false;
-    bool prof_wave_open[RING] = {false, false, false, false}, prof_commit_open[RING] = {false, false, false, false};
-    cudaEvent_t pev[RING][7] = {};
-    double prof_ms[5] = {0, 0, 0, 0, 0};
+    bool prof_open[RING] = {};
+    cudaEvent_t pev[RING][8] = {};
+    double prof_ms[5] = {0, 0, 0, 0, 0};   // sample, nearest_old, nearest_delta, steer, commit
     double prof_work[4] = {0, 0, 0, 0};    // nearest pairs (W*N), nearest bytes (W*N*n*sizeof T), samples, waves
-    int prof_W[RING] = {0, 0, 0, 0};
+    int prof_W[RING] = {};
 
     ~EngineImpl() override {
         cudaSetDevice(device);
         for (auto* b : feas_bufs) delete b;
         for (auto* b : grid_bufs) delete b;
-        if (h_stats) cudaFreeHost(h_stats);
+        if (h_ring) cudaFreeHost(h_ring);
+        if (h_stop) cudaFreeHost(h_stop);
         if (h_misc) cudaFreeHost(h_misc);
-        for (auto& e : ev_stats) if (e) cudaEventDestroy(e);
         for (auto& r : pev) for (auto& e : r) if (e) cudaEventDestroy(e);
         for (auto& e : ev_sampled) if (e) cudaEventDestroy(e);
         for (auto& e : ev_consumed) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_commit) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_scan) if (e) cudaEventDestroy(e);
+        if (ev_in) cudaEventDestroy(ev_in);
+        if (ev_begin) cudaEventDestroy(ev_begin);
+        if (ev_end) cudaEventDestroy(ev_end);
         if (aux) cudaStreamDestroy(aux);
+        if (s_chain) cudaStreamDestroy(s_chain);
+        if (s_scan) cudaStreamDestroy(s_scan);
     }
 
     template <typename U>
@@ -352,7 +382,7 @@ struct EngineImpl : lq_engine {
             auto* ob = new DevBuf<T>(); feas_bufs.push_back(ob);
             if (int r = upload(*ob, obs)) return r;
             d.obs = ob->p;
-            d.cell_start = nullptr; d.cell_items = nullptr;
+            d.cell_start = nullptr; d.cell_items = nullptr; d.n_cells = d.n_items = 0;
             d.hull_axes = nullptr; d.hull_nx = d.hull_ny = 0;
             if (s.kind == LQ_FEAS_CIRCLES_CLOUD || s.kind == LQ_FEAS_BOXES_CLOUD) {
                 if (s.n_verts < 1 || !s.verts) LQ_FAIL(LQ_ERR_ARG, "cloud primitive %d needs vertices", pi);
@@ -393,6 +423,22 @@ struct EngineImpl : lq_engine {
                 if (int r = build_grid(s, d)) return r;
         }
 
+        // shared-memory staging plan for the rollout kernels: all tables of the small obstacle fields, as long
+        // as they fit next to four resident CTAs per SM
+        {
+            memset(&stage_plan, 0, sizeof stage_plan);
+            int total = 0;
+            for (int pi = 0; pi < md.feas.n_prims; pi++) {
+                const FeasPrim<T>& d = md.feas.prims[pi];
+                const bool tabular = d.kind == LQ_FEAS_CIRCLES_POINT || d.kind == LQ_FEAS_SPHERES_POINT ||
+                                     d.kind == LQ_FEAS_CIRCLES_CLOUD || d.kind == LQ_FEAS_BOXES_CLOUD;
+                if (!tabular || d.n_obs < 1) continue;
+                const int b = stage_bytes(d);
+                if (total + b <= 40 * 1024) { stage_plan.on[pi] = 1; total += b; }
+            }
+            stage_plan.bytes = total;
+        }
+
         // tree
         LQ_CUDA(t_state.alloc((size_t)N * cap));
         LQ_CUDA(t_K.alloc((size_t)M * N * cap));
@@ -402,33 +448,34 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(t_ignore.alloc(cap)); LQ_CUDA(t_owner.alloc(cap)); LQ_CUDA(t_scal.alloc(8)); LQ_CUDA(t_best.alloc(1));
         tv.state = t_state.p; tv.K = t_K.p; tv.parent = t_parent.p; tv.cost = t_cost.p; tv.edge_len = t_elen.p;
         tv.ignore = t_ignore.p; tv.owner = t_owner.p; tv.edge_x = t_ex.p; tv.edge_u = t_eu.p;
-        tv.size = t_scal.p; tv.n_ignored = t_scal.p + 1; tv.n_goal = t_scal.p + 2; tv.done = (unsigned*)(t_scal.p + 3);
+        tv.size = t_scal.p; tv.n_ignored = t_scal.p + 1; tv.n_goal = t_scal.p + 2;
         tv.best = t_best.p; tv.cap = cap; tv.limit = c->node_capacity;
         LQ_CUDA(cudaMemset(t_scal.p, 0, 8 * sizeof(int)));
+        LQ_CUDA(w_ctl.alloc(1));
+        LQ_CUDA(cudaMemset(w_ctl.p, 0, sizeof(WaveCtl)));
 
-        // wave working set
-        // samples / sampler tries are double-buffered: with LQ_OPT_SAMPLE_PREFETCH the next wave's sampler
-        // runs on a side stream while this wave's scan and rollouts still read theirs
+        // wave working set; samples / tries / partial minima / per-query metrics / exchange segments are
+        // double-buffered by wave parity: wave k+1's sampler and old-tree scan run while wave k still reads its own
         LQ_CUDA(w_samples.alloc((size_t)2 * N * Wc)); LQ_CUDA(w_ncost.alloc(Wc)); LQ_CUDA(w_nidx.alloc(Wc));
-        cur_samples = w_samples.p;
-        LQ_CUDA(w_pcost.alloc((size_t)MAX_SPLIT * Wc)); LQ_CUDA(w_pidx.alloc((size_t)MAX_SPLIT * Wc));
+        LQ_CUDA(w_pcost.alloc((size_t)2 * MAX_SLOTS * Wc)); LQ_CUDA(w_pidx.alloc((size_t)2 * MAX_SLOTS * Wc));
         LQ_CUDA(w_xs.alloc((size_t)Wc * H * N)); LQ_CUDA(w_us.alloc((size_t)Wc * H * M));
-        LQ_CUDA(w_len.alloc(Wc)); LQ_CUDA(w_tries.alloc((size_t)2 * Wc)); LQ_CUDA(w_pick.alloc(Wc)); LQ_CUDA(w_src.alloc(Wc));
-        LQ_CUDA(w_xnew.alloc((size_t)N * Wc)); LQ_CUDA(w_Knew.alloc((size_t)M * N * Wc));
-        LQ_CUDA(w_misc.alloc(8)); LQ_CUDA(w_stats.alloc(1)); LQ_CUDA(w_votes.alloc(Wc)); LQ_CUDA(w_hor.alloc(1));
+        LQ_CUDA(w_len.alloc(Wc)); LQ_CUDA(w_tries.alloc((size_t)2 * Wc)); LQ_CUDA(w_pick.alloc(Wc));
+        LQ_CUDA(w_misc.alloc(8)); LQ_CUDA(w_hor.alloc(1));
         { const int h0 = c->hfactor ? c->hspan_lo : c->horizon_iters; LQ_CUDA(cudaMemcpy(w_hor.p, &h0, sizeof(int), cudaMemcpyHostToDevice)); }
         md.horizon = w_hor.p;
-        LQ_CUDA(cudaMemset(w_votes.p, 0, Wc)); LQ_CUDA(w_goal.alloc(2 * LQ_MAX_N));
-        rec_sz = rec_bytes<T>(Wc, N, M, H);
-        LQ_CUDA(w_rec.alloc(rec_sz));
-        LQ_CUDA(cudaMemset(w_rec.p, 0, rec_sz));
+        LQ_CUDA(w_goal.alloc(2 * LQ_MAX_N));
+        seg_sz = seg_bytes<T>(Wc, N, M);
+        LQ_CUDA(w_seg.alloc(2 * seg_sz));
+        LQ_CUDA(cudaMemset(w_seg.p, 0, 2 * seg_sz));
         LQ_CUDA(cudaMemset(w_tries.p, 0, (size_t)2 * Wc * sizeof(int)));
-        cur_tries = w_tries.p;
-        LQ_CUDA(cudaMallocHost((void**)&h_stats, RING * sizeof(lq_wave_stats)));
+        LQ_CUDA(cudaHostAlloc((void**)&h_ring, RING * sizeof(DevStats), cudaHostAllocMapped));
+        LQ_CUDA(cudaHostGetDevicePointer((void**)&d_ring, h_ring, 0));
+        LQ_CUDA(cudaHostAlloc((void**)&h_stop, 64, cudaHostAllocMapped));
+        LQ_CUDA(cudaHostGetDevicePointer((void**)&d_stop, h_stop, 0));
         LQ_CUDA(cudaMallocHost((void**)&h_misc, 8 * sizeof(int)));
-        memset(h_stats, 0, RING * sizeof(lq_wave_stats));
+        memset(h_ring, 0, RING * sizeof(DevStats));
+        *h_stop = 0;
         memset(&last_stats, 0, sizeof last_stats);
-        for (auto& e : ev_stats) LQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
         // metric: constant providers are classified once (planner.py:348 evaluates lqr at every sample)
         if (Lqr::CONST_METRIC) {
@@ -451,7 +498,7 @@ struct EngineImpl : lq_engine {
                 dmet.w[i] = (T)w; dmet.period[i] = (T)(6.283185307179586 * w); dmet.sdiag[i] = (T)Sconst[i * N + i];
             }
         } else {
-            LQ_CUDA(w_Sp.alloc((size_t)NS * Wc));
+            LQ_CUDA(w_Sp.alloc((size_t)2 * NS * Wc));
             if (Lqr::CONST_METRIC) {
                 std::vector<T> sp_h((size_t)NS * Wc);
                 int s = N;
@@ -460,7 +507,8 @@ struct EngineImpl : lq_engine {
                     for (int b = a + 1; b < N; b++, s++)
                         for (int j = 0; j < Wc; j++) sp_h[(size_t)s * Wc + j] = (T)(Sconst[a * N + b] + Sconst[b * N + a]);
                 }
-                LQ_CUDA(cudaMemcpy(w_Sp.p, sp_h.data(), sp_h.size() * sizeof(T), cudaMemcpyHostToDevice));
+                for (int par = 0; par < 2; par++)
+                    LQ_CUDA(cudaMemcpy(w_Sp.p + (size_t)par * NS * Wc, sp_h.data(), sp_h.size() * sizeof(T), cudaMemcpyHostToDevice));
             }
         }
         // heuristic: split the obstacle tables over a warp once they dominate a rollout step
@@ -535,6 +583,7 @@ struct EngineImpl : lq_engine {
         if (items_tmp.empty()) items_tmp.push_back(0);
         if (int r = upload(*ci, items_tmp)) return r;
         d.cell_start = cs->p; d.cell_items = ci->p;
+        d.n_cells = (int)ncell; d.n_items = (int)items_tmp.size();
         for (int k = 0; k < 3; k++) { d.g0[k] = (T)blo[k]; d.ginv[k] = (T)(1.0 / cell[k]); d.gn[k] = gn[k]; }
         return LQ_OK;
     }
@@ -603,7 +652,7 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(cudaMemsetAsync(t_elen.p, 0, count * sizeof(int), st));
         LQ_CUDA(cudaMemsetAsync(t_ignore.p, 0, cap, st));
         LQ_CUDA(cudaMemsetAsync(t_owner.p, 0, cap, st));
-        tree_scalars_kernel<T><<<1, 1, 0, st>>>(tv, count); launches++;
+        tree_scalars_kernel<T><<<1, 1, 0, st>>>(tv, count, w_ctl.p); launches++;
         init_gain_kernel<T, Sys, Lqr><<<(count + 127) / 128, 128, 0, st>>>(md, t_state.p, t_K.p, cap, count); launches++;
         LQ_CUDA(cudaGetLastError());
         LQ_CUDA(cudaStreamSynchronize(st));     // host staging vectors die here
@@ -611,7 +660,8 @@ struct EngineImpl : lq_engine {
         memset(&last_stats, 0, sizeof last_stats);
         last_stats.tree_size = count; last_stats.best_node = -1; last_stats.best_cost = -1;
         q_head = q_tail = 0;
-        for (int k = 0; k < RING; k++) prof_wave_open[k] = prof_commit_open[k] = false;
+        for (int k = 0; k < RING; k++) prof_open[k] = false;
+        sample_parity = 0; consumed_valid[0] = consumed_valid[1] = false;
         return LQ_OK;
     }
 
@@ -624,36 +674,45 @@ struct EngineImpl : lq_engine {
     }
 
     // ---- K1 -------------------------------------------------------------------
-    // idx == nullptr: leave the per-split partials for the consumer (steer_kernel) and report the split count
-    int launch_nearest(const T* q, int qstride, int W, int use_ignore, int* idx, T* cost, cudaStream_t st, int* nsplit_out = nullptr) {
-        const int Nub = std::max(1, size_ub);
-        const int max_splits = std::min(MAX_SPLIT, (Nub + NEAR_BLOCK - 1) / NEAR_BLOCK);
-        // measured (profiles/README.md, sweep_k1_r1): 16 CTAs per SM fill the machine better on the n <= 6 trees
-        // (mid-size waves), the 12-state scan prefers 8
-        const int target = 148 * (near_ctas_per_sm > 0 ? near_ctas_per_sm : (N <= 6 ? 16 : 8));
-        int nsplit_used = 1;
-        auto plan = [&](int qper, int& nqb, int& chunk, int& nsplit) {
-            nqb = (W + NEAR_BLOCK * qper - 1) / (NEAR_BLOCK * qper);
-            nsplit = std::max(1, std::min(max_splits, (target + nqb - 1) / nqb));
-            chunk = (Nub + nsplit - 1) / nsplit;
-            chunk = (chunk + NEAR_BLOCK - 1) / NEAR_BLOCK * NEAR_BLOCK;
-            nsplit = (Nub + chunk - 1) / chunk;
+    // One scan launch over the node range [*d_lo, *d_hi) (d_lo == nullptr: from 0) for the first *d_count (or W)
+    // queries of `q`; per-split partial minima go to slots [slot0, slot0 + nsplit) of parity `par`'s partials.
+    // W, n_ub are host-side bounds used only to shape the grid; returns the number of slots written.
+    T* pcost_of(int par) { return w_pcost.p + (size_t)par * MAX_SLOTS * Wc; }
+    int* pidx_of(int par) { return w_pidx.p + (size_t)par * MAX_SLOTS * Wc; }
+    T* sp_of(int par) { return w_Sp.p ? w_Sp.p + (size_t)par * NS * Wc : nullptr; }
+    T* samples_of(int par) { return w_samples.p + (size_t)par * N * Wc; }
+    int* tries_of(int par) { return w_tries.p + (size_t)par * Wc; }
+    char* seg_of(int par) { return w_seg.p + (size_t)par * seg_sz; }
+
+    // Slots: [slot_base, slot_base + nsplit), or -- end_aligned -- [slot_base - nsplit, slot_base), so that an old-tree
+    // scan and a delta scan of the same wave leave one contiguous range around MAX_SPLIT_OLD for the rollout kernel.
+    int launch_scan(const T* q, int qstride, int W, const int* d_count, const int* d_lo, const int* d_hi, int n_ub,
+                    const int* d_nign, int use_ignore, int par, int slot_base, bool end_aligned, int max_split, int target_ctas,
+                    cudaStream_t st, int* nsplit_out) {
+        const int Nub = std::max(1, n_ub);
+        const int max_splits = std::max(1, std::min(max_split, (Nub + NEAR_BLOCK - 1) / NEAR_BLOCK));
+        ScanArgs sa;
+        sa.d_lo = d_lo; sa.d_hi = d_hi; sa.d_count = d_count; sa.d_nignored = d_nign; sa.W = W; sa.slot0 = slot_base;
+        sa.use_ignore = use_ignore;
+        auto plan = [&](int qper) {
+            sa.nqb = std::max(1, (W + NEAR_BLOCK * qper - 1) / (NEAR_BLOCK * qper));
+            sa.nsplit = std::max(1, std::min(max_splits, (target_ctas + sa.nqb - 1) / sa.nqb));
+            sa.slot0 = end_aligned ? slot_base - sa.nsplit : slot_base;
         };
+        T* pc = pcost_of(par); int* pi = pidx_of(par);
         // the erf masks of the shipped vehicles get compile-time kernels; anything else the generic one
         const int cmask = md.angle_mask == 0u ? 0 : (md.angle_mask == 4u && N >= 3 ? 4 : (md.angle_mask == 1u ? 1 : -1));
         if (metric_diag) {
             constexpr int QBIG = sizeof(T) == 4 ? 4 : 2;
             constexpr bool EX = sizeof(T) == 8;
-            int nqb, chunk, nsplit;
-            plan(QBIG, nqb, chunk, nsplit);
-            bool big = (long long)nqb * max_splits >= 148 * 2;
+            plan(QBIG);
+            bool big = (long long)sa.nqb * max_splits >= 148 * 2;
             if (near_q == 1) big = false;
             if (near_q > 1) big = true;
-            if (!big) plan(1, nqb, chunk, nsplit);
+            if (!big) plan(1);
 #define LQ_NEAR_DIAG(QQ, MM)                                                                              \
-    nearest_diag_kernel<T, N, QQ, NEAR_BLOCK, MM, EX><<<nqb * nsplit, NEAR_BLOCK, 0, st>>>(               \
-        t_state.p, cap, t_ignore.p, tv.size, tv.n_ignored, use_ignore, q, qstride, W, dmet, nqb, chunk, \
-        w_pcost.p, w_pidx.p, Wc)
+    nearest_diag_kernel<T, N, QQ, NEAR_BLOCK, MM, EX><<<sa.nqb * sa.nsplit, NEAR_BLOCK, 0, st>>>(         \
+        t_state.p, cap, t_ignore.p, sa, q, qstride, dmet, pc, pi, Wc)
 #define LQ_NEAR_DIAG_M(QQ)                                  \
     do {                                                    \
         if (cmask == 0) LQ_NEAR_DIAG(QQ, 0);                \
@@ -662,12 +721,11 @@ struct EngineImpl : lq_engine {
         else LQ_NEAR_DIAG(QQ, -1);                          \
     } while (0)
 #define LQ_NEAR_PK(QQ, MB, PK, MM)                                                                         \
-    nearest_diag_pk_kernel<N, QQ, NEAR_BLOCK, MM, 8, MB, PK><<<nqb * nsplit, NEAR_BLOCK, 0, st>>>(          \
-        t_state.p, cap, t_ignore.p, tv.size, tv.n_ignored, use_ignore, q, qstride, W, dmet, nqb, chunk,   \
-        w_pcost.p, w_pidx.p, Wc)
+    nearest_diag_pk_kernel<N, QQ, NEAR_BLOCK, MM, 8, MB, PK><<<sa.nqb * sa.nsplit, NEAR_BLOCK, 0, st>>>(    \
+        t_state.p, cap, t_ignore.p, sa, q, qstride, dmet, pc, pi, Wc)
 #define LQ_NEAR_PK_M(QQ, MB, PK)                                  \
     do {                                                          \
-        plan(QQ, nqb, chunk, nsplit);                             \
+        plan(QQ);                                                 \
         if (cmask == 0) LQ_NEAR_PK(QQ, MB, PK, 0);                \
         else if (cmask == 4) LQ_NEAR_PK(QQ, MB, PK, (N >= 3 ? 4 : 0)); \
         else if (cmask == 1) LQ_NEAR_PK(QQ, MB, PK, 1);           \
@@ -681,15 +739,14 @@ struct EngineImpl : lq_engine {
                     // minimum CTAs per SM = the register budget each variant is compiled for (128-thread CTAs)
                     case LQ_NEAREST_PACKED: LQ_NEAR_PK_M(4, (N <= 6 ? 8 : 4), true); break;
                     case LQ_NEAREST_PACKED_Q8: LQ_NEAR_PK_M(8, (N <= 6 ? 4 : 2), true); break;
-                    case LQ_NEAREST_PREFIX:                // experimental partial-distance filter on the leading (position) dims
+                    case LQ_NEAREST_PREFIX:                // partial-distance filter on the leading (position) dims
                         if constexpr (N >= 3) {
                             constexpr int PFX = N >= 12 ? 3 : 2;          // leading position dims used as the bound
                             if ((md.angle_mask & ((1u << PFX) - 1u)) == 0u && (cmask == 0 || cmask == 4)) {
-                                plan(4, nqb, chunk, nsplit);
+                                plan(4);
 #define LQ_NEAR_PFX(MM)                                                                                   \
-    nearest_diag_prefix_kernel<N, 4, NEAR_BLOCK, MM, PFX><<<nqb * nsplit, NEAR_BLOCK, 0, st>>>(             \
-        t_state.p, cap, t_ignore.p, tv.size, tv.n_ignored, use_ignore, q, qstride, W, dmet, nqb, chunk,   \
-        w_pcost.p, w_pidx.p, Wc)
+    nearest_diag_prefix_kernel<N, 4, NEAR_BLOCK, MM, PFX><<<sa.nqb * sa.nsplit, NEAR_BLOCK, 0, st>>>(       \
+        t_state.p, cap, t_ignore.p, sa, q, qstride, dmet, pc, pi, Wc)
                                 if (cmask == 0) LQ_NEAR_PFX(0); else LQ_NEAR_PFX((N >= 3 ? 4 : 0));
 #undef LQ_NEAR_PFX
                                 break;
@@ -705,41 +762,42 @@ struct EngineImpl : lq_engine {
 #undef LQ_NEAR_PK
 #undef LQ_NEAR_DIAG_M
 #undef LQ_NEAR_DIAG
-            nsplit_used = nsplit;
         } else {
             if (qstride != Wc) LQ_FAIL(LQ_ERR_STATE, "dense-metric search needs queries in the engine's wave layout");
-            if (!Lqr::CONST_METRIC) {
-                if (Lqr::COOP) {
-                    constexpr int ML = 8;
-                    metric_coop_kernel<T, Sys, Lqr, ML><<<(unsigned)(((long long)W * ML + 31) / 32), 32,
-                                                          (32 / ML) * Lqr::COOP_SCALARS * sizeof(T), st>>>(md, q, qstride, W, w_Sp.p);
-                } else {
-                    metric_kernel<T, Sys, Lqr><<<(W + 63) / 64, 64, 0, st>>>(md.sys, md.lqr, md.dt, q, qstride, W, w_Sp.p);
-                }
-                launches++;
-            }
-            int nqb, chunk, nsplit;
-            plan(1, nqb, chunk, nsplit);
+            plan(1);
+            const T* Sp = sp_of(par);
 #define LQ_NEAR_DENSE(MM)                                                                                  \
-    nearest_dense_kernel<T, N, NEAR_BLOCK, MM><<<nqb * nsplit, NEAR_BLOCK, 0, st>>>(                       \
-        t_state.p, cap, t_ignore.p, tv.size, tv.n_ignored, use_ignore, q, qstride, W, w_Sp.p, md.angle_mask, \
-        nqb, chunk, w_pcost.p, w_pidx.p, Wc)
+    nearest_dense_kernel<T, N, NEAR_BLOCK, MM><<<sa.nqb * sa.nsplit, NEAR_BLOCK, 0, st>>>(                 \
+        t_state.p, cap, t_ignore.p, sa, q, qstride, Sp, md.angle_mask, pc, pi, Wc)
             if (cmask == 0) LQ_NEAR_DENSE(0);
             else if (cmask == 4) LQ_NEAR_DENSE((N >= 3 ? 4 : 0));
             else if (cmask == 1) LQ_NEAR_DENSE(1);
             else LQ_NEAR_DENSE(-1);
 #undef LQ_NEAR_DENSE
-            nsplit_used = nsplit;
         }
         launches++;
-        if (nsplit_out) *nsplit_out = nsplit_used;
-        if (idx) {
-            nearest_finalize_kernel<T><<<(W + 127) / 128, 128, 0, st>>>(w_pcost.p, w_pidx.p, Wc, nsplit_used, W, idx, cost);
-            launches++;
-        }
+        if (nsplit_out) *nsplit_out = sa.nsplit;
         LQ_CUDA(cudaGetLastError());
         return LQ_OK;
     }
+
+    // S = lqr(sample, 0).S per query for state-dependent providers (planner.py:348), into parity `par`
+    int launch_metric(const T* q, int qstride, int W, const int* d_count, int par, cudaStream_t st) {
+        if (metric_diag || Lqr::CONST_METRIC) return LQ_OK;
+        if (W < 1) return LQ_OK;
+        if (Lqr::COOP) {
+            constexpr int ML = 8;
+            metric_coop_kernel<T, Sys, Lqr, ML><<<(unsigned)(((long long)W * ML + 31) / 32), 32,
+                                                  (32 / ML) * Lqr::COOP_SCALARS * sizeof(T), st>>>(md, q, qstride, W, d_count, sp_of(par));
+        } else {
+            metric_kernel<T, Sys, Lqr><<<(W + 63) / 64, 64, 0, st>>>(md.sys, md.lqr, md.dt, q, qstride, W, d_count, sp_of(par));
+        }
+        launches++;
+        LQ_CUDA(cudaGetLastError());
+        return LQ_OK;
+    }
+
+    int scan_target() const { return 148 * (near_ctas_per_sm > 0 ? near_ctas_per_sm : (N <= 6 ? 16 : 8)); }
 
     int nearest(const void* d_q, int W, int use_ignore, int* d_idx, void* d_cost, cudaStream_t st) override {
         LQ_CUDA(cudaSetDevice(device));
@@ -750,46 +808,53 @@ struct EngineImpl : lq_engine {
             for (int d = 0; d < N; d++)
                 LQ_CUDA(cudaMemcpyAsync(w_samples.p + (size_t)d * Wc, q + (size_t)d * W, W * sizeof(T), cudaMemcpyDeviceToDevice, st));
             q = w_samples.p; qstride = Wc;
+            if (int r = launch_metric(q, qstride, W, nullptr, 0, st)) return r;
         }
-        return launch_nearest(q, qstride, W, use_ignore, d_idx, (T*)d_cost, st);
+        int nsplit = 1;
+        if (int r = launch_scan(q, qstride, W, nullptr, nullptr, tv.size, size_ub, tv.n_ignored, use_ignore, 0, 0, false, MAX_SPLIT,
+                                scan_target(), st, &nsplit)) return r;
+        nearest_finalize_kernel<T><<<(W + 127) / 128, 128, 0, st>>>(pcost_of(0), pidx_of(0), Wc, nsplit, W, d_idx, (T*)d_cost);
+        launches++;
+        LQ_CUDA(cudaGetLastError());
+        return LQ_OK;
     }
 
     // ---- K2 -------------------------------------------------------------------
-    // Rollouts are latency bound with wildly different trip counts: small CTAs spread a wave over all
-    // 148 SMs, larger ones only pay off once every SM already holds several.
+    // Rollouts have wildly different trip counts: small CTAs spread a wave over all 148 SMs, larger ones
+    // amortise the shared-memory staging of the obstacle tables once every SM already holds several.
+    template <class Kern>
+    int steer_smem(Kern kern, size_t bytes) {
+        if (bytes > 48 * 1024) LQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        return LQ_OK;
+    }
+    StagePlan stage_for_launch() const {
+        StagePlan sp = stage_plan;
+        if (!stage_tables_on) { memset(&sp, 0, sizeof sp); }
+        return sp;
+    }
     template <int LANES>
-    void launch_steer_l(const int* ids, NearPartials<T> np, const T* targets, int tstride, int W, T* xs, T* us, int* len,
-                        T* xnew, T* Knew, int ostride, cudaStream_t st) {
+    int launch_steer_l(const int* ids, const T* targets, int tstride, int W, T* xs, T* us, int* len, cudaStream_t st) {
         const long long threads = (long long)W * LANES;
-        uint8_t* votes = md.hfactor ? w_votes.p : nullptr;
-        // cooperative providers keep their matrices in a per-group slice of shared memory: one warp per CTA
-        const size_t coop32 = (size_t)(32 / LANES) * Lqr::COOP_SCALARS * sizeof(T);
+        const StagePlan sp = stage_for_launch();
         if (threads >= 148LL * 8 * 128 && !(Lqr::COOP && LANES > 1)) {
-            steer_kernel<T, Sys, Lqr, LANES, 128><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
-                md, t_state.p, t_K.p, cap, ids, np, targets, tstride, W, xs, us, len, xnew, Knew, ostride, votes);
+            const size_t sm = steer_coop_bytes<T, Lqr, LANES, 128>() + sp.bytes;
+            auto kern = steer_kernel<T, Sys, Lqr, LANES, 128>;
+            if (int r = steer_smem(kern, sm)) return r;
+            kern<<<(unsigned)((threads + 127) / 128), 128, sm, st>>>(md, sp, t_state.p, t_K.p, cap, ids, targets, tstride, W, xs, us, len);
         } else {
-            steer_kernel<T, Sys, Lqr, LANES, 32><<<(unsigned)((threads + 31) / 32), 32, LANES > 1 ? coop32 : 0, st>>>(
-                md, t_state.p, t_K.p, cap, ids, np, targets, tstride, W, xs, us, len, xnew, Knew, ostride, votes);
+            const size_t sm = steer_coop_bytes<T, Lqr, LANES, 32>() + sp.bytes;
+            auto kern = steer_kernel<T, Sys, Lqr, LANES, 32>;
+            if (int r = steer_smem(kern, sm)) return r;
+            kern<<<(unsigned)((threads + 31) / 32), 32, sm, st>>>(md, sp, t_state.p, t_K.p, cap, ids, targets, tstride, W, xs, us, len);
         }
         launches++;
+        LQ_CUDA(cudaGetLastError());
+        return LQ_OK;
     }
-    void launch_sample(uint64_t seed, uint32_t wave, int first, int count, cudaStream_t st) {
-        constexpr int TL = 16;                       // >= tries_capacity
-        const long long threads = (long long)count * TL;
-        if (threads >= 148LL * 8 * 128) {
-            sample_kernel<T, Sys, Lqr, TL, 128><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
-                md, sp, seed, wave, first, count, cur_samples, Wc, cur_tries);
-        } else {
-            sample_kernel<T, Sys, Lqr, TL, 32><<<(unsigned)((threads + 31) / 32), 32, 0, st>>>(
-                md, sp, seed, wave, first, count, cur_samples, Wc, cur_tries);
-        }
-        launches++;
-    }
-    void launch_steer(const int* ids, NearPartials<T> np, const T* targets, int tstride, int W, T* xs, T* us, int* len,
-                      T* xnew, T* Knew, int ostride, cudaStream_t st) {
-        if (steer_lanes >= 32) launch_steer_l<32>(ids, np, targets, tstride, W, xs, us, len, xnew, Knew, ostride, st);
-        else if (steer_lanes >= 8) launch_steer_l<8>(ids, np, targets, tstride, W, xs, us, len, xnew, Knew, ostride, st);
-        else launch_steer_l<1>(ids, np, targets, tstride, W, xs, us, len, xnew, Knew, ostride, st);
+    int launch_steer(const int* ids, const T* targets, int tstride, int W, T* xs, T* us, int* len, cudaStream_t st) {
+        if (steer_lanes >= 32) return launch_steer_l<32>(ids, targets, tstride, W, xs, us, len, st);
+        if (steer_lanes >= 8) return launch_steer_l<8>(ids, targets, tstride, W, xs, us, len, st);
+        return launch_steer_l<1>(ids, targets, tstride, W, xs, us, len, st);
     }
 
     int steer(const int* d_ids, const void* d_t, int W, void* d_x, void* d_u, int* d_len, cudaStream_t st) override {
@@ -799,57 +864,103 @@ struct EngineImpl : lq_engine {
         T* us = d_u ? (T*)d_u : w_us.p;
         if (d_x) LQ_CUDA(cudaMemsetAsync(xs, 0, (size_t)W * H * N * sizeof(T), st));
         if (d_u) LQ_CUDA(cudaMemsetAsync(us, 0, (size_t)W * H * M * sizeof(T), st));
-        launch_steer(d_ids, NearPartials<T>{nullptr, nullptr, 0, 0, nullptr}, (const T*)d_t, W, W, xs, us,
-                     d_len ? d_len : w_len.p, nullptr, nullptr, 0, st);
-        LQ_CUDA(cudaGetLastError());
-        return LQ_OK;
+        return launch_steer(d_ids, (const T*)d_t, W, W, xs, us, d_len ? d_len : w_len.p, st);
     }
 
-    // ---- one wave -------------------------------------------------------------
-    int expand_from_samples(int count, int use_ignore, int flags, cudaStream_t st) {
-        const int slot = q_tail % RING;
-        if (prof_on) cudaEventRecord(pev[slot][1], st);
-        int nsplit = 1;
-        if (int r = launch_nearest(cur_samples, Wc, count, use_ignore, nullptr, nullptr, st, &nsplit)) return r;
-        if (prof_on) cudaEventRecord(pev[slot][2], st);
-        launch_steer(nullptr, NearPartials<T>{w_pcost.p, w_pidx.p, Wc, nsplit, w_nidx.p}, cur_samples, Wc, count,
-                     w_xs.p, w_us.p, w_len.p, w_xnew.p, w_Knew.p, Wc, st);
-        if (prof_on) cudaEventRecord(pev[slot][3], st);
-        RecView<T> rv = rec_view<T>(w_rec.p, Wc, N, M, H);
-        PeerDst pd = next_peer_dst();
-        pack_kernel<T, 256><<<(count + 255) / 256, 256, 0, st>>>(w_len.p, cur_tries, w_nidx.p, w_xnew.p, w_Knew.p, Wc, count,
-                                                                rv, w_src.p, Wc, N, M, H, flags, pd,
-                                                                md.hfactor ? w_votes.p : nullptr);
+    // The wave's rollout kernel: nearest selection from the partial slots [slot_lo, slot_lo + nslots) of parity `par`,
+    // rollouts of the first ring[slot].count samples, results into `dst`.
+    template <int LANES>
+    int launch_steer_x_l(int W, int slot, int par, int slot_lo, int nslots, int use_ignore, const ExDst& dst, int flags,
+                         bool use_stop_word, cudaStream_t st) {
+        const long long threads = (long long)std::max(1, W) * LANES;
+        const StagePlan sp = stage_for_launch();
+        PartialsIn<T> pin{pcost_of(par) + (size_t)slot_lo * Wc, pidx_of(par) + (size_t)slot_lo * Wc, Wc, nslots};
+        NearMetric<T, N> nm;
+        nm.dmet = dmet; nm.dmet.angle_mask = md.angle_mask; nm.Spacked = sp_of(par); nm.diag = metric_diag ? 1 : 0;
+        const int* stopw = use_stop_word ? d_stop : nullptr;
+        int block = steer_block;
+        if (block != 32 && block != 128) block = (threads >= 148LL * 2 * 128 && !(Lqr::COOP && LANES > 1)) ? 128 : 32;
+        if (Lqr::COOP && LANES > 1) block = 32;
+#define LQ_STEER_X(BB)                                                                                         \
+    do {                                                                                                       \
+        const size_t sm = steer_coop_bytes<T, Lqr, LANES, BB>() + sp.bytes;                                    \
+        auto kern = steer_x_kernel<T, Sys, Lqr, LANES, BB>;                                                    \
+        if (int r = steer_smem(kern, sm)) return r;                                                            \
+        kern<<<(unsigned)((threads + BB - 1) / BB), BB, sm, st>>>(                                             \
+            md, sp, t_state.p, t_K.p, cap, t_ignore.p, tv.size, tv.n_ignored, w_ctl.p, slot, pin, nm,          \
+            samples_of(par), Wc, tries_of(par), use_ignore, force_rescan, w_xs.p, w_us.p, dst, Wc, flags, stopw); \
+    } while (0)
+        if (block == 128) LQ_STEER_X(128); else LQ_STEER_X(32);
+#undef LQ_STEER_X
         launches++;
-        if (prof_on) { cudaEventRecord(pev[slot][4], st); prof_wave_open[slot] = true; prof_W[slot] = count; }
         LQ_CUDA(cudaGetLastError());
-        last_stream = st;
+        return LQ_OK;
+    }
+    int launch_steer_x(int W, int slot, int par, int slot_lo, int nslots, int use_ignore, const ExDst& dst, int flags,
+                       bool use_stop_word, cudaStream_t st) {
+        if (steer_lanes >= 32) return launch_steer_x_l<32>(W, slot, par, slot_lo, nslots, use_ignore, dst, flags, use_stop_word, st);
+        if (steer_lanes >= 8) return launch_steer_x_l<8>(W, slot, par, slot_lo, nslots, use_ignore, dst, flags, use_stop_word, st);
+        return launch_steer_x_l<1>(W, slot, par, slot_lo, nslots, use_ignore, dst, flags, use_stop_word, st);
+    }
+
+    int launch_sample(uint64_t seed, uint32_t wave, int slot, int par, int count_ub, cudaStream_t st) {
+        constexpr int TL = 16;                       // >= tries_capacity
+        const long long threads = (long long)std::max(1, count_ub) * TL;
+        const WaveSlot* ws = &w_ctl.p->ring[slot];
+        if (threads >= 148LL * 8 * 128) {
+            sample_kernel<T, Sys, Lqr, TL, 128><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
+                md, sp, seed, wave, ws, samples_of(par), Wc, tries_of(par));
+        } else {
+            sample_kernel<T, Sys, Lqr, TL, 32><<<(unsigned)((threads + 31) / 32), 32, 0, st>>>(
+                md, sp, seed, wave, ws, samples_of(par), Wc, tries_of(par));
+        }
+        launches++;
+        LQ_CUDA(cudaGetLastError());
         return LQ_OK;
     }
 
-    size_t peer_flags_offset() const { return (size_t)2 * peer_world * rec_sz; }
-    // destinations of this wave's pack (advances the wave sequence number)
-    PeerDst next_peer_dst() {
-        PeerDst pd;
-        memset(&pd, 0, sizeof pd);
-        if (peer_world <= 1) return pd;
+    // ---- exchange destinations ------------------------------------------------
+    size_t peer_flags_offset() const { return (size_t)2 * peer_world * seg_sz; }
+    // where this wave's rollout kernel sends its results (advances the wave sequence number in peer mode)
+    ExDst next_dst(int par) {
+        ExDst d;
+        memset(&d, 0, sizeof d);
+        if (peer_world <= 1) { d.n = 1; d.seg[0] = seg_of(par); return d; }
         peer_seq++;
-        const int par = peer_seq & 1;
-        pd.n = peer_world; pd.seq = peer_seq; pd.done = tv.done + 1;
+        const int pp = peer_seq & 1;
+        d.n = peer_world; d.seq = peer_seq;
         for (int p = 0; p < peer_world; p++) {
-            pd.seg[p] = peer_buf[p] + ((size_t)par * peer_world + peer_rank) * rec_sz;
-            pd.flag[p] = (unsigned*)(peer_buf[p] + peer_flags_offset()) + par * peer_world + peer_rank;
+            d.seg[p] = peer_buf[p] + ((size_t)pp * peer_world + peer_rank) * seg_sz;
+            d.flag[p] = (unsigned*)(peer_buf[p] + peer_flags_offset()) + pp * peer_world + peer_rank;
         }
-        return pd;
+        return d;
     }
     int set_peers(int world, int rank, void* const* bufs, uint64_t bytes) override {
         if (world < 0 || world > MAX_PEERS || (world > 0 && (rank < 0 || rank >= world))) LQ_FAIL(LQ_ERR_ARG, "bad world/rank");
         if (world > 1) {
-            const uint64_t need = (uint64_t)2 * world * rec_sz + (uint64_t)2 * world * sizeof(unsigned);
+            const uint64_t need = (uint64_t)2 * world * seg_sz + (uint64_t)2 * world * sizeof(unsigned);
             if (!bufs || bytes < need) LQ_FAIL(LQ_ERR_ARG, "peer buffers must hold %llu bytes", (unsigned long long)need);
             for (int p = 0; p < world; p++) { if (!bufs[p]) LQ_FAIL(LQ_ERR_ARG, "null peer buffer"); peer_buf[p] = (char*)bufs[p]; }
         }
         peer_world = world > 1 ? world : 0; peer_rank = rank; peer_seq = 0;
+        return LQ_OK;
+    }
+
+    // ---- one wave, stepwise driver (the host sizes and launches every wave) ------
+    int expand_from_samples(int count, int use_ignore, int flags, cudaStream_t st) {
+        const int slot = 0, par = cur_parity;
+        const int ps = q_tail % RING;
+        if (prof_on) cudaEventRecord(pev[ps][1], st);
+        if (int r = launch_metric(samples_of(par), Wc, count, nullptr, par, st)) return r;
+        int nsplit = 1;
+        // stepwise: one scan over the whole tree (n_old = 0), written to the "delta" slots
+        if (int r = launch_scan(samples_of(par), Wc, count, nullptr, nullptr, tv.size, size_ub, nullptr, use_ignore, par,
+                                MAX_SPLIT_OLD, false, MAX_SPLIT_NEW, scan_target(), st, &nsplit)) return r;
+        if (prof_on) { cudaEventRecord(pev[ps][2], st); cudaEventRecord(pev[ps][3], st); }
+        const ExDst dst = next_dst(peer_world > 1 ? 0 : par);
+        if (int r = launch_steer_x(count, slot, par, MAX_SPLIT_OLD, nsplit, use_ignore, dst, flags, false, st)) return r;
+        if (prof_on) { cudaEventRecord(pev[ps][4], st); prof_open[ps] = true; prof_W[ps] = count; }
+        last_stream = st;
         return LQ_OK;
     }
 
@@ -859,43 +970,32 @@ struct EngineImpl : lq_engine {
         if (count < 0 || count > Wc) LQ_FAIL(LQ_ERR_ARG, "count=%d outside 0..wave_capacity=%d", count, Wc);
         if (!have_goal) LQ_FAIL(LQ_ERR_STATE, "lq_set_goal has not been called");
         if (q_tail - q_head >= (unsigned)RING) LQ_FAIL(LQ_ERR_STATE, "%d committed waves are unread: call lq_wave_stats_get", RING);
-        if (count == 0 && peer_world > 1) {
-            pack_empty_peer_kernel<<<1, 32, 0, st>>>(next_peer_dst(), flags); launches++;
-            LQ_CUDA(cudaGetLastError());
-            last_stream = st;
-            return LQ_OK;
-        }
-        if (count == 0) {
-            RecView<T> rv = rec_view<T>(w_rec.p, Wc, N, M, H);
-            int hdr[REC_HEADER_INTS] = {0};
-            hdr[HDR_FLAGS] = flags;
-            LQ_CUDA(cudaMemcpyAsync(rv.header, hdr, sizeof hdr, cudaMemcpyHostToDevice, st));
-            LQ_CUDA(cudaStreamSynchronize(st));
-            last_stream = st;
-            return LQ_OK;
-        }
-        if (prof_on) cudaEventRecord(pev[q_tail % RING][0], st);
-        cur_samples = w_samples.p; cur_tries = w_tries.p;
-        if (h_samples) {
+        const int ps = q_tail % RING;
+        if (prof_on) cudaEventRecord(pev[ps][0], st);
+        cur_parity = 0;
+        if (!h_samples && count > 0 && prefetch_on) { cur_parity = sample_parity; }
+        ctl_set_kernel<<<1, 1, 0, st>>>(w_ctl.p, 0, count, first, count, 0); launches++;
+        if (count > 0 && h_samples) {
             std::vector<T> soa((size_t)N * count);
             for (int j = 0; j < count; j++)
                 for (int d = 0; d < N; d++) soa[(size_t)d * count + j] = (T)h_samples[(size_t)j * N + d];
             for (int d = 0; d < N; d++)
-                LQ_CUDA(cudaMemcpyAsync(w_samples.p + (size_t)d * Wc, soa.data() + (size_t)d * count, count * sizeof(T),
+                LQ_CUDA(cudaMemcpyAsync(samples_of(0) + (size_t)d * Wc, soa.data() + (size_t)d * count, count * sizeof(T),
                                         cudaMemcpyHostToDevice, st));
-            LQ_CUDA(cudaMemsetAsync(w_tries.p, 0, count * sizeof(int), st));
+            LQ_CUDA(cudaMemsetAsync(tries_of(0), 0, count * sizeof(int), st));
             LQ_CUDA(cudaStreamSynchronize(st));
-        } else {
+        } else if (count > 0) {
             if (!have_sampling) LQ_FAIL(LQ_ERR_STATE, "lq_set_sampling has not been called");
             if (prefetch_on) {
                 // The sampler reads nothing of the tree (planner.py:201-211), and the host enqueues wave k+1
                 // while wave k is still running: issue it on the side stream into the other buffer, so it
-                // overlaps wave k's scan / rollouts instead of heading wave k+1's dependent chain.
+                // overlaps wave k's scan / rollouts instead of heading wave k+1's dependent chain.  The slice
+                // is passed through a side-stream copy of the control slot (slot 1).
                 if (int r = prefetch_setup()) return r;
                 const int par = sample_parity; sample_parity ^= 1;
-                cur_samples = w_samples.p + (size_t)par * N * Wc; cur_tries = w_tries.p + (size_t)par * Wc;
-                if (consumed_valid[par]) LQ_CUDA(cudaStreamWaitEvent(aux, ev_consumed[par], 0));   // its last reader (pack, two waves ago)
-                launch_sample(seed, wave, first, count, aux);
+                if (consumed_valid[par]) LQ_CUDA(cudaStreamWaitEvent(aux, ev_consumed[par], 0));   // its last reader (two waves ago)
+                ctl_set_kernel<<<1, 1, 0, aux>>>(w_ctl.p, 2 + par, count, first, count, 0); launches++;
+                if (int r = launch_sample(seed, wave, 2 + par, par, count, aux)) return r;
                 LQ_CUDA(cudaEventRecord(ev_sampled[par], aux));
                 LQ_CUDA(cudaStreamWaitEvent(st, ev_sampled[par], 0));
                 const int r = expand_from_samples(count, use_ignore, flags, st);
@@ -903,7 +1003,7 @@ struct EngineImpl : lq_engine {
                 consumed_valid[par] = true;
                 return r;
             }
-            launch_sample(seed, wave, first, count, st);
+            if (int r = launch_sample(seed, wave, 0, 0, count, st)) return r;
         }
         return expand_from_samples(count, use_ignore, flags, st);
     }
@@ -917,6 +1017,8 @@ struct EngineImpl : lq_engine {
         if (w_cand.n < (size_t)N * n_cand) { LQ_CUDA(w_cand.alloc((size_t)N * n_cand)); LQ_CUDA(w_candok.alloc(n_cand)); }
         if (q_tail - q_head >= (unsigned)RING) LQ_FAIL(LQ_ERR_STATE, "%d committed waves are unread: call lq_wave_stats_get", RING);
         if (prof_on) cudaEventRecord(pev[q_tail % RING][0], st);
+        cur_parity = 0;
+        ctl_set_kernel<<<1, 1, 0, st>>>(w_ctl.p, 0, count, 0, count, 0); launches++;
         std::vector<T> soa((size_t)N * n_cand);
         for (int j = 0; j < n_cand; j++)
             for (int d = 0; d < N; d++) soa[(size_t)d * n_cand + j] = (T)h_cand[(size_t)j * N + d];
@@ -924,10 +1026,9 @@ struct EngineImpl : lq_engine {
         candidates_feasible_kernel<T, Sys, Lqr><<<(n_cand + 127) / 128, 128, 0, st>>>(md, w_cand.p, n_cand, n_cand, w_candok.p);
         launches++;
         candidates_select_kernel<T, N><<<1, 256, 0, st>>>(w_cand.p, n_cand, w_candok.p, n_cand, count, tries,
-                                                          w_samples.p, Wc, w_pick.p, w_misc.p);
+                                                          samples_of(0), Wc, w_pick.p, w_misc.p);
         launches++;
-        LQ_CUDA(cudaMemsetAsync(w_tries.p, 0, count * sizeof(int), st));
-        cur_samples = w_samples.p; cur_tries = w_tries.p;
+        LQ_CUDA(cudaMemsetAsync(tries_of(0), 0, count * sizeof(int), st));
         LQ_CUDA(cudaMemcpyAsync(h_misc, w_misc.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         if (int r = expand_from_samples(count, use_ignore, 0, st)) return r;
         LQ_CUDA(cudaStreamSynchronize(st));
@@ -936,8 +1037,19 @@ struct EngineImpl : lq_engine {
     }
 
     int wave_records(void** d, uint64_t* bytes) override {
-        if (d) *d = w_rec.p;
-        if (bytes) *bytes = rec_sz;
+        if (d) *d = seg_of(cur_parity);
+        if (bytes) *bytes = seg_sz;
+        return LQ_OK;
+    }
+
+    int launch_commit(int wave_k, const char* segs, int n_seg, int my_seg, int slots_ub, const WavePolicy& pol,
+                      const unsigned* arrive, unsigned seq, int ring_slot, unsigned out_seq, cudaStream_t st) {
+        const int ctas = std::max(1, (slots_ub + COMMIT_SLOTS - 1) / COMMIT_SLOTS);
+        commit_x_kernel<T><<<ctas, COMMIT_BLOCK, 0, st>>>(tv, w_ctl.p, wave_k, segs, seg_sz, n_seg, my_seg, w_xs.p, w_us.p,
+                                                          Wc, N, M, H, w_goal.p, w_goal.p + LQ_MAX_N, pol, d_ring + ring_slot, out_seq,
+                                                          arrive, seq, w_hor.p, md.hfactor, md.hlo, md.hhi);
+        launches++;
+        LQ_CUDA(cudaGetLastError());
         return LQ_OK;
     }
 
@@ -946,54 +1058,80 @@ struct EngineImpl : lq_engine {
         if (n_seg < 1 || n_seg > 255) LQ_FAIL(LQ_ERR_ARG, "n_segments must be in 1..255");
         if (my_seg < 0 || my_seg >= n_seg) LQ_FAIL(LQ_ERR_ARG, "my_segment must be in 0..n_segments-1");
         last_my_seg = my_seg;
-        const char* rec = d_records ? (const char*)d_records : w_rec.p;
+        const char* segs = d_records ? (const char*)d_records : seg_of(cur_parity);
         const unsigned* arrive = nullptr;
         if (!d_records && peer_world > 1) {             // fused exchange: my own receive buffer, current parity
             if (n_seg != peer_world || my_seg != peer_rank) LQ_FAIL(LQ_ERR_ARG, "peer mode commits world segments as rank");
-            const int par = peer_seq & 1;
-            rec = peer_buf[peer_rank] + (size_t)par * peer_world * rec_sz;
-            arrive = (const unsigned*)(peer_buf[peer_rank] + peer_flags_offset()) + par * peer_world;
+            const int pp = peer_seq & 1;
+            segs = peer_buf[peer_rank] + (size_t)pp * peer_world * seg_sz;
+            arrive = (const unsigned*)(peer_buf[peer_rank] + peer_flags_offset()) + pp * peer_world;
         }
         if (q_tail - q_head >= (unsigned)RING) LQ_FAIL(LQ_ERR_STATE, "%d committed waves are unread: call lq_wave_stats_get", RING);
-        const int slot = q_tail % RING;
-        const long long warps = (long long)n_seg * Wc;
-        if (prof_on) cudaEventRecord(pev[slot][5], st);
-        commit_kernel<T><<<(unsigned)((warps * 32 + 255) / 256), 256, 0, st>>>(tv, rec, rec_sz, n_seg, my_seg, w_src.p,
-                                                                                w_xs.p, w_us.p, Wc, N, M, H,
-                                                                                w_goal.p, w_goal.p + LQ_MAX_N, w_stats.p, arrive, peer_seq,
-                                                                                w_hor.p, md.hfactor, md.hlo, md.hhi);
-        launches++;
-        if (prof_on) { cudaEventRecord(pev[slot][6], st); prof_commit_open[slot] = true; }
-        LQ_CUDA(cudaGetLastError());
-        LQ_CUDA(cudaMemcpyAsync(&h_stats[slot], w_stats.p, sizeof(DevStats), cudaMemcpyDeviceToHost, st));
-        LQ_CUDA(cudaEventRecord(ev_stats[slot], st));
-        q_add[slot] = n_seg * Wc;
+        const int ps = q_tail % RING;
+        WavePolicy pol;
+        memset(&pol, 0, sizeof pol);
+        pol.world = 1; pol.device_schedule = 0;
+        if (prof_on) cudaEventRecord(pev[ps][5], st);
+        ++stat_seq;
+        if (int r = launch_commit(0, segs, n_seg, my_seg, n_seg * Wc, pol, arrive, peer_seq, ps, stat_seq, st)) return r;
+        if (prof_on) cudaEventRecord(pev[ps][6], st);
+        q_seq[ps] = stat_seq; q_stream[ps] = st;
+        q_add[ps] = n_seg * Wc;
         q_tail++;
         size_ub = std::min(cap, size_ub + n_seg * Wc);
+        last_stream = st;
         return LQ_OK;
+    }
+
+    // Block until the commit that carries sequence number `seq` has published ring slot `ps`.
+    int wait_stats(int ps, unsigned seq, cudaStream_t st) {
+        volatile unsigned* s = &h_ring[ps].seq;
+        unsigned spins = 0;
+        while ((int)(*s - seq) < 0) {
+            if ((++spins & 0x3ff) == 0) {
+                const cudaError_t e = cudaStreamQuery(st);
+                if (e == cudaSuccess) {
+                    if ((int)(*s - seq) >= 0) break;
+                    LQ_FAIL(LQ_ERR_STATE, "the stream drained but the wave counters never arrived");
+                }
+                if (e != cudaErrorNotReady) LQ_CUDA(e);
+            }
+        }
+        if (h_ring[ps].v[10]) LQ_FAIL(LQ_ERR_STATE, "a peer GPU never delivered its wave records (exchange timed out)");
+        return LQ_OK;
+    }
+
+    void account_profile(int ps, int local_count, int size_before) {
+        if (!prof_on || !prof_open[ps]) return;
+        float ms = 0;
+        auto el = [&](int a, int b) { ms = 0; cudaEventElapsedTime(&ms, pev[ps][a], pev[ps][b]); return (double)ms; };
+        prof_ms[0] += el(0, 1); prof_ms[1] += el(1, 2); prof_ms[2] += el(3, 4) - 0.0; prof_ms[3] += el(4, 5); prof_ms[4] += el(5, 6);
+        prof_work[0] += (double)local_count * size_before;
+        prof_work[1] += (double)local_count * size_before * N * sizeof(T);
+        prof_work[2] += local_count; prof_work[3] += 1;
+        prof_open[ps] = false;
     }
 
     int wave_stats(lq_wave_stats* out) override {
         LQ_CUDA(cudaSetDevice(device));
         if (q_head != q_tail) {                       // oldest committed, unread wave
-            const int slot = q_head % RING;
+            const int ps = q_head % RING;
             const int size_before = size_ub_exact;
-            LQ_CUDA(cudaEventSynchronize(ev_stats[slot]));
-            if (prof_on) {
+            if (int r = wait_stats(ps, q_seq[ps], q_stream[ps])) return r;
+            if (prof_on && prof_open[ps]) {
+                LQ_CUDA(cudaEventSynchronize(pev[ps][6]));
+                // stepwise events: 0 start | 1 sampled | 2 scanned (= 3) | 4 rolled out | 5 (= 4) | 6 committed
                 float ms = 0;
-                if (prof_wave_open[slot]) {
-                    for (int k = 0; k < 4; k++) { cudaEventElapsedTime(&ms, pev[slot][k], pev[slot][k + 1]); prof_ms[k] += ms; }
-                    prof_work[0] += (double)prof_W[slot] * size_before;
-                    prof_work[1] += (double)prof_W[slot] * size_before * N * sizeof(T);
-                    prof_work[2] += prof_W[slot]; prof_work[3] += 1;
-                    prof_wave_open[slot] = false;
-                }
-                if (prof_commit_open[slot]) {
-                    cudaEventElapsedTime(&ms, pev[slot][5], pev[slot][6]); prof_ms[4] += ms;
-                    prof_commit_open[slot] = false;
-                }
+                cudaEventElapsedTime(&ms, pev[ps][0], pev[ps][1]); prof_ms[0] += ms;
+                cudaEventElapsedTime(&ms, pev[ps][1], pev[ps][2]); prof_ms[2] += ms;
+                cudaEventElapsedTime(&ms, pev[ps][3], pev[ps][4]); prof_ms[3] += ms;
+                cudaEventElapsedTime(&ms, pev[ps][5], pev[ps][6]); prof_ms[4] += ms;
+                prof_work[0] += (double)prof_W[ps] * size_before;
+                prof_work[1] += (double)prof_W[ps] * size_before * N * sizeof(T);
+                prof_work[2] += prof_W[ps]; prof_work[3] += 1;
+                prof_open[ps] = false;
             }
-            last_stats = h_stats[slot];
+            memcpy(&last_stats, h_ring[ps].v, sizeof last_stats);
             q_head++;
             size_ub_exact = last_stats.tree_size;
             int ub = last_stats.tree_size;                // exact size + what the waves still in flight may add
@@ -1003,6 +1141,185 @@ struct EngineImpl : lq_engine {
         if (out) *out = last_stats;
         return LQ_OK;
     }
+
+    // ---- the device-scheduled driver (lq_plan_run) -------------------------------------------------------
+    // The whole expand loop of one plan (planner.py:233-311) as a pipeline the host only feeds: wave sizes, slices,
+    // the old/new node split of the scan and the stop decision live in the device control block, so waves are
+    // enqueued DEPTH ahead of the counters the host has seen.  Per wave k:
+    //   scan stream   wait commit k-2 | sampler k | [metric k] | old-tree scan k over [0, N_{k-1})
+    //   chain stream  wait scan k     | delta scan k over [N_{k-1}, N_k) | rollouts + exchange k | commit k
+    // so wave k+1's scan of the old tree runs while wave k's rollouts, exchange and commit are in flight, and the
+    // dependent chain of a wave is delta scan -> rollouts -> commit.  The tree is the one the stepwise driver grows
+    // with the same wave sizes (lexicographic merge of the partial minima, per-query check of the ignore marks).
+    int ensure_streams() {
+        if (s_chain) return LQ_OK;
+        int lo = 0, hi = 0;
+        LQ_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // lo = least priority (numerically greatest)
+        LQ_CUDA(cudaStreamCreateWithPriority(&s_chain, cudaStreamNonBlocking, hi));
+        LQ_CUDA(cudaStreamCreateWithPriority(&s_scan, cudaStreamNonBlocking, lo));
+        for (auto& e : ev_commit) LQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : ev_scan) LQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        LQ_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+        LQ_CUDA(cudaEventCreate(&ev_begin));
+        LQ_CUDA(cudaEventCreate(&ev_end));
+        return LQ_OK;
+    }
+
+    int plan_run(const lq_plan_args* a, lq_plan_summary* out, cudaStream_t st) override {
+        LQ_CUDA(cudaSetDevice(device));
+        if (!a || !out) LQ_FAIL(LQ_ERR_ARG, "null argument");
+        memset(out, 0, sizeof *out);
+        if (!have_goal) LQ_FAIL(LQ_ERR_STATE, "lq_set_goal has not been called");
+        if (!have_sampling) LQ_FAIL(LQ_ERR_STATE, "lq_set_sampling has not been called");
+        if (q_head != q_tail) LQ_FAIL(LQ_ERR_STATE, "stepwise waves are still unread");
+        const int world = std::max(1, a->world), rank = a->rank;
+        if (rank < 0 || rank >= world) LQ_FAIL(LQ_ERR_ARG, "bad world/rank");
+        if (world > 1 && (peer_world != world || peer_rank != rank)) LQ_FAIL(LQ_ERR_STATE, "lq_plan_run on several GPUs needs lq_wave_set_peers first");
+        if (world == 1 && peer_world > 1) LQ_FAIL(LQ_ERR_STATE, "peer buffers are set for %d ranks", peer_world);
+        WavePolicy pol;
+        memset(&pol, 0, sizeof pol);
+        pol.fixed = a->wave_fixed; pol.wmin = a->wave_min; pol.wmax = a->wave_max; pol.growth = a->growth;
+        pol.world = world; pol.rank = rank; pol.device_schedule = 1;
+        const int wtop = pol.fixed > 0 ? pol.fixed : pol.wmax;
+        if (wtop < 1 || (wtop + world - 1) / world > Wc) LQ_FAIL(LQ_ERR_ARG, "largest wave %d over %d ranks exceeds wave_capacity %d", wtop, world, Wc);
+        if (pol.fixed <= 0 && (pol.wmin < 1 || pol.wmax < pol.wmin || !(pol.growth > 0))) LQ_FAIL(LQ_ERR_ARG, "bad wave policy");
+        if (int r = ensure_streams()) return r;
+        const int DEPTH = std::max(1, std::min(a->depth > 0 ? a->depth : 4, RING - 2));
+        const bool spec = spec_scan != 0;
+        const int use_ignore = a->use_ignore ? 1 : 0;
+        last_my_seg = rank;
+
+        // the chain stream picks up after the caller's stream (reset / goal / sampling uploads)
+        LQ_CUDA(cudaEventRecord(ev_in, st));
+        LQ_CUDA(cudaStreamWaitEvent(s_chain, ev_in, 0));
+        *h_stop = 0;
+        ctl_start_kernel<<<1, 1, 0, s_chain>>>(w_ctl.p, tv.size, pol); launches++;
+        LQ_CUDA(cudaEventRecord(ev_begin, s_chain));
+        LQ_CUDA(cudaStreamWaitEvent(s_scan, ev_begin, 0));         // waves 0 and 1 start from the initial control block
+
+        // host mirror of the schedule as upper bounds (they only shape grids): Nub[k] >= N_k, the tree size wave k
+        // starts from, and Wub[k] >= W_k = policy(N_{k-1}) (W_0 = W_1 = policy(N_0))
+        const int n0 = size_ub_exact;
+        std::vector<int> Nub, Wub;
+        std::vector<int> n_start;                    // exact N_k once known (for the profile's pair counts)
+        int enq = 0, rd = 0;
+        bool stop_enqueue = false;
+        long long samples_total = 0;
+        int exact_upto = 0;                          // n_start[k] = N_k is known for k <= exact_upto
+        memset(&last_stats, 0, sizeof last_stats);
+        last_stats.tree_size = n0; last_stats.best_node = -1; last_stats.best_cost = -1;
+        std::vector<unsigned> seq_of_wave;
+
+        auto enqueue = [&](int k) -> int {
+            // bounds for wave k, re-derived from the newest exact size
+            if ((int)Nub.size() <= k) { Nub.resize(k + 1); Wub.resize(k + 1); }
+            for (int i = std::max(0, exact_upto - 2); i <= k; i++) {
+                Nub[i] = i <= exact_upto ? n_start[i] : std::min(tv.limit, Nub[i - 1] + Wub[i - 1]);
+                Wub[i] = policy_wave(pol, i < 2 ? n0 : Nub[i - 1]);
+            }
+            const int w = Wub[k];
+            const int cub = (w + world - 1) / world;
+            const int slot = k % CTL_RING, par = k & 1, ps = k % RING;
+            const int n_old_ub = k == 0 ? n0 : Nub[k - 1];
+            const int delta_ub = k == 0 ? 1 : std::max(1, std::min(Wub[k - 1], tv.limit));
+            const int* d_count = &w_ctl.p->ring[slot].count;
+            const int* d_nold = &w_ctl.p->ring[slot].n_old;
+            // ---- scan stream: sampler, [metric], old-tree scan
+            if (k >= 2) LQ_CUDA(cudaStreamWaitEvent(s_scan, ev_commit[(k - 2) % EVR], 0));
+            if (prof_on) cudaEventRecord(pev[ps][0], s_scan);
+            if (int r = launch_sample(a->seed, a->wave_ctr0 + (uint32_t)k, slot, par, cub, s_scan)) return r;
+            if (int r = launch_metric(samples_of(par), Wc, cub, d_count, par, s_scan)) return r;
+            if (prof_on) cudaEventRecord(pev[ps][1], s_scan);
+            int ns_old = 0, ns_new = 0;
+            if (spec) {
+                if (int r = launch_scan(samples_of(par), Wc, cub, d_count, nullptr, d_nold, n_old_ub, nullptr, use_ignore, par,
+                                        MAX_SPLIT_OLD, true, MAX_SPLIT_OLD, scan_target(), s_scan, &ns_old)) return r;
+            }
+            if (prof_on) cudaEventRecord(pev[ps][2], s_scan);
+            LQ_CUDA(cudaEventRecord(ev_scan[k % EVR], s_scan));
+            // ---- chain stream: delta scan (the whole tree when not speculating), rollouts + exchange, commit
+            LQ_CUDA(cudaStreamWaitEvent(s_chain, ev_scan[k % EVR], 0));
+            if (prof_on) cudaEventRecord(pev[ps][3], s_chain);
+            if (spec) {
+                if (int r = launch_scan(samples_of(par), Wc, cub, d_count, d_nold, tv.size, delta_ub, nullptr, use_ignore, par,
+                                        MAX_SPLIT_OLD, false, MAX_SPLIT_NEW, scan_target() / 2, s_chain, &ns_new)) return r;
+            } else {
+                if (int r = launch_scan(samples_of(par), Wc, cub, d_count, nullptr, tv.size, Nub[k], nullptr, use_ignore, par,
+                                        MAX_SPLIT_OLD, false, MAX_SPLIT_NEW, scan_target(), s_chain, &ns_new)) return r;
+            }
+            if (prof_on) cudaEventRecord(pev[ps][4], s_chain);
+            const ExDst dst = next_dst(par);
+            if (int r = launch_steer_x(cub, slot, par, MAX_SPLIT_OLD - ns_old, ns_old + ns_new, use_ignore, dst, 0, true, s_chain)) return r;
+            if (prof_on) cudaEventRecord(pev[ps][5], s_chain);
+            const char* segs = seg_of(par);
+            const unsigned* arrive = nullptr;
+            if (peer_world > 1) {
+                const int pp = peer_seq & 1;
+                segs = peer_buf[peer_rank] + (size_t)pp * peer_world * seg_sz;
+                arrive = (const unsigned*)(peer_buf[peer_rank] + peer_flags_offset()) + pp * peer_world;
+            }
+            ++stat_seq;
+            seq_of_wave.push_back(stat_seq);
+            if (int r = launch_commit(k, segs, world, rank, w, pol, arrive, peer_seq, ps, stat_seq, s_chain)) return r;
+            if (prof_on) { cudaEventRecord(pev[ps][6], s_chain); prof_open[ps] = true; }
+            LQ_CUDA(cudaEventRecord(ev_commit[k % EVR], s_chain));
+            return LQ_OK;
+        };
+
+        // Every rank enqueues wave k only after it has seen the counters of wave k - DEPTH without a stop in them, and
+        // the stop (rank 0's request, or a full tree) is published by the commits identically on every rank -- so all
+        // ranks enqueue the same number of waves and nobody waits for a peer that has left.
+        n_start.push_back(n0);
+        int rc = LQ_OK;
+        while (true) {
+            while (!stop_enqueue && enq - rd < DEPTH) {
+                if ((rc = enqueue(enq)) != LQ_OK) break;
+                enq++;
+            }
+            if (rc != LQ_OK || rd == enq) break;
+            const int ps = rd % RING;
+            if ((rc = wait_stats(ps, seq_of_wave[rd], s_chain)) != LQ_OK) break;
+            lq_wave_stats stw;
+            memcpy(&stw, h_ring[ps].v, sizeof stw);
+            if (prof_on && prof_open[ps]) {
+                cudaEventSynchronize(pev[ps][6]);
+                int first = 0, cnt = 0;
+                policy_slice(stw.n_sampled, rank, world, &first, &cnt);
+                account_profile(ps, cnt, n_start[rd]);
+            }
+            samples_total += stw.n_sampled;
+            exact_upto = rd + 1;
+            n_start.push_back(stw.tree_size);
+            last_stats = stw;
+            out->waves = rd + 1;
+            if (stw.flags) stop_enqueue = true;                 // the device has stopped: later waves are no-ops
+            if (a->on_wave) {
+                const int want = a->on_wave(a->user, &stw);     // planner.py:286-311 on the host's clock
+                if (want && !stop_enqueue) *(volatile int*)h_stop = want;   // reaches every rank through rank 0's segment header
+            }
+            rd++;
+        }
+        if (rc != LQ_OK) {                                       // leave nothing in flight behind an error
+            cudaStreamSynchronize(s_scan); cudaStreamSynchronize(s_chain);
+            return rc;
+        }
+        LQ_CUDA(cudaEventRecord(ev_end, s_chain));
+        LQ_CUDA(cudaStreamSynchronize(s_scan));
+        LQ_CUDA(cudaStreamSynchronize(s_chain));
+        LQ_CUDA(cudaStreamWaitEvent(st, ev_end, 0));            // later work on the caller's stream sees the finished tree
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_begin, ev_end);
+        out->device_ms = ms;
+        out->waves_enqueued = enq;
+        out->samples = samples_total;
+        out->last = last_stats;
+        out->stop_code = last_stats.flags;
+        size_ub = size_ub_exact = last_stats.tree_size;
+        last_stream = st;
+        return LQ_OK;
+    }
+
+    int stop_word(int** outp) override { *outp = h_stop; return LQ_OK; }
 
     // ---- close-out ------------------------------------------------------------
     int closest(const double* xg, const uint8_t* colmask, int* id, cudaStream_t st) override {
@@ -1074,7 +1391,8 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(cudaMemcpy(t_parent.p + sz, &parent, sizeof(int), cudaMemcpyHostToDevice));
         LQ_CUDA(cudaMemcpy(t_cost.p + sz, &c, sizeof(int), cudaMemcpyHostToDevice));
         LQ_CUDA(cudaMemcpy(t_elen.p + sz, &keep, sizeof(int), cudaMemcpyHostToDevice));
-        const uint8_t own = (uint8_t)last_my_seg;
+        // every rank appends this node itself (the edge arrives from the host): owner 255 = "held by all"
+        const uint8_t own = 255;
         LQ_CUDA(cudaMemcpy(t_owner.p + sz, &own, 1, cudaMemcpyHostToDevice));
         // the reference stores lqr=None for this node (planner.py:299); K = lqr(state, 0) keeps it steerable
         init_gain_kernel<T, Sys, Lqr><<<1, 32, 0, st>>>(md, t_state.p + sz, t_K.p + sz, cap, 1); launches++;
@@ -1245,6 +1563,12 @@ struct EngineImpl : lq_engine {
             near_ctas_per_sm = value; return LQ_OK;
         case LQ_OPT_SAMPLE_PREFETCH:
             prefetch_on = value != 0; return LQ_OK;
+        case LQ_OPT_SPECULATIVE_SCAN: spec_scan = value != 0; return LQ_OK;
+        case LQ_OPT_FORCE_RESCAN: force_rescan = value != 0; return LQ_OK;
+        case LQ_OPT_STAGE_TABLES: stage_tables_on = value != 0; return LQ_OK;
+        case LQ_OPT_STEER_BLOCK:
+            if (value != 0 && value != 32 && value != 128) LQ_FAIL(LQ_ERR_ARG, "rollout CTA size must be 0 (auto), 32 or 128");
+            steer_block = value; return LQ_OK;
         default: LQ_FAIL(LQ_ERR_ARG, "unknown option %d", option);
         }
     }
@@ -1253,6 +1577,10 @@ struct EngineImpl : lq_engine {
         case LQ_OPT_NEAREST_KERNEL: *value = near_kernel; return LQ_OK;
         case LQ_OPT_NEAREST_CTAS_PER_SM: *value = near_ctas_per_sm; return LQ_OK;
         case LQ_OPT_SAMPLE_PREFETCH: *value = prefetch_on ? 1 : 0; return LQ_OK;
+        case LQ_OPT_SPECULATIVE_SCAN: *value = spec_scan; return LQ_OK;
+        case LQ_OPT_FORCE_RESCAN: *value = force_rescan; return LQ_OK;
+        case LQ_OPT_STAGE_TABLES: *value = stage_tables_on; return LQ_OK;
+        case LQ_OPT_STEER_BLOCK: *value = steer_block; return LQ_OK;
         default: LQ_FAIL(LQ_ERR_ARG, "unknown option %d", option);
         }
     }
@@ -1261,7 +1589,7 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(cudaSetDevice(device));
         if (on && !pev[0][0]) for (auto& r : pev) for (auto& e : r) LQ_CUDA(cudaEventCreate(&e));
         prof_on = on != 0;
-        for (int k = 0; k < RING; k++) prof_wave_open[k] = prof_commit_open[k] = false;
+        for (int k = 0; k < RING; k++) prof_open[k] = false;
         return LQ_OK;
     }
     int profile_read(double* ms, double* work, int reset) override {

@@ -96,10 +96,22 @@ template <typename T> struct BoatSys {            // demos/demo_boat_{novice,int
         const T wx = c * vx - s * vy;               // R(h) v, world-frame velocity
         const T wy = s * vx + c * vy;
         if (use_rudder) {                           // intermediate:71-77, advanced:101-108
-            const T ang = atan2_t(wy, wx);
-            T sg, cg;
-            sincos_t(ang, &sg, &cg);
-            u[2] = u[2] + rudder * wrap_sc(s, c, sg, cg);
+            // The reference wraps (course angle - heading): ang = atan2(R(h) v), then atan2(sin(ang - h), cos(ang - h)).
+            // R(h) v is v turned by h, so that difference IS the body-frame course angle atan2(vy, vx) -- one
+            // atan2 instead of atan2 + sincos + atan2 on the rollout's dependent chain.  float32 engines take the
+            // short form (it differs from the long one by rounding only); float64 engines keep the reference's
+            // literal sequence, and so does v = 0 (seed states, the no-reverse clamp), where the reference's
+            // atan2(+-0, +-0) of the rotated zero vector makes the term -h or pi - h instead of 0.
+            T wr;
+            if (sizeof(T) == 4 && !(vx == T(0) && vy == T(0))) {
+                wr = atan2_t(vy, vx);
+            } else {
+                const T ang = atan2_t(wy, wx);
+                T sg, cg;
+                sincos_t(ang, &sg, &cg);
+                wr = wrap_sc(s, c, sg, cg);
+            }
+            u[2] = u[2] + rudder * wr;
         }
         if (thruster_clip) {                        // advanced:111  u = B clip(invB u, +-tmax)
             T th[4];
@@ -619,6 +631,7 @@ template <typename T> struct FeasPrim {
     // obstacle that can be hit from p always has p inside its zone.  cell_start == nullptr => brute force.
     const int* cell_start;
     const int* cell_items;
+    int n_cells, n_items;  // entries of cell_start (minus one) / cell_items
     T g0[3], ginv[3];
     int gn[3];
     // Product-grid hull (every demo's vertex cloud is np.mgrid, demo_car.py:77-90): verts = {hx_i} x {hy_j}.
@@ -633,11 +646,32 @@ template <typename T> struct FeasSet {
     FeasPrim<T> prims[LQ_MAX_PRIMS];
 };
 
-// Candidate obstacle range for a query position: [*b, *e) indexes p.cell_items (or the table itself
+// Where a primitive's tables are read from.  The rollout kernel copies the tables of a small obstacle field
+// (grid cell lists, obstacle rows, hull axes: 18 KB for C4's 500 circles) into shared memory once per CTA, so
+// the 3-4 dependent loads of every feasibility test cost shared-memory latency (29 cycles) instead of L2
+// latency (~250 cycles each) on the rollout's dependent chain; kernels that do not stage read global memory.
+template <typename T> struct FeasTab {
+    const T* obs;
+    const int* cell_start;
+    const int* cell_items;
+    const T* hull_axes;
+};
+
+// one obstacle row {a, b, c, d} with vector loads (rows are 16-byte aligned: cudaMalloc / 16-byte staged)
+__device__ __forceinline__ void load_row4(const float* p, float& a, float& b, float& c, float& d) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    a = v.x; b = v.y; c = v.z; d = v.w;
+}
+__device__ __forceinline__ void load_row4(const double* p, double& a, double& b, double& c, double& d) {
+    const double2 v = *reinterpret_cast<const double2*>(p), w = *reinterpret_cast<const double2*>(p + 2);
+    a = v.x; b = v.y; c = w.x; d = w.y;
+}
+
+// Candidate obstacle range for a query position: [*b, *e) indexes cell_items (or the table itself
 // when there is no grid).  Returns false if the position lies outside every zone of influence.
 template <typename T>
-__device__ __forceinline__ bool feas_candidates(const FeasPrim<T>& p, T px, T py, T pz, int nd, int* b, int* e) {
-    if (!p.cell_start) { *b = 0; *e = p.n_obs; return true; }
+__device__ __forceinline__ bool feas_candidates(const FeasPrim<T>& p, const int* cell_start, T px, T py, T pz, int nd, int* b, int* e) {
+    if (!cell_start) { *b = 0; *e = p.n_obs; return true; }
     const T fx = (px - p.g0[0]) * p.ginv[0], fy = (py - p.g0[1]) * p.ginv[1];
     if (!(fx >= T(0) && fy >= T(0) && fx < (T)p.gn[0] && fy < (T)p.gn[1])) return false;
     int cell = (int)fy * p.gn[0] + (int)fx;
@@ -646,7 +680,7 @@ __device__ __forceinline__ bool feas_candidates(const FeasPrim<T>& p, T px, T py
         if (!(fz >= T(0) && fz < (T)p.gn[2])) return false;
         cell += (int)fz * p.gn[0] * p.gn[1];
     }
-    *b = p.cell_start[cell]; *e = p.cell_start[cell + 1];
+    *b = cell_start[cell]; *e = cell_start[cell + 1];
     return true;
 }
 
@@ -654,9 +688,10 @@ __device__ __forceinline__ bool feas_candidates(const FeasPrim<T>& p, T px, T py
 // same (x,u); obstacle loops are strided by lane.  Returns this lane's verdict;
 // the caller combines lanes (AND).  lanes == 1 is the scalar case.
 // hdim >= 0: (hs, hc) = sincos(x[hdim]) is supplied and reused by the hull rotations on that dim.
+// tabs: per-primitive table pointers (shared-memory copies in the rollout kernel); nullptr = the global tables.
 template <typename T, int N, int M>
 __device__ __forceinline__ bool feasible_eval(const FeasSet<T>& fs, const T* x, const T* u, int lane = 0, int lanes = 1,
-                                              int hdim = -1, T hs = T(0), T hc = T(1)) {
+                                              int hdim = -1, T hs = T(0), T hc = T(1), const FeasTab<T>* tabs = nullptr) {
     for (int pi = 0; pi < fs.n_prims; pi++) {
         const FeasPrim<T>& p = fs.prims[pi];
         switch (p.kind) {
@@ -680,6 +715,9 @@ __device__ __forceinline__ bool feasible_eval(const FeasSet<T>& fs, const T* x, 
         }
         case LQ_FEAS_CIRCLES_POINT:                 // demo_boat_novice.py:160-164
         case LQ_FEAS_SPHERES_POINT: {
+            const T* obs = tabs ? tabs[pi].obs : p.obs;
+            const int* cs = tabs ? tabs[pi].cell_start : p.cell_start;
+            const int* ci = tabs ? tabs[pi].cell_items : p.cell_items;
             const bool sph = p.kind == LQ_FEAS_SPHERES_POINT;
             T px = T(0), py = T(0), pz = T(0);
 #pragma unroll
@@ -689,18 +727,24 @@ __device__ __forceinline__ bool feasible_eval(const FeasSet<T>& fs, const T* x, 
                 if (sph && i == p.dims[2]) pz = x[i];
             }
             int b, e;
-            if (!feas_candidates(p, px, py, pz, sph ? 3 : 2, &b, &e)) break;
+            if (!feas_candidates(p, cs, px, py, pz, sph ? 3 : 2, &b, &e)) break;
             for (int k = b + lane; k < e; k += lanes) {
-                const int o = p.cell_start ? p.cell_items[k] : k;
-                const T dx = px - p.obs[o * 4 + 0], dy = py - p.obs[o * 4 + 1];
-                const T dz = sph ? pz - p.obs[o * 4 + 2] : T(0);
-                const T rr = sph ? p.obs[o * 4 + 3] : p.obs[o * 4 + 2];      // inflate + r, host-added in float64
+                const int o = cs ? ci[k] : k;
+                T ox, oy, oc, od;
+                load_row4(obs + o * 4, ox, oy, oc, od);
+                const T dx = px - ox, dy = py - oy;
+                const T dz = sph ? pz - oc : T(0);
+                const T rr = sph ? od : oc;                                   // inflate + r, host-added in float64
                 if (dx * dx + dy * dy + dz * dz <= rr * rr) return false;
             }
             break;
         }
         case LQ_FEAS_CIRCLES_CLOUD:                 // demo_boat_intermediate.py:198-210, demo_car.py:168-180
         case LQ_FEAS_BOXES_CLOUD: {
+            const T* obs = tabs ? tabs[pi].obs : p.obs;
+            const int* cs = tabs ? tabs[pi].cell_start : p.cell_start;
+            const int* ci = tabs ? tabs[pi].cell_items : p.cell_items;
+            const T* hull = tabs ? tabs[pi].hull_axes : p.hull_axes;
             T px = T(0), py = T(0), ph = T(0);
 #pragma unroll
             for (int i = 0; i < N; i++) {
@@ -712,39 +756,41 @@ __device__ __forceinline__ bool feasible_eval(const FeasSet<T>& fs, const T* x, 
             int b, e;
             if (p.flags & 1) {                      // demo_car.py:175: an extra vertex at 2 * position
                 const T qx = px + px, qy = py + py;
-                if (feas_candidates(p, qx, qy, T(0), 2, &b, &e)) {
+                if (feas_candidates(p, cs, qx, qy, T(0), 2, &b, &e)) {
                     for (int k = b + lane; k < e; k += lanes) {
-                        const int o = p.cell_start ? p.cell_items[k] : k;
-                        const T ex = qx - p.obs[o * 4 + 0], ey = qy - p.obs[o * 4 + 1];
-                        const T a = p.obs[o * 4 + 2], bb = p.obs[o * 4 + 3];
+                        const int o = cs ? ci[k] : k;
+                        T ox, oy, a, bb;
+                        load_row4(obs + o * 4, ox, oy, a, bb);
+                        const T ex = qx - ox, ey = qy - oy;
                         if (circ ? (ex * ex + ey * ey <= a * a) : (abs_t(ex) <= a && abs_t(ey) <= bb)) return false;
                     }
                 }
             }
-            if (!feas_candidates(p, px, py, T(0), 2, &b, &e)) break;
+            if (!feas_candidates(p, cs, px, py, T(0), 2, &b, &e)) break;
             T s = hs, c = hc;
             if (p.dims[2] != hdim) sincos_t(ph, &s, &c);
-            if (circ && p.hull_axes) {
+            if (circ && hull) {
                 // lanes split the candidate list; each candidate is O(nx + ny)
                 for (int k = b + lane; k < e; k += lanes) {
-                    const int o = p.cell_start ? p.cell_items[k] : k;
-                    const T rx = p.obs[o * 4 + 0] - px, ry = p.obs[o * 4 + 1] - py;   // centre relative to the hull origin
-                    const T a = p.obs[o * 4 + 2];
+                    const int o = cs ? ci[k] : k;
+                    T ox, oy, a, unused;
+                    load_row4(obs + o * 4, ox, oy, a, unused);
+                    const T rx = ox - px, ry = oy - py;                               // centre relative to the hull origin
                     const T reach = a + p.bound_r;
                     if (rx * rx + ry * ry > reach * reach * T(1.0001)) continue;
                     const T bx = c * rx + s * ry, by = c * ry - s * rx;                // ... in the body frame
                     T mx = Num<T>::inf(), my = Num<T>::inf();
-                    for (int i = 0; i < p.hull_nx; i++) { const T d = bx - p.hull_axes[i]; mx = min_t(mx, d * d); }
-                    for (int j = 0; j < p.hull_ny; j++) { const T d = by - p.hull_axes[p.hull_nx + j]; my = min_t(my, d * d); }
+                    for (int i = 0; i < p.hull_nx; i++) { const T d = bx - hull[i]; mx = min_t(mx, d * d); }
+                    for (int j = 0; j < p.hull_ny; j++) { const T d = by - hull[p.hull_nx + j]; my = min_t(my, d * d); }
                     if (mx + my <= a * a) return false;
                 }
                 break;
             }
             // general cloud: every lane walks the (short) candidate list, the vertices are what the lanes split
             for (int k = b; k < e; k++) {
-                const int o = p.cell_start ? p.cell_items[k] : k;
-                const T ox = p.obs[o * 4 + 0], oy = p.obs[o * 4 + 1];
-                const T a = p.obs[o * 4 + 2], bb = p.obs[o * 4 + 3];
+                const int o = cs ? ci[k] : k;
+                T ox, oy, a, bb;
+                load_row4(obs + o * 4, ox, oy, a, bb);
                 // hull bounding circle vs obstacle bounding circle (conservative)
                 const T dx = px - ox, dy = py - oy;
                 const T reach = (circ ? a : sqrt_t(a * a + bb * bb)) + p.bound_r;
@@ -784,6 +830,65 @@ __device__ __forceinline__ bool feasible_eval(const FeasSet<T>& fs, const T* x, 
         }
     }
     return true;
+}
+
+// ---- shared-memory staging of the obstacle tables (rollout kernels) --------------------------------------
+// Host-side plan: which primitives are staged and how many bytes that takes; the kernel lays the tables out
+// in this order in dynamic shared memory, each 16-byte aligned.
+struct StagePlan {
+    int on[LQ_MAX_PRIMS];
+    int bytes;                 // total dynamic shared memory the staged tables need
+};
+
+__host__ __device__ inline int stage_align(int b) { return (b + 15) & ~15; }
+
+template <typename T>
+__host__ __device__ inline int stage_bytes(const FeasPrim<T>& p) {
+    int b = stage_align(p.n_obs * 4 * (int)sizeof(T));
+    if (p.cell_start) b += stage_align((p.n_cells + 1) * (int)sizeof(int)) + stage_align(p.n_items * (int)sizeof(int));
+    if (p.hull_axes) b += stage_align((p.hull_nx + p.hull_ny) * (int)sizeof(T));
+    return b;
+}
+
+// Called by every thread of the CTA; `tabs` (LQ_MAX_PRIMS entries) and `raw` live in shared memory.  Ends
+// with a __syncthreads().
+template <typename T>
+__device__ __forceinline__ void stage_tables(const FeasSet<T>& fs, const StagePlan& sp, FeasTab<T>* tabs, unsigned char* raw) {
+    int off = 0;
+    for (int pi = 0; pi < fs.n_prims; pi++) {
+        const FeasPrim<T>& p = fs.prims[pi];
+        FeasTab<T> t{p.obs, p.cell_start, p.cell_items, p.hull_axes};
+        const bool tabular = p.kind == LQ_FEAS_CIRCLES_POINT || p.kind == LQ_FEAS_SPHERES_POINT ||
+                             p.kind == LQ_FEAS_CIRCLES_CLOUD || p.kind == LQ_FEAS_BOXES_CLOUD;
+        if (tabular && sp.on[pi]) {
+            {
+                const int4* src = reinterpret_cast<const int4*>(p.obs);
+                int4* dst = reinterpret_cast<int4*>(raw + off);
+                const int n16 = p.n_obs * 4 * (int)sizeof(T) / 16;
+                for (int k = threadIdx.x; k < n16; k += blockDim.x) dst[k] = src[k];
+                t.obs = reinterpret_cast<const T*>(raw + off);
+                off += stage_align(p.n_obs * 4 * (int)sizeof(T));
+            }
+            if (p.cell_start) {
+                int* d1 = reinterpret_cast<int*>(raw + off);
+                for (int k = threadIdx.x; k < p.n_cells + 1; k += blockDim.x) d1[k] = p.cell_start[k];
+                t.cell_start = d1;
+                off += stage_align((p.n_cells + 1) * (int)sizeof(int));
+                int* d2 = reinterpret_cast<int*>(raw + off);
+                for (int k = threadIdx.x; k < p.n_items; k += blockDim.x) d2[k] = p.cell_items[k];
+                t.cell_items = d2;
+                off += stage_align(p.n_items * (int)sizeof(int));
+            }
+            if (p.hull_axes) {
+                T* d3 = reinterpret_cast<T*>(raw + off);
+                for (int k = threadIdx.x; k < p.hull_nx + p.hull_ny; k += blockDim.x) d3[k] = p.hull_axes[k];
+                t.hull_axes = d3;
+                off += stage_align((p.hull_nx + p.hull_ny) * (int)sizeof(T));
+            }
+        }
+        if (threadIdx.x == 0) tabs[pi] = t;
+    }
+    __syncthreads();
 }
 
 }  // namespace lq

@@ -32,6 +32,43 @@ template <typename T, int N> struct DiagMetric {
 
 template <int N> struct PadDim { static constexpr int V = (N + 3) / 4 * 4; };
 
+// What one scan launch covers.  Node range and query count are DEVICE scalars, so a launch can be enqueued
+// before the wave that determines them has committed (the host only supplies upper bounds for the grid):
+//   * old-tree scan of wave k+1: nodes [0, n_old) -- the tree as of the start of wave k, immutable -- on a
+//     side stream while wave k's rollouts and commit run;
+//   * delta scan: nodes [n_old, size) after commit k, on the wave's own stream;
+//   * stepwise / stand-alone calls: d_lo = nullptr, the whole tree.
+// Every CTA derives its node chunk from the actual range, so the work is balanced whatever the host's bound
+// was.  Partial minima go to slots [slot0, slot0 + nsplit) of the partials arrays; consumers reduce them with
+// a lexicographic (cost, index) minimum, so the lowest node index wins exact ties (np.argmin) in any order.
+struct ScanArgs {
+    const int* d_lo;         // first node (nullptr = 0)
+    const int* d_hi;         // one past the last node
+    const int* d_count;      // number of queries (nullptr = W)
+    const int* d_nignored;   // non-null: plain argmin when every node is ignored (planner.py:244-245) is decided
+                             // here; null: ignored nodes never win and the consumer handles "none left"
+    int W;                   // host-side query count (bound): the grid was planned for it
+    int nqb, nsplit, slot0;
+    int use_ignore;
+};
+
+struct ScanRange { int qb, split, W, n0, n1; bool mask_on; };
+
+__device__ __forceinline__ bool scan_setup(const ScanArgs& a, int tile, int queries_per_cta, ScanRange& r) {
+    r.qb = blockIdx.x % a.nqb;
+    r.split = blockIdx.x / a.nqb;
+    r.W = a.d_count ? min(*a.d_count, a.W) : a.W;
+    if (r.qb * queries_per_cta >= r.W) return false;             // no query in this block: nothing to write
+    const int hi = *a.d_hi;
+    const int lo = a.d_lo ? min(*a.d_lo, hi) : 0;
+    int chunk = (hi - lo + a.nsplit - 1) / a.nsplit;
+    chunk = (chunk + tile - 1) / tile * tile;
+    r.n0 = min(lo + r.split * chunk, hi);
+    r.n1 = min(r.n0 + chunk, hi);
+    r.mask_on = a.use_ignore && (!a.d_nignored || *a.d_nignored < hi);
+    return true;
+}
+
 template <typename T>
 __device__ __forceinline__ T reduce_period(T a) {   // a -> a - 2 pi rint(a / 2 pi)
     return a - Num<T>::two_pi() * rint_t(a * Num<T>::inv_two_pi());
@@ -43,28 +80,31 @@ __device__ __forceinline__ T reduce_period(T a) {   // a -> a - 2 pi rint(a / 2 
 __device__ __forceinline__ float prescale(float a, float w) { return __fmul_rn(a, w); }
 __device__ __forceinline__ double prescale(double a, double w) { return __dmul_rn(a, w); }
 
+// The per-dim arithmetic of the diagonal scans, shared with the per-query rescan of the rollout kernel
+// (steer.cuh rescan_nearest) so both produce the same bits.
+template <typename T>
+__device__ __forceinline__ T diag_term_exact(T c, T e, T sd) { return c + e * sd * e; }     // float64 parity form: d S d
+template <typename T>
+__device__ __forceinline__ T diag_wrap_scaled(T e, T period) { const T a = abs_t(e); return min_t(a, period - a); }
+
 // MASK >= 0: the erf angle mask is a compile-time constant (the common masks are instantiated, see
 // engine.cuh), so only the wrapped dims pay for the wrap and the others are one FADD + one FFMA.
 // MASK < 0: generic fallback reading met.angle_mask at run time.  EXACT selects the float64 parity
 // formula d*S*d with an rint wrap; otherwise operands are pre-scaled by sqrt(S_ii) while staging.
 template <typename T, int N, int Q, int BLOCK, int MASK, bool EXACT>
 __global__ void __launch_bounds__(BLOCK)
-nearest_diag_kernel(const T* __restrict__ state, int cap, const uint8_t* __restrict__ ignore,
-                    const int* __restrict__ d_size, const int* __restrict__ d_nignored, int use_ignore,
-                    const T* __restrict__ queries, int qstride, int W,
-                    DiagMetric<T, N> met, int nqb, int chunk,
+nearest_diag_kernel(const T* __restrict__ state, int cap, const uint8_t* __restrict__ ignore, ScanArgs sa,
+                    const T* __restrict__ queries, int qstride, DiagMetric<T, N> met,
                     T* __restrict__ pcost, int* __restrict__ pidx, int pstride) {
     constexpr int NP = PadDim<N>::V;
     constexpr int TILE = BLOCK;
     __shared__ __align__(16) T tile[TILE * NP];
     const uint32_t mask = MASK >= 0 ? (uint32_t)MASK : met.angle_mask;
 
-    const int qb = blockIdx.x % nqb;
-    const int split = blockIdx.x / nqb;
-    const int size = *d_size;
-    const bool mask_on = use_ignore && (*d_nignored < size);
-    const int n0 = split * chunk;
-    const int n1 = min(n0 + chunk, size);
+    ScanRange sr;
+    if (!scan_setup(sa, TILE, BLOCK * Q, sr)) return;
+    const int qb = sr.qb, split = sa.slot0 + sr.split, W = sr.W, n0 = sr.n0, n1 = sr.n1;
+    const bool mask_on = sr.mask_on;
 
     T q[Q][N];
     T best[Q];
@@ -122,12 +162,9 @@ nearest_diag_kernel(const T* __restrict__ state, int cap, const uint8_t* __restr
                     T e = q[k][d] - v[d];
                     if (EXACT) {
                         if (mask & (1u << d)) e = reduce_period(e);
-                        c += e * met.sdiag[d] * e;
+                        c = diag_term_exact(c, e, met.sdiag[d]);
                     } else {
-                        if (mask & (1u << d)) {
-                            const T a = abs_t(e);
-                            e = min_t(a, met.period[d] - a);
-                        }
+                        if (mask & (1u << d)) e = diag_wrap_scaled(e, met.period[d]);
                         c = fma(e, e, c);
                     }
                 }
@@ -187,10 +224,8 @@ __device__ __forceinline__ float2 pair_cost(const float2 (&q)[N], const float2* 
 
 template <int N, int Q, int BLOCK, int MASK, int SB, int MINB, bool PACKED>
 __global__ void __launch_bounds__(BLOCK, MINB)
-nearest_diag_pk_kernel(const float* __restrict__ state, int cap, const uint8_t* __restrict__ ignore,
-                       const int* __restrict__ d_size, const int* __restrict__ d_nignored, int use_ignore,
-                       const float* __restrict__ queries, int qstride, int W,
-                       DiagMetric<float, N> met, int nqb, int chunk,
+nearest_diag_pk_kernel(const float* __restrict__ state, int cap, const uint8_t* __restrict__ ignore, ScanArgs sa,
+                       const float* __restrict__ queries, int qstride, DiagMetric<float, N> met,
                        float* __restrict__ pcost, int* __restrict__ pidx, int pstride) {
     static_assert(Q % 2 == 0 && BLOCK % SB == 0, "queries are processed in pairs, tiles in whole sub-blocks");
     constexpr int NE = (N + 1) / 2 * 2;      // dims per node row, even: one LDS.128 = two (v, v) pairs
@@ -199,12 +234,10 @@ nearest_diag_pk_kernel(const float* __restrict__ state, int cap, const uint8_t* 
     __shared__ __align__(16) float2 tile[TILE * NE];
     const uint32_t mask = MASK >= 0 ? (uint32_t)MASK : met.angle_mask;
 
-    const int qb = blockIdx.x % nqb;
-    const int split = blockIdx.x / nqb;
-    const int size = *d_size;
-    const bool mask_on = use_ignore && (*d_nignored < size);
-    const int n0 = split * chunk;
-    const int n1 = min(n0 + chunk, size);
+    ScanRange sr;
+    if (!scan_setup(sa, TILE, BLOCK * Q, sr)) return;
+    const int qb = sr.qb, split = sa.slot0 + sr.split, W = sr.W, n0 = sr.n0, n1 = sr.n1;
+    const bool mask_on = sr.mask_on;
 
     float2 q[QP][N];
     float best[Q];
@@ -302,10 +335,8 @@ nearest_diag_pk_kernel(const float* __restrict__ state, int cap, const uint8_t* 
 // for round 2.  Leading dims must not be wrapped (the engine checks the mask).
 template <int N, int Q, int BLOCK, int MASK, int PREFIX>
 __global__ void __launch_bounds__(BLOCK)
-nearest_diag_prefix_kernel(const float* __restrict__ state, int cap, const uint8_t* __restrict__ ignore,
-                           const int* __restrict__ d_size, const int* __restrict__ d_nignored, int use_ignore,
-                           const float* __restrict__ queries, int qstride, int W,
-                           DiagMetric<float, N> met, int nqb, int chunk,
+nearest_diag_prefix_kernel(const float* __restrict__ state, int cap, const uint8_t* __restrict__ ignore, ScanArgs sa,
+                           const float* __restrict__ queries, int qstride, DiagMetric<float, N> met,
                            float* __restrict__ pcost, int* __restrict__ pidx, int pstride) {
     static_assert(PREFIX >= 1 && PREFIX < N, "the prefix is a proper, non-empty part of the state");
     constexpr int NP = PadDim<N>::V;
@@ -313,12 +344,10 @@ nearest_diag_prefix_kernel(const float* __restrict__ state, int cap, const uint8
     __shared__ __align__(16) float tile[TILE * NP];
     const uint32_t mask = MASK >= 0 ? (uint32_t)MASK : met.angle_mask;
 
-    const int qb = blockIdx.x % nqb;
-    const int split = blockIdx.x / nqb;
-    const int size = *d_size;
-    const bool mask_on = use_ignore && (*d_nignored < size);
-    const int n0 = split * chunk;
-    const int n1 = min(n0 + chunk, size);
+    ScanRange sr;
+    if (!scan_setup(sa, TILE, BLOCK * Q, sr)) return;
+    const int qb = sr.qb, split = sa.slot0 + sr.split, W = sr.W, n0 = sr.n0, n1 = sr.n1;
+    const bool mask_on = sr.mask_on;
 
     float q[Q][N];
     float best[Q];
@@ -390,15 +419,29 @@ nearest_diag_prefix_kernel(const float* __restrict__ state, int cap, const uint8
     }
 }
 
+// d' S d with S symmetrised and packed (diagonal, then doubled upper triangle); shared with steer.cuh rescan_nearest
+template <typename T, int N>
+__device__ __forceinline__ T dense_cost(const T (&e)[N], const T* S) {
+    T c = T(0);
+    int s = N;
+#pragma unroll
+    for (int a = 0; a < N; a++) {
+        T r = S[a] * e[a];
+#pragma unroll
+        for (int b = a + 1; b < N; b++) r = fma(S[s++], e[b], r);
+        c = fma(e[a], r, c);
+    }
+    return c;
+}
+
 // Dense per-query metric: cost = d' S d with S symmetrised and packed
 // (diagonal, then doubled upper triangle), NS = N (N + 1) / 2 coefficients per
 // query held in registers.
 template <typename T, int N, int BLOCK, int MASK>
 __global__ void __launch_bounds__(BLOCK)
-nearest_dense_kernel(const T* __restrict__ state, int cap, const uint8_t* __restrict__ ignore,
-                     const int* __restrict__ d_size, const int* __restrict__ d_nignored, int use_ignore,
-                     const T* __restrict__ queries, int qstride, int W,
-                     const T* __restrict__ Spacked, uint32_t angle_mask_rt, int nqb, int chunk,
+nearest_dense_kernel(const T* __restrict__ state, int cap, const uint8_t* __restrict__ ignore, ScanArgs sa,
+                     const T* __restrict__ queries, int qstride,
+                     const T* __restrict__ Spacked, uint32_t angle_mask_rt,
                      T* __restrict__ pcost, int* __restrict__ pidx, int pstride) {
     constexpr int NP = PadDim<N>::V;
     constexpr int NS = N * (N + 1) / 2;
@@ -406,12 +449,10 @@ nearest_dense_kernel(const T* __restrict__ state, int cap, const uint8_t* __rest
     __shared__ __align__(16) T tile[TILE * NP];
     const uint32_t angle_mask = MASK >= 0 ? (uint32_t)MASK : angle_mask_rt;
 
-    const int qb = blockIdx.x % nqb;
-    const int split = blockIdx.x / nqb;
-    const int size = *d_size;
-    const bool mask_on = use_ignore && (*d_nignored < size);
-    const int n0 = split * chunk;
-    const int n1 = min(n0 + chunk, size);
+    ScanRange sr;
+    if (!scan_setup(sa, TILE, BLOCK, sr)) return;
+    const int qb = sr.qb, split = sa.slot0 + sr.split, W = sr.W, n0 = sr.n0, n1 = sr.n1;
+    const bool mask_on = sr.mask_on;
     const int j = qb * BLOCK + threadIdx.x;
 
     T q[N], S[NS];
@@ -440,15 +481,7 @@ nearest_dense_kernel(const T* __restrict__ state, int cap, const uint8_t* __rest
                 e[d] = q[d] - tile[i * NP + d];
                 if (angle_mask & (1u << d)) e[d] = reduce_period(e[d]);
             }
-            T c = T(0);
-            int s = N;
-#pragma unroll
-            for (int a = 0; a < N; a++) {
-                T r = S[a] * e[a];
-#pragma unroll
-                for (int b = a + 1; b < N; b++) r = fma(S[s++], e[b], r);
-                c = fma(e[a], r, c);
-            }
+            const T c = dense_cost<T, N>(e, S);
             // a dead (inf) node yields inf or NaN; neither compares below best
             if (c < best) { best = c; bidx = base + i; }
         }
@@ -461,6 +494,13 @@ nearest_dense_kernel(const T* __restrict__ state, int cap, const uint8_t* __rest
 
 // Reduce the per-split partials in ascending split order with a strict '<':
 // lowest node index wins ties, as NumPy's argmin / first-in-argsort does.
+// (cost, index) candidates merge by the lexicographic minimum: associative and commutative, so partials can be
+// combined in any order and the lowest node index still wins exact cost ties.
+template <typename T>
+__device__ __forceinline__ void merge_candidate(T& best, int& b, T c, int i) {
+    if (i >= 0 && (b < 0 || c < best || (c == best && i < b))) { best = c; b = i; }
+}
+
 template <typename T>
 __global__ void nearest_finalize_kernel(const T* __restrict__ pcost, const int* __restrict__ pidx, int pstride,
                                         int nsplit, int W, int* __restrict__ idx, T* __restrict__ cost) {
@@ -468,11 +508,7 @@ __global__ void nearest_finalize_kernel(const T* __restrict__ pcost, const int* 
     if (j >= W) return;
     T best = Num<T>::inf();
     int b = -1;
-    for (int s = 0; s < nsplit; s++) {
-        const T c = pcost[(size_t)s * pstride + j];
-        const int i = pidx[(size_t)s * pstride + j];
-        if (i >= 0 && (b < 0 || c < best)) { best = c; b = i; }
-    }
+    for (int s = 0; s < nsplit; s++) merge_candidate(best, b, pcost[(size_t)s * pstride + j], pidx[(size_t)s * pstride + j]);
     idx[j] = b < 0 ? 0 : b;
     if (cost) cost[j] = best;
 }
@@ -481,10 +517,10 @@ __global__ void nearest_finalize_kernel(const T* __restrict__ pcost, const int* 
 // at the sample), packed for nearest_dense_kernel.
 template <typename T, class Sys, class Lqr>
 __global__ void metric_kernel(Sys sys, Lqr lqr, T dt, const T* __restrict__ queries, int qstride, int W,
-                              T* __restrict__ Spacked) {
+                              const int* __restrict__ d_count, T* __restrict__ Spacked) {
     constexpr int N = Sys::N;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= W) return;
+    if (j >= (d_count ? min(*d_count, W) : W)) return;
     T x[N], S[N * N], u0[Sys::M];
 #pragma unroll
     for (int d = 0; d < N; d++) x[d] = queries[(size_t)d * qstride + j];

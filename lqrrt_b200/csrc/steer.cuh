@@ -1,6 +1,8 @@
 // K2: Planner._steer(ID, xtar, force_arrive=False) for a whole wave
 // (reference lqrrt/planner.py:354-438; exact control flow SURVEY.md section 3.2),
-// fused with the lqr provider, the dynamics step and is_feasible.
+// fused with the lqr provider, the dynamics step and is_feasible -- and, inside a wave, with the
+// selection of the nearest node from K1's partial minima (planner.py:239-247) in its prologue and the
+// exchange of the result with every replica of the tree in its epilogue.
 //
 // One sample per group of LANES threads.  All lanes of a group carry the same
 // state/gain in registers and execute the same instruction stream (results are
@@ -8,10 +10,12 @@
 // split across the lanes, and the verdict is combined with a group ballot.
 // LANES = 1 is thread-per-sample; LANES = 32 is warp-per-sample for heavy
 // collision fields.  Rollout is latency/issue bound: tiny matrices, no tensor
-// cores.
+// cores; small obstacle tables are staged in shared memory once per CTA (models.cuh stage_tables).
 #pragma once
 #include <cooperative_groups.h>
 #include "models.cuh"
+#include "nearest.cuh"
+#include "wave.cuh"
 
 namespace lq {
 namespace cg = cooperative_groups;
@@ -78,51 +82,17 @@ __device__ __forceinline__ bool group_all(bool ok) {
     return cg::tiled_partition<LANES>(cg::this_thread_block()).all(ok);
 }
 
-// Outputs per sample j (all optional except len):
-//   xseq [j][H][N], useq [j][H][M]   recorded edge (sample-major)
-//   len  [j]                          kept length after the FPR cut
-//   xnew [N][ostride], Knew [M*N][ostride]   final state and K = lqr(xnew, u_last).K (planner.py:256-257)
-// The node to steer from is either given (ids) or, inside a wave, reduced here from K1's per-split partial
-// minima (pcost/pidx, ascending split order with a strict '<' so the lowest index wins ties, as
-// nearest_finalize_kernel does) and published in ids_out for the pack stage.
-template <typename T>
-struct NearPartials { const T* pcost; const int* pidx; int pstride; int nsplit; int* ids_out; };
-
-template <typename T, class Sys, class Lqr, int LANES, int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
-steer_kernel(Model<T, Sys, Lqr> md,
-             const T* __restrict__ tstate, const T* __restrict__ tK, int cap,
-             const int* __restrict__ ids, NearPartials<T> np, const T* __restrict__ targets, int tstride, int W,
-             T* __restrict__ xseq, T* __restrict__ useq, int* __restrict__ len_out,
-             T* __restrict__ xnew_out, T* __restrict__ Knew_out, int ostride, uint8_t* __restrict__ votes) {
+// ---- the rollout itself (planner.py:373-438) --------------------------------------------------------------
+// In: x = the node's state, xt = the target, K = the node's stored gain.  The recorded edge goes to
+// xrow [H][N] / urow [H][M] (lane 0 writes).  Out: len = kept length after the FPR cut, vote = the
+// adaptive-horizon vote, and -- when len > 0 -- x / K hold the new node: the last KEPT state and
+// lqr(xnew, u_seq[-1]).K (planner.py:256-257).
+template <typename T, class Sys, class Lqr, int LANES>
+__device__ __forceinline__ void rollout(const Model<T, Sys, Lqr>& md, const FeasTab<T>* tabs,
+                                        T (&x)[Sys::N], const T (&xt)[Sys::N], T (&K)[Sys::M * Sys::N],
+                                        T* __restrict__ xrow, T* __restrict__ urow, int lane, T* coop,
+                                        int& len_out, unsigned& vote_out) {
     constexpr int N = Sys::N, M = Sys::M;
-    extern __shared__ __align__(16) unsigned char coop_raw[];
-    T* coop = reinterpret_cast<T*>(coop_raw) + (size_t)(threadIdx.x / LANES) * Lqr::COOP_SCALARS;
-    const int gid = (blockIdx.x * BLOCK + threadIdx.x) / LANES;
-    const int lane = threadIdx.x % LANES;
-    if (gid >= W) return;                  // whole groups leave together (BLOCK % LANES == 0)
-    const int j = gid;
-    int id;
-    if (np.pidx) {
-        T best = Num<T>::inf();
-        int b = -1;
-        for (int sp = 0; sp < np.nsplit; sp++) {
-            const T c = np.pcost[(size_t)sp * np.pstride + j];
-            const int i2 = np.pidx[(size_t)sp * np.pstride + j];
-            if (i2 >= 0 && (b < 0 || c < best)) { best = c; b = i2; }
-        }
-        id = b < 0 ? 0 : b;
-        if (lane == 0) np.ids_out[j] = id;
-    } else {
-        id = ids[j];
-    }
-
-    T x[N], xt[N], K[M * N];
-#pragma unroll
-    for (int d = 0; d < N; d++) { x[d] = tstate[(size_t)d * cap + id]; xt[d] = targets[(size_t)d * tstride + j]; }
-#pragma unroll
-    for (int k = 0; k < M * N; k++) K[k] = tK[(size_t)k * cap + id];
-
     // sin/cos of the heading-like dim are evaluated once per state and shared by erf, dynamics,
     // the hull rotation in is_feasible and the gain (they were ~half of a step's instructions)
     constexpr int HD = Sys::HEADING;
@@ -137,8 +107,6 @@ steer_kernel(Model<T, Sys, Lqr> md,
     T last_emag[N];
 #pragma unroll
     for (int d = 0; d < N; d++) last_emag[d] = Num<T>::inf();
-    T* xrow = xseq + (size_t)j * md.H * N;      // never NULL: the engine supplies scratch
-    T* urow = useq + (size_t)j * md.H * M;
 
     while (true) {
         T e[N], u[M], uw[M], xn[N];
@@ -153,7 +121,7 @@ steer_kernel(Model<T, Sys, Lqr> md,
         md.sys.step_sc(x, uw, md.dt, xn, sh, ch);                // planner.py:390 (uw = the copy dynamics may clip)
         T sn = T(0), cn = T(1);
         if (HD >= 0) sincos_t(xn[HD < 0 ? 0 : HD], &sn, &cn);
-        const bool ok = group_all<LANES>(feasible_eval<T, N, M>(md.feas, xn, u, lane, LANES, HD, sn, cn));   // planner.py:393
+        const bool ok = group_all<LANES>(feasible_eval<T, N, M>(md.feas, xn, u, lane, LANES, HD, sn, cn, tabs));   // planner.py:393
         if (!ok) { len = fpr_keep(md, nrec); break; }            // planner.py:394-396
         i += 1;                                                  // planner.py:414
         bool conv = true;
@@ -185,7 +153,7 @@ steer_kernel(Model<T, Sys, Lqr> md,
     // The node is the last KEPT state and its gain is lqr(xnew, u_seq[-1]).K (planner.py:256-257).  Without an
     // FPR cut, x / K already hold exactly that; after a cut (0 < len < nrec) the kept tail is re-read from
     // the group's own edge rows (written by lane 0) and the gain recomputed by the whole group.
-    if (xnew_out && len > 0 && len < nrec) {
+    if (len > 0 && len < nrec) {
         GroupSync<LANES>()();
         T uk[M];
 #pragma unroll
@@ -196,14 +164,242 @@ steer_kernel(Model<T, Sys, Lqr> md,
         if (HD >= 0) sincos_t(x[HD < 0 ? 0 : HD], &s2, &c2);
         group_gain<T, Sys, Lqr, LANES>(md, x, uk, K, s2, c2, coop, lane);
     }
-    if (lane == 0) {
-        len_out[j] = len;
-        if (votes) votes[j] = (uint8_t)vote;
-        if (xnew_out && len > 0) {
+    len_out = len;
+    vote_out = vote;
+}
+
+// dynamic shared memory of the rollout kernels: [cooperative-provider slices][staged obstacle tables]
+template <typename T, class Lqr, int LANES, int BLOCK>
+__host__ __device__ constexpr size_t steer_coop_bytes() {
+    return (Lqr::COOP && LANES > 1) ? align16((size_t)(BLOCK / LANES) * Lqr::COOP_SCALARS * sizeof(T)) : 0;
+}
+
+// ---- stand-alone rollouts: lq_steer (W given (node, target) pairs) ---------------------------------------
+// Outputs per pair j: xseq [j][H][N], useq [j][H][M] recorded edge (sample-major), len [j].
+template <typename T, class Sys, class Lqr, int LANES, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+steer_kernel(Model<T, Sys, Lqr> md, StagePlan stg,
+             const T* __restrict__ tstate, const T* __restrict__ tK, int cap,
+             const int* __restrict__ ids, const T* __restrict__ targets, int tstride, int W,
+             T* __restrict__ xseq, T* __restrict__ useq, int* __restrict__ len_out) {
+    constexpr int N = Sys::N, M = Sys::M;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ FeasTab<T> tabs[LQ_MAX_PRIMS];
+    T* coop = reinterpret_cast<T*>(dyn_smem) + (size_t)(threadIdx.x / LANES) * Lqr::COOP_SCALARS;
+    stage_tables(md.feas, stg, tabs, dyn_smem + steer_coop_bytes<T, Lqr, LANES, BLOCK>());
+    const int j = (blockIdx.x * BLOCK + threadIdx.x) / LANES;
+    const int lane = threadIdx.x % LANES;
+    if (j >= W) return;                    // whole groups leave together (BLOCK % LANES == 0)
+    const int id = ids[j];
+    T x[N], xt[N], K[M * N];
 #pragma unroll
-            for (int d = 0; d < N; d++) xnew_out[(size_t)d * ostride + j] = x[d];
+    for (int d = 0; d < N; d++) { x[d] = tstate[(size_t)d * cap + id]; xt[d] = targets[(size_t)d * tstride + j]; }
 #pragma unroll
-            for (int k = 0; k < M * N; k++) Knew_out[(size_t)k * ostride + j] = K[k];
+    for (int k = 0; k < M * N; k++) K[k] = tK[(size_t)k * cap + id];
+    int len; unsigned vote;
+    rollout<T, Sys, Lqr, LANES>(md, tabs, x, xt, K, xseq + (size_t)j * md.H * N, useq + (size_t)j * md.H * M, lane, coop, len, vote);
+    if (lane == 0) len_out[j] = len;
+}
+
+// ---- nearest selection in the rollout kernel's prologue ----------------------------------------------------
+template <typename T>
+struct PartialsIn { const T* pcost; const int* pidx; int pstride; int nslots; };
+
+// How K1 measured distance for this engine: the rare per-query rescan below must reproduce it bit for bit.
+template <typename T, int N>
+struct NearMetric {
+    DiagMetric<T, N> dmet;
+    const T* Spacked;        // per-query packed S (dense metrics), [NS][sstride]
+    int diag;
+};
+
+// One query's brute-force scan by its own group of LANES threads: the exact arithmetic of the K1 kernels
+// (nearest.cuh), lexicographic (cost, index) minimum.  Used when the merged winner of the speculative scans
+// turned out to be ignored (a commit that ran concurrently with the old-tree scan marked it) or when no
+// un-ignored node is left (planner.py:244-245: plain argmin) -- rare by construction.
+template <typename T, int N, int LANES>
+__device__ __noinline__ int rescan_nearest(const T* __restrict__ tstate, int cap, const uint8_t* __restrict__ ignore,
+                                           int size, bool mask_on, const NearMetric<T, N>& nm, const T (&xq)[N],
+                                           int j, int sstride, int lane) {
+    constexpr bool EXACT = sizeof(T) == 8;
+    constexpr int NS = N * (N + 1) / 2;
+    const uint32_t mask = nm.dmet.angle_mask;
+    T q[N], S[NS];
+    if (nm.diag) {
+#pragma unroll
+        for (int d = 0; d < N; d++) {
+            T v = xq[d];
+            if (!EXACT) { if (mask & (1u << d)) v = reduce_period(v); v = prescale(v, nm.dmet.w[d]); }
+            q[d] = v;
+        }
+    } else {
+#pragma unroll
+        for (int d = 0; d < N; d++) q[d] = xq[d];
+#pragma unroll
+        for (int s = 0; s < NS; s++) S[s] = nm.Spacked[(size_t)s * sstride + j];
+    }
+    T best = Num<T>::inf();
+    int b = -1;
+    for (int node = lane; node < size; node += LANES) {
+        if (mask_on && ignore[node]) continue;
+        T c;
+        if (nm.diag) {
+            c = T(0);
+#pragma unroll
+            for (int d = 0; d < N; d++) {
+                T a = tstate[(size_t)d * cap + node];
+                if (EXACT) {
+                    T e = q[d] - a;
+                    if (mask & (1u << d)) e = reduce_period(e);
+                    c = diag_term_exact(c, e, nm.dmet.sdiag[d]);
+                } else {
+                    if (mask & (1u << d)) a = reduce_period(a);
+                    a = prescale(a, nm.dmet.w[d]);
+                    T e = q[d] - a;
+                    if (mask & (1u << d)) e = diag_wrap_scaled(e, nm.dmet.period[d]);
+                    c = fma(e, e, c);
+                }
+            }
+        } else {
+            T e[N];
+#pragma unroll
+            for (int d = 0; d < N; d++) {
+                e[d] = q[d] - tstate[(size_t)d * cap + node];
+                if (mask & (1u << d)) e[d] = reduce_period(e[d]);
+            }
+            c = dense_cost<T, N>(e, S);
+        }
+        if (c < best) { best = c; b = node; }            // ascending per lane: the first minimum of this lane
+    }
+    if (LANES > 1) {
+        auto tile = cg::tiled_partition<LANES>(cg::this_thread_block());
+#pragma unroll
+        for (int o = LANES / 2; o > 0; o >>= 1) {
+            const T c2 = tile.shfl_xor(best, o);
+            const int i2 = tile.shfl_xor(b, o);
+            merge_candidate(best, b, c2, i2);
+        }
+    }
+    return b;
+}
+
+// ---- one wave's rollouts (the wave pipeline's K2) ----------------------------------------------------------
+// For every sample j of this rank's slice (count read from the wave's control slot):
+//   prologue  merge K1's partial minima (old-tree scan + delta scan slots) into the nearest node, check
+//             that it is still un-ignored (rescan otherwise);
+//   rollout   as above, edge into the per-sample scratch rows xseq / useq;
+//   epilogue  meta word + (if a node came out) parent and record row into segment `rank` of every
+//             destination in `dst`; in peer mode the last CTA raises this rank's arrival flag on every peer.
+template <typename T, class Sys, class Lqr, int LANES, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+steer_x_kernel(Model<T, Sys, Lqr> md, StagePlan stg,
+               const T* __restrict__ tstate, const T* __restrict__ tK, int cap,
+               const uint8_t* __restrict__ ignore, const int* __restrict__ d_size, const int* __restrict__ d_nignored,
+               WaveCtl* __restrict__ ctl, int slot, PartialsIn<T> pin, NearMetric<T, Sys::N> nm,
+               const T* __restrict__ samples, int sstride, const int* __restrict__ tries_used,
+               int use_ignore, int force_rescan,
+               T* __restrict__ xseq, T* __restrict__ useq,
+               ExDst dst, int Wc, int host_flags, const int* __restrict__ h_stop) {
+    constexpr int N = Sys::N, M = Sys::M;
+    constexpr int PER16 = 16 / (int)sizeof(T);
+    constexpr int RW = (N + M * N + PER16 - 1) / PER16 * PER16;
+    constexpr int NCH = RW / PER16;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ FeasTab<T> tabs[LQ_MAX_PRIMS];
+    __shared__ bool s_last;
+    T* coop = reinterpret_cast<T*>(dyn_smem) + (size_t)(threadIdx.x / LANES) * Lqr::COOP_SCALARS;
+
+    const int count = ctl->ring[slot].count;
+    const int j = (blockIdx.x * BLOCK + threadIdx.x) / LANES;
+    const int lane = threadIdx.x % LANES;
+    const bool active = j < count;                      // whole groups (BLOCK % LANES == 0)
+
+    if (blockIdx.x == 0 && threadIdx.x == 0) {          // this rank's segment header, on every replica
+        int flags = host_flags;
+        if (h_stop) flags |= *(const volatile int*)h_stop;      // the host's stop request (mapped host memory)
+        for (int p = 0; p < dst.n; p++) {
+            int* h = (int*)dst.seg[p];
+            h[HDR_SAMPLED] = count; h[HDR_FLAGS] = flags;
+        }
+    }
+    // nothing to roll out in this CTA: skip the table staging
+    const bool cta_active = blockIdx.x * (BLOCK / LANES) < count;
+    if (cta_active) stage_tables(md.feas, stg, tabs, dyn_smem + steer_coop_bytes<T, Lqr, LANES, BLOCK>());
+
+    if (active) {
+        T x[N], xt[N], K[M * N];
+#pragma unroll
+        for (int d = 0; d < N; d++) xt[d] = samples[(size_t)d * sstride + j];
+        // ---- nearest node: lexicographic merge of the partial minima, lanes split the slots
+        int id;
+        {
+            T best = Num<T>::inf();
+            int b = -1;
+            for (int sp = lane; sp < pin.nslots; sp += LANES)
+                merge_candidate(best, b, pin.pcost[(size_t)sp * pin.pstride + j], pin.pidx[(size_t)sp * pin.pstride + j]);
+            if (LANES > 1) {
+                auto tile = cg::tiled_partition<LANES>(cg::this_thread_block());
+#pragma unroll
+                for (int o = LANES / 2; o > 0; o >>= 1) {
+                    const T c2 = tile.shfl_xor(best, o);
+                    const int i2 = tile.shfl_xor(b, o);
+                    merge_candidate(best, b, c2, i2);
+                }
+            }
+            // The scans treat ignored nodes as absent.  A winner that is ignored NOW was marked by a commit
+            // that overlapped the old-tree scan; no winner means every node is ignored.  Either way this
+            // query is searched again against the tree as it is (marks only ever get added, so a winner
+            // that is still un-ignored is the winner of the up-to-date candidate set too).
+            if (force_rescan || b < 0 || (use_ignore && ignore[b])) {
+                const int size = *d_size;
+                const bool mask_on = use_ignore && (*d_nignored < size);
+                b = rescan_nearest<T, N, LANES>(tstate, cap, ignore, size, mask_on, nm, xt, j, sstride, lane);
+            }
+            id = b < 0 ? 0 : b;
+        }
+#pragma unroll
+        for (int d = 0; d < N; d++) x[d] = tstate[(size_t)d * cap + id];
+#pragma unroll
+        for (int k = 0; k < M * N; k++) K[k] = tK[(size_t)k * cap + id];
+
+        int len; unsigned vote;
+        rollout<T, Sys, Lqr, LANES>(md, tabs, x, xt, K, xseq + (size_t)j * md.H * N, useq + (size_t)j * md.H * M, lane, coop, len, vote);
+
+        // ---- epilogue: results to every replica
+        const unsigned meta = meta_pack(len, vote, tries_used ? tries_used[j] : 0);
+        for (int p = 0; p < dst.n; p++) {
+            const SegView<T> sv = seg_view<T>(dst.seg[p], Wc, N, M);
+            if (lane == 0) { sv.meta[j] = meta; if (len > 0) sv.parent[j] = id; }
+            if (len > 0) {
+                T* row = sv.rec + (size_t)j * RW;
+#pragma unroll
+                for (int c = 0; c < NCH; c++) {
+                    if (c % LANES == lane) {
+                        T v[PER16];
+#pragma unroll
+                        for (int t = 0; t < PER16; t++) {
+                            const int e = c * PER16 + t;          // compile-time after unrolling: registers only
+                            v[t] = e < N ? x[e < N ? e : 0] : (e < N + M * N ? K[(e >= N && e < N + M * N) ? e - N : 0] : T(0));
+                        }
+                        if constexpr (sizeof(T) == 4) *reinterpret_cast<float4*>(row + c * PER16) = make_float4(v[0], v[1], v[2], v[3]);
+                        else *reinterpret_cast<double2*>(row + c * PER16) = make_double2(v[0], v[1]);
+                    }
+                }
+            }
+        }
+    }
+
+    if (dst.flag[0]) {
+        // fused exchange: my stores are visible system-wide before I count myself done; the last CTA of the
+        // grid then raises this rank's arrival flag on every peer (after the data)
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(&ctl->done_steer, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (s_last && threadIdx.x == 0) {
+            __threadfence_system();
+            for (int p = 0; p < dst.n; p++) *(volatile unsigned*)dst.flag[p] = dst.seq;
+            ctl->done_steer = 0;
         }
     }
 }
@@ -212,13 +408,14 @@ steer_kernel(Model<T, Sys, Lqr> md,
 // (the thread-per-query metric_kernel in nearest.cuh serves the others).  Packed like metric_kernel.
 template <typename T, class Sys, class Lqr, int LANES>
 __global__ void __launch_bounds__(32)
-metric_coop_kernel(Model<T, Sys, Lqr> md, const T* __restrict__ queries, int qstride, int W, T* __restrict__ Spacked) {
+metric_coop_kernel(Model<T, Sys, Lqr> md, const T* __restrict__ queries, int qstride, int W,
+                   const int* __restrict__ d_count, T* __restrict__ Spacked) {
     constexpr int N = Sys::N, M = Sys::M;
     extern __shared__ __align__(16) unsigned char coop_raw[];
     T* coop = reinterpret_cast<T*>(coop_raw) + (size_t)(threadIdx.x / LANES) * Lqr::COOP_SCALARS;
     const int j = (blockIdx.x * 32 + threadIdx.x) / LANES;
     const int lane = threadIdx.x % LANES;
-    if (j >= W) return;
+    if (j >= (d_count ? min(*d_count, W) : W)) return;
     T x[N], u0[M];
 #pragma unroll
     for (int d = 0; d < N; d++) x[d] = queries[(size_t)d * qstride + j];

@@ -439,7 +439,46 @@ class System(object):
         return self._eval
 
 
-_RECOGNISED = {}       # (id(dynamics), id(lqr), id(erf), id(is_feasible)) -> verified System
+def system_digest(system):
+    """Content key of everything a System uploads to the device (dynamics / lqr blobs, erf mask, every
+    feasibility table).  The Planner rebuilds its engine when this changes, so a spec edited in place between
+    plans (new obstacles in Feasibility.prims[i].obs, retuned gains) is never planned against stale tables."""
+    n, m = system.nstates, system.ncontrols
+    parts = [('sys', system.dynamics.kind), np.asarray(system.dynamics.blob(), dtype=np.float64).tobytes(),
+             ('lqr', system.lqr.kind), np.asarray(system.lqr.blob(n, m), dtype=np.float64).tobytes(),
+             ('erf', system.erf.mask(n))]
+    for p in system.is_feasible.prims:
+        parts.append((p.kind, p.flags, float(p.inflate), tuple(int(d) for d in p.dims)))
+        for a in (p.obs, p.verts, p.lo, p.hi):
+            parts.append(b'' if a is None else np.ascontiguousarray(np.asarray(a, dtype=np.float64)).tobytes())
+    return hash(tuple(parts))
+
+
+# verified Systems of plain-callable models: id-tuple -> (the callables themselves, fingerprint of the globals
+# they close over, System).  Holding the callables keeps their ids from being reused by reloaded code, and the
+# fingerprint notices a user who rebinds or mutates `obs`, `vps`, the gains ... between plans -- the model is
+# then recognised (and verified against the user's functions) again instead of planning on stale tables.
+_RECOGNISED = {}
+_GLOBAL_NAMES = ('B', 'D', 'D_neg', 'D_pos', 'invB', 'invM', 'kd', 'kp', 'magic_rudder', 'thrust_max', 'u_max',
+                 'velmax', 'velmax_neg', 'velmax_neg_plan', 'velmax_pos', 'velmax_pos_plan', 'vps', 'obs',
+                 'boat_length', 'car_length', 'planning', 'umax_plan')
+
+
+def _globals_fingerprint(fns):
+    import hashlib
+    h = hashlib.sha1()
+    for fn in fns:
+        g = getattr(fn, '__globals__', None)
+        if g is None:
+            continue
+        for name in _GLOBAL_NAMES:
+            if name in g:
+                h.update(name.encode())
+                try:
+                    h.update(np.ascontiguousarray(np.array(g[name], dtype=np.float64)).tobytes())
+                except Exception:
+                    h.update(repr(g[name]).encode())
+    return h.hexdigest()
 
 
 def bundle_of(dynamics, lqr, erf, is_feasible, nstates=None, ncontrols=None):
@@ -453,11 +492,14 @@ def bundle_of(dynamics, lqr, erf, is_feasible, nstates=None, ncontrols=None):
     if not any(isinstance(s, _Spec) for s in specs) and all(hasattr(s, '__call__') for s in specs) \
             and nstates is not None:
         key = (id(dynamics), id(lqr), id(erf), id(is_feasible))
-        if key not in _RECOGNISED:
+        fns = (dynamics, lqr, erf, is_feasible)
+        fp = _globals_fingerprint(fns)
+        hit = _RECOGNISED.get(key)
+        if hit is None or hit[1] != fp or any(a is not b for a, b in zip(hit[0], fns)):
             from . import recognize
             from ._native import NativeError
             try:
-                _RECOGNISED[key] = recognize.recognise(dynamics, lqr, erf, is_feasible, int(nstates), int(ncontrols))
+                _RECOGNISED[key] = (fns, fp, recognize.recognise(dynamics, lqr, erf, is_feasible, int(nstates), int(ncontrols)))
             except recognize.NotRecognised as e:
                 raise TypeError(
                     "lqrrt_b200 runs the planner on the GPU and needs device model specs (lqrrt_b200.models); the "
@@ -468,7 +510,7 @@ def bundle_of(dynamics, lqr, erf, is_feasible, nstates=None, ncontrols=None):
                     "plain Python callables can only be accepted after the device model has been verified "
                     "against them on the GPU, and the engine is not available ({}). There is no CPU fallback."
                     .format(e))
-        return _RECOGNISED[key]
+        return _RECOGNISED[key][2]
     for s, nm in zip(specs, ('dynamics', 'lqr', 'is_feasible')):
         if not isinstance(s, _Spec):
             raise TypeError(

@@ -27,6 +27,14 @@ New keyword arguments (all optional, defaults keep reference call sites valid):
   comm      torch.distributed process group (or True for WORLD): the wave is
             sharded over the ranks and accepted nodes are all-gathered so every
             rank's tree stays identical
+  schedule  'device' (default where it applies: device sampler, pipeline on, wave != 1, exchange 'peer' or one
+            GPU) = the whole loop runs as lq_plan_run: waves are sized on the device from the tree size the
+            previous wave started with, enqueued ahead of the host, and the scan of the old part of the tree
+            overlaps the previous wave's rollouts; 'host' = one lq_wave_expand / lq_wave_commit per wave, sized
+            by the host.  Both grow the same tree for the same wave sizes.
+  fresh_samples  True (default): the Philox wave counter keeps counting across update_plan calls, so a replan
+            draws new samples as the reference's global NumPy stream does; assigning `planner.seed` restarts
+            it.  False: every plan replays the same sample sequence.
 
 dynamics / lqr / erf / constraints.is_feasible must be `lqrrt_b200.models`
 specs; there is no CPU fallback for arbitrary Python callables.
@@ -62,8 +70,16 @@ class Planner(object):
                  min_time=0.5, max_time=1, max_nodes=1E5,
                  goal0=None, sys_time=time.time, printing=True,
                  wave=None, wave_max=8192, dtype='f32', rng='philox', seed=0, device=None, comm=None,
-                 wave_growth=1.0, pipeline=True, exchange='peer', nearest_kernel=None, prefetch=None):
+                 wave_growth=1.0, pipeline=True, exchange='peer', nearest_kernel=None, prefetch=None,
+                 schedule=None, fresh_samples=True, depth=0):
         self._engine = None
+        if schedule not in (None, 'device', 'host'):
+            raise ValueError("schedule must be 'device' or 'host'")
+        self.schedule = schedule or os.environ.get('LQRRT_SCHEDULE') or 'device'
+        self.fresh_samples = bool(fresh_samples)
+        self.depth = int(depth)
+        self._wave_base = 0
+        self.engine_options = {}       # {LQ_OPT_*: value} applied to the engine before every plan (tests, tuning)
         if nearest_kernel is None:
             nearest_kernel = os.environ.get('LQRRT_NEAREST') or DEFAULT_NEAREST_KERNEL
         from ._native import NEAREST_KERNELS
@@ -101,6 +117,15 @@ class Planner(object):
         self.killed = False
         self.stats = {}
 
+    @property
+    def seed(self):
+        return self._seed
+
+    @seed.setter
+    def seed(self, value):
+        self._seed = int(value)
+        self._wave_base = 0           # a newly assigned key starts its sample stream from the beginning
+
     # ------------------------------------------------------------------ comm
     def _set_comm(self, comm):
         self.comm = None
@@ -117,7 +142,7 @@ class Planner(object):
 
     @property
     def prefetch_active(self):
-        return bool(self.prefetch and self.pipeline and (self.world == 1 or self._prefetch_explicit))
+        return bool(self.prefetch and self.pipeline)
 
     # ---------------------------------------------------------------- engine
     def _device(self):
@@ -141,7 +166,7 @@ class Planner(object):
         # with the adaptive heuristic horizon_iters is run-time state (planner.py:421,424) and the longest edge
         # is hspan[1]; with a fixed horizon it is baked in
         H = int(self.hspan[1]) if self.hfactor else int(self.horizon_iters)
-        key = (id(self._system), H, int(self.hfactor), int(self.hspan[0]), int(self.hspan[1]), float(self.dt),
+        key = (_models.system_digest(self._system), H, int(self.hfactor), int(self.hspan[0]), int(self.hspan[1]), float(self.dt),
                float(self.FPR), tuple(tol.tolist()),
                int(self.max_nodes) + 1, self._wave_capacity(), self.dtype, self._device())
         if self._engine is None or key != self._engine_key:
@@ -157,9 +182,14 @@ class Planner(object):
             if tune:
                 t = [int(v) for v in tune.split(',')] + [0]
                 self._engine.set_tuning(t[0], t[1])
-        from ._native import LQ_OPT_NEAREST_KERNEL, LQ_OPT_SAMPLE_PREFETCH, NEAREST_KERNELS
+        from ._native import LQ_OPT_NEAREST_KERNEL, LQ_OPT_SAMPLE_PREFETCH, LQ_OPT_NEAREST_CTAS_PER_SM, NEAREST_KERNELS
         self._engine.set_option(LQ_OPT_NEAREST_KERNEL, NEAREST_KERNELS[self.nearest_kernel])
         self._engine.set_option(LQ_OPT_SAMPLE_PREFETCH, int(self.prefetch_active))
+        for env, opt in (('LQRRT_SPEC', 4), ('LQRRT_STEER_BLOCK', 7), ('LQRRT_SCAN_CTAS', LQ_OPT_NEAREST_CTAS_PER_SM), ('LQRRT_STAGE', 6)):
+            if os.environ.get(env):                          # experiments (tools/gpu_*.sh): issue-level options only
+                self._engine.set_option(opt, int(os.environ[env]))
+        for opt, val in self.engine_options.items():
+            self._engine.set_option(opt, val)
         return self._engine
 
     @staticmethod
@@ -263,19 +293,69 @@ class Planner(object):
         time_start = self.sys_time()
         t_loop0 = time.perf_counter()
 
+        # Device-scheduled loop (lq_plan_run): nothing a wave needs comes from the host, so the engine sizes,
+        # samples, scans, rolls out and commits wave after wave by itself; the host only reads each wave's
+        # counters, applies the reference's stop rules on its own clock and raises a stop word.
+        use_device = (self.schedule == 'device' and mode == 'philox' and self.pipeline and self.wave != 1 and
+                      (self.world == 1 or isinstance(exchange, _waves.PeerExchange)))
+        if use_device:
+            state = dict(best_node=-1, elapsed=0.0, waves=0, samples=0)
+
+            def on_wave(st):
+                if 'stop' not in state:
+                    state['waves'] += 1          # waves that expanded samples (the one that saw the stop included)
+                state['samples'] += st.n_sampled
+                self.tree._set_size(st.tree_size)
+                if self.hfactor:
+                    self.horizon_iters = int(st.horizon_iters)
+                if st.best_node >= 0 and st.best_node != state['best_node']:        # planner.py:260-283
+                    state['best_node'] = st.best_node
+                    self.plan_reached_goal = True
+                    self.T = (1 + st.best_cost) * self.dt
+                    if self.printing:
+                        print("Found plan at elapsed time: {} s".format(np.round(state['elapsed'], 6)))
+                if st.flags:                     # the device has already stopped: these are the no-op tail waves
+                    if 'stop' not in state:
+                        state['stop'] = st.flags
+                    return 0
+                state['elapsed'] = self.sys_time() - time_start
+                if self.killed:                                                        # planner.py:289
+                    return _waves.STOP_KILL
+                if (self.plan_reached_goal and state['elapsed'] >= min_time) or \
+                        state['elapsed'] >= max_time or self.tree.size > self.max_nodes:    # planner.py:293, 311
+                    return _waves.STOP_DONE
+                return _waves.STOP_NONE
+
+            summ = eng.plan_run(self.seed, self._wave_base, 0 if self.wave is None else int(self.wave), 32, self.wave_max,
+                                self.wave_growth, pruning, on_wave, world=self.world, rank=self.rank, depth=self.depth,
+                                stream=stream)
+            wave_ctr = state['waves']
+            waves_enqueued = summ.waves_enqueued
+            samples_total = int(summ.samples)
+            time_elapsed = state['elapsed']
+            best_node = state['best_node']
+            self.tree._set_size(summ.last.tree_size)
+            stop = state.get('stop', summ.stop_code)
+            # a full tree stops the device with code 1 as well; `killed` is what tells a kill from a normal end
+            outcome = 'killed' if (stop == _waves.STOP_KILL or (self.killed and stop != 0)) else 'done'
+            self.stats_device_ms = float(summ.device_ms)
+
         # Software pipeline: with the device sampler nothing a wave needs comes from the host, so wave k+1
         # is enqueued before the host blocks on wave k's counters and the GPU never waits for the round
         # trip.  Host-fed samplers (the reference's MT19937 stream, user callables that may look at the
         # tree) stay strictly synchronous, as does wave=1.
+        # Wave k is sized from the tree size wave k-1 started with (waves 0 and 1 from the initial tree): that is
+        # all the host can know when it runs one wave ahead, it does not depend on the pipeline depth, and it is
+        # the rule the device-scheduled loop follows, so both drivers grow the same tree.
         depth = 1 if (mode == 'philox' and self.pipeline and self.wave != 1) else 0
         inflight = 0
         stopping = False
-        known_size = 1
+        sizes = [1]                      # sizes[k] = tree size wave k starts from
 
         def launch(W):
             first, count = _waves.partition(W, self.rank, self.world)
             if mode == 'philox':
-                eng.wave_expand(self.seed, wave_ctr, first, count, None, pruning, stop_request, stream)
+                eng.wave_expand(self.seed, self._wave_base + wave_ctr, first, count, None, pruning, stop_request, stream)
             elif mode == 'numpy':
                 # planner.py:201-211 on the reference's own stream: draw the most tries this wave could
                 # use from a snapshot, let the device pick, then advance the real stream by what was used
@@ -298,17 +378,15 @@ class Planner(object):
                 recv = exchange.gather(self._send_view(eng))
                 eng.wave_commit(recv.data_ptr(), self.world, stream, my_segment=self.rank)
 
-        while True:
-            while inflight <= depth and not stopping:
-                launch(_waves.wave_size(known_size, self.wave, wave_max=self.wave_max, growth=self.wave_growth))
+        while not use_device:
+            while inflight <= depth and not stopping and (wave_ctr < 2 or len(sizes) >= wave_ctr):
+                launch(_waves.wave_size(sizes[max(0, wave_ctr - 1)], self.wave, wave_max=self.wave_max, growth=self.wave_growth))
                 wave_ctr += 1
                 inflight += 1
-                if wave_ctr == 1:
-                    break                       # the first wave's size is the only thing known so far
             st = eng.wave_stats()
             inflight -= 1
             samples_total += st.n_sampled
-            known_size = st.tree_size
+            sizes.append(st.tree_size)
             self.tree._set_size(st.tree_size)
             if self.hfactor:
                 self.horizon_iters = int(st.horizon_iters)
@@ -348,12 +426,18 @@ class Planner(object):
             outcome = 'reached' if self.plan_reached_goal else 'timeout'
 
         t_loop1 = time.perf_counter()
-        self.stats = dict(waves=wave_ctr, samples=samples_total, nodes=self.tree.size,
+        self.stats = dict(waves=wave_ctr, waves_enqueued=waves_enqueued if use_device else wave_ctr,
+                          samples=samples_total, nodes=self.tree.size,
                           elapsed=time_elapsed, gpu_launches=eng.launch_count() - launches0,
                           host_setup_s=t_loop0 - t_call, host_loop_s=t_loop1 - t_loop0)
         if ev0 is not None:
             ev1.record(); ev1.synchronize()
             self.stats['device_ms'] = ev0.elapsed_time(ev1)      # wave loop only, on the launching stream
+        if use_device:
+            self.stats['device_ms'] = self.stats_device_ms       # CUDA events on the pipeline's own chain stream
+        self.stats['schedule'] = 'device' if use_device else 'host'
+        if self.fresh_samples:
+            self._wave_base += waves_enqueued if use_device else wave_ctr
 
         if self.plan_reached_goal:
             # the plan attributes the reference fills inside its loop (planner.py:276-281)
@@ -525,6 +609,12 @@ class Planner(object):
         """Abruptly terminates update_plan at its next wave boundary (planner.py:596-601); callable from
         any thread."""
         self.killed = True
+        eng = self._engine
+        if eng is not None:
+            try:
+                eng.request_stop(_waves.STOP_KILL)      # the device-scheduled loop polls this word
+            except Exception:
+                pass
 
     def unkill(self):
         """planner.py:605-610."""

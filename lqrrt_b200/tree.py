@@ -154,6 +154,36 @@ class Tree(object):
             self._long_edges[self._size] = (x_seq, u_seq)
         self._size += 1
 
+    def nearest(self, x, use_ignore=False):
+        """Nearest node(s) to the state(s) `x` in cost-to-go, the reference's `_costs_to_go` + selection
+        (planner.py:239-247, 340-350; BASELINE.json calls it Tree.nearest): S = lqr(x, 0).S at the query,
+        cost_i = erf(x, v_i)' S erf(x, v_i) over every node, lowest cost wins, lowest ID on exact ties.  With
+        `use_ignore` nodes on finished plans are skipped unless every node is (planner.py:240-245).  Runs the
+        engine's scan kernel (lq_nearest).  x: (n,) -> (ID, cost);  (W, n) -> (IDs, costs)."""
+        import torch
+        q = np.asarray(x, dtype=np.float64)
+        single = q.ndim == 1
+        q = q.reshape(-1, self.nstates)
+        if q.shape[0] < 1:
+            raise ValueError("Expected at least one query state.")
+        dev = torch.device('cuda', self._eng.device)
+        tdt = torch.float32 if self._eng.dtype == 'f32' else torch.float64
+        ids = np.zeros(len(q), dtype=np.int64); costs = np.zeros(len(q))
+        cap = self._eng.wave_capacity
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream().cuda_stream
+            for lo in range(0, len(q), cap):
+                part = q[lo:lo + cap]
+                dq = torch.tensor(np.ascontiguousarray(part.T), dtype=tdt, device=dev)       # dim-major, as the scan reads it
+                di = torch.empty(len(part), dtype=torch.int32, device=dev)
+                dc = torch.empty(len(part), dtype=tdt, device=dev)
+                self._eng.nearest(dq.data_ptr(), len(part), bool(use_ignore), di.data_ptr(), dc.data_ptr(), st)
+                ids[lo:lo + len(part)] = di.cpu().numpy()
+                costs[lo:lo + len(part)] = dc.double().cpu().numpy()
+        if single:
+            return int(ids[0]), float(costs[0])
+        return ids, costs
+
     def climb(self, ID):
         """Node IDs from the seed to ID (tree.py:100-117)."""
         if ID >= self.size or ID < 0:

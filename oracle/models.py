@@ -328,9 +328,40 @@ def make_is_feasible_batch(spec):
     return feas
 
 
-def make_callbacks(system, dt):
+def make_is_feasible_allobs(spec):
+    """`make_is_feasible` with the per-obstacle Python loop of the cloud / point primitives folded into one NumPy
+    expression over all obstacles.  Same elementwise arithmetic (sqrt of a two- or three-term sum of squares, the
+    same comparisons), so the verdicts are identical -- tests/test_oracle_golden.py checks that -- only ~50x
+    faster on the 500-obstacle field, which is what lets the wave oracle follow 1024-sample waves in a test."""
+    prims = list(spec.prims)
+
+    def is_feasible(x, u):
+        for p in prims:
+            k = p.kind
+            if k == M.FEAS_CIRCLES_CLOUD and len(p.obs):
+                verts = _cloud_world(p, x)
+                d = np.sqrt(((verts[None, :, :] - p.obs[:, None, :2]) ** 2).sum(-1))
+                if np.any(d <= p.obs[:, None, 2]):
+                    return False
+            elif k == M.FEAS_BOXES_CLOUD and len(p.obs):
+                verts = _cloud_world(p, x)
+                if np.any((np.abs(verts[None, :, 0] - p.obs[:, None, 0]) <= p.obs[:, None, 2]) &
+                          (np.abs(verts[None, :, 1] - p.obs[:, None, 1]) <= p.obs[:, None, 3])):
+                    return False
+            elif k in (M.FEAS_CIRCLES_POINT, M.FEAS_SPHERES_POINT) and len(p.obs):
+                nd = 2 if k == M.FEAS_CIRCLES_POINT else 3
+                pos = np.array([x[d] for d in p.dims[:nd]])
+                if np.any(np.sqrt(((pos[None, :] - p.obs[:, :nd]) ** 2).sum(-1)) <= p.inflate + p.obs[:, nd]):
+                    return False
+            elif not _prim_ok(p, x, u):
+                return False
+        return True
+    return is_feasible
+
+
+def make_callbacks(system, dt, all_obstacles_at_once=False):
     dynamics = make_dynamics(system.dynamics)
     lqr = make_lqr(system.lqr, system.dynamics, dt)
     erf = make_erf(system.erf)
-    is_feasible = make_is_feasible(system.is_feasible)
+    is_feasible = (make_is_feasible_allobs if all_obstacles_at_once else make_is_feasible)(system.is_feasible)
     return dynamics, lqr, erf, is_feasible

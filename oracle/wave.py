@@ -29,7 +29,7 @@ class WaveOracle(object):
     def __init__(self, system, goal, goal_buffer, horizon, dt, FPR, error_tol, node_capacity=1 << 30):
         self.sys = system
         self.n = system.nstates; self.m = system.ncontrols
-        self.dynamics, self.lqr, self.erf, self.is_feasible = make_callbacks(system, dt)
+        self.dynamics, self.lqr, self.erf, self.is_feasible = make_callbacks(system, dt, all_obstacles_at_once=True)
         self.feas_batch = make_is_feasible_batch(system.is_feasible)
         self.angle_dims = tuple(system.erf.angle_dims)
         self.dt = dt; self.FPR = FPR

@@ -131,3 +131,51 @@ def test_nearest_riccati_metric(cuda_device):
         c = orc.costs(Q[j]); best = int(np.argmin(c))
         assert idx[j] == best or c[idx[j]] <= c[best] * (1 + 1e-6)
         assert abs(cost[j] - c[idx[j]]) <= 1e-5 * max(1.0, c[best])
+
+
+@pytest.mark.parametrize('dtype', ['f64', 'f32'])
+def test_diagonal_non_identity_metric_vs_reference(cuda_device, dtype):
+    """The ROS car's S = diag(1, 1, 1, 0, 0) (demos/lqrrt_ros/behaviors/car.py:65) through the pre-scaled form of
+    the diagonal scan ((w q - w v)^2 per dim, w = sqrt(S_ii)) against the reference's own `_costs_to_go` with that
+    S on the demo_car tree (tests/golden/make_golden_r2.py); also a non-representable weight set vs the oracle."""
+    from lqrrt_b200 import configs, models
+    g = load_golden('r2_extra'); base = problem('demo_car')
+    car = base.system
+    system = models.System(car.dynamics, models.PDRotatedLqr(car.lqr.kp, car.lqr.kd, S=g['ds_S']), models.Erf([2]),
+                           car.is_feasible)
+    prob = configs.Problem('ros_car_metric', system, base.x0, base.goal, base.goal_buffer, base.error_tol,
+                           base.sample_space, base.goal_bias, base.horizon, base.dt, base.FPR)
+    eng = make_engine(prob, dtype, node_capacity=len(g['ds_state']) + 8, wave_capacity=64)
+    eng.load_nodes(g['ds_state'])
+    idx, cost = nearest(eng, g['ds_q'])
+    if dtype == 'f64':
+        assert np.array_equal(idx, g['ds_argmin'])
+        assert np.allclose(cost, g['ds_mincost'], rtol=1e-12, atol=1e-12)
+    else:
+        orc = _oracle_for(prob); orc.load(g['ds_state'], [-1] * len(g['ds_state']), K=[None] * len(g['ds_state']))
+        for j in range(len(idx)):
+            c = orc.costs(g['ds_q'][j])
+            assert idx[j] == g['ds_argmin'][j] or c[idx[j]] <= c.min() * (1 + 1e-6) + 1e-9
+        assert np.allclose(cost, g['ds_mincost'], rtol=1e-5, atol=1e-6)
+    eng.close()
+    # weights whose square roots are not exactly representable, boat (wrapped heading dim carries 3.3)
+    bp = problem('demo_boat_novice')
+    S = np.diag([2.0, 0.7, 3.3, 0.1, 5.0, 1.9])
+    wsys = models.System(bp.system.dynamics, models.PDRotatedLqr(np.diag([120, 120, 350]), np.diag([120, 120, 100]), S=S),
+                         models.Erf([2]), bp.system.is_feasible)
+    wprob = configs.Problem('weighted', wsys, bp.x0, bp.goal, bp.goal_buffer, bp.error_tol, bp.sample_space,
+                            bp.goal_bias, bp.horizon, bp.dt, bp.FPR)
+    rng = np.random.RandomState(5)
+    ss = np.array(bp.sample_space)
+    nodes = ss[:, 0] + (ss[:, 1] - ss[:, 0]) * rng.rand(4000, 6); nodes[:, 2] = 15 * (rng.rand(4000) - 0.5)
+    Q = ss[:, 0] + (ss[:, 1] - ss[:, 0]) * rng.rand(300, 6)
+    eng = make_engine(wprob, dtype, node_capacity=4008, wave_capacity=304)
+    eng.load_nodes(nodes)
+    idx, cost = nearest(eng, Q)
+    orc = _oracle_for(wprob); orc.load(nodes, [-1] * 4000, K=[None] * 4000)
+    for j in range(len(Q)):
+        c = orc.costs(Q[j])
+        best = int(np.argmin(c))
+        assert idx[j] == best or (dtype == 'f32' and c[idx[j]] <= c[best] * (1 + 1e-6) + 1e-9)
+        assert abs(cost[j] - c[idx[j]]) <= (1e-11 if dtype == 'f64' else 2e-5) * max(1.0, c[best])
+    eng.close()

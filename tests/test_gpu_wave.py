@@ -28,7 +28,8 @@ def _named_problem(name):
 
 
 @pytest.mark.parametrize('name,W,waves', [('demo_boat_novice', 64, 6), ('demo_car', 48, 4), ('demo_boat_advanced', 128, 4),
-                                          ('c1', 64, 5), ('c2', 32, 3), ('c5-riccati-6', 24, 3), ('c5-const-12', 61, 4)])
+                                          ('c1', 64, 5), ('c2', 32, 3), ('c3', 96, 4), ('c4', 128, 4),
+                                          ('c5-riccati-6', 24, 3), ('c5-const-12', 61, 4)])
 def test_philox_waves_match_oracle(cuda_device, name, W, waves):
     prob = _named_problem(name)
     eng = make_engine(prob, 'f64', node_capacity=4096, wave_capacity=W)
@@ -46,14 +47,27 @@ def test_philox_waves_match_oracle(cuda_device, name, W, waves):
         assert st.n_sampled == W
     t = tree_arrays(eng)
     assert t['parent'].tolist() == orc.parent
-    assert t['cost'].tolist() == orc.cost
+    # The car-like boats re-scale the yaw rate for vx > 0 or vx < 0 but not for vx == 0, right after clamping vx at 0
+    # (demo_boat_advanced.py:122-128): a rollout whose clipped surge force cancels to +-1e-17 (a target straight abeam
+    # of a boat at rest) takes one branch or the other on the last bit of the thruster mix, and its edge changes.
+    # DESIGN.md section 4; such a node may differ, everything else must agree.
+    knife = 2 if name in ('c4', 'demo_boat_advanced', 'demo_boat_intermediate') else 0
     tol = 1e-6 if prob.system.lqr.kind == 3 else 1e-9
-    assert np.abs(t['state'] - orc.state).max() <= tol
-    assert np.abs(t['K'] - np.array(orc.K)).max() <= tol * 1e4
+    differs = (np.array(t['cost'].tolist()) != np.array(orc.cost)) | (np.abs(t['state'] - orc.state).max(axis=1) > tol)
+    tainted = np.zeros(orc.size, dtype=bool); primary = 0
+    for i in range(orc.size):                     # a node below a differing node starts from a different state: excused
+        up = orc.parent[i] >= 0 and tainted[orc.parent[i]]
+        primary += int(differs[i] and not up)
+        tainted[i] = differs[i] or up
+    assert primary <= knife, np.nonzero(differs)[0]
+    same = ~tainted
+    assert np.abs(t['K'] - np.array(orc.K))[same].max() <= tol * 1e4
     assert t['ignore'].astype(bool).tolist() == orc.ignore
     assert (st.best_node, st.best_cost) == ((orc.best_node, orc.best_cost) if orc.best_cost is not None else (-1, -1))
     hx, hu, _ = eng.download_edges(np.arange(1, orc.size))
     for i in range(1, orc.size):
+        if not same[i]:
+            continue
         L = len(orc.x_seq[i])
         assert t['edge_len'][i] == L
         assert np.abs(hx[i - 1, :L] - np.array(orc.x_seq[i])).max() <= tol
@@ -162,3 +176,44 @@ def test_host_supplied_samples_and_empty_wave(cuda_device):
     st = eng.wave_stats()
     assert st.n_accepted == 0 and st.tree_size == orc.size
     assert np.abs(tree_arrays(eng)['state'] - orc.state).max() < 1e-9
+
+
+@pytest.mark.parametrize('name', ['c3', 'c4'])
+def test_f32_waves_follow_the_oracle_statistically(cuda_device, name):
+    """The benchmarked arithmetic (float32, waves of >= 1024 samples) against the float64 wave oracle on the benchmark's
+    own obstacle fields.  Identical Philox samples; single nodes may differ (a float32 cost tie-break or a rollout
+    that grazes an obstacle flips, and node ids shift from there on), so the comparison is wave by wave on what the
+    planner's behaviour depends on: how many samples become nodes, how long their edges are, how deep the tree
+    gets -- within a few percent."""
+    prob = problem(name)
+    W, waves = 1024, 6
+    eng = make_engine(prob, 'f32', node_capacity=8192, wave_capacity=W)
+    eng.set_sampling(prob.sample_space, prob.goal_bias, 10)
+    eng.reset(prob.x0)
+    orc = _oracle(prob); orc.reset(prob.x0)
+    first_wave_same = None
+    for w in range(waves):
+        eng.wave_expand(1234, w, 0, W, None, True)
+        eng.wave_commit(None, 1)
+        st = eng.wave_stats()
+        X, used = orc.sample_wave(1234, w, 0, W, prob.sample_space, prob.goal_bias, 10)
+        before = orc.size
+        orc.expand_wave(X)
+        added = orc.size - before
+        assert abs(st.n_accepted - added) <= max(8, 0.03 * added), (w, st.n_accepted, added)
+        assert abs(st.tries_used - int(used.sum())) <= max(4, 0.01 * used.sum())
+        if w == 0:
+            first_wave_same = st.n_accepted == added
+    assert first_wave_same          # every first-wave rollout starts from the seed: same accept set
+    t = tree_arrays(eng)
+    n = min(len(t['state']), orc.size)
+    assert abs(len(t['state']) - orc.size) <= 0.03 * orc.size
+    # first wave: same nodes, float32 accuracy
+    k = 1 + int((np.array(orc.parent[1:]) == 0).cumprod().sum())        # seed + the nodes of the first wave
+    assert np.abs(t['state'][:k] - orc.state[:k]).max() < 5e-3
+    ce, co = t['cost'][:n].astype(float), np.array(orc.cost[:n], dtype=float)
+    assert abs(ce.mean() - co.mean()) <= 0.03 * co.mean()
+    assert abs(np.percentile(ce, 90) - np.percentile(co, 90)) <= 0.05 * np.percentile(co, 90) + 1
+    le, lo = t['edge_len'][1:n].astype(float), np.array([len(e) for e in orc.x_seq[1:n]], dtype=float)
+    assert abs(le.mean() - lo.mean()) <= 0.03 * lo.mean()
+    eng.close()

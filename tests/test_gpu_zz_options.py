@@ -111,11 +111,7 @@ def test_prefetch_across_plans_and_wave_sizes(cuda_device):
     assert out[0] == out[1]
 
 
-# ---- not yet run on a GPU (written after the round's GPU budget was spent): opt in with LQRRT_EXPERIMENTAL=1
-import os  # noqa: E402
-
-experimental = pytest.mark.skipif(os.environ.get('LQRRT_EXPERIMENTAL') != '1',
-                                  reason="experimental scan variant / weight case, not measured yet (set LQRRT_EXPERIMENTAL=1)")
+# ---- the partial-distance scan variant and non-identity weights (first run on a B200 in round 2)
 PREFIX = 4
 
 
@@ -130,7 +126,6 @@ def _weighted_problem():
                            base.goal_bias, base.horizon, base.dt, base.FPR)
 
 
-@experimental
 @pytest.mark.parametrize('name,N,W', [('demo_boat_novice', 20000, 1500), ('demo_boat_novice', 129, 1027), ('c4', 100000, 2048),
                                       ('c5k', 5003, 600), ('demo_car', 9001, 700)])
 def test_prefix_filter_scan_is_bit_identical(cuda_device, name, N, W):
@@ -149,7 +144,6 @@ def test_prefix_filter_scan_is_bit_identical(cuda_device, name, N, W):
     assert np.array_equal(j0, j1) and np.array_equal(d0.view(np.int64), d1.view(np.int64))
 
 
-@experimental
 @pytest.mark.parametrize('kernel', [PACKED, PACKED_Q8, TWO_LEVEL, PREFIX])
 def test_variants_agree_for_non_identity_weights(cuda_device, kernel):
     """Pre-scaling is a rounded multiply of its own in every variant (csrc/nearest.cuh prescale), so the

@@ -92,7 +92,7 @@ def test_engine_option_arguments(monkeypatch):
     monkeypatch.delenv('LQRRT_PREFETCH', raising=False)
     prob, p = _planner()
     assert p.nearest_kernel == pl.DEFAULT_NEAREST_KERNEL and p.prefetch == pl.DEFAULT_PREFETCH
-    assert p.prefetch_active == (pl.DEFAULT_PREFETCH and p.world == 1)
+    assert p.prefetch_active == pl.DEFAULT_PREFETCH
     with pytest.raises(ValueError, match="nearest_kernel must be one of"):
         _planner(nearest_kernel='fastest')
     _, q = _planner(nearest_kernel='scalar', prefetch=False)
@@ -103,14 +103,16 @@ def test_engine_option_arguments(monkeypatch):
     monkeypatch.setenv('LQRRT_PREFETCH', '0')
     _, e = _planner()
     assert e.nearest_kernel == 'two_level' and not e.prefetch
-    # a multi-GPU planner takes the prefetch only when asked (planner.py DEFAULT_PREFETCH note)
+    # multi-GPU planners take the prefetch too (host-scheduled waves; the device-scheduled loop runs every wave's
+    # sampler on its scan stream anyway)
     monkeypatch.delenv('LQRRT_PREFETCH', raising=False)
     _, m = _planner()
     m.world = 2
-    assert not m.prefetch_active
-    _, m2 = _planner(prefetch=True)
-    m2.world = 2
-    assert m2.prefetch_active
+    assert m.prefetch_active
+    with pytest.raises(ValueError, match="schedule must be"):
+        _planner(schedule='gpu')
+    _, h = _planner(schedule='host', fresh_samples=False)
+    assert h.schedule == 'host' and not h.fresh_samples
 
 
 def test_bench_cli_defaults():

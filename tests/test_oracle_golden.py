@@ -24,6 +24,22 @@ def test_callbacks_bit_exact(name):
         assert np.array_equal(erf(np.copy(xg), np.copy(x)), g['cb_erf'][i])
         assert bool(feas(x, u)) == bool(g['cb_feas'][i])
     assert 0 < g['cb_feas'].sum() < len(g['cb_feas'])        # both verdicts are exercised
+    # the wave oracle's all-obstacles-at-once form of is_feasible gives the same verdicts, also right on obstacle rims
+    fast = om.make_callbacks(prob.system, prob.dt, all_obstacles_at_once=True)[3]
+    rng = np.random.RandomState(1)
+    X = np.vstack((g['cb_x'], g['state'][rng.randint(0, len(g['state']), 400)] + 0.5 * rng.randn(400, g['state'].shape[1])))
+    obs = g['obs'][g['obs'][:, 0] > -1000]
+    if len(obs):
+        rim = X[:200].copy()
+        pick = obs[rng.randint(0, len(obs), 200)]
+        ang = 2 * np.pi * rng.rand(200)
+        rim[:, 0] = pick[:, 0] + (pick[:, 2] + 3 * rng.rand(200)) * np.cos(ang)
+        rim[:, 1] = pick[:, 1] + (pick[:, 2] + 3 * rng.rand(200)) * np.sin(ang)
+        X = np.vstack((X, rim))
+    u0 = np.zeros(prob.ncontrols)
+    verdicts = [bool(feas(x, u0)) for x in X]
+    assert verdicts == [bool(fast(x, u0)) for x in X]
+    assert 0 < sum(verdicts) < len(verdicts)
 
 
 @pytest.mark.parametrize('name', DEMOS)
@@ -99,3 +115,32 @@ def test_adaptive_horizon_two_plans_bit_exact():
         assert sp.horizon_iters == int(g['horizon_iters%d' % k])
         assert sp.T == float(g['T%d' % k])
     assert g['edge_len0'].max() > 20          # edges longer than the fixed-horizon demos' 20 steps occur
+
+
+def test_force_arrive_steer_bit_exact():
+    """`_steer(ID, xtar, force_arrive=True)` (planner.py:294-303, 399-410) of the reference on its own boat_novice
+    tree (tests/golden/make_golden_r2.py): targets it reaches and targets behind an obstacle."""
+    g = load_golden('r2_extra')
+    sp, prob = _run_seq('demo_boat_novice', 400)
+    assert np.array_equal(sp.tree.state, g['fa_state'])
+    off = 0
+    for ID, xt, L in zip(g['fa_ids'], g['fa_targets'], g['fa_len']):
+        xs, us = sp.steer_force(int(ID), xt, max_steps=10 ** 6)
+        assert len(xs) == int(L)
+        assert np.array_equal(np.array(xs).reshape(-1, 6), g['fa_x'][off:off + L])
+        assert np.array_equal(np.array(us).reshape(-1, 3), g['fa_u'][off:off + L])
+        off += int(L)
+    assert g['fa_len'].max() > 1000 and g['fa_len'].min() < 100      # both exits are exercised
+
+
+def test_diagonal_non_identity_metric_bit_exact():
+    """`_costs_to_go` with the ROS car's S = diag(1, 1, 1, 0, 0) (behaviors/car.py:65) on the demo_car tree."""
+    g = load_golden('r2_extra')
+    prob = problem('demo_car')
+    dyn, lqr, erf, feas = om.make_callbacks(prob.system, prob.dt)
+    S = g['ds_S']
+    erf_v = make_erf_v(erf)
+    for j, q in enumerate(g['ds_q']):
+        c = costs_to_go(lambda x, u: (S, lqr(x, u)[1]), erf_v, 2, g['ds_state'], q)
+        assert int(np.argmin(c)) == int(g['ds_argmin'][j])
+        assert c.min() == g['ds_mincost'][j]

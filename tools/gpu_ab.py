@@ -93,7 +93,7 @@ def plan_case(torch, cfg_name, nearest, prefetch, wave_max, growth, steps=5, war
     emit({"what": "plan", "config": cfg_name, "nearest": nearest, "prefetch": prefetch, "wave_max": wave_max, "growth": growth,
           "nodes_per_s": float(np.sum(nodes)) / (float(np.sum(dev)) / 1e3), "e2e_nodes_per_s": float(np.sum(nodes)) / (float(np.sum(host)) / 1e3),
           "ms_per_plan": float(np.mean(dev)), "waves": float(np.mean(waves)), "yield": float(np.sum(nodes)) / float(np.sum(samples)),
-          "stage_ms_per_plan": {k: v / steps for k, v in prof['ms'].items()}, "pairs_per_s": prof['pairs'] / (prof['ms']['nearest'] / 1e3),
+          "stage_ms_per_plan": {k: v / steps for k, v in prof['ms'].items()}, "pairs_per_s": prof['pairs'] / ((prof['ms']['nearest_old'] + prof['ms']['nearest_delta']) / 1e3),
           "last_tree_digest": digest, "depth": len(planner.node_seq)})
     planner._engine.close(); planner._engine = None
 

@@ -84,8 +84,8 @@ def plan(torch, name, ctas, steps=4, warmup=2, growth=2.0):
             dev.append(planner.stats['device_ms']); nodes.append(planner.stats['nodes'] - 1)
     prof = planner._engine.profile_read()
     emit({"what": "plan", "kernel": name, "ctas_per_sm": ctas, "growth": growth, "nodes_per_s": float(np.sum(nodes)) / (float(np.sum(dev)) / 1e3),
-          "ms_per_plan": float(np.mean(dev)), "nearest_ms_per_plan": prof['ms']['nearest'] / steps,
-          "pairs_per_s": prof['pairs'] / (prof['ms']['nearest'] / 1e3)})
+          "ms_per_plan": float(np.mean(dev)), "nearest_ms_per_plan": (prof['ms']['nearest_old'] + prof['ms']['nearest_delta']) / steps,
+          "pairs_per_s": prof['pairs'] / ((prof['ms']['nearest_old'] + prof['ms']['nearest_delta']) / 1e3)})
     planner._engine.close(); planner._engine = None
 
 
