@@ -232,6 +232,12 @@ typedef struct lq_plan_summary {
     lq_wave_stats last;
 } lq_plan_summary;
 int lq_plan_run(lq_engine* h, const lq_plan_args* args, lq_plan_summary* out, void* stream);
+/* The wave-sizing rule of the device schedule, as plain host functions (what the commit kernel evaluates):
+ * W = wave_fixed if > 0, else clamp(int(growth * tree_size), wave_min, wave_max) in float64; and the contiguous
+ * slice [first, first + count) of a wave of W samples that `rank` of `world` expands (rank-order concatenation of
+ * the slices is sample order).  Mirrors lqrrt_b200/waves.py wave_size / partition. */
+int lq_policy_wave(int wave_fixed, int wave_min, int wave_max, double growth, int tree_size);
+int lq_policy_slice(int W, int rank, int world, int32_t* first, int32_t* count);
 /* The host word the rollout kernels poll for a stop request (mapped pinned memory): another thread may set it to
  * 1 (done) or 2 (kill) at any time, e.g. Planner.kill_update (planner.py:596-601); lq_plan_run clears it on entry. */
 int lq_stop_word(lq_engine* h, int32_t** out);
@@ -284,7 +290,9 @@ enum { LQ_OPT_NEAREST_KERNEL = 1, LQ_OPT_SAMPLE_PREFETCH = 2,
        LQ_OPT_SPECULATIVE_SCAN = 4,     /* lq_plan_run: 1 (default) = old-tree scan of wave k+1 on a side stream under wave k */
        LQ_OPT_FORCE_RESCAN = 5,         /* tests: every query takes the rollout kernel's own rescan path */
        LQ_OPT_STAGE_TABLES = 6,         /* 1 (default) = obstacle tables staged in shared memory by the rollout kernels */
-       LQ_OPT_STEER_BLOCK = 7           /* CTA size of the wave rollout kernel: 0 = auto, 32, 128 */ };
+       LQ_OPT_STEER_BLOCK = 7,          /* CTA size of the wave rollout kernel: 0 = auto, 32, 128 */
+       LQ_OPT_PDL = 8                   /* 1 (default) = rollout and commit kernels of a wave are launched programmatically
+                                           dependent: they start (and stage their tables) while the kernel in front drains */ };
 enum { LQ_NEAREST_SCALAR = 0, LQ_NEAREST_PACKED = 1,
        /* tuning variants, same results: 8 queries per thread (best on the 12-state scan), and the two-level
         * argmin with one-lane-at-a-time arithmetic */

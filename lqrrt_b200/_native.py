@@ -21,7 +21,7 @@ LQ_MAX_N = 12
 LQ_F32, LQ_F64 = 0, 1
 LQ_OPT_NEAREST_KERNEL, LQ_OPT_SAMPLE_PREFETCH = 1, 2
 LQ_OPT_NEAREST_CTAS_PER_SM = 3
-LQ_OPT_SPECULATIVE_SCAN, LQ_OPT_FORCE_RESCAN, LQ_OPT_STAGE_TABLES, LQ_OPT_STEER_BLOCK = 4, 5, 6, 7
+LQ_OPT_SPECULATIVE_SCAN, LQ_OPT_FORCE_RESCAN, LQ_OPT_STAGE_TABLES, LQ_OPT_STEER_BLOCK, LQ_OPT_PDL = 4, 5, 6, 7, 8
 NEAREST_KERNELS = {'scalar': 0, 'packed': 1, 'packed_q8': 2, 'two_level': 3, 'prefix': 4}
 
 
@@ -97,6 +97,8 @@ SYMBOLS = {
     'lq_wave_stats_get': (C.c_int, [_P, C.POINTER(lq_wave_stats)]),
     'lq_plan_run': (C.c_int, [_P, C.POINTER(lq_plan_args), C.POINTER(lq_plan_summary), _P]),
     'lq_stop_word': (C.c_int, [_P, C.POINTER(C.POINTER(C.c_int32))]),
+    'lq_policy_wave': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]),
+    'lq_policy_slice': (C.c_int, [C.c_int, C.c_int, C.c_int, _I, _I]),
     'lq_closest': (C.c_int, [_P, _D, _U8, C.POINTER(C.c_int), _P]),
     'lq_steer_force': (C.c_int, [_P, C.c_int, _D, C.c_int, _D, _D, C.POINTER(C.c_int), _P]),
     'lq_append_node': (C.c_int, [_P, C.c_int, _D, _D, _D, C.c_int, _P]),

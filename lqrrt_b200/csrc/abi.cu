@@ -98,6 +98,18 @@ int lq_wave_records(lq_engine* h, void** d, uint64_t* bytes) { LQ_H(h); LQ_TRY(h
 int lq_wave_commit(lq_engine* h, const void* rec, int nseg, int myseg, void* st) { LQ_H(h); LQ_TRY(h->wave_commit(rec, nseg, myseg, (cudaStream_t)st)) }
 int lq_wave_stats_get(lq_engine* h, lq_wave_stats* out) { LQ_H(h); LQ_TRY(h->wave_stats(out)) }
 int lq_plan_run(lq_engine* h, const lq_plan_args* a, lq_plan_summary* out, void* st) { LQ_H(h); if (!a || !out) return LQ_ERR_ARG; LQ_TRY(h->plan_run(a, out, (cudaStream_t)st)) }
+int lq_policy_wave(int wave_fixed, int wave_min, int wave_max, double growth, int tree_size) {
+    lq::WavePolicy p; memset(&p, 0, sizeof p);
+    p.fixed = wave_fixed; p.wmin = wave_min; p.wmax = wave_max; p.growth = growth;
+    return lq::policy_wave(p, tree_size);
+}
+int lq_policy_slice(int W, int rank, int world, int32_t* first, int32_t* count) {
+    if (!first || !count || world < 1 || rank < 0 || rank >= world || W < 0) return LQ_ERR_ARG;
+    int f = 0, c = 0;
+    lq::policy_slice(W, rank, world, &f, &c);
+    *first = f; *count = c;
+    return LQ_OK;
+}
 int lq_stop_word(lq_engine* h, int32_t** out) { LQ_H(h); if (!out) return LQ_ERR_ARG; LQ_TRY(h->stop_word(out)) }
 int lq_closest(lq_engine* h, const double* xg, const uint8_t* mask, int* id, void* st) {
     LQ_H(h); if (!xg || !id) return LQ_ERR_ARG; LQ_TRY(h->closest(xg, mask, id, (cudaStream_t)st)) }

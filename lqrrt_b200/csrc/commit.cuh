@@ -72,6 +72,7 @@ commit_x_kernel(TreeView<T> tv, WaveCtl* __restrict__ ctl, int wave_k,
     __shared__ int s_err;
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_wait();                          // launched early (PDL): the rollout kernel in front has finished from here on
     if (threadIdx.x == 0) s_err = 0;
     if (arrive) {                        // fused exchange: wait until every peer's results of this wave landed
         __syncthreads();

@@ -81,10 +81,25 @@ namespace lq {
         return code;                             \
     } while (0)
 
+// <<<>>> with the programmatic-dependent-launch attribute (see nearest.cuh pdl_wait): the kernel may start while
+// its predecessor in the stream drains.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_maybe_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, bool pdl,
+                                    Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static_assert(sizeof(lq_wave_stats) == 12 * sizeof(int), "device stats block must mirror lq_wave_stats");
 // partial-minimum slots per query: the old-tree scan writes [0, MAX_SPLIT_OLD), the delta scan (or the one full
 // scan of a stepwise wave) [MAX_SPLIT_OLD, MAX_SLOTS)
-constexpr int MAX_SPLIT_OLD = 192;
+constexpr int MAX_SPLIT_OLD = 384;
 constexpr int MAX_SPLIT_NEW = 128;
 constexpr int MAX_SLOTS = MAX_SPLIT_OLD + MAX_SPLIT_NEW;
 constexpr int MAX_SPLIT = MAX_SPLIT_NEW;
@@ -211,6 +226,7 @@ struct EngineImpl : lq_engine {
     int force_rescan = 0;                  // lq_set_option(LQ_OPT_FORCE_RESCAN): tests -- every query takes the rescan path
     int spec_scan = 1;                     // lq_set_option(LQ_OPT_SPECULATIVE_SCAN): old-tree scan on the side stream
     int stage_tables_on = 1;               // lq_set_option(LQ_OPT_STAGE_TABLES)
+    int pdl_on = 1;                        // lq_set_option(LQ_OPT_PDL): programmatic dependent launch of rollouts and commit
     // lq_set_option(LQ_OPT_SAMPLE_PREFETCH): sampler of the next wave on a side stream (stepwise driver)
     bool prefetch_on = false;
     cudaStream_t aux = nullptr;
@@ -344,6 +360,7 @@ struct EngineImpl : lq_engine {
             if (is_box) {
                 d.nbox = s.kind == LQ_FEAS_EFFORT_BOX ? M : N;
                 if (!s.lo || !s.hi) LQ_FAIL(LQ_ERR_ARG, "box primitive %d needs lo/hi", pi);
+                for (int k = 0; k < LQ_MAX_N; k++) { d.lo[k] = -Num<T>::inf(); d.hi[k] = Num<T>::inf(); }   // dims beyond nbox never trip
                 for (int k = 0; k < d.nbox; k++) { d.lo[k] = (T)s.lo[k]; d.hi[k] = (T)s.hi[k]; }
                 continue;
             }
@@ -423,21 +440,9 @@ struct EngineImpl : lq_engine {
                 if (int r = build_grid(s, d)) return r;
         }
 
-        // shared-memory staging plan for the rollout kernels: all tables of the small obstacle fields, as long
-        // as they fit next to four resident CTAs per SM
-        {
-            memset(&stage_plan, 0, sizeof stage_plan);
-            int total = 0;
-            for (int pi = 0; pi < md.feas.n_prims; pi++) {
-                const FeasPrim<T>& d = md.feas.prims[pi];
-                const bool tabular = d.kind == LQ_FEAS_CIRCLES_POINT || d.kind == LQ_FEAS_SPHERES_POINT ||
-                                     d.kind == LQ_FEAS_CIRCLES_CLOUD || d.kind == LQ_FEAS_BOXES_CLOUD;
-                if (!tabular || d.n_obs < 1) continue;
-                const int b = stage_bytes(d);
-                if (total + b <= 40 * 1024) { stage_plan.on[pi] = 1; total += b; }
-            }
-            stage_plan.bytes = total;
-        }
+        // shared-memory staging image for the rollout kernels: all tables of the small obstacle fields, as long as
+        // they fit next to four resident CTAs per SM, laid out as the kernels read them (models.cuh stage_tables)
+        if (int r = build_stage_image()) return r;
 
         // tree
         LQ_CUDA(t_state.alloc((size_t)N * cap));
@@ -588,6 +593,52 @@ struct EngineImpl : lq_engine {
         return LQ_OK;
     }
     std::vector<int> items_tmp;
+    DevBuf<unsigned char> stage_img;
+
+    int build_stage_image() {
+        memset(&stage_plan, 0, sizeof stage_plan);
+        for (int pi = 0; pi < LQ_MAX_PRIMS; pi++) stage_plan.off_obs[pi] = stage_plan.off_cs[pi] = stage_plan.off_ci[pi] = stage_plan.off_hull[pi] = -1;
+        std::vector<unsigned char> img;
+        auto put = [&](const void* src, size_t bytes) -> int {
+            const int off = (int)img.size();
+            img.resize(off + stage_align((int)bytes), 0);
+            memcpy(img.data() + off, src, bytes);
+            return off;
+        };
+        for (int pi = 0; pi < md.feas.n_prims; pi++) {
+            const FeasPrim<T>& d = md.feas.prims[pi];
+            const bool tabular = d.kind == LQ_FEAS_CIRCLES_POINT || d.kind == LQ_FEAS_SPHERES_POINT ||
+                                 d.kind == LQ_FEAS_CIRCLES_CLOUD || d.kind == LQ_FEAS_BOXES_CLOUD;
+            if (!tabular || d.n_obs < 1) continue;
+            int need = stage_align(d.n_obs * 4 * (int)sizeof(T));
+            if (d.cell_start) need += stage_align((d.n_cells + 1) * (int)sizeof(int)) + stage_align(d.n_items * (int)sizeof(int));
+            if (d.hull_axes) need += stage_align((d.hull_nx + d.hull_ny) * (int)sizeof(T));
+            if ((int)img.size() + need > 40 * 1024) continue;
+            // read the tables back from the device: they are what the un-staged path would read
+            std::vector<T> obs((size_t)d.n_obs * 4);
+            LQ_CUDA(cudaMemcpy(obs.data(), d.obs, obs.size() * sizeof(T), cudaMemcpyDeviceToHost));
+            stage_plan.off_obs[pi] = put(obs.data(), obs.size() * sizeof(T));
+            if (d.cell_start) {
+                std::vector<int> cs((size_t)d.n_cells + 1), ci((size_t)std::max(1, d.n_items));
+                LQ_CUDA(cudaMemcpy(cs.data(), d.cell_start, cs.size() * sizeof(int), cudaMemcpyDeviceToHost));
+                LQ_CUDA(cudaMemcpy(ci.data(), d.cell_items, (size_t)d.n_items * sizeof(int), cudaMemcpyDeviceToHost));
+                stage_plan.off_cs[pi] = put(cs.data(), cs.size() * sizeof(int));
+                stage_plan.off_ci[pi] = put(ci.data(), (size_t)d.n_items * sizeof(int));
+            }
+            if (d.hull_axes) {
+                std::vector<T> hx((size_t)d.hull_nx + d.hull_ny);
+                LQ_CUDA(cudaMemcpy(hx.data(), d.hull_axes, hx.size() * sizeof(T), cudaMemcpyDeviceToHost));
+                stage_plan.off_hull[pi] = put(hx.data(), hx.size() * sizeof(T));
+            }
+            stage_plan.on[pi] = 1;
+        }
+        stage_plan.bytes = (int)img.size();
+        if (!img.empty()) {
+            if (int r = upload(stage_img, img)) return r;
+            stage_plan.image = stage_img.p;
+        }
+        return LQ_OK;
+    }
 
     const T* const_metric_ptr() { return const_metric_ptr_impl(md.lqr, 0); }
     template <class L> static auto const_metric_ptr_impl(L& l, int) -> decltype((const T*)l.S) { return l.S; }
@@ -798,6 +849,9 @@ struct EngineImpl : lq_engine {
     }
 
     int scan_target() const { return 148 * (near_ctas_per_sm > 0 ? near_ctas_per_sm : (N <= 6 ? 16 : 8)); }
+    // the old-tree scan shares the GPU with the rollout chain of the wave before: more, shorter CTAs let the chain's
+    // (higher-priority) CTAs in sooner (measured on C4: 32 per SM 9.06 ms per plan, 16: 9.26, 8: 9.47)
+    int old_scan_target() const { return near_ctas_per_sm > 0 ? 148 * near_ctas_per_sm : 2 * scan_target(); }
 
     int nearest(const void* d_q, int W, int use_ignore, int* d_idx, void* d_cost, cudaStream_t st) override {
         LQ_CUDA(cudaSetDevice(device));
@@ -886,9 +940,9 @@ struct EngineImpl : lq_engine {
         const size_t sm = steer_coop_bytes<T, Lqr, LANES, BB>() + sp.bytes;                                    \
         auto kern = steer_x_kernel<T, Sys, Lqr, LANES, BB>;                                                    \
         if (int r = steer_smem(kern, sm)) return r;                                                            \
-        kern<<<(unsigned)((threads + BB - 1) / BB), BB, sm, st>>>(                                             \
+        LQ_CUDA(launch_maybe_pdl(kern, (unsigned)((threads + BB - 1) / BB), BB, sm, st, pdl_on != 0,          \
             md, sp, t_state.p, t_K.p, cap, t_ignore.p, tv.size, tv.n_ignored, w_ctl.p, slot, pin, nm,          \
-            samples_of(par), Wc, tries_of(par), use_ignore, force_rescan, w_xs.p, w_us.p, dst, Wc, flags, stopw); \
+            samples_of(par), Wc, tries_of(par), use_ignore, force_rescan, w_xs.p, w_us.p, dst, Wc, flags, stopw)); \
     } while (0)
         if (block == 128) LQ_STEER_X(128); else LQ_STEER_X(32);
 #undef LQ_STEER_X
@@ -1045,9 +1099,10 @@ struct EngineImpl : lq_engine {
     int launch_commit(int wave_k, const char* segs, int n_seg, int my_seg, int slots_ub, const WavePolicy& pol,
                       const unsigned* arrive, unsigned seq, int ring_slot, unsigned out_seq, cudaStream_t st) {
         const int ctas = std::max(1, (slots_ub + COMMIT_SLOTS - 1) / COMMIT_SLOTS);
-        commit_x_kernel<T><<<ctas, COMMIT_BLOCK, 0, st>>>(tv, w_ctl.p, wave_k, segs, seg_sz, n_seg, my_seg, w_xs.p, w_us.p,
-                                                          Wc, N, M, H, w_goal.p, w_goal.p + LQ_MAX_N, pol, d_ring + ring_slot, out_seq,
-                                                          arrive, seq, w_hor.p, md.hfactor, md.hlo, md.hhi);
+        LQ_CUDA(launch_maybe_pdl(commit_x_kernel<T>, (unsigned)ctas, COMMIT_BLOCK, 0, st, pdl_on != 0 && pol.device_schedule != 0,
+                                 tv, w_ctl.p, wave_k, segs, seg_sz, n_seg, my_seg, (const T*)w_xs.p, (const T*)w_us.p,
+                                 Wc, N, M, H, (const T*)w_goal.p, (const T*)(w_goal.p + LQ_MAX_N), pol, d_ring + ring_slot, out_seq,
+                                 arrive, seq, w_hor.p, md.hfactor, md.hlo, md.hhi));
         launches++;
         LQ_CUDA(cudaGetLastError());
         return LQ_OK;
@@ -1233,7 +1288,7 @@ struct EngineImpl : lq_engine {
             int ns_old = 0, ns_new = 0;
             if (spec) {
                 if (int r = launch_scan(samples_of(par), Wc, cub, d_count, nullptr, d_nold, n_old_ub, nullptr, use_ignore, par,
-                                        MAX_SPLIT_OLD, true, MAX_SPLIT_OLD, scan_target(), s_scan, &ns_old)) return r;
+                                        MAX_SPLIT_OLD, true, MAX_SPLIT_OLD, old_scan_target(), s_scan, &ns_old)) return r;
             }
             if (prof_on) cudaEventRecord(pev[ps][2], s_scan);
             LQ_CUDA(cudaEventRecord(ev_scan[k % EVR], s_scan));
@@ -1566,6 +1621,7 @@ struct EngineImpl : lq_engine {
         case LQ_OPT_SPECULATIVE_SCAN: spec_scan = value != 0; return LQ_OK;
         case LQ_OPT_FORCE_RESCAN: force_rescan = value != 0; return LQ_OK;
         case LQ_OPT_STAGE_TABLES: stage_tables_on = value != 0; return LQ_OK;
+        case LQ_OPT_PDL: pdl_on = value != 0; return LQ_OK;
         case LQ_OPT_STEER_BLOCK:
             if (value != 0 && value != 32 && value != 128) LQ_FAIL(LQ_ERR_ARG, "rollout CTA size must be 0 (auto), 32 or 128");
             steer_block = value; return LQ_OK;
@@ -1581,6 +1637,7 @@ struct EngineImpl : lq_engine {
         case LQ_OPT_FORCE_RESCAN: *value = force_rescan; return LQ_OK;
         case LQ_OPT_STAGE_TABLES: *value = stage_tables_on; return LQ_OK;
         case LQ_OPT_STEER_BLOCK: *value = steer_block; return LQ_OK;
+        case LQ_OPT_PDL: *value = pdl_on; return LQ_OK;
         default: LQ_FAIL(LQ_ERR_ARG, "unknown option %d", option);
         }
     }

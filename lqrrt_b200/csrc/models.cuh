@@ -22,19 +22,56 @@ template <> struct Num<double> {
     static __device__ __forceinline__ double inv_two_pi() { return 0.15915494309189535; }
 };
 
-// float: libm sincosf by default.  -DLQ_FAST_TRIG swaps in a one-period reduction + the SFU sine/cosine
-// (abs error ~5e-7); measured on C4 it shortens a rollout step by only ~3 % (profiles/README.md), so the
-// accurate version stays the default.  double always uses libm.
-#ifndef LQ_FAST_TRIG
-__device__ __forceinline__ void sincos_t(float a, float* s, float* c) { sincosf(a, s, c); }
-#else
+// float sine / cosine for the rollout's dependent chain: one Cody-Waite reduction by pi/2 and the two degree-7/8
+// minimax polynomials of the usual single-precision kernels (max error ~1 ulp on the reduced range), WITHOUT libm's
+// Payne-Hanek path for |a| > 1e5 rad inlined three times per rollout step (it is never taken -- headings are a few
+// turns at most -- but costs ~700 instructions of code per step and the instruction-cache misses that go with
+// them).  Arguments beyond the reduction's exact range are first folded by whole turns.  double uses libm.
 __device__ __forceinline__ void sincos_t(float a, float* s, float* c) {
-    const float r = fmaf(-6.283185307179586f, rintf(a * 0.15915494309189535f), a);
-    __sincosf(r, s, c);
+    if (fabsf(a) > 50000.f) a = fmaf(-6.283185307179586f, rintf(a * 0.15915494309189535f), a);
+    const float q = rintf(a * 0.63661977236758138f);            // nearest multiple of pi/2
+    const int iq = (int)q;
+    float r = fmaf(q, -1.5707962512969970703f, a);              // pi/2 split in three, each product exact inside the FMA
+    r = fmaf(q, -7.5497894158615963534e-08f, r);
+    r = fmaf(q, -5.3903029534742383927e-15f, r);
+    const float r2 = r * r;
+    float sp = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+    sp = fmaf(sp, r2, -1.6666654611e-1f);
+    sp = fmaf(sp * r2, r, r);
+    float cp = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    cp = fmaf(cp, r2, 4.166664568298827e-2f);
+    cp = fmaf(cp, r2, -0.5f);
+    cp = fmaf(cp, r2, 1.0f);
+    const float ss = (iq & 1) ? cp : sp, cc = (iq & 1) ? sp : cp;
+    *s = (iq & 2) ? -ss : ss;
+    *c = ((iq + 1) & 2) ? -cc : cc;
 }
-#endif
 __device__ __forceinline__ void sincos_t(double a, double* s, double* c) { sincos(a, s, c); }
 __device__ __forceinline__ float atan2_t(float y, float x) { return atan2f(y, x); }
+// atan2 for the float32 rollout chain: |error| < 2e-7 rad (odd degree-17 polynomial, Abramowitz & Stegun 4.4.49, on
+// min/max in [0, 1] with the SFU reciprocal), no special-case branches.  atan2(0, 0) = 0 regardless of the zeros'
+// signs and x = -0 counts as +0 -- callers that need IEEE's signed-zero cases (the reference's v = 0 quirk in the
+// rudder term) call atan2_t.
+__device__ __forceinline__ float atan2_fast(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float t = __fdividef(mn, mx);
+    t = mx == 0.f ? 0.f : t;
+    const float t2 = t * t;
+    float p = 0.0028662257f;
+    p = fmaf(p, t2, -0.0161657367f);
+    p = fmaf(p, t2, 0.0429096138f);
+    p = fmaf(p, t2, -0.0752896400f);
+    p = fmaf(p, t2, 0.1065626393f);
+    p = fmaf(p, t2, -0.1420889944f);
+    p = fmaf(p, t2, 0.1999355085f);
+    p = fmaf(p, t2, -0.3333314528f);
+    float r = fmaf(p * t2, t, t);
+    r = ay > ax ? 1.57079637f - r : r;
+    r = x < 0.f ? 3.14159274f - r : r;
+    return copysignf(r, y);
+}
+__device__ __forceinline__ double atan2_fast(double y, double x) { return atan2(y, x); }
 __device__ __forceinline__ double atan2_t(double y, double x) { return atan2(y, x); }
 __device__ __forceinline__ float rint_t(float a) { return rintf(a); }
 __device__ __forceinline__ double rint_t(double a) { return rint(a); }
@@ -51,7 +88,7 @@ __device__ __forceinline__ double sqrt_t(double a) { return sqrt(a); }
 // atan2(sg*c - cg*s, cg*c + sg*s) (demos/demo_boat_novice.py:112-117).
 template <typename T>
 __device__ __forceinline__ T wrap_sc(T s_from, T c_from, T s_to, T c_to) {
-    return atan2_t(s_to * c_from - c_to * s_from, c_to * c_from + s_to * s_from);
+    return atan2_fast(s_to * c_from - c_to * s_from, c_to * c_from + s_to * s_from);
 }
 
 // ---------------------------------------------------------------------------
@@ -64,7 +101,7 @@ template <typename T> struct BoatSys {            // demos/demo_boat_{novice,int
     static constexpr int N = 6, M = 3;
     static constexpr int KIND = LQ_SYS_BOAT;
     T invM[3], Dpos[3], Dneg[3], umax[3], B[12], invB[12], tmax[4];
-    T rudder, vpos0, vneg0;
+    T rudder, vpos0, vneg0, inv_vpos0, inv_vneg0;
     int thruster_clip, carlike, use_rudder;
 
     __host__ void unpack(const double* p) {
@@ -77,6 +114,7 @@ template <typename T> struct BoatSys {            // demos/demo_boat_{novice,int
         for (int i = 0; i < 12; i++) invB[i] = (T)p[k++];
         for (int i = 0; i < 4; i++) tmax[i] = (T)p[k++];
         rudder = (T)p[k++]; vpos0 = (T)p[k++]; vneg0 = (T)p[k++];
+        inv_vpos0 = (T)(1.0 / p[k - 2]); inv_vneg0 = (T)(1.0 / p[k - 1]);
         thruster_clip = p[k++] != 0.0; carlike = p[k++] != 0.0; use_rudder = p[k++] != 0.0;
     }
     static constexpr int NPARAMS = 46;
@@ -104,7 +142,7 @@ template <typename T> struct BoatSys {            // demos/demo_boat_{novice,int
             // atan2(+-0, +-0) of the rotated zero vector makes the term -h or pi - h instead of 0.
             T wr;
             if (sizeof(T) == 4 && !(vx == T(0) && vy == T(0))) {
-                wr = atan2_t(vy, vx);
+                wr = atan2_fast(vy, vx);
             } else {
                 const T ang = atan2_t(wy, wx);
                 T sg, cg;
@@ -135,8 +173,15 @@ template <typename T> struct BoatSys {            // demos/demo_boat_{novice,int
         xn[4] = vy + (invM[1] * (u[1] - D1 * vy)) * dt;
         xn[5] = vh + (invM[2] * (u[2] - D2 * vh)) * dt;
         if (carlike) {                              // intermediate:88-98, advanced:120-128
-            if (vx > T(0)) xn[5] = min_t(abs_t(xn[3] / vpos0), T(1)) * xn[5];
-            else if (vx < T(0)) xn[5] = min_t(abs_t(xn[3] / vneg0), T(1)) * xn[5];
+            // float32: |xn3 / vmax| as a product with the host-rounded reciprocal (one FMUL instead of the 10-instruction
+            // IEEE division on the chain; differs from the quotient by 1 ulp at most); float64 divides like the reference
+            if (sizeof(T) == 4) {
+                if (vx > T(0)) xn[5] = min_t(abs_t(xn[3] * inv_vpos0), T(1)) * xn[5];
+                else if (vx < T(0)) xn[5] = min_t(abs_t(xn[3] * inv_vneg0), T(1)) * xn[5];
+            } else {
+                if (vx > T(0)) xn[5] = min_t(abs_t(xn[3] / vpos0), T(1)) * xn[5];
+                else if (vx < T(0)) xn[5] = min_t(abs_t(xn[3] / vneg0), T(1)) * xn[5];
+            }
             if (xn[3] < T(0)) xn[3] = T(0);
         }
     }
@@ -233,24 +278,27 @@ __device__ __forceinline__ void erf_eval(uint32_t angle_mask, const T* xgoal, co
     }
 }
 
-// Same, with sin/cos of dim HD of both states supplied by the caller.
+// Same, with sin/cos of dim HD of both states supplied by the caller (the rollout caches them per state).  The common
+// case -- no wrapped dim, or only HD -- is straight-line code; other wrapped dims take the general path out of line,
+// so their sin/cos/atan2 code is not replicated N times into the rollout loop.
+template <typename T, int N>
+__device__ __noinline__ void erf_wrap_others(uint32_t rest_mask, const T* xgoal, const T* x, T* e) {
+    for (int i = 0; i < N; i++) {
+        if (rest_mask & (1u << i)) {
+            T s2, c2, sg2, cg2;
+            sincos_t(x[i], &s2, &c2);
+            sincos_t(xgoal[i], &sg2, &cg2);
+            e[i] = wrap_sc(s2, c2, sg2, cg2);
+        }
+    }
+}
 template <typename T, int N, int HD>
 __device__ __forceinline__ void erf_eval_sc(uint32_t angle_mask, const T* xgoal, const T* x, T* e, T sg, T cg, T s, T c) {
 #pragma unroll
-    for (int i = 0; i < N; i++) {
-        if (angle_mask & (1u << i)) {
-            if (i == HD) {
-                e[i] = wrap_sc(s, c, sg, cg);
-            } else {
-                T s2, c2, sg2, cg2;
-                sincos_t(x[i], &s2, &c2);
-                sincos_t(xgoal[i], &sg2, &cg2);
-                e[i] = wrap_sc(s2, c2, sg2, cg2);
-            }
-        } else {
-            e[i] = xgoal[i] - x[i];
-        }
-    }
+    for (int i = 0; i < N; i++) e[i] = xgoal[i] - x[i];
+    constexpr uint32_t hbit = HD >= 0 ? (1u << (HD < 0 ? 0 : HD)) : 0u;
+    if (HD >= 0 && (angle_mask & hbit)) e[HD < 0 ? 0 : HD] = wrap_sc(s, c, sg, cg);
+    if (angle_mask & ~hbit) erf_wrap_others<T, N>(angle_mask & ~hbit, xgoal, x, e);
 }
 
 // ---------------------------------------------------------------------------
@@ -695,16 +743,20 @@ __device__ __forceinline__ bool feasible_eval(const FeasSet<T>& fs, const T* x, 
     for (int pi = 0; pi < fs.n_prims; pi++) {
         const FeasPrim<T>& p = fs.prims[pi];
         switch (p.kind) {
-        case LQ_FEAS_STATE_BOX:
+        case LQ_FEAS_STATE_BOX: {                   // unused dims carry -inf / +inf bounds (engine.cuh init)
+            bool out = false;
 #pragma unroll
-            for (int i = 0; i < N; i++)
-                if (i < p.nbox && (x[i] > p.hi[i] || x[i] < p.lo[i])) return false;
+            for (int i = 0; i < N; i++) out = out || x[i] > p.hi[i] || x[i] < p.lo[i];
+            if (out) return false;
             break;
-        case LQ_FEAS_EFFORT_BOX:
+        }
+        case LQ_FEAS_EFFORT_BOX: {
+            bool out = false;
 #pragma unroll
-            for (int i = 0; i < M; i++)
-                if (i < p.nbox && abs_t(u[i]) > p.hi[i]) return false;
+            for (int i = 0; i < M; i++) out = out || abs_t(u[i]) > p.hi[i];
+            if (out) return false;
             break;
+        }
         case LQ_FEAS_STATE_REGION: {
             bool inside = true;
 #pragma unroll
@@ -833,62 +885,65 @@ __device__ __forceinline__ bool feasible_eval(const FeasSet<T>& fs, const T* x, 
 }
 
 // ---- shared-memory staging of the obstacle tables (rollout kernels) --------------------------------------
-// Host-side plan: which primitives are staged and how many bytes that takes; the kernel lays the tables out
-// in this order in dynamic shared memory, each 16-byte aligned.
+// The engine keeps one contiguous IMAGE of all staged tables in global memory, laid out exactly as the kernel
+// wants them in shared memory (every table 16-byte aligned; host-side layout in engine.cuh build_stage_image).
+// A CTA brings it in with ONE bulk asynchronous copy (TMA: cp.async.bulk.shared.global, completion counted on
+// an mbarrier), i.e. one L2 round trip for all ~18 KB instead of a dependent load -> store chain per element.
 struct StagePlan {
     int on[LQ_MAX_PRIMS];
-    int bytes;                 // total dynamic shared memory the staged tables need
+    int off_obs[LQ_MAX_PRIMS], off_cs[LQ_MAX_PRIMS], off_ci[LQ_MAX_PRIMS], off_hull[LQ_MAX_PRIMS];   // byte offsets, -1 = none
+    int bytes;                 // image size = dynamic shared memory the staged tables need (multiple of 16)
+    const unsigned char* image;
 };
 
 __host__ __device__ inline int stage_align(int b) { return (b + 15) & ~15; }
 
-template <typename T>
-__host__ __device__ inline int stage_bytes(const FeasPrim<T>& p) {
-    int b = stage_align(p.n_obs * 4 * (int)sizeof(T));
-    if (p.cell_start) b += stage_align((p.n_cells + 1) * (int)sizeof(int)) + stage_align(p.n_items * (int)sizeof(int));
-    if (p.hull_axes) b += stage_align((p.hull_nx + p.hull_ny) * (int)sizeof(T));
-    return b;
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src), "r"(bytes),
+                   "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned done = 0;
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    }
 }
 
-// Called by every thread of the CTA; `tabs` (LQ_MAX_PRIMS entries) and `raw` live in shared memory.  Ends
-// with a __syncthreads().
+// Called by every thread of the CTA; `tabs` (LQ_MAX_PRIMS entries), `bar` and `raw` (16-byte aligned, sp.bytes
+// long) live in shared memory.  Returns once the tables are readable by the whole CTA.
 template <typename T>
-__device__ __forceinline__ void stage_tables(const FeasSet<T>& fs, const StagePlan& sp, FeasTab<T>* tabs, unsigned char* raw) {
-    int off = 0;
-    for (int pi = 0; pi < fs.n_prims; pi++) {
-        const FeasPrim<T>& p = fs.prims[pi];
-        FeasTab<T> t{p.obs, p.cell_start, p.cell_items, p.hull_axes};
-        const bool tabular = p.kind == LQ_FEAS_CIRCLES_POINT || p.kind == LQ_FEAS_SPHERES_POINT ||
-                             p.kind == LQ_FEAS_CIRCLES_CLOUD || p.kind == LQ_FEAS_BOXES_CLOUD;
-        if (tabular && sp.on[pi]) {
-            {
-                const int4* src = reinterpret_cast<const int4*>(p.obs);
-                int4* dst = reinterpret_cast<int4*>(raw + off);
-                const int n16 = p.n_obs * 4 * (int)sizeof(T) / 16;
-                for (int k = threadIdx.x; k < n16; k += blockDim.x) dst[k] = src[k];
-                t.obs = reinterpret_cast<const T*>(raw + off);
-                off += stage_align(p.n_obs * 4 * (int)sizeof(T));
-            }
-            if (p.cell_start) {
-                int* d1 = reinterpret_cast<int*>(raw + off);
-                for (int k = threadIdx.x; k < p.n_cells + 1; k += blockDim.x) d1[k] = p.cell_start[k];
-                t.cell_start = d1;
-                off += stage_align((p.n_cells + 1) * (int)sizeof(int));
-                int* d2 = reinterpret_cast<int*>(raw + off);
-                for (int k = threadIdx.x; k < p.n_items; k += blockDim.x) d2[k] = p.cell_items[k];
-                t.cell_items = d2;
-                off += stage_align(p.n_items * (int)sizeof(int));
-            }
-            if (p.hull_axes) {
-                T* d3 = reinterpret_cast<T*>(raw + off);
-                for (int k = threadIdx.x; k < p.hull_nx + p.hull_ny; k += blockDim.x) d3[k] = p.hull_axes[k];
-                t.hull_axes = d3;
-                off += stage_align((p.hull_nx + p.hull_ny) * (int)sizeof(T));
-            }
+__device__ __forceinline__ void stage_tables(const FeasSet<T>& fs, const StagePlan& sp, FeasTab<T>* tabs, unsigned char* raw,
+                                             unsigned long long* bar) {
+    if (threadIdx.x == 0) {
+        if (sp.bytes > 0) {
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, (unsigned)sp.bytes);
+            bulk_copy_g2s(raw, sp.image, (unsigned)sp.bytes, bar);
         }
-        if (threadIdx.x == 0) tabs[pi] = t;
+        for (int pi = 0; pi < fs.n_prims; pi++) {
+            const FeasPrim<T>& p = fs.prims[pi];
+            FeasTab<T> t{p.obs, p.cell_start, p.cell_items, p.hull_axes};
+            if (sp.on[pi]) {
+                if (sp.off_obs[pi] >= 0) t.obs = reinterpret_cast<const T*>(raw + sp.off_obs[pi]);
+                if (sp.off_cs[pi] >= 0) t.cell_start = reinterpret_cast<const int*>(raw + sp.off_cs[pi]);
+                if (sp.off_ci[pi] >= 0) t.cell_items = reinterpret_cast<const int*>(raw + sp.off_ci[pi]);
+                if (sp.off_hull[pi] >= 0) t.hull_axes = reinterpret_cast<const T*>(raw + sp.off_hull[pi]);
+            }
+            tabs[pi] = t;
+        }
     }
-    __syncthreads();
+    __syncthreads();                       // barrier initialised, table pointers published
+    if (sp.bytes > 0) mbar_wait(bar, 0);   // ... and the image has landed
 }
 
 }  // namespace lq

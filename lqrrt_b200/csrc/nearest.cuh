@@ -54,7 +54,15 @@ struct ScanArgs {
 
 struct ScanRange { int qb, split, W, n0, n1; bool mask_on; };
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor in the stream is still running and blocks in pdl_wait() until the predecessor has
+// finished and its writes are visible; pdl_trigger() in the predecessor lets that early start happen as soon as every
+// one of its CTAs has got going.  Both are no-ops for plain launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ bool scan_setup(const ScanArgs& a, int tile, int queries_per_cta, ScanRange& r) {
+    pdl_trigger();                      // the rollout kernel behind a delta scan may set itself up meanwhile
     r.qb = blockIdx.x % a.nqb;
     r.split = blockIdx.x / a.nqb;
     r.W = a.d_count ? min(*a.d_count, a.W) : a.W;

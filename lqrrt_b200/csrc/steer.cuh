@@ -185,8 +185,9 @@ steer_kernel(Model<T, Sys, Lqr> md, StagePlan stg,
     constexpr int N = Sys::N, M = Sys::M;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ FeasTab<T> tabs[LQ_MAX_PRIMS];
+    __shared__ __align__(8) unsigned long long stage_bar;
     T* coop = reinterpret_cast<T*>(dyn_smem) + (size_t)(threadIdx.x / LANES) * Lqr::COOP_SCALARS;
-    stage_tables(md.feas, stg, tabs, dyn_smem + steer_coop_bytes<T, Lqr, LANES, BLOCK>());
+    stage_tables(md.feas, stg, tabs, dyn_smem + steer_coop_bytes<T, Lqr, LANES, BLOCK>(), &stage_bar);
     const int j = (blockIdx.x * BLOCK + threadIdx.x) / LANES;
     const int lane = threadIdx.x % LANES;
     if (j >= W) return;                    // whole groups leave together (BLOCK % LANES == 0)
@@ -306,6 +307,7 @@ steer_x_kernel(Model<T, Sys, Lqr> md, StagePlan stg,
     constexpr int NCH = RW / PER16;
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     __shared__ FeasTab<T> tabs[LQ_MAX_PRIMS];
+    __shared__ __align__(8) unsigned long long stage_bar;
     __shared__ bool s_last;
     T* coop = reinterpret_cast<T*>(dyn_smem) + (size_t)(threadIdx.x / LANES) * Lqr::COOP_SCALARS;
 
@@ -324,8 +326,10 @@ steer_x_kernel(Model<T, Sys, Lqr> md, StagePlan stg,
     }
     // nothing to roll out in this CTA: skip the table staging
     const bool cta_active = blockIdx.x * (BLOCK / LANES) < count;
-    if (cta_active) stage_tables(md.feas, stg, tabs, dyn_smem + steer_coop_bytes<T, Lqr, LANES, BLOCK>());
+    if (cta_active) stage_tables(md.feas, stg, tabs, dyn_smem + steer_coop_bytes<T, Lqr, LANES, BLOCK>(), &stage_bar);
 
+    pdl_trigger();                      // the commit kernel may be launched; it waits for this grid to finish
+    pdl_wait();                         // the scan in front of this kernel has finished: its partial minima are visible
     if (active) {
         T x[N], xt[N], K[M * N];
 #pragma unroll

@@ -143,3 +143,33 @@ def test_bench_cli_defaults():
     ns = captured['ns']
     assert (ns.gpus, ns.config, ns.impl, ns.wave, ns.growth, ns.nearest, ns.prefetch) == (1, 'c4', 'ours', 8192, 2.0, None, None)
     assert ns.steps >= 1 and ns.warmup >= 3
+
+
+def test_device_schedule_rule_mirrors_the_host_rule():
+    """The commit kernel sizes waves with policy_wave / policy_slice (csrc/wave.cuh, exported as plain host functions):
+    they must agree with lqrrt_b200.waves.wave_size / partition, which the host-scheduled loop and the multi-rank
+    gloo test use, for every size the planner can see -- no GPU needed."""
+    import ctypes as C
+    from lqrrt_b200 import _native, waves
+    lib = _native.load_library()
+    rng = np.random.RandomState(0)
+    for _ in range(4000):
+        n = int(rng.choice([1, 2, 33, 100, 4095, 4096, 4097, 10 ** 5, 10 ** 6, int(rng.randint(1, 2 * 10 ** 6))]))
+        growth = float(rng.choice([0.5, 1.0, 2.0, 3.7, 4.0]))
+        wmax = int(rng.choice([32, 512, 8192, 65536]))
+        fixed = int(rng.choice([0, 0, 0, 1, 64, 1000]))
+        want = waves.wave_size(n, fixed or None, wave_min=32, wave_max=wmax, growth=growth)
+        assert lib.lq_policy_wave(fixed, 32, wmax, growth, n) == want
+        world = int(rng.choice([1, 2, 3, 4, 8])); rank = int(rng.randint(world))
+        f = C.c_int32(); c = C.c_int32()
+        assert lib.lq_policy_slice(want, rank, world, C.byref(f), C.byref(c)) == 0
+        assert (f.value, c.value) == waves.partition(want, rank, world)
+    # slices tile the wave in rank order
+    for W in (0, 1, 7, 8192, 8191):
+        for world in (1, 2, 3, 8):
+            pos = 0
+            for r in range(world):
+                first, count = waves.partition(W, r, world)
+                assert first == pos
+                pos += count
+            assert pos == W
