@@ -280,7 +280,7 @@ def goal_leg(prob, args, comm, local, plans):
     `--plan-wave` samples -- depth grows one edge per wave and the goal is >= 130 edges away), stopping at the first
     plan found (min_time = 0).  Outside the timed region of `value`."""
     planner = prob.make_planner(dtype=args.dtype, wave=None, wave_max=args.plan_wave, wave_growth=1.0, max_nodes=prob.max_nodes,
-                                min_time=0.0, max_time=10.0, comm=comm, device=local,
+                                min_time=0.0, max_time=10.0, comm=comm, device=local, lag=1,
                                 exchange=os.environ.get('LQRRT_EXCHANGE', 'peer'))
     ms = []; T = []; nodes = []; waves = []; reached = 0
     for s in range(plans + 1):
@@ -293,7 +293,7 @@ def goal_leg(prob, args, comm, local, plans):
         if planner.plan_reached_goal:
             reached += 1
             ms.append(dt * 1e3); T.append(float(planner.T)); nodes.append(planner.tree.size); waves.append(planner.stats['waves'])
-    out = {"policy": "adaptive clamp(N, 32, {}) waves, stop at the first plan (min_time 0)".format(args.plan_wave),
+    out = {"policy": "adaptive clamp(N, 32, {}) waves, lag 1, stop at the first plan (min_time 0)".format(args.plan_wave),
            "plans_reaching_goal": "{}/{}".format(reached, plans)}
     if reached:
         out.update({"time_to_first_plan_ms": float(np.mean(ms)), "time_to_first_plan_ms_max": float(np.max(ms)),
@@ -327,7 +327,7 @@ def run_gpu_arm(args):
     planner = prob.make_planner(dtype=args.dtype, wave=None, wave_max=wave_max, wave_growth=args.growth, max_nodes=prob.max_nodes,
                                 min_time=1e9, max_time=1e9, comm=comm, device=local,
                                 exchange=os.environ.get('LQRRT_EXCHANGE', 'peer'),
-                                nearest_kernel=args.nearest, prefetch=args.prefetch, schedule=args.schedule)
+                                nearest_kernel=args.nearest, prefetch=args.prefetch, schedule=args.schedule, lag=args.lag)
     packed = planner.nearest_kernel != 'scalar' and args.dtype == 'f32'
     # FMA-pipe cycles per (query, node) pair of the scan's inner loop, n dims of which w wrap (cuobjdump -sass of
     # csrc/nearest.cuh, checked against ncu's instruction counts in profiles/README.md): FFMA2/FADD2 hold the pipe 2
@@ -358,13 +358,16 @@ def run_gpu_arm(args):
     barrier()
     with ClockSampler(local) as clk:
         host_times = []; dev_ms = []; nodes = []; samples = []; waves = []; launches = 0; d2h = 0; h2d = 0
-        phases = np.zeros(3); reached = 0; depth = []; plan_T = []
+        phases = np.zeros(3); reached = 0; depth = []; plan_T = []; hostpipe = np.zeros(3)
         for s in range(args.steps):
             host_s, st = one_plan(s)
             host_times.append(host_s); dev_ms.append(st['device_ms']); nodes.append(st['nodes'] - 1)
             samples.append(st['samples']); waves.append(st['waves']); launches += st['gpu_launches']
             d2h += st['d2h_bytes']; h2d += st['h2d_bytes']
             phases += [st['host_setup_s'], st['host_loop_s'], st['host_closeout_s']]
+            hp = st.get('host_pipeline_ms')
+            if hp:
+                hostpipe += [hp['enqueue_ms'], hp['wait_ms'], hp['callback_ms']]
             reached += int(planner.plan_reached_goal); depth.append(len(planner.node_seq)); plan_T.append(float(planner.T))
         barrier()
     prof = planner._engine.profile_read()
@@ -425,6 +428,8 @@ def run_gpu_arm(args):
             "config": {"workload": workload_name(prob, args.config), "max_nodes": int(prob.max_nodes),
                        "wave": "adaptive clamp({:g}*N, 32, {}), wave k sized from the tree wave k-1 started with".format(args.growth, wave_max),
                        "wave_per_gpu_max": wave_max // world, "schedule": schedule_used,
+                       "lag": "{} ({})".format(planner.stats.get('lag'), "pipelined waves: wave k searches the tree committed by wave k-2"
+                                               if planner.stats.get('lag') == 2 else "wave k searches the tree committed by wave k-1"),
                        "waves_per_step": float(np.mean(waves)), "samples_per_step": float(np.mean(samples)),
                        "yield": total_nodes / float(np.sum(samples)), "sampler": "philox4x32-10 on device, new seed per step",
                        "nearest_kernel": planner.nearest_kernel,
@@ -437,7 +442,8 @@ def run_gpu_arm(args):
                              "grows a new tree from new samples (no reuse between timed steps)"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
                     "ms_per_step": tot_host / args.steps * 1e3,
-                    "host_ms_per_step": dict(zip(("setup", "wave_loop", "closeout"), (phases / args.steps * 1e3).round(3).tolist()))},
+                    "host_ms_per_step": dict(zip(("setup", "wave_loop", "closeout"), (phases / args.steps * 1e3).round(3).tolist())),
+                    "wave_loop_host_ms_per_step": dict(zip(("enqueue", "wait_for_counters", "callback"), (hostpipe / args.steps).round(3).tolist()))},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32_pipe", "kernel": "nearest_diag_pk_kernel" if packed else "nearest_diag_kernel",
                          "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
@@ -488,6 +494,9 @@ def main():
     ap.add_argument('--nearest', default=None, help="nearest-scan kernel (default: the planner's)")
     ap.add_argument('--prefetch', default=None, type=int, choices=[0, 1], help="side-stream sampler prefetch of the host-scheduled loop")
     ap.add_argument('--schedule', default=None, choices=['device', 'host'], help="wave scheduling (default: the planner's, 'device')")
+    ap.add_argument('--lag', type=int, default=2, choices=[1, 2],
+                    help="wave semantics of the throughput leg: 2 = pipelined waves (wave k searches the tree of wave k-2; the "
+                         "Planner's own default is 1, which the goal-reaching leg uses)")
     ap.add_argument('--plan-leg', type=int, default=10, help="goal-reaching plans timed after the throughput steps (0 = skip)")
     ap.add_argument('--plan-wave', type=int, default=512, help="wave cap of the goal-reaching policy")
     ap.add_argument('--cpu-seconds', type=float, default=15.0)

@@ -199,9 +199,10 @@ int lq_wave_stats_get(lq_engine* h, lq_wave_stats* out);
  * Planner.update_plan's `while True:` (planner.py:233-311) as one call: waves of Philox samples are sized on the
  * device (W = clamp(int(growth * N), wave_min, wave_max), or wave_fixed), enqueued `depth` waves ahead of the
  * counters the host has seen, and the scan of the part of the tree a wave cannot have changed runs on a side
- * stream under the previous wave's rollouts and commit.  Wave k is sized from the tree size wave k-1 started
- * with (waves 0 and 1 from the initial tree); the nodes it appends are exactly those of the stepwise calls
- * lq_wave_expand / lq_wave_commit with the same sizes.
+ * stream under the previous wave's rollouts and commit (lag 1) -- or whole waves overlap pairwise (lag 2, see
+ * `lag`).  Wave k is sized from the tree size wave k-1 started with (waves 0 and 1 from the initial tree); the
+ * nodes it appends are exactly those of the stepwise calls lq_wave_expand / lq_wave_commit with the same sizes
+ * (and the same lag).
  *   on_wave   called on the caller's thread once per committed wave, in order, with that wave's counters;
  *             returns 0 to go on, 1 to stop (planner.py:293/311: done) or 2 (planner.py:289: killed).  The
  *             request reaches the device through mapped host memory; `flags` of the counters tell when it
@@ -219,6 +220,9 @@ typedef struct lq_plan_args {
     int32_t use_ignore;            /* pruning (planner.py:239-245) */
     int32_t world, rank;
     int32_t depth;                 /* waves in flight ahead of the host (0 = default) */
+    int32_t lag;                   /* 1: wave k searches the tree as committed by wave k-1 (speculative old-tree scan + delta scan);
+                                      2: pipelined waves -- wave k searches the tree (nodes and ignore marks) as committed by wave
+                                      k-2, so the rollouts of two consecutive waves are in flight together.  0 = 1. */
     lq_wave_callback on_wave;
     void* user;
 } lq_plan_args;
@@ -229,6 +233,9 @@ typedef struct lq_plan_summary {
     int32_t reserved;
     int64_t samples;
     double device_ms;              /* CUDA-event time of the wave pipeline on its own stream */
+    double host_enqueue_ms;        /* host time spent enqueuing waves / waiting for counters / in on_wave: if the first */
+    double host_wait_ms;           /* approaches device_ms the pipeline is fed too slowly (launch-bound) */
+    double host_callback_ms;
     lq_wave_stats last;
 } lq_plan_summary;
 int lq_plan_run(lq_engine* h, const lq_plan_args* args, lq_plan_summary* out, void* stream);
@@ -258,6 +265,14 @@ int lq_mark_ignore(lq_engine* h, const int32_t* h_ids, int count, void* stream);
 /* Tree.climb, tree.py:100-117: node ids from the seed (first) to `node` (last), walked on the device so a
  * plan read-out does not have to download the whole parent array. */
 int lq_climb(lq_engine* h, int node, int32_t* h_ids, int max_len, int* h_len, void* stream);
+
+/* The plan in one call (planner.py:266-281 when the goal was reached, :313-324 otherwise): node >= 0 climbs from that
+ * node; node < 0 first finds the node closest to h_xguide as lq_closest does.  h_ids receives the path seed-first
+ * (*h_len entries, at most max_len); h_x (max_len x H x n), h_u (max_len x H x m), h_edge_len, when non-NULL, the
+ * edges of those nodes in the same order (zeros beyond an edge's length and for edges held by another GPU, as
+ * lq_download_edges).  Two host synchronisations in total. */
+int lq_plan_readout(lq_engine* h, int node, const double* h_xguide, const uint8_t* h_colmask, int max_len,
+                    int32_t* h_ids, int* h_len, double* h_x, double* h_u, int32_t* h_edge_len, void* stream);
 
 /* ---- read-back (Tree.state / pID / lqr / x_seq / u_seq, tree.py:62-70) --- */
 int lq_download_nodes(lq_engine* h, int first, int count, double* h_state, int32_t* h_parent,

@@ -62,12 +62,13 @@ class lq_plan_args(C.Structure):
     _fields_ = [('seed', C.c_uint64), ('wave_ctr0', C.c_uint32), ('wave_fixed', C.c_int32),
                 ('wave_min', C.c_int32), ('wave_max', C.c_int32), ('growth', C.c_double),
                 ('use_ignore', C.c_int32), ('world', C.c_int32), ('rank', C.c_int32), ('depth', C.c_int32),
-                ('on_wave', WAVE_CALLBACK), ('user', C.c_void_p)]
+                ('lag', C.c_int32), ('on_wave', WAVE_CALLBACK), ('user', C.c_void_p)]
 
 
 class lq_plan_summary(C.Structure):
     _fields_ = [('waves', C.c_int32), ('waves_enqueued', C.c_int32), ('stop_code', C.c_int32), ('reserved', C.c_int32),
-                ('samples', C.c_int64), ('device_ms', C.c_double), ('last', lq_wave_stats)]
+                ('samples', C.c_int64), ('device_ms', C.c_double), ('host_enqueue_ms', C.c_double),
+                ('host_wait_ms', C.c_double), ('host_callback_ms', C.c_double), ('last', lq_wave_stats)]
 
 
 # every symbol include/lqrrt_b200.h declares: (restype, argtypes)
@@ -97,6 +98,7 @@ SYMBOLS = {
     'lq_wave_stats_get': (C.c_int, [_P, C.POINTER(lq_wave_stats)]),
     'lq_plan_run': (C.c_int, [_P, C.POINTER(lq_plan_args), C.POINTER(lq_plan_summary), _P]),
     'lq_stop_word': (C.c_int, [_P, C.POINTER(C.POINTER(C.c_int32))]),
+    'lq_plan_readout': (C.c_int, [_P, C.c_int, _D, _U8, C.c_int, _I, C.POINTER(C.c_int), _D, _D, _I, _P]),
     'lq_policy_wave': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]),
     'lq_policy_slice': (C.c_int, [C.c_int, C.c_int, C.c_int, _I, _I]),
     'lq_closest': (C.c_int, [_P, _D, _U8, C.POINTER(C.c_int), _P]),
@@ -343,7 +345,7 @@ class Engine(object):
         return st
 
     def plan_run(self, seed, wave_ctr0, wave_fixed, wave_min, wave_max, growth, use_ignore, on_wave=None,
-                 world=1, rank=0, depth=0, stream=None):
+                 world=1, rank=0, depth=0, stream=None, lag=1):
         """The whole expand loop of one plan on the device-scheduled pipeline (lq_plan_run).  `on_wave(stats)`
         is called once per committed wave and returns 0 / 1 (done) / 2 (kill).  Returns the summary struct."""
         err = []
@@ -359,7 +361,7 @@ class Engine(object):
         a.seed = int(seed) & 0xFFFFFFFFFFFFFFFF; a.wave_ctr0 = int(wave_ctr0) & 0xFFFFFFFF
         a.wave_fixed = int(wave_fixed or 0); a.wave_min = int(wave_min); a.wave_max = int(wave_max)
         a.growth = float(growth); a.use_ignore = int(bool(use_ignore)); a.world = int(world); a.rank = int(rank)
-        a.depth = int(depth); a.on_wave = cb; a.user = None
+        a.depth = int(depth); a.lag = int(lag); a.on_wave = cb; a.user = None
         out = lq_plan_summary()
         rc = self.lib.lq_plan_run(self.h, C.byref(a), C.byref(out), self._stream(stream))
         if err:
@@ -367,6 +369,28 @@ class Engine(object):
         self._ck(rc)
         self.d2h_bytes += out.waves * 64
         return out
+
+    def plan_readout(self, node=None, xguide=None, colmask=None, max_len=4096, stream=None):
+        """[closest-to-guide ->] climb -> edges of the path in one call.  Returns (ids, hx, hu, edge_len); grows
+        max_len and retries if the path is longer."""
+        xg = None if xguide is None else _c64(xguide)
+        mk = None if colmask is None else np.ascontiguousarray(colmask, dtype=np.uint8)
+        while True:
+            ids = np.zeros(max_len, dtype=np.int32); ln = C.c_int(0)
+            hx = np.zeros((max_len, self.H, self.n)); hu = np.zeros((max_len, self.H, self.m))
+            el = np.zeros(max_len, dtype=np.int32)
+            rc = self.lib.lq_plan_readout(self.h, -1 if node is None else int(node), None if xg is None else _dp(xg),
+                                          None if mk is None else mk.ctypes.data_as(_U8), int(max_len), _ip(ids), C.byref(ln),
+                                          _dp(hx), _dp(hu), _ip(el), self._stream(stream))
+            if rc == -3 and b'longer than' in self.lib.lq_last_error(self.h) and max_len < (1 << 22):
+                max_len *= 8
+                continue
+            self._ck(rc)
+            break
+        L = ln.value
+        self.h2d_bytes += self.n * (self.n + 1) * self.elt if node is None else 4
+        self.d2h_bytes += 4 * (max_len + 2) + L * (self.H * (self.n + self.m) * self.elt + 4)
+        return ids[:L].tolist(), hx[:L], hu[:L], el[:L]
 
     def request_stop(self, code):
         """Write the stop word the rollout kernels poll (callable from any thread; 1 = done, 2 = kill)."""

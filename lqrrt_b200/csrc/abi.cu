@@ -98,6 +98,10 @@ int lq_wave_records(lq_engine* h, void** d, uint64_t* bytes) { LQ_H(h); LQ_TRY(h
 int lq_wave_commit(lq_engine* h, const void* rec, int nseg, int myseg, void* st) { LQ_H(h); LQ_TRY(h->wave_commit(rec, nseg, myseg, (cudaStream_t)st)) }
 int lq_wave_stats_get(lq_engine* h, lq_wave_stats* out) { LQ_H(h); LQ_TRY(h->wave_stats(out)) }
 int lq_plan_run(lq_engine* h, const lq_plan_args* a, lq_plan_summary* out, void* st) { LQ_H(h); if (!a || !out) return LQ_ERR_ARG; LQ_TRY(h->plan_run(a, out, (cudaStream_t)st)) }
+int lq_plan_readout(lq_engine* h, int node, const double* xg, const uint8_t* mask, int max_len, int32_t* ids, int* len,
+                    double* x, double* u, int32_t* elen, void* st) {
+    LQ_H(h); if (!ids || !len || (x && (!u || !elen))) return LQ_ERR_ARG;
+    LQ_TRY(h->plan_readout(node, xg, mask, max_len, ids, len, x, u, elen, (cudaStream_t)st)) }
 int lq_policy_wave(int wave_fixed, int wave_min, int wave_max, double growth, int tree_size) {
     lq::WavePolicy p; memset(&p, 0, sizeof p);
     p.fixed = wave_fixed; p.wmin = wave_min; p.wmax = wave_max; p.growth = growth;

@@ -17,15 +17,15 @@
 namespace lq {
 
 template <typename T>
-__device__ __forceinline__ void mark_path(const TreeView<T>& tv, int node) {
+__device__ __forceinline__ void mark_path(const TreeView<T>& tv, int copy, int node) {
     // planner.py:266-270: ignores |= climb(node).  Stops at the first ancestor that is already marked:
     // whoever marked it also walks (or walked) on to the seed.
     while (node >= 0) {
-        unsigned* word = (unsigned*)(tv.ignore + (node & ~3));
+        unsigned* word = (unsigned*)(tv.ignore[copy] + (node & ~3));
         const unsigned bit = 1u << (8 * (node & 3));
         const unsigned old = atomicOr(word, bit);
         if (old & bit) break;
-        atomicAdd(tv.n_ignored, 1);
+        atomicAdd(tv.n_ignored2[copy], 1);
         node = tv.parent[node];
     }
 }
@@ -47,7 +47,7 @@ static __global__ void ctl_start_kernel(WaveCtl* ctl, const int* d_size, WavePol
         if (k < 2) { s.W = W; policy_slice(W, pol.rank, pol.world, &s.first, &s.count); }
         ctl->ring[k] = s;
     }
-    ctl->stopped = 0; ctl->acc[0] = ctl->acc[1] = ctl->acc[2] = 0; ctl->done_steer = 0; ctl->done_commit = 0;
+    ctl->stopped = 0; ctl->acc[0] = ctl->acc[1] = ctl->acc[2] = 0; ctl->done_steer[0] = ctl->done_steer[1] = 0; ctl->done_commit = 0;
 }
 
 constexpr int COMMIT_BLOCK = 128;
@@ -67,7 +67,7 @@ commit_x_kernel(TreeView<T> tv, WaveCtl* __restrict__ ctl, int wave_k,
                 const T* __restrict__ goal_lo, const T* __restrict__ goal_hi,
                 WavePolicy pol, DevStats* __restrict__ out, unsigned out_seq,
                 const unsigned* __restrict__ arrive, unsigned seq,
-                int* __restrict__ horizon, int hfactor, int hlo, int hhi) {
+                int* __restrict__ horizon, int hfactor, int hlo, int hhi, int copy, int lag2) {
     __shared__ int s_part[COMMIT_BLOCK / 32];
     __shared__ int s_err;
     __shared__ bool s_last;
@@ -92,6 +92,14 @@ commit_x_kernel(TreeView<T> tv, WaveCtl* __restrict__ ctl, int wave_k,
     }
     const int old_size = *tv.size;
     const int rw = rec_words<T>(N, M);
+    // a plan that has stopped appends nothing more (with pipelined waves the rollouts of the wave after the stop were
+    // already in flight when the stop was decided)
+    const bool dead = pol.device_schedule && ctl->stopped != 0;
+    if (lag2) {                          // replay the goal paths of the commit before into this commit's copy of the marks
+        const int n = min(*tv.goal_count[copy ^ 1], tv.goal_cap);
+        for (int i = blockIdx.x * COMMIT_BLOCK + threadIdx.x; i < n; i += gridDim.x * COMMIT_BLOCK)
+            mark_path(tv, copy, tv.goal_list[copy ^ 1][i]);
+    }
 
     // global slot g -> (segment, sample); segments hold HDR_SAMPLED samples each.  The CTA's threads split the
     // metas that precede its 32 slots; lane `lane` of every warp owns slot g0 + lane.
@@ -104,7 +112,16 @@ commit_x_kernel(TreeView<T> tv, WaveCtl* __restrict__ ctl, int wave_k,
         const int c = min(max(((const int*)base)[HDR_SAMPLED], 0), Wc);
         const SegView<T> sv = seg_view<T>((void*)base, Wc, N, M);
         const int upto = min(c, g0 - off);                      // this segment's samples that precede the CTA's slots
-        for (int i = threadIdx.x; i < upto; i += COMMIT_BLOCK) before += meta_len(sv.meta[i]) > 0 ? 1 : 0;
+        {                                                       // four meta words per load, several loads in flight
+            const uint4* m4 = reinterpret_cast<const uint4*>(sv.meta);
+            const int n4 = max(upto, 0) >> 2;
+#pragma unroll 4
+            for (int i = threadIdx.x; i < n4; i += COMMIT_BLOCK) {
+                const uint4 v = m4[i];
+                before += (meta_len(v.x) > 0) + (meta_len(v.y) > 0) + (meta_len(v.z) > 0) + (meta_len(v.w) > 0);
+            }
+            for (int i = (n4 << 2) + threadIdx.x; i < upto; i += COMMIT_BLOCK) before += meta_len(sv.meta[i]) > 0 ? 1 : 0;
+        }
         if (g >= off && g < off + c) { seg = s; idx = g - off; meta = sv.meta[idx]; }
         off += c;
     }
@@ -115,7 +132,7 @@ commit_x_kernel(TreeView<T> tv, WaveCtl* __restrict__ ctl, int wave_k,
     __syncthreads();
     before = 0;
     for (int w = 0; w < COMMIT_BLOCK / 32; w++) before += s_part[w];
-    const bool mine = seg >= 0 && meta_len(meta) > 0;
+    const bool mine = seg >= 0 && meta_len(meta) > 0 && !dead;
     const unsigned acc_mask = __ballot_sync(0xffffffffu, mine);
     const int rank_in_cta = __popc(acc_mask & ((1u << lane) - 1u));
     const int node_mine = old_size + before + rank_in_cta;
@@ -181,7 +198,11 @@ commit_x_kernel(TreeView<T> tv, WaveCtl* __restrict__ ctl, int wave_k,
             if (in_goal) {                                                  // planner.py:260-281
                 atomicAdd(tv.n_goal, 1);
                 atomicMin(tv.best, ((unsigned long long)(unsigned)c << 32) | (unsigned)node);
-                mark_path(tv, node);
+                mark_path(tv, copy, node);
+                if (lag2) {
+                    const int gi = atomicAdd(tv.goal_count[copy], 1);
+                    if (gi < tv.goal_cap) tv.goal_list[copy][gi] = node; else atomicExch(&ctl->acc[2], 2);
+                }
             }
         }
     }
@@ -229,6 +250,7 @@ commit_x_kernel(TreeView<T> tv, WaveCtl* __restrict__ ctl, int wave_k,
             ctl->ring[(wave_k + 2) % CTL_RING] = nxt;
             ctl->stopped = stopped;
         }
+        if (lag2) *tv.goal_count[copy ^ 1] = 0;        // replayed by every CTA of this commit; the next commit refills it
         ctl->acc[0] = 0; ctl->acc[1] = 0; ctl->acc[2] = 0; ctl->done_commit = 0;
         __threadfence();
         *tv.size = nsz;

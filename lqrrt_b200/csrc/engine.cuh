@@ -10,6 +10,8 @@
 #include <cstring>
 #include <cstdio>
 #include <cmath>
+#include <chrono>
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: ranges cost nothing unless a profiler is attached
 #include <algorithm>
 
 #include "models.cuh"
@@ -40,6 +42,8 @@ struct lq_engine {
     virtual int wave_stats(lq_wave_stats* out) = 0;
     virtual int plan_run(const lq_plan_args* a, lq_plan_summary* out, cudaStream_t st) = 0;
     virtual int stop_word(int** out) = 0;
+    virtual int plan_readout(int node, const double* xg, const uint8_t* colmask, int max_len, int* ids, int* len,
+                             double* hx, double* hu, int* elen, cudaStream_t st) = 0;
     virtual int closest(const double* xg, const uint8_t* colmask, int* id, cudaStream_t st) = 0;
     virtual int steer_force(int node, const double* xtar, int max_steps, double* hx, double* hu, int* len, cudaStream_t st) = 0;
     virtual int append_node(int parent, const double* state, const double* hx, const double* hu, int len, cudaStream_t st) = 0;
@@ -100,7 +104,7 @@ static_assert(sizeof(lq_wave_stats) == 12 * sizeof(int), "device stats block mus
 // partial-minimum slots per query: the old-tree scan writes [0, MAX_SPLIT_OLD), the delta scan (or the one full
 // scan of a stepwise wave) [MAX_SPLIT_OLD, MAX_SLOTS)
 constexpr int MAX_SPLIT_OLD = 384;
-constexpr int MAX_SPLIT_NEW = 128;
+constexpr int MAX_SPLIT_NEW = 32;
 constexpr int MAX_SLOTS = MAX_SPLIT_OLD + MAX_SPLIT_NEW;
 constexpr int MAX_SPLIT = MAX_SPLIT_NEW;
 constexpr int NEAR_BLOCK = 128;
@@ -157,9 +161,11 @@ __global__ void mark_ignore_kernel(TreeView<T> tv, const int* __restrict__ ids, 
     if (i >= count) return;
     const int node = ids[i];
     if (node < 0 || node >= *tv.size) return;
-    unsigned* word = (unsigned*)(tv.ignore + (node & ~3));
     const unsigned bit = 1u << (8 * (node & 3));
-    if (!(atomicOr(word, bit) & bit)) atomicAdd(tv.n_ignored, 1);
+    for (int c = 0; c < 2; c++) {
+        unsigned* word = (unsigned*)(tv.ignore[c] + (node & ~3));
+        if (!(atomicOr(word, bit) & bit)) atomicAdd(tv.n_ignored2[c], 1);
+    }
 }
 
 template <typename T>
@@ -186,10 +192,19 @@ __global__ void climb_kernel(TreeView<T> tv, int node, int* __restrict__ ids, in
     *len = node >= 0 ? -1 : n;          // -1: path longer than the buffer
 }
 
+// climb from the node held in *d_node (the closest-to-guide result) -- lets closest and climb share one host sync
+template <typename T>
+__global__ void climb_from_kernel(TreeView<T> tv, const int* __restrict__ d_node, int* __restrict__ ids, int max_len, int* __restrict__ len) {
+    int node = *d_node, n = 0;
+    while (node >= 0 && n < max_len) { ids[n++] = node; node = tv.parent[node]; }
+    *len = node >= 0 ? -1 : n;
+}
+
 template <typename T>
 __global__ void tree_scalars_kernel(TreeView<T> tv, int size, WaveCtl* ctl) {
-    *tv.size = size; *tv.n_ignored = 0; *tv.n_goal = 0; *tv.best = ~0ull;
-    ctl->stopped = 0; ctl->acc[0] = ctl->acc[1] = ctl->acc[2] = 0; ctl->done_steer = 0; ctl->done_commit = 0;
+    *tv.size = size; *tv.n_goal = 0; *tv.best = ~0ull;
+    for (int c = 0; c < 2; c++) { *tv.n_ignored2[c] = 0; *tv.goal_count[c] = 0; }
+    ctl->stopped = 0; ctl->acc[0] = ctl->acc[1] = ctl->acc[2] = 0; ctl->done_steer[0] = ctl->done_steer[1] = 0; ctl->done_commit = 0;
     for (int k = 0; k < CTL_RING; k++) ctl->ring[k] = WaveSlot{0, 0, 0, size};
 }
 
@@ -243,6 +258,9 @@ struct EngineImpl : lq_engine {
     DevBuf<T> t_state, t_K, t_ex, t_eu;
     DevBuf<int> t_parent, t_cost, t_elen, t_scal;
     DevBuf<uint8_t> t_ignore, t_owner;
+    DevBuf<int> t_goals;
+    static constexpr int GOAL_CAP = 1 << 16;
+    int ign_copy = 0;                // copy of the ignore marks the last commit wrote (read-back, stand-alone searches)
     int last_my_seg = 0;             // segment index this GPU committed as (its rank)
     // fused exchange over peer-mapped symmetric memory (lq_wave_set_peers); layout of every rank's buffer:
     // [2 parities][world segments][seg_sz] then [2][world] arrival flags
@@ -281,7 +299,7 @@ struct EngineImpl : lq_engine {
     cudaStream_t q_stream[RING] = {};
     cudaStream_t last_stream = nullptr;
     // the device-scheduled driver's own streams: rollout chain (high priority) and scan / sampler (low priority)
-    cudaStream_t s_chain = nullptr, s_scan = nullptr;
+    cudaStream_t s_chain = nullptr, s_scan = nullptr, s_chain2 = nullptr;
     static constexpr int EVR = 8;
     cudaEvent_t ev_commit[EVR] = {}, ev_scan[EVR] = {}, ev_in = nullptr, ev_begin = nullptr, ev_end = nullptr;
     // optional per-stage CUDA-event timing (bench.py roofline): sample | nearest (old-tree + delta) | steer | commit
@@ -310,6 +328,7 @@ struct EngineImpl : lq_engine {
         if (aux) cudaStreamDestroy(aux);
         if (s_chain) cudaStreamDestroy(s_chain);
         if (s_scan) cudaStreamDestroy(s_scan);
+        if (s_chain2) cudaStreamDestroy(s_chain2);
     }
 
     template <typename U>
@@ -450,10 +469,13 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(t_ex.alloc((size_t)cap * H * N));
         LQ_CUDA(t_eu.alloc((size_t)cap * H * M));
         LQ_CUDA(t_parent.alloc(cap)); LQ_CUDA(t_cost.alloc(cap)); LQ_CUDA(t_elen.alloc(cap));
-        LQ_CUDA(t_ignore.alloc(cap)); LQ_CUDA(t_owner.alloc(cap)); LQ_CUDA(t_scal.alloc(8)); LQ_CUDA(t_best.alloc(1));
+        LQ_CUDA(t_ignore.alloc((size_t)2 * cap)); LQ_CUDA(t_owner.alloc(cap)); LQ_CUDA(t_scal.alloc(8)); LQ_CUDA(t_best.alloc(1));
+        LQ_CUDA(t_goals.alloc((size_t)2 * GOAL_CAP));
         tv.state = t_state.p; tv.K = t_K.p; tv.parent = t_parent.p; tv.cost = t_cost.p; tv.edge_len = t_elen.p;
-        tv.ignore = t_ignore.p; tv.owner = t_owner.p; tv.edge_x = t_ex.p; tv.edge_u = t_eu.p;
-        tv.size = t_scal.p; tv.n_ignored = t_scal.p + 1; tv.n_goal = t_scal.p + 2;
+        tv.ignore[0] = t_ignore.p; tv.ignore[1] = t_ignore.p + cap; tv.owner = t_owner.p; tv.edge_x = t_ex.p; tv.edge_u = t_eu.p;
+        tv.size = t_scal.p; tv.n_ignored2[0] = t_scal.p + 1; tv.n_goal = t_scal.p + 2; tv.n_ignored2[1] = t_scal.p + 3;
+        tv.goal_count[0] = t_scal.p + 4; tv.goal_count[1] = t_scal.p + 5;
+        tv.goal_list[0] = t_goals.p; tv.goal_list[1] = t_goals.p + GOAL_CAP; tv.goal_cap = GOAL_CAP;
         tv.best = t_best.p; tv.cap = cap; tv.limit = c->node_capacity;
         LQ_CUDA(cudaMemset(t_scal.p, 0, 8 * sizeof(int)));
         LQ_CUDA(w_ctl.alloc(1));
@@ -463,7 +485,7 @@ struct EngineImpl : lq_engine {
         // double-buffered by wave parity: wave k+1's sampler and old-tree scan run while wave k still reads its own
         LQ_CUDA(w_samples.alloc((size_t)2 * N * Wc)); LQ_CUDA(w_ncost.alloc(Wc)); LQ_CUDA(w_nidx.alloc(Wc));
         LQ_CUDA(w_pcost.alloc((size_t)2 * MAX_SLOTS * Wc)); LQ_CUDA(w_pidx.alloc((size_t)2 * MAX_SLOTS * Wc));
-        LQ_CUDA(w_xs.alloc((size_t)Wc * H * N)); LQ_CUDA(w_us.alloc((size_t)Wc * H * M));
+        LQ_CUDA(w_xs.alloc((size_t)2 * Wc * H * N)); LQ_CUDA(w_us.alloc((size_t)2 * Wc * H * M));
         LQ_CUDA(w_len.alloc(Wc)); LQ_CUDA(w_tries.alloc((size_t)2 * Wc)); LQ_CUDA(w_pick.alloc(Wc));
         LQ_CUDA(w_misc.alloc(8)); LQ_CUDA(w_hor.alloc(1));
         { const int h0 = c->hfactor ? c->hspan_lo : c->horizon_iters; LQ_CUDA(cudaMemcpy(w_hor.p, &h0, sizeof(int), cudaMemcpyHostToDevice)); }
@@ -701,7 +723,7 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(cudaMemcpyAsync(t_parent.p, par.data(), count * sizeof(int), cudaMemcpyHostToDevice, st));
         LQ_CUDA(cudaMemcpyAsync(t_cost.p, cst.data(), count * sizeof(int), cudaMemcpyHostToDevice, st));
         LQ_CUDA(cudaMemsetAsync(t_elen.p, 0, count * sizeof(int), st));
-        LQ_CUDA(cudaMemsetAsync(t_ignore.p, 0, cap, st));
+        LQ_CUDA(cudaMemsetAsync(t_ignore.p, 0, (size_t)2 * cap, st)); ign_copy = 0;
         LQ_CUDA(cudaMemsetAsync(t_owner.p, 0, cap, st));
         tree_scalars_kernel<T><<<1, 1, 0, st>>>(tv, count, w_ctl.p); launches++;
         init_gain_kernel<T, Sys, Lqr><<<(count + 127) / 128, 128, 0, st>>>(md, t_state.p, t_K.p, cap, count); launches++;
@@ -734,12 +756,15 @@ struct EngineImpl : lq_engine {
     T* samples_of(int par) { return w_samples.p + (size_t)par * N * Wc; }
     int* tries_of(int par) { return w_tries.p + (size_t)par * Wc; }
     char* seg_of(int par) { return w_seg.p + (size_t)par * seg_sz; }
+    T* xs_of(int par) { return w_xs.p + (size_t)par * Wc * H * N; }
+    T* us_of(int par) { return w_us.p + (size_t)par * Wc * H * M; }
 
     // Slots: [slot_base, slot_base + nsplit), or -- end_aligned -- [slot_base - nsplit, slot_base), so that an old-tree
     // scan and a delta scan of the same wave leave one contiguous range around MAX_SPLIT_OLD for the rollout kernel.
     int launch_scan(const T* q, int qstride, int W, const int* d_count, const int* d_lo, const int* d_hi, int n_ub,
                     const int* d_nign, int use_ignore, int par, int slot_base, bool end_aligned, int max_split, int target_ctas,
-                    cudaStream_t st, int* nsplit_out) {
+                    cudaStream_t st, int* nsplit_out, int copy = 0) {
+        const uint8_t* ignp = tv.ignore[copy];
         const int Nub = std::max(1, n_ub);
         const int max_splits = std::max(1, std::min(max_split, (Nub + NEAR_BLOCK - 1) / NEAR_BLOCK));
         ScanArgs sa;
@@ -763,7 +788,7 @@ struct EngineImpl : lq_engine {
             if (!big) plan(1);
 #define LQ_NEAR_DIAG(QQ, MM)                                                                              \
     nearest_diag_kernel<T, N, QQ, NEAR_BLOCK, MM, EX><<<sa.nqb * sa.nsplit, NEAR_BLOCK, 0, st>>>(         \
-        t_state.p, cap, t_ignore.p, sa, q, qstride, dmet, pc, pi, Wc)
+        t_state.p, cap, ignp, sa, q, qstride, dmet, pc, pi, Wc)
 #define LQ_NEAR_DIAG_M(QQ)                                  \
     do {                                                    \
         if (cmask == 0) LQ_NEAR_DIAG(QQ, 0);                \
@@ -773,7 +798,7 @@ struct EngineImpl : lq_engine {
     } while (0)
 #define LQ_NEAR_PK(QQ, MB, PK, MM)                                                                         \
     nearest_diag_pk_kernel<N, QQ, NEAR_BLOCK, MM, 8, MB, PK><<<sa.nqb * sa.nsplit, NEAR_BLOCK, 0, st>>>(    \
-        t_state.p, cap, t_ignore.p, sa, q, qstride, dmet, pc, pi, Wc)
+        t_state.p, cap, ignp, sa, q, qstride, dmet, pc, pi, Wc)
 #define LQ_NEAR_PK_M(QQ, MB, PK)                                  \
     do {                                                          \
         plan(QQ);                                                 \
@@ -797,7 +822,7 @@ struct EngineImpl : lq_engine {
                                 plan(4);
 #define LQ_NEAR_PFX(MM)                                                                                   \
     nearest_diag_prefix_kernel<N, 4, NEAR_BLOCK, MM, PFX><<<sa.nqb * sa.nsplit, NEAR_BLOCK, 0, st>>>(       \
-        t_state.p, cap, t_ignore.p, sa, q, qstride, dmet, pc, pi, Wc)
+        t_state.p, cap, ignp, sa, q, qstride, dmet, pc, pi, Wc)
                                 if (cmask == 0) LQ_NEAR_PFX(0); else LQ_NEAR_PFX((N >= 3 ? 4 : 0));
 #undef LQ_NEAR_PFX
                                 break;
@@ -819,7 +844,7 @@ struct EngineImpl : lq_engine {
             const T* Sp = sp_of(par);
 #define LQ_NEAR_DENSE(MM)                                                                                  \
     nearest_dense_kernel<T, N, NEAR_BLOCK, MM><<<sa.nqb * sa.nsplit, NEAR_BLOCK, 0, st>>>(                 \
-        t_state.p, cap, t_ignore.p, sa, q, qstride, Sp, md.angle_mask, pc, pi, Wc)
+        t_state.p, cap, ignp, sa, q, qstride, Sp, md.angle_mask, pc, pi, Wc)
             if (cmask == 0) LQ_NEAR_DENSE(0);
             else if (cmask == 4) LQ_NEAR_DENSE((N >= 3 ? 4 : 0));
             else if (cmask == 1) LQ_NEAR_DENSE(1);
@@ -848,6 +873,14 @@ struct EngineImpl : lq_engine {
         return LQ_OK;
     }
 
+    int launch_reduce(int par, int slot_lo, int nslots, int W, const int* d_count, cudaStream_t st) {
+        if (nslots <= 1 || W < 1) return LQ_OK;
+        reduce_partials_kernel<T><<<(W + 31) / 32, 256, 0, st>>>(pcost_of(par), pidx_of(par), Wc, slot_lo, nslots, W, d_count);
+        launches++;
+        LQ_CUDA(cudaGetLastError());
+        return LQ_OK;
+    }
+
     int scan_target() const { return 148 * (near_ctas_per_sm > 0 ? near_ctas_per_sm : (N <= 6 ? 16 : 8)); }
     // the old-tree scan shares the GPU with the rollout chain of the wave before: more, shorter CTAs let the chain's
     // (higher-priority) CTAs in sooner (measured on C4: 32 per SM 9.06 ms per plan, 16: 9.26, 8: 9.47)
@@ -865,8 +898,8 @@ struct EngineImpl : lq_engine {
             if (int r = launch_metric(q, qstride, W, nullptr, 0, st)) return r;
         }
         int nsplit = 1;
-        if (int r = launch_scan(q, qstride, W, nullptr, nullptr, tv.size, size_ub, tv.n_ignored, use_ignore, 0, 0, false, MAX_SPLIT,
-                                scan_target(), st, &nsplit)) return r;
+        if (int r = launch_scan(q, qstride, W, nullptr, nullptr, tv.size, size_ub, tv.n_ignored2[ign_copy], use_ignore, 0, 0, false, MAX_SPLIT,
+                                scan_target(), st, &nsplit, ign_copy)) return r;
         nearest_finalize_kernel<T><<<(W + 127) / 128, 128, 0, st>>>(pcost_of(0), pidx_of(0), Wc, nsplit, W, d_idx, (T*)d_cost);
         launches++;
         LQ_CUDA(cudaGetLastError());
@@ -923,9 +956,11 @@ struct EngineImpl : lq_engine {
 
     // The wave's rollout kernel: nearest selection from the partial slots [slot_lo, slot_lo + nslots) of parity `par`,
     // rollouts of the first ring[slot].count samples, results into `dst`.
+    // copy: which copy of the ignore marks the wave searches; d_vis: the tree size it searches (device scalar);
+    // xpar: which rollout scratch / completion counter it uses (two waves may be in flight with pipelined waves)
     template <int LANES>
     int launch_steer_x_l(int W, int slot, int par, int slot_lo, int nslots, int use_ignore, const ExDst& dst, int flags,
-                         bool use_stop_word, cudaStream_t st) {
+                         bool use_stop_word, cudaStream_t st, int copy, const int* d_vis, int xpar) {
         const long long threads = (long long)std::max(1, W) * LANES;
         const StagePlan sp = stage_for_launch();
         PartialsIn<T> pin{pcost_of(par) + (size_t)slot_lo * Wc, pidx_of(par) + (size_t)slot_lo * Wc, Wc, nslots};
@@ -941,8 +976,8 @@ struct EngineImpl : lq_engine {
         auto kern = steer_x_kernel<T, Sys, Lqr, LANES, BB>;                                                    \
         if (int r = steer_smem(kern, sm)) return r;                                                            \
         LQ_CUDA(launch_maybe_pdl(kern, (unsigned)((threads + BB - 1) / BB), BB, sm, st, pdl_on != 0,          \
-            md, sp, t_state.p, t_K.p, cap, t_ignore.p, tv.size, tv.n_ignored, w_ctl.p, slot, pin, nm,          \
-            samples_of(par), Wc, tries_of(par), use_ignore, force_rescan, w_xs.p, w_us.p, dst, Wc, flags, stopw)); \
+            md, sp, t_state.p, t_K.p, cap, (const uint8_t*)tv.ignore[copy], d_vis, (const int*)tv.n_ignored2[copy], w_ctl.p, slot, pin, nm, \
+            samples_of(par), Wc, tries_of(par), use_ignore, force_rescan, xs_of(xpar), us_of(xpar), dst, Wc, flags, stopw, xpar)); \
     } while (0)
         if (block == 128) LQ_STEER_X(128); else LQ_STEER_X(32);
 #undef LQ_STEER_X
@@ -951,10 +986,11 @@ struct EngineImpl : lq_engine {
         return LQ_OK;
     }
     int launch_steer_x(int W, int slot, int par, int slot_lo, int nslots, int use_ignore, const ExDst& dst, int flags,
-                       bool use_stop_word, cudaStream_t st) {
-        if (steer_lanes >= 32) return launch_steer_x_l<32>(W, slot, par, slot_lo, nslots, use_ignore, dst, flags, use_stop_word, st);
-        if (steer_lanes >= 8) return launch_steer_x_l<8>(W, slot, par, slot_lo, nslots, use_ignore, dst, flags, use_stop_word, st);
-        return launch_steer_x_l<1>(W, slot, par, slot_lo, nslots, use_ignore, dst, flags, use_stop_word, st);
+                       bool use_stop_word, cudaStream_t st, int copy = 0, const int* d_vis = nullptr, int xpar = 0) {
+        if (!d_vis) d_vis = tv.size;
+        if (steer_lanes >= 32) return launch_steer_x_l<32>(W, slot, par, slot_lo, nslots, use_ignore, dst, flags, use_stop_word, st, copy, d_vis, xpar);
+        if (steer_lanes >= 8) return launch_steer_x_l<8>(W, slot, par, slot_lo, nslots, use_ignore, dst, flags, use_stop_word, st, copy, d_vis, xpar);
+        return launch_steer_x_l<1>(W, slot, par, slot_lo, nslots, use_ignore, dst, flags, use_stop_word, st, copy, d_vis, xpar);
     }
 
     int launch_sample(uint64_t seed, uint32_t wave, int slot, int par, int count_ub, cudaStream_t st) {
@@ -974,14 +1010,22 @@ struct EngineImpl : lq_engine {
     }
 
     // ---- exchange destinations ------------------------------------------------
-    size_t peer_flags_offset() const { return (size_t)2 * peer_world * seg_sz; }
+    // every rank's receive buffer: [PEER_PAR parities][world segments][seg_sz], then [PEER_PAR][world] arrival flags.
+    // A wave uses parity seq % peer_mod: 2 suffice when a rank's waves are strictly sequential, pipelined waves (two in
+    // flight per rank) need 4 so that a peer still committing wave k-2 is never overwritten by wave k's results.
+    static constexpr int PEER_PAR = 4;
+    int peer_mod = 2;
+    size_t peer_flags_offset() const { return (size_t)PEER_PAR * peer_world * seg_sz; }
+    int peer_parity() const { return (int)(peer_seq % (unsigned)peer_mod); }
+    const char* peer_segs() const { return peer_buf[peer_rank] + (size_t)peer_parity() * peer_world * seg_sz; }
+    const unsigned* peer_arrive() const { return (const unsigned*)(peer_buf[peer_rank] + peer_flags_offset()) + peer_parity() * peer_world; }
     // where this wave's rollout kernel sends its results (advances the wave sequence number in peer mode)
     ExDst next_dst(int par) {
         ExDst d;
         memset(&d, 0, sizeof d);
         if (peer_world <= 1) { d.n = 1; d.seg[0] = seg_of(par); return d; }
         peer_seq++;
-        const int pp = peer_seq & 1;
+        const int pp = peer_parity();
         d.n = peer_world; d.seq = peer_seq;
         for (int p = 0; p < peer_world; p++) {
             d.seg[p] = peer_buf[p] + ((size_t)pp * peer_world + peer_rank) * seg_sz;
@@ -992,7 +1036,7 @@ struct EngineImpl : lq_engine {
     int set_peers(int world, int rank, void* const* bufs, uint64_t bytes) override {
         if (world < 0 || world > MAX_PEERS || (world > 0 && (rank < 0 || rank >= world))) LQ_FAIL(LQ_ERR_ARG, "bad world/rank");
         if (world > 1) {
-            const uint64_t need = (uint64_t)2 * world * seg_sz + (uint64_t)2 * world * sizeof(unsigned);
+            const uint64_t need = (uint64_t)PEER_PAR * world * seg_sz + (uint64_t)PEER_PAR * world * sizeof(unsigned);
             if (!bufs || bytes < need) LQ_FAIL(LQ_ERR_ARG, "peer buffers must hold %llu bytes", (unsigned long long)need);
             for (int p = 0; p < world; p++) { if (!bufs[p]) LQ_FAIL(LQ_ERR_ARG, "null peer buffer"); peer_buf[p] = (char*)bufs[p]; }
         }
@@ -1011,7 +1055,9 @@ struct EngineImpl : lq_engine {
         if (int r = launch_scan(samples_of(par), Wc, count, nullptr, nullptr, tv.size, size_ub, nullptr, use_ignore, par,
                                 MAX_SPLIT_OLD, false, MAX_SPLIT_NEW, scan_target(), st, &nsplit)) return r;
         if (prof_on) { cudaEventRecord(pev[ps][2], st); cudaEventRecord(pev[ps][3], st); }
-        const ExDst dst = next_dst(peer_world > 1 ? 0 : par);
+        // stepwise: rollouts and commit of a wave run back to back on one stream, so the engine's own exchange segment
+        // needs no double buffering (and the NCCL path's zero-copy send view keeps one fixed address)
+        const ExDst dst = next_dst(0);
         if (int r = launch_steer_x(count, slot, par, MAX_SPLIT_OLD, nsplit, use_ignore, dst, flags, false, st)) return r;
         if (prof_on) { cudaEventRecord(pev[ps][4], st); prof_open[ps] = true; prof_W[ps] = count; }
         last_stream = st;
@@ -1091,18 +1137,20 @@ struct EngineImpl : lq_engine {
     }
 
     int wave_records(void** d, uint64_t* bytes) override {
-        if (d) *d = seg_of(cur_parity);
+        if (d) *d = seg_of(0);
         if (bytes) *bytes = seg_sz;
         return LQ_OK;
     }
 
     int launch_commit(int wave_k, const char* segs, int n_seg, int my_seg, int slots_ub, const WavePolicy& pol,
-                      const unsigned* arrive, unsigned seq, int ring_slot, unsigned out_seq, cudaStream_t st) {
+                      const unsigned* arrive, unsigned seq, int ring_slot, unsigned out_seq, cudaStream_t st,
+                      int copy = 0, int lag2 = 0, int xpar = 0, bool pdl = true) {
+        ign_copy = copy;
         const int ctas = std::max(1, (slots_ub + COMMIT_SLOTS - 1) / COMMIT_SLOTS);
-        LQ_CUDA(launch_maybe_pdl(commit_x_kernel<T>, (unsigned)ctas, COMMIT_BLOCK, 0, st, pdl_on != 0 && pol.device_schedule != 0,
-                                 tv, w_ctl.p, wave_k, segs, seg_sz, n_seg, my_seg, (const T*)w_xs.p, (const T*)w_us.p,
+        LQ_CUDA(launch_maybe_pdl(commit_x_kernel<T>, (unsigned)ctas, COMMIT_BLOCK, 0, st, pdl && pdl_on != 0 && pol.device_schedule != 0,
+                                 tv, w_ctl.p, wave_k, segs, seg_sz, n_seg, my_seg, (const T*)xs_of(xpar), (const T*)us_of(xpar),
                                  Wc, N, M, H, (const T*)w_goal.p, (const T*)(w_goal.p + LQ_MAX_N), pol, d_ring + ring_slot, out_seq,
-                                 arrive, seq, w_hor.p, md.hfactor, md.hlo, md.hhi));
+                                 arrive, seq, w_hor.p, md.hfactor, md.hlo, md.hhi, copy, lag2));
         launches++;
         LQ_CUDA(cudaGetLastError());
         return LQ_OK;
@@ -1113,13 +1161,12 @@ struct EngineImpl : lq_engine {
         if (n_seg < 1 || n_seg > 255) LQ_FAIL(LQ_ERR_ARG, "n_segments must be in 1..255");
         if (my_seg < 0 || my_seg >= n_seg) LQ_FAIL(LQ_ERR_ARG, "my_segment must be in 0..n_segments-1");
         last_my_seg = my_seg;
-        const char* segs = d_records ? (const char*)d_records : seg_of(cur_parity);
+        const char* segs = d_records ? (const char*)d_records : seg_of(0);
         const unsigned* arrive = nullptr;
         if (!d_records && peer_world > 1) {             // fused exchange: my own receive buffer, current parity
             if (n_seg != peer_world || my_seg != peer_rank) LQ_FAIL(LQ_ERR_ARG, "peer mode commits world segments as rank");
-            const int pp = peer_seq & 1;
-            segs = peer_buf[peer_rank] + (size_t)pp * peer_world * seg_sz;
-            arrive = (const unsigned*)(peer_buf[peer_rank] + peer_flags_offset()) + pp * peer_world;
+            segs = peer_segs();
+            arrive = peer_arrive();
         }
         if (q_tail - q_head >= (unsigned)RING) LQ_FAIL(LQ_ERR_STATE, "%d committed waves are unread: call lq_wave_stats_get", RING);
         const int ps = q_tail % RING;
@@ -1212,6 +1259,7 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // lo = least priority (numerically greatest)
         LQ_CUDA(cudaStreamCreateWithPriority(&s_chain, cudaStreamNonBlocking, hi));
         LQ_CUDA(cudaStreamCreateWithPriority(&s_scan, cudaStreamNonBlocking, lo));
+        LQ_CUDA(cudaStreamCreateWithPriority(&s_chain2, cudaStreamNonBlocking, hi));
         for (auto& e : ev_commit) LQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& e : ev_scan) LQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         LQ_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
@@ -1242,6 +1290,10 @@ struct EngineImpl : lq_engine {
         const int DEPTH = std::max(1, std::min(a->depth > 0 ? a->depth : 4, RING - 2));
         const bool spec = spec_scan != 0;
         const int use_ignore = a->use_ignore ? 1 : 0;
+        const bool lag2 = a->lag == 2;
+        if (a->lag != 0 && a->lag != 1 && a->lag != 2) LQ_FAIL(LQ_ERR_ARG, "lag must be 1 or 2");
+        peer_mod = lag2 ? 4 : 2;
+        if (peer_world > 1 && (peer_seq % 4u) != 0) peer_seq += 4u - (peer_seq % 4u);     // every rank alike: start on parity 0
         last_my_seg = rank;
 
         // the chain stream picks up after the caller's stream (reset / goal / sampling uploads)
@@ -1251,6 +1303,7 @@ struct EngineImpl : lq_engine {
         ctl_start_kernel<<<1, 1, 0, s_chain>>>(w_ctl.p, tv.size, pol); launches++;
         LQ_CUDA(cudaEventRecord(ev_begin, s_chain));
         LQ_CUDA(cudaStreamWaitEvent(s_scan, ev_begin, 0));         // waves 0 and 1 start from the initial control block
+        LQ_CUDA(cudaStreamWaitEvent(s_chain2, ev_begin, 0));
 
         // host mirror of the schedule as upper bounds (they only shape grids): Nub[k] >= N_k, the tree size wave k
         // starts from, and Wub[k] >= W_k = policy(N_{k-1}) (W_0 = W_1 = policy(N_0))
@@ -1265,7 +1318,10 @@ struct EngineImpl : lq_engine {
         last_stats.tree_size = n0; last_stats.best_node = -1; last_stats.best_cost = -1;
         std::vector<unsigned> seq_of_wave;
 
+        struct NvtxRange { explicit NvtxRange(const char* n) { nvtxRangePushA(n); } ~NvtxRange() { nvtxRangePop(); } };
+        NvtxRange plan_range("lq_plan_run");
         auto enqueue = [&](int k) -> int {
+            NvtxRange wave_range(lag2 ? "lq wave (pipelined): sample|scan|fold|rollout+exchange|commit" : "lq wave: sample|old scan|fold || delta scan|rollout+exchange|commit");
             // bounds for wave k, re-derived from the newest exact size
             if ((int)Nub.size() <= k) { Nub.resize(k + 1); Wub.resize(k + 1); }
             for (int i = std::max(0, exact_upto - 2); i <= k; i++) {
@@ -1279,6 +1335,36 @@ struct EngineImpl : lq_engine {
             const int delta_ub = k == 0 ? 1 : std::max(1, std::min(Wub[k - 1], tv.limit));
             const int* d_count = &w_ctl.p->ring[slot].count;
             const int* d_nold = &w_ctl.p->ring[slot].n_old;
+            if (lag2) {
+                // Pipelined waves: wave k lives on chain stream k & 1 -- sampler, scan of the tree as of commit k-2
+                // ([0, n_old): that is everything the wave may see, so there is no delta scan), fold of the partial minima,
+                // rollouts + exchange -- and only its commit waits for commit k-1.  Wave k+1's whole front half runs on the
+                // other stream meanwhile.
+                cudaStream_t sc = (k & 1) ? s_chain2 : s_chain;
+                const int copy = k & 1;
+                if (prof_on) cudaEventRecord(pev[ps][0], sc);
+                if (int r = launch_sample(a->seed, a->wave_ctr0 + (uint32_t)k, slot, par, cub, sc)) return r;
+                if (int r = launch_metric(samples_of(par), Wc, cub, d_count, par, sc)) return r;
+                if (prof_on) cudaEventRecord(pev[ps][1], sc);
+                int ns = 0;
+                if (int r = launch_scan(samples_of(par), Wc, cub, d_count, nullptr, d_nold, n_old_ub, nullptr, use_ignore, par,
+                                        MAX_SPLIT_OLD, true, MAX_SPLIT_OLD, scan_target(), sc, &ns, copy)) return r;
+                if (int r = launch_reduce(par, MAX_SPLIT_OLD - ns, ns, cub, d_count, sc)) return r;
+                if (prof_on) { cudaEventRecord(pev[ps][2], sc); cudaEventRecord(pev[ps][3], sc); cudaEventRecord(pev[ps][4], sc); }
+                const ExDst dst = next_dst(par);
+                if (int r = launch_steer_x(cub, slot, par, MAX_SPLIT_OLD - 1, 1, use_ignore, dst, 0, true, sc, copy, d_nold, par)) return r;
+                if (prof_on) cudaEventRecord(pev[ps][5], sc);
+                if (k >= 1) LQ_CUDA(cudaStreamWaitEvent(sc, ev_commit[(k - 1) % EVR], 0));
+                const char* segs = seg_of(par);
+                const unsigned* arrive = nullptr;
+                if (peer_world > 1) { segs = peer_segs(); arrive = peer_arrive(); }
+                ++stat_seq;
+                seq_of_wave.push_back(stat_seq);
+                if (int r = launch_commit(k, segs, world, rank, w, pol, arrive, peer_seq, ps, stat_seq, sc, copy, 1, par, false)) return r;
+                if (prof_on) { cudaEventRecord(pev[ps][6], sc); prof_open[ps] = true; }
+                LQ_CUDA(cudaEventRecord(ev_commit[k % EVR], sc));
+                return LQ_OK;
+            }
             // ---- scan stream: sampler, [metric], old-tree scan
             if (k >= 2) LQ_CUDA(cudaStreamWaitEvent(s_scan, ev_commit[(k - 2) % EVR], 0));
             if (prof_on) cudaEventRecord(pev[ps][0], s_scan);
@@ -1289,6 +1375,11 @@ struct EngineImpl : lq_engine {
             if (spec) {
                 if (int r = launch_scan(samples_of(par), Wc, cub, d_count, nullptr, d_nold, n_old_ub, nullptr, use_ignore, par,
                                         MAX_SPLIT_OLD, true, MAX_SPLIT_OLD, old_scan_target(), s_scan, &ns_old)) return r;
+            }
+            if (spec) {
+                // fold the old-tree partials into one slot here, off the rollout chain
+                if (int r = launch_reduce(par, MAX_SPLIT_OLD - ns_old, ns_old, cub, d_count, s_scan)) return r;
+                if (ns_old > 0) ns_old = 1;
             }
             if (prof_on) cudaEventRecord(pev[ps][2], s_scan);
             LQ_CUDA(cudaEventRecord(ev_scan[k % EVR], s_scan));
@@ -1308,11 +1399,7 @@ struct EngineImpl : lq_engine {
             if (prof_on) cudaEventRecord(pev[ps][5], s_chain);
             const char* segs = seg_of(par);
             const unsigned* arrive = nullptr;
-            if (peer_world > 1) {
-                const int pp = peer_seq & 1;
-                segs = peer_buf[peer_rank] + (size_t)pp * peer_world * seg_sz;
-                arrive = (const unsigned*)(peer_buf[peer_rank] + peer_flags_offset()) + pp * peer_world;
-            }
+            if (peer_world > 1) { segs = peer_segs(); arrive = peer_arrive(); }
             ++stat_seq;
             seq_of_wave.push_back(stat_seq);
             if (int r = launch_commit(k, segs, world, rank, w, pol, arrive, peer_seq, ps, stat_seq, s_chain)) return r;
@@ -1326,14 +1413,23 @@ struct EngineImpl : lq_engine {
         // ranks enqueue the same number of waves and nobody waits for a peer that has left.
         n_start.push_back(n0);
         int rc = LQ_OK;
+        using clk = std::chrono::steady_clock;
+        auto ms_since = [](clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); };
+        double t_enq = 0, t_wait = 0, t_cb = 0;
         while (true) {
+            auto t0 = clk::now();
             while (!stop_enqueue && enq - rd < DEPTH) {
                 if ((rc = enqueue(enq)) != LQ_OK) break;
                 enq++;
             }
+            t_enq += ms_since(t0);
             if (rc != LQ_OK || rd == enq) break;
             const int ps = rd % RING;
-            if ((rc = wait_stats(ps, seq_of_wave[rd], s_chain)) != LQ_OK) break;
+            t0 = clk::now();
+            NvtxRange wait_range("lq wait for wave counters");
+            rc = wait_stats(ps, seq_of_wave[rd], (lag2 && (rd & 1)) ? s_chain2 : s_chain);
+            t_wait += ms_since(t0);
+            if (rc != LQ_OK) break;
             lq_wave_stats stw;
             memcpy(&stw, h_ring[ps].v, sizeof stw);
             if (prof_on && prof_open[ps]) {
@@ -1349,22 +1445,29 @@ struct EngineImpl : lq_engine {
             out->waves = rd + 1;
             if (stw.flags) stop_enqueue = true;                 // the device has stopped: later waves are no-ops
             if (a->on_wave) {
+                t0 = clk::now();
                 const int want = a->on_wave(a->user, &stw);     // planner.py:286-311 on the host's clock
+                t_cb += ms_since(t0);
                 if (want && !stop_enqueue) *(volatile int*)h_stop = want;   // reaches every rank through rank 0's segment header
             }
             rd++;
         }
         if (rc != LQ_OK) {                                       // leave nothing in flight behind an error
-            cudaStreamSynchronize(s_scan); cudaStreamSynchronize(s_chain);
+            cudaStreamSynchronize(s_scan); cudaStreamSynchronize(s_chain2); cudaStreamSynchronize(s_chain);
             return rc;
+        }
+        if (lag2 && enq > 0) {                                   // the last commit may sit on the second chain stream
+            LQ_CUDA(cudaStreamWaitEvent(s_chain, ev_commit[(enq - 1) % EVR], 0));
         }
         LQ_CUDA(cudaEventRecord(ev_end, s_chain));
         LQ_CUDA(cudaStreamSynchronize(s_scan));
+        LQ_CUDA(cudaStreamSynchronize(s_chain2));
         LQ_CUDA(cudaStreamSynchronize(s_chain));
         LQ_CUDA(cudaStreamWaitEvent(st, ev_end, 0));            // later work on the caller's stream sees the finished tree
         float ms = 0;
         cudaEventElapsedTime(&ms, ev_begin, ev_end);
         out->device_ms = ms;
+        out->host_enqueue_ms = t_enq; out->host_wait_ms = t_wait; out->host_callback_ms = t_cb;
         out->waves_enqueued = enq;
         out->samples = samples_total;
         out->last = last_stats;
@@ -1492,6 +1595,71 @@ struct EngineImpl : lq_engine {
         return LQ_OK;
     }
 
+    // Plan read-out in one call (planner.py:266-281 / 313-324): [closest-to-guide ->] climb -> the edges of the path.
+    // Two host round trips (ids, then edges) on persistent scratch instead of a dozen small synchronous copies and
+    // three cudaMalloc/cudaFree pairs; what `update_plan` spends after its loop is part of the end-to-end figure.
+    DevBuf<int> r_ids, r_len;
+    DevBuf<T> r_x, r_u;
+    int r_cap = 0;
+    std::vector<T> r_hx, r_hu;
+    int plan_readout(int node, const double* xg, const uint8_t* colmask, int max_len, int* ids, int* len,
+                     double* hx, double* hu, int* elen, cudaStream_t st) override {
+        LQ_CUDA(cudaSetDevice(device));
+        if (max_len < 1) LQ_FAIL(LQ_ERR_ARG, "max_len must be >= 1");
+        if (r_cap < max_len) {
+            LQ_CUDA(r_ids.alloc((size_t)max_len + 2)); LQ_CUDA(r_len.alloc(max_len));
+            LQ_CUDA(r_x.alloc((size_t)max_len * H * N)); LQ_CUDA(r_u.alloc((size_t)max_len * H * M));
+            r_cap = max_len;
+        }
+        int* d_node = r_ids.p + max_len + 1;
+        int* d_plen = r_ids.p + max_len;
+        if (node < 0) {                      // closest-to-guide first (planner.py:313-318)
+            if (!xg) LQ_FAIL(LQ_ERR_ARG, "closest-to-guide needs the guide state");
+            FullMetric<T, N> fm;
+            double S[N * N];
+            if (Lqr::CONST_METRIC) {
+                for (int k = 0; k < N * N; k++) S[k] = Sconst[k];
+            } else {
+                double K[M * N], u0[M] = {0};
+                if (int r = eval_lqr(1, xg, u0, S, K)) return r;
+            }
+            for (int i = 0; i < N; i++) {
+                fm.x[i] = (T)xg[i];
+                for (int j = 0; j < N; j++) fm.S[i * N + j] = (colmask && colmask[j]) ? T(0) : (T)S[i * N + j];
+            }
+            fm.angle_mask = md.angle_mask;
+            closest_kernel<T, N><<<1, 1024, 0, st>>>(t_state.p, cap, tv.size, fm, d_node); launches++;
+        } else {
+            LQ_CUDA(cudaMemcpyAsync(d_node, &node, sizeof(int), cudaMemcpyHostToDevice, st));
+        }
+        climb_from_kernel<T><<<1, 1, 0, st>>>(tv, d_node, r_ids.p, max_len, d_plen); launches++;
+        LQ_CUDA(cudaGetLastError());
+        std::vector<int> tmp((size_t)max_len + 2);
+        LQ_CUDA(cudaMemcpyAsync(tmp.data(), r_ids.p, ((size_t)max_len + 2) * sizeof(int), cudaMemcpyDeviceToHost, st));
+        LQ_CUDA(cudaStreamSynchronize(st));
+        const int L = tmp[max_len];
+        if (L < 0) LQ_FAIL(LQ_ERR_STATE, "path from node %d is longer than %d", tmp[max_len + 1], max_len);
+        for (int k = 0; k < L; k++) ids[k] = tmp[L - 1 - k];          // seed first, as tree.py:117
+        *len = L;
+        if (L == 0 || !hx) return LQ_OK;
+        // edges of the path, leaf-first on the device, reordered seed-first on the way out
+        gather_edges_kernel<T><<<L, 128, 0, st>>>(tv, r_ids.p, L, last_my_seg, H, H * N, H * M, r_x.p, r_u.p, r_len.p); launches++;
+        LQ_CUDA(cudaGetLastError());
+        r_hx.resize((size_t)L * H * N); r_hu.resize((size_t)L * H * M);
+        std::vector<int> el(L);
+        LQ_CUDA(cudaMemcpyAsync(r_hx.data(), r_x.p, r_hx.size() * sizeof(T), cudaMemcpyDeviceToHost, st));
+        LQ_CUDA(cudaMemcpyAsync(r_hu.data(), r_u.p, r_hu.size() * sizeof(T), cudaMemcpyDeviceToHost, st));
+        LQ_CUDA(cudaMemcpyAsync(el.data(), r_len.p, (size_t)L * sizeof(int), cudaMemcpyDeviceToHost, st));
+        LQ_CUDA(cudaStreamSynchronize(st));
+        for (int k = 0; k < L; k++) {
+            const int src = L - 1 - k;
+            for (int q = 0; q < H * N; q++) hx[(size_t)k * H * N + q] = (double)r_hx[(size_t)src * H * N + q];
+            for (int q = 0; q < H * M; q++) hu[(size_t)k * H * M + q] = (double)r_hu[(size_t)src * H * M + q];
+            elen[k] = el[src];
+        }
+        return LQ_OK;
+    }
+
     // ---- read-back --------------------------------------------------------------
     int download_nodes(int first, int count, double* state, int* parent, int* cost, int* elen, uint8_t* ign,
                        uint8_t* owner, double* K, cudaStream_t st) override {
@@ -1518,7 +1686,7 @@ struct EngineImpl : lq_engine {
         if (parent) LQ_CUDA(cudaMemcpy(parent, t_parent.p + first, count * sizeof(int), cudaMemcpyDeviceToHost));
         if (cost) LQ_CUDA(cudaMemcpy(cost, t_cost.p + first, count * sizeof(int), cudaMemcpyDeviceToHost));
         if (elen) LQ_CUDA(cudaMemcpy(elen, t_elen.p + first, count * sizeof(int), cudaMemcpyDeviceToHost));
-        if (ign) LQ_CUDA(cudaMemcpy(ign, t_ignore.p + first, count, cudaMemcpyDeviceToHost));
+        if (ign) LQ_CUDA(cudaMemcpy(ign, tv.ignore[ign_copy] + first, count, cudaMemcpyDeviceToHost));
         if (owner) LQ_CUDA(cudaMemcpy(owner, t_owner.p + first, count, cudaMemcpyDeviceToHost));
         return LQ_OK;
     }

@@ -521,6 +521,36 @@ __global__ void nearest_finalize_kernel(const T* __restrict__ pcost, const int* 
     if (cost) cost[j] = best;
 }
 
+// Fold the partial minima of slots [slot_lo, slot_lo + nslots) into the last of them, so that the rollout kernel has a
+// single old-tree candidate per query to merge (reading hundreds of slots in its prologue cost more than its rollouts
+// at small waves).  Block = 32 queries x 8 slot phases: every warp reads one slot row for 32 consecutive queries.
+template <typename T>
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(T* __restrict__ pcost, int* __restrict__ pidx, int pstride, int slot_lo, int nslots, int W,
+                       const int* __restrict__ d_count) {
+    __shared__ T sc[8][32];
+    __shared__ int si[8][32];
+    const int lane = threadIdx.x & 31, phase = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + lane;
+    const int count = d_count ? min(*d_count, W) : W;
+    T best = Num<T>::inf();
+    int b = -1;
+    if (j < count) {
+#pragma unroll 4
+        for (int s = slot_lo + phase; s < slot_lo + nslots; s += 8)
+            merge_candidate(best, b, pcost[(size_t)s * pstride + j], pidx[(size_t)s * pstride + j]);
+    }
+    sc[phase][lane] = best; si[phase][lane] = b;
+    __syncthreads();
+    if (phase == 0 && j < count) {
+#pragma unroll
+        for (int p = 1; p < 8; p++) merge_candidate(best, b, sc[p][lane], si[p][lane]);
+        const int out = slot_lo + nslots - 1;
+        pcost[(size_t)out * pstride + j] = best;
+        pidx[(size_t)out * pstride + j] = b;
+    }
+}
+
 // Per-query metric for state-dependent providers (planner.py:348: S = lqr(x, 0)[0]
 // at the sample), packed for nearest_dense_kernel.
 template <typename T, class Sys, class Lqr>

@@ -300,7 +300,7 @@ steer_x_kernel(Model<T, Sys, Lqr> md, StagePlan stg,
                const T* __restrict__ samples, int sstride, const int* __restrict__ tries_used,
                int use_ignore, int force_rescan,
                T* __restrict__ xseq, T* __restrict__ useq,
-               ExDst dst, int Wc, int host_flags, const int* __restrict__ h_stop) {
+               ExDst dst, int Wc, int host_flags, const int* __restrict__ h_stop, int done_slot) {
     constexpr int N = Sys::N, M = Sys::M;
     constexpr int PER16 = 16 / (int)sizeof(T);
     constexpr int RW = (N + M * N + PER16 - 1) / PER16 * PER16;
@@ -396,14 +396,16 @@ steer_x_kernel(Model<T, Sys, Lqr> md, StagePlan stg,
     if (dst.flag[0]) {
         // fused exchange: my stores are visible system-wide before I count myself done; the last CTA of the
         // grid then raises this rank's arrival flag on every peer (after the data)
-        __threadfence_system();
         __syncthreads();
-        if (threadIdx.x == 0) s_last = atomicAdd(&ctl->done_steer, 1u) == gridDim.x - 1;
+        if (threadIdx.x == 0) {
+            __threadfence_system();                      // cumulative: covers the CTA's stores ordered before the barrier
+            s_last = atomicAdd(&ctl->done_steer[done_slot], 1u) == gridDim.x - 1;
+        }
         __syncthreads();
         if (s_last && threadIdx.x == 0) {
             __threadfence_system();
             for (int p = 0; p < dst.n; p++) *(volatile unsigned*)dst.flag[p] = dst.seq;
-            ctl->done_steer = 0;
+            ctl->done_steer[done_slot] = 0;
         }
     }
 }

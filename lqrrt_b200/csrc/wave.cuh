@@ -22,7 +22,8 @@ struct WaveCtl {
     WaveSlot ring[CTL_RING];
     int stopped;                    // sticky: a commit saw a stop request (1 done, 2 kill) or filled the tree
     int acc[3];                     // per-commit accumulators: accepted, tries (reset by the publishing CTA)
-    unsigned done_steer, done_commit;   // CTA completion counters (reset by the last CTA)
+    unsigned done_steer[2];         // CTA completion counters of the rollout kernels, by wave parity (two waves may be in
+    unsigned done_commit;           // flight with pipelined waves); commits are serialised (reset by the last CTA)
 };
 
 // How the next waves are sized on the device: the host's waves.wave_size, evaluated in float64 like Python.
@@ -112,12 +113,19 @@ template <typename T> struct TreeView {
     int* parent;       // [cap]
     int* cost;         // [cap] cumulative recorded steps from the seed; T_plan = (1 + cost) dt
     int* edge_len;     // [cap]
-    uint8_t* ignore;   // [cap] (word-aligned: marks are set with atomicOr on the containing word)
+    // Ignore marks (planner.py:270), [cap] bytes, word-aligned (set with atomicOr on the containing word).  Two copies:
+    // with pipelined waves (lag 2) wave k searches the marks as of commit k-2 while commit k-1 is adding its own,
+    // so commit j marks copy j & 1 -- its own goal paths directly, those of commit j-1 replayed from goal_list --
+    // and wave k reads copy k & 1.  Everything else uses copy 0.
+    uint8_t* ignore[2];
+    int* n_ignored2[2];   // marks per copy
+    int* goal_list[2];    // goal nodes appended by the last commit of each parity (for the replay), [goal_cap]
+    int* goal_count[2];
+    int goal_cap;
     uint8_t* owner;    // [cap] rank (record segment) whose GPU holds the node's edge
     T* edge_x;         // [cap][H*N]
     T* edge_u;         // [cap][H*M]
     int* size;         // device scalar
-    int* n_ignored;    // device scalar
     int* n_goal;       // device scalar
     unsigned long long* best;   // (cost << 32 | node), ~0 = none
     int cap;           // array stride (node_capacity rounded up to 4)

@@ -11,7 +11,8 @@ commit, include/lqrrt_b200.h) instead of one sample in Python.
 New keyword arguments (all optional, defaults keep reference call sites valid):
   wave      None = adaptive wave size, int = fixed global wave size
             (1 reproduces the reference's sequential semantics)
-  wave_max  cap of the adaptive wave size;  wave_growth: adaptive W = wave_growth * tree size
+  wave_max  cap of the adaptive wave size;  wave_growth: adaptive W = wave_growth * tree size (default 2: what bench.py
+            measures; 1 spends ~30 more small waves on a 100k-node tree for a deeper tree per sample)
   dtype     'f32' (throughput) or 'f64' (reference-parity arithmetic)
   rng       'philox' = counter-based device sampler; 'numpy' = the reference's
             global MT19937 stream, drawn on the host in the reference's order
@@ -32,6 +33,13 @@ New keyword arguments (all optional, defaults keep reference call sites valid):
             previous wave started with, enqueued ahead of the host, and the scan of the old part of the tree
             overlaps the previous wave's rollouts; 'host' = one lq_wave_expand / lq_wave_commit per wave, sized
             by the host.  Both grow the same tree for the same wave sizes.
+  lag       device schedule only.  1 (default): wave k searches the tree as committed by wave k-1.
+            2: pipelined waves -- wave k searches the tree as committed by wave k-2, so two consecutive waves'
+            scans and rollouts are in flight together and only the commits are serial.  Waves complete faster once
+            they are latency-bound (several GPUs), but the tree gets one edge deeper per two waves instead of per wave:
+            the choice for filling a tree fast (bench.py's throughput leg), not for reaching a distant goal with
+            small waves (measured on C4: lag 1 reaches the goal 283 m away in 56 ms, lag 2 fills 100k nodes first).
+            oracle/wave.py defines both.
   fresh_samples  True (default): the Philox wave counter keeps counting across update_plan calls, so a replan
             draws new samples as the reference's global NumPy stream does; assigning `planner.seed` restarts
             it.  False: every plan replays the same sample sequence.
@@ -70,14 +78,19 @@ class Planner(object):
                  min_time=0.5, max_time=1, max_nodes=1E5,
                  goal0=None, sys_time=time.time, printing=True,
                  wave=None, wave_max=8192, dtype='f32', rng='philox', seed=0, device=None, comm=None,
-                 wave_growth=1.0, pipeline=True, exchange='peer', nearest_kernel=None, prefetch=None,
-                 schedule=None, fresh_samples=True, depth=0):
+                 wave_growth=2.0, pipeline=True, exchange='peer', nearest_kernel=None, prefetch=None,
+                 schedule=None, fresh_samples=True, depth=0, lag=None):
         self._engine = None
         if schedule not in (None, 'device', 'host'):
             raise ValueError("schedule must be 'device' or 'host'")
         self.schedule = schedule or os.environ.get('LQRRT_SCHEDULE') or 'device'
         self.fresh_samples = bool(fresh_samples)
         self.depth = int(depth)
+        if lag is None:
+            lag = int(os.environ.get('LQRRT_LAG') or 1)
+        if lag not in (1, 2):
+            raise ValueError("lag must be 1 or 2")
+        self.lag = lag
         self._wave_base = 0
         self.engine_options = {}       # {LQ_OPT_*: value} applied to the engine before every plan (tests, tuning)
         if nearest_kernel is None:
@@ -328,7 +341,7 @@ class Planner(object):
 
             summ = eng.plan_run(self.seed, self._wave_base, 0 if self.wave is None else int(self.wave), 32, self.wave_max,
                                 self.wave_growth, pruning, on_wave, world=self.world, rank=self.rank, depth=self.depth,
-                                stream=stream)
+                                stream=stream, lag=self.lag)
             wave_ctr = state['waves']
             waves_enqueued = summ.waves_enqueued
             samples_total = int(summ.samples)
@@ -339,6 +352,8 @@ class Planner(object):
             # a full tree stops the device with code 1 as well; `killed` is what tells a kill from a normal end
             outcome = 'killed' if (stop == _waves.STOP_KILL or (self.killed and stop != 0)) else 'done'
             self.stats_device_ms = float(summ.device_ms)
+            self.stats_host = dict(enqueue_ms=float(summ.host_enqueue_ms), wait_ms=float(summ.host_wait_ms),
+                                   callback_ms=float(summ.host_callback_ms))
 
         # Software pipeline: with the device sampler nothing a wave needs comes from the host, so wave k+1
         # is enqueued before the host blocks on wave k's counters and the GPU never waits for the round
@@ -435,14 +450,15 @@ class Planner(object):
             self.stats['device_ms'] = ev0.elapsed_time(ev1)      # wave loop only, on the launching stream
         if use_device:
             self.stats['device_ms'] = self.stats_device_ms       # CUDA events on the pipeline's own chain stream
+            self.stats['host_pipeline_ms'] = self.stats_host
         self.stats['schedule'] = 'device' if use_device else 'host'
+        self.stats['lag'] = self.lag if use_device else 1
         if self.fresh_samples:
             self._wave_base += waves_enqueued if use_device else wave_ctr
 
         if self.plan_reached_goal:
             # the plan attributes the reference fills inside its loop (planner.py:276-281)
-            self.node_seq = self.tree.climb(best_node)
-            self.x_seq, self.u_seq = self.tree.trajectory(self.node_seq)
+            self.node_seq, self.x_seq, self.u_seq = self.tree.plan(best_node)
             self.T = len(self.x_seq) * self.dt
             self.t_seq = np.arange(len(self.x_seq)) * self.dt
 
@@ -466,9 +482,7 @@ class Planner(object):
 
         elif outcome == 'timeout':                                  # planner.py:311-328
             colmask = np.isinf(self.constraints.goal_buffer)
-            closestID = eng.closest(self.xguide, colmask, stream)
-            self.node_seq = self.tree.climb(closestID)
-            self.x_seq, self.u_seq = self.tree.trajectory(self.node_seq)
+            self.node_seq, self.x_seq, self.u_seq = self.tree.plan(None, self.xguide, colmask)
             self.T = len(self.x_seq) * self.dt
             self.t_seq = np.arange(len(self.x_seq)) * self.dt
             if self.printing:

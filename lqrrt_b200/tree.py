@@ -197,6 +197,30 @@ class Tree(object):
         path.reverse()
         return path
 
+    def plan(self, ID=None, xguide=None, colmask=None):
+        """(node_seq, x_seq, u_seq) of the plan that ends in node ID -- climb + trajectory (tree.py:100-132) -- or, with
+        ID None, in the node closest to `xguide` (planner.py:313-318), read out by one engine call."""
+        ids, hx, hu, el = self._eng.plan_readout(ID, xguide, colmask)
+        if self._world > 1:                     # an edge lives on the GPU that rolled it out: sum the per-rank answers
+            import torch
+            import torch.distributed as dist
+            dev = torch.device('cuda', self._eng.device) if dist.get_backend(self._comm) == 'nccl' else torch.device('cpu')
+            buf = torch.from_numpy(np.concatenate((hx.reshape(len(ids), -1), hu.reshape(len(ids), -1)), axis=1)).to(dev)
+            dist.all_reduce(buf, group=self._comm)
+            buf = buf.cpu().numpy()
+            nx = self._eng.H * self.nstates
+            hx = buf[:, :nx].reshape(hx.shape); hu = buf[:, nx:].reshape(hu.shape)
+        x_full = []; u_full = []
+        for k, node in enumerate(ids):
+            if node == 0:                        # tree.py:69-70: the seed's edge is [seed], [zeros]
+                x_full.append(self._seed); u_full.append(np.zeros(self.ncontrols))
+            elif node in self._long_edges:
+                x_full.extend(self._long_edges[node][0]); u_full.extend(self._long_edges[node][1])
+            else:
+                L = int(el[k])
+                x_full.extend(hx[k, i].copy() for i in range(L)); u_full.extend(hu[k, i].copy() for i in range(L))
+        return ids, x_full, u_full
+
     def trajectory(self, IDs):
         """Concatenated edges of the listed nodes (tree.py:121-132)."""
         xs, us = self._edges(list(IDs))

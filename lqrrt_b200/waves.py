@@ -75,7 +75,8 @@ class PeerExchange(object):
         import torch.distributed._symmetric_memory as symm
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        self.nbytes = 2 * self.world * int(segment_bytes) + 2 * self.world * 4
+        # four wave parities of world segments each, then the arrival flags (csrc/engine.cuh PEER_PAR)
+        self.nbytes = 4 * self.world * int(segment_bytes) + 4 * self.world * 4
         self.nbytes = (self.nbytes + 255) & ~255
         self.buf = symm.empty(self.nbytes, dtype=torch.uint8, device=device)
         self.buf.zero_()

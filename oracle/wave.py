@@ -18,6 +18,11 @@ Wave semantics (identical in csrc/engine.cu):
      (planner.py:253-257, tree.py:77-96)
   5. goal tests / ignore marks / best plan are applied in node order
      (planner.py:260-281), so they affect the *next* wave's searches.
+
+Pipelined waves (`lag = 2`, the device-scheduled driver's default): wave k searches the tree -- nodes AND
+ignore marks -- as committed by wave k-2 instead of k-1, so that the rollouts of two consecutive waves are
+independent of each other and can be in flight together; everything else is unchanged (nodes are still
+appended wave after wave in sample order).  `expand_wave(..., lag=2)` keeps the snapshots.
 """
 import numpy as np
 
@@ -58,6 +63,7 @@ class WaveOracle(object):
         self.x_seq = [[x0]]; self.u_seq = [[np.zeros(self.m)]]
         self.best_node = -1; self.best_cost = None
         self.goal_nodes = []
+        self.__dict__.pop('_snapshots', None)
 
     def load(self, state, parent, cost=None, K=None):
         """Inject a frozen tree (level-1 tests)."""
@@ -113,11 +119,13 @@ class WaveOracle(object):
         d = self.diffs(x)
         return np.sum(d.dot(S) * d, axis=1)
 
-    def nearest(self, X, use_ignore=True):
+    def nearest(self, X, use_ignore=True, visible=None):
+        """`visible` = (size, ignore list) snapshot the search is restricted to (pipelined waves); None = the tree as it is."""
         ids = np.zeros(len(X), dtype=np.int64); best = np.zeros(len(X))
-        ign = np.array(self.ignore, dtype=bool)
+        nvis = self.size if visible is None else visible[0]
+        ign = np.array(self.ignore if visible is None else visible[1], dtype=bool)[:nvis]
         for j, x in enumerate(X):
-            c = self.costs(x)
+            c = self.costs(x)[:nvis]
             if use_ignore and not ign.all():
                 c2 = np.where(ign, np.inf, c)
                 ids[j] = int(np.argmin(c2))
@@ -199,13 +207,20 @@ class WaveOracle(object):
                     self.best_cost = self.cost[node]; self.best_node = node
         return added
 
-    def expand_wave(self, X, use_ignore=True):
-        ids, _ = self.nearest(X, use_ignore)
+    def expand_wave(self, X, use_ignore=True, lag=1):
+        visible = None
+        if lag > 1:
+            # snapshots after every commit; wave k sees the state after commit k - lag (the initial tree before that)
+            hist = self.__dict__.setdefault('_snapshots', [(self.size, list(self.ignore))])
+            visible = hist[max(0, len(hist) - lag)]
+        ids, _ = self.nearest(X, use_ignore, visible)
         votes = []
         edges = [self.steer(int(i), x, votes) for i, x in zip(ids, X)]
         added = self.commit(ids, edges)
         if self.hfactor:
             self.apply_votes(votes)
+        if lag > 1:
+            self._snapshots.append((self.size, list(self.ignore)))
         return added, ids, edges
 
     def climb(self, ID):

@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-def _grow(rank, world, port, out, dtype, exchange='peer'):
+def _grow(rank, world, port, out, dtype, exchange='peer', lag=2):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
     import torch
     import torch.distributed as dist
@@ -32,7 +32,7 @@ def _grow(rank, world, port, out, dtype, exchange='peer'):
         comm = True
     prob = configs.demo_boat_intermediate(0)
     planner = prob.make_planner(dtype=dtype, seed=11, wave_max=512, max_nodes=6000, min_time=1e9, max_time=1e9,
-                                comm=comm, device=rank, exchange=exchange)
+                                comm=comm, device=rank, exchange=exchange, lag=lag)
     # the wave schedule follows the tree size the host last saw, which must not depend on G
     planner.pipeline = True
     ok = planner.update_plan(prob.x0, prob.sample_space, goal_bias=prob.goal_bias)
@@ -45,8 +45,8 @@ def _grow(rank, world, port, out, dtype, exchange='peer'):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('dtype,exchange', [('f32', 'peer'), ('f64', 'peer'), ('f32', 'nccl')])
-def test_two_gpu_tree_equals_one_gpu_tree(dtype, exchange):
+@pytest.mark.parametrize('dtype,exchange,lag', [('f32', 'peer', 2), ('f64', 'peer', 2), ('f32', 'peer', 1), ('f32', 'nccl', 1)])
+def test_two_gpu_tree_equals_one_gpu_tree(dtype, exchange, lag):
     import torch
     import torch.multiprocessing as mp
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
@@ -54,8 +54,9 @@ def test_two_gpu_tree_equals_one_gpu_tree(dtype, exchange):
     world = min(torch.cuda.device_count(), 4)
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_grow, args=(1, _free_port(), out, dtype), nprocs=1, join=True)
-    mp.spawn(_grow, args=(world, _free_port(), out, dtype, exchange), nprocs=world, join=True)
+    # (the host-scheduled NCCL path has the lag-1 wave semantics; the 1-GPU tree to compare with is grown with the same lag)
+    mp.spawn(_grow, args=(1, _free_port(), out, dtype, 'peer', lag), nprocs=1, join=True)
+    mp.spawn(_grow, args=(world, _free_port(), out, dtype, exchange, lag), nprocs=world, join=True)
     one = out[(1, 0)]
     assert one['size'] == 6001 and one['ok'] is False          # stopped by max_nodes (planner.py:330-336)
     for r in range(world):

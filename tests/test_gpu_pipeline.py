@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _grow(prob, dtype, schedule, opts=None, goal_bias=None, **kw):
-    args = dict(dtype=dtype, seed=11, max_nodes=3000, min_time=1e9, max_time=1e9, wave_max=512, schedule=schedule)
+    args = dict(dtype=dtype, seed=11, max_nodes=3000, min_time=1e9, max_time=1e9, wave_max=512, schedule=schedule, lag=1)
     args.update(kw)
     planner = prob.make_planner(**args)
     planner.engine_options = dict(opts or {})
@@ -74,22 +74,50 @@ def test_goal_reaching_plans_with_ignore_marks_agree(cuda_device, pruning_bias):
     _same(host, dev)
 
 
-def test_fixed_waves_match_the_wave_oracle(cuda_device):
-    """Node-for-node against oracle/wave.py through the device-scheduled driver (float64, fixed waves)."""
+@pytest.mark.parametrize('lag', [1, 2])
+@pytest.mark.parametrize('name,W,nodes,bias', [('demo_boat_novice', 48, 400, None), ('demo_boat_novice', 64, 4000, [0.9, 0.9, 0, 0, 0, 0]),
+                                               ('c1', 40, 600, None)])
+def test_fixed_waves_match_the_wave_oracle(cuda_device, lag, name, W, nodes, bias):
+    """Node-for-node against oracle/wave.py through the device-scheduled driver (float64, fixed waves), for both wave
+    semantics: lag 1 (wave k searches the tree of wave k-1) and lag 2 (pipelined waves: the tree AND the ignore marks of
+    wave k-2).  The strongly goal-biased case reaches the goal early, so most of its waves run with ignore marks being
+    added by every commit -- the case the two copies of the marks exist for."""
     from oracle.wave import WaveOracle
-    prob = problem('demo_boat_novice')
-    planner = prob.make_planner(dtype='f64', wave=48, seed=5, max_nodes=400, min_time=1e9, max_time=1e9, schedule='device')
-    planner.update_plan(prob.x0, prob.sample_space, goal_bias=prob.goal_bias, xrand_gen=10)
-    assert planner.stats['schedule'] == 'device'
+    prob = problem(name)
+    gb = prob.goal_bias if bias is None else bias
+    planner = prob.make_planner(dtype='f64', wave=W, seed=5, max_nodes=nodes, min_time=1e9, max_time=1e9, schedule='device', lag=lag)
+    planner.update_plan(prob.x0, prob.sample_space, goal_bias=gb, xrand_gen=10)
+    assert planner.stats['schedule'] == 'device' and planner.stats['lag'] == lag
     orc = WaveOracle(prob.system, prob.goal, prob.goal_buffer, prob.horizon, prob.dt, prob.FPR, prob.error_tol,
                      node_capacity=int(planner.max_nodes) + 1)
     orc.reset(prob.x0)
     for w in range(planner.stats['waves']):
-        X, _ = orc.sample_wave(5, w, 0, 48, prob.sample_space, prob.goal_bias, 10)
-        orc.expand_wave(X)
+        X, _ = orc.sample_wave(5, w, 0, W, prob.sample_space, gb, 10)
+        orc.expand_wave(X, lag=lag)
     assert planner.tree.size == orc.size
     assert planner.tree.pID == orc.parent
-    assert np.abs(planner.tree.state - orc.state).max() < 1e-9
+    tol = 1e-6 if prob.system.lqr.kind == 3 else 1e-9
+    assert np.abs(planner.tree.state - orc.state).max() < tol
+    if bias is not None:
+        assert len(orc.goal_nodes) > 3 and sum(orc.ignore) > 10           # the marks were exercised
+        assert planner.plan_reached_goal and planner.T == orc.T
+
+
+@pytest.mark.parametrize('name,dtype', [('demo_boat_novice', 'f32'), ('c4', 'f32'), ('demo_car', 'f64')])
+def test_pipelined_waves_do_not_depend_on_issue_options(cuda_device, name, dtype):
+    """lag 2: the same tree with every query forced through the rollout kernel's rescan, with the tables read from
+    global memory, and with both rollout CTA sizes (adaptive waves, pruning on)."""
+    prob = problem(name)
+    base = _grow(prob, dtype, 'device', lag=2)
+    assert base['size'] == 3001
+    _same(base, _grow(prob, dtype, 'device', {nat.LQ_OPT_FORCE_RESCAN: 1}, lag=2))
+    _same(base, _grow(prob, dtype, 'device', {nat.LQ_OPT_STAGE_TABLES: 0}, lag=2))
+    _same(base, _grow(prob, dtype, 'device', {nat.LQ_OPT_STEER_BLOCK: 32}, lag=2))
+    _same(base, _grow(prob, dtype, 'device', {nat.LQ_OPT_STEER_BLOCK: 128}, lag=2))
+    gb = [0.9, 0.9] + [0] * (prob.nstates - 2)
+    a = _grow(prob, dtype, 'device', goal_bias=gb, lag=2, max_nodes=5000, wave_max=128)
+    b = _grow(prob, dtype, 'device', {nat.LQ_OPT_FORCE_RESCAN: 1}, goal_bias=gb, lag=2, max_nodes=5000, wave_max=128)
+    _same(a, b)
 
 
 def test_replans_draw_fresh_samples_unless_asked_not_to(cuda_device):
