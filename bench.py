@@ -485,7 +485,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='c4')
     ap.add_argument('--dtype', default='f32', choices=['f32', 'f64'])
-    ap.add_argument('--wave', type=int, default=8192, help="largest wave per GPU")
+    ap.add_argument('--wave', type=int, default=16384, help="largest wave per GPU")
     ap.add_argument('--scaling', default='strong', choices=['weak', 'strong'],
                     help="strong: same global wave schedule for every N (bit-identical tree); weak: 8192 samples per GPU per wave")
     ap.add_argument('--growth', type=float, default=2.0,

@@ -306,8 +306,20 @@ enum { LQ_OPT_NEAREST_KERNEL = 1, LQ_OPT_SAMPLE_PREFETCH = 2,
        LQ_OPT_FORCE_RESCAN = 5,         /* tests: every query takes the rollout kernel's own rescan path */
        LQ_OPT_STAGE_TABLES = 6,         /* 1 (default) = obstacle tables staged in shared memory by the rollout kernels */
        LQ_OPT_STEER_BLOCK = 7,          /* CTA size of the wave rollout kernel: 0 = auto, 32, 128 */
-       LQ_OPT_PDL = 8                   /* 1 (default) = rollout and commit kernels of a wave are launched programmatically
-                                           dependent: they start (and stage their tables) while the kernel in front drains */ };
+       LQ_OPT_PDL = 8,                  /* 1 (default) = rollout and commit kernels of a wave are launched programmatically
+                                           dependent: they start (and stage their tables) while the kernel in front drains */
+       /* Indexed nearest search (csrc/grid.cuh): the tree keeps a uniform grid over its first two state dims and a
+        * query only evaluates the nodes of cells whose lower cost bound is below its best cost so far -- the same
+        * pair arithmetic and tie rule as the brute-force scan, hence the same answer bit for bit.  Needs a constant
+        * diagonal metric with positive weights on two un-wrapped leading dims; 1 = use it for scans of at least
+        * LQ_OPT_GRID_MIN_KPAIRS x 1024 (query, node) pairs, 0 (default) = always scan everything.  Measured on C4
+        * (profiles/README.md): wave-grown trees are so clustered in (x, y) -- thousands of nodes per cell that differ
+        * in heading and velocity only -- that a query still evaluates ~30 000 candidates, one dependent load at a
+        * time, and loses to the brute-force scan; kept for sparse, wide trees. */
+       LQ_OPT_NEAREST_GRID = 9,
+       LQ_OPT_GRID_MIN_KPAIRS = 10,
+       LQ_OPT_SAMPLE_AHEAD = 11         /* pipelined waves: 1 (default) = once the wave size is known to the host (top of the
+                                           policy, fixed waves) the sampler runs on a side stream ahead of the wave's chain */ };
 enum { LQ_NEAREST_SCALAR = 0, LQ_NEAREST_PACKED = 1,
        /* tuning variants, same results: 8 queries per thread (best on the 12-state scan), and the two-level
         * argmin with one-lane-at-a-time arithmetic */

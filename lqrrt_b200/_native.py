@@ -22,6 +22,7 @@ LQ_F32, LQ_F64 = 0, 1
 LQ_OPT_NEAREST_KERNEL, LQ_OPT_SAMPLE_PREFETCH = 1, 2
 LQ_OPT_NEAREST_CTAS_PER_SM = 3
 LQ_OPT_SPECULATIVE_SCAN, LQ_OPT_FORCE_RESCAN, LQ_OPT_STAGE_TABLES, LQ_OPT_STEER_BLOCK, LQ_OPT_PDL = 4, 5, 6, 7, 8
+LQ_OPT_NEAREST_GRID, LQ_OPT_GRID_MIN_KPAIRS, LQ_OPT_SAMPLE_AHEAD = 9, 10, 11
 NEAREST_KERNELS = {'scalar': 0, 'packed': 1, 'packed_q8': 2, 'two_level': 3, 'prefix': 4}
 
 
@@ -265,8 +266,12 @@ class Engine(object):
     # -------------------------------------------------------------- problem
     def set_goal(self, goal, buffer):
         g = _c64(goal); b = _c64(buffer)
+        key = g.tobytes() + b.tobytes()
+        if key == getattr(self, '_goal_key', None):      # unchanged since the last plan: the device copy stands
+            return
         self.h2d_bytes += 2 * LQ_MAX_N * self.elt
         self._ck(self.lib.lq_set_goal(self.h, _dp(g), _dp(b)))
+        self._goal_key = key
 
     def set_horizon(self, horizon_iters, stream=None):
         self._ck(self.lib.lq_set_horizon(self.h, int(horizon_iters), self._stream(stream)))
@@ -376,9 +381,10 @@ class Engine(object):
         xg = None if xguide is None else _c64(xguide)
         mk = None if colmask is None else np.ascontiguousarray(colmask, dtype=np.uint8)
         while True:
-            ids = np.zeros(max_len, dtype=np.int32); ln = C.c_int(0)
-            hx = np.zeros((max_len, self.H, self.n)); hu = np.zeros((max_len, self.H, self.m))
-            el = np.zeros(max_len, dtype=np.int32)
+            # the engine fills the first `len` rows; nothing else is read (no zero-fill of max_len rows per plan)
+            ids = np.empty(max_len, dtype=np.int32); ln = C.c_int(0)
+            hx = np.empty((max_len, self.H, self.n)); hu = np.empty((max_len, self.H, self.m))
+            el = np.empty(max_len, dtype=np.int32)
             rc = self.lib.lq_plan_readout(self.h, -1 if node is None else int(node), None if xg is None else _dp(xg),
                                           None if mk is None else mk.ctypes.data_as(_U8), int(max_len), _ip(ids), C.byref(ln),
                                           _dp(hx), _dp(hu), _ip(el), self._stream(stream))

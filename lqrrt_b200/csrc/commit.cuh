@@ -13,6 +13,7 @@
 // crossing NVLink for every accepted node.
 #pragma once
 #include "steer.cuh"
+#include "grid.cuh"
 
 namespace lq {
 
@@ -185,6 +186,9 @@ commit_x_kernel(TreeView<T> tv, WaveCtl* __restrict__ ctl, int wave_k,
         }
         for (int q = lane + 96; q < nrec; q += 32) tv.K[(size_t)(q - N) * tv.cap + node] = row[q];       // wide models
         in_goal = __all_sync(0xffffffffu, in_goal);
+        // position for the spatial index (lanes dx, dy of the first chunk hold those dims)
+        const float gpx = (float)__shfl_sync(0xffffffffu, rv[0], tv.grid.dx & 31);
+        const float gpy = (float)__shfl_sync(0xffffffffu, rv[0], tv.grid.dy & 31);
         T* dx = tv.edge_x + (size_t)node * H * N; T* du = tv.edge_u + (size_t)node * H * M;
 #pragma unroll
         for (int c = 0; c < 4; c++) { const int q = lane + 32 * c; if (q < nx) dx[q] = ex[c]; }
@@ -195,6 +199,7 @@ commit_x_kernel(TreeView<T> tv, WaveCtl* __restrict__ ctl, int wave_k,
         if (lane == 0) {
             const int c = pc + L;
             tv.parent[node] = par; tv.cost[node] = c; tv.edge_len[node] = L; tv.owner[node] = (uint8_t)sg;
+            if (tv.grid.on) grid_insert(tv.grid, node, gpx, gpy);
             if (in_goal) {                                                  // planner.py:260-281
                 atomicAdd(tv.n_goal, 1);
                 atomicMin(tv.best, ((unsigned long long)(unsigned)c << 32) | (unsigned)node);

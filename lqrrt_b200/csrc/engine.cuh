@@ -19,6 +19,7 @@
 #include "steer.cuh"
 #include "sample.cuh"
 #include "commit.cuh"
+#include "grid.cuh"
 
 struct lq_engine {
     std::string err;
@@ -200,6 +201,13 @@ __global__ void climb_from_kernel(TreeView<T> tv, const int* __restrict__ d_node
     *len = node >= 0 ? -1 : n;
 }
 
+template <typename T, int N> struct SeedArgs { T x[N]; };
+template <typename T, int N>
+__global__ void seed_kernel(TreeView<T> tv, SeedArgs<T, N> s) {
+    if (threadIdx.x < N) tv.state[(size_t)threadIdx.x * tv.cap] = s.x[threadIdx.x];
+    if (threadIdx.x == 0) { tv.parent[0] = -1; tv.cost[0] = 0; tv.edge_len[0] = 0; }
+}
+
 template <typename T>
 __global__ void tree_scalars_kernel(TreeView<T> tv, int size, WaveCtl* ctl) {
     *tv.size = size; *tv.n_goal = 0; *tv.best = ~0ull;
@@ -250,6 +258,14 @@ struct EngineImpl : lq_engine {
     int sample_parity = 0;
     int cur_parity = 0;              // sample / partials / segment parity of the wave being expanded
     bool metric_diag = true;
+    // spatial index of the tree for the indexed nearest search (grid.cuh); kept whenever the metric allows it
+    DevBuf<int> g_head, g_next;
+    DevBuf<unsigned> g_bits;
+    bool grid_ok = false;                  // constant diagonal metric with positive weights on the un-wrapped dims 0, 1
+    bool grid_dirty = false;               // the extents changed under a non-empty tree: re-link before the next search
+    bool grid_have_extents = false;
+    int grid_opt = 0;                      // lq_set_option(LQ_OPT_NEAREST_GRID)
+    int grid_min_kpairs = 16384;           // lq_set_option(LQ_OPT_GRID_MIN_KPAIRS)
     DiagMetric<T, N> dmet;
     double Sconst[N * N];
     StagePlan stage_plan;
@@ -302,6 +318,9 @@ struct EngineImpl : lq_engine {
     cudaStream_t s_chain = nullptr, s_scan = nullptr, s_chain2 = nullptr;
     static constexpr int EVR = 8;
     cudaEvent_t ev_commit[EVR] = {}, ev_scan[EVR] = {}, ev_in = nullptr, ev_begin = nullptr, ev_end = nullptr;
+    cudaEvent_t ev_steer[EVR] = {}, ev_samp[EVR] = {};     // pipelined waves: sampler ahead of the chain
+    int sample_ahead = 1;                                  // lq_set_option(LQ_OPT_SAMPLE_AHEAD)
+    int prof_scan_ev[RING] = {};                           // which event marks the start of the scan stage
     // optional per-stage CUDA-event timing (bench.py roofline): sample | nearest (old-tree + delta) | steer | commit
     bool prof_on = false;
     bool prof_open[RING] = {};
@@ -322,6 +341,8 @@ struct EngineImpl : lq_engine {
         for (auto& e : ev_consumed) if (e) cudaEventDestroy(e);
         for (auto& e : ev_commit) if (e) cudaEventDestroy(e);
         for (auto& e : ev_scan) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_steer) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_samp) if (e) cudaEventDestroy(e);
         if (ev_in) cudaEventDestroy(ev_in);
         if (ev_begin) cudaEventDestroy(ev_begin);
         if (ev_end) cudaEventDestroy(ev_end);
@@ -545,8 +566,54 @@ struct EngineImpl : lq_engine {
         // lists and cut the divergence of thread-per-sample rollouts; without obstacle tables one lane is enough
         steer_lanes = obs_work > 0 ? 8 : 1;
         if (Lqr::COOP) steer_lanes = 32;       // a warp per sample shares the Riccati sweep (measured 1.7x over 8 lanes on C5)
+        memset(&tv.grid, 0, sizeof tv.grid);
+        grid_ok = metric_diag && N >= 2 && !(md.angle_mask & 3u) && Sconst[0] > 0 && Sconst[N + 1] > 0;
+        if (grid_ok) {
+            constexpr int FW = GRID_F * GRID_F / 32, CW = GRID_C * GRID_C / 32;
+            LQ_CUDA(g_head.alloc((size_t)GRID_F * GRID_F)); LQ_CUDA(g_next.alloc(cap)); LQ_CUDA(g_bits.alloc(FW + CW));
+            tv.grid.head = g_head.p; tv.grid.next = g_next.p; tv.grid.fine = g_bits.p; tv.grid.coarse = g_bits.p + FW;
+            tv.grid.dx = 0; tv.grid.dy = 1; tv.grid.on = 0;         // linked and searched only while the option is on
+            grid_extents(0.0, 1.0, 0.0, 1.0);
+            grid_have_extents = false; grid_dirty = false;
+        }
         return LQ_OK;
     }
+
+    // ---- spatial index ----------------------------------------------------------
+    // Any extents are correct (everything beyond the grid is filed under its border cells); they only decide how
+    // well the cells resolve the tree.  Taken from the sample box (planner.py:194-198), else from the loaded nodes.
+    void grid_extents(double lo0, double hi0, double lo1, double hi1) {
+        if (!grid_ok) return;
+        auto axis = [](double lo, double hi, float* origin, float* inv_h, double* h) {
+            if (!(hi > lo) || !std::isfinite(lo) || !std::isfinite(hi)) { lo = lo - 0.5; hi = lo + 1.0; if (!std::isfinite(lo)) { lo = 0; hi = 1; } }
+            const double pad = 0.02 * (hi - lo);
+            lo -= pad; hi += pad;
+            *h = (hi - lo) / GRID_F;
+            *origin = (float)lo; *inv_h = (float)(1.0 / *h);
+        };
+        GridView g = tv.grid;
+        double hx = 1, hy = 1;
+        axis(lo0, hi0, &g.x0, &g.inv_hx, &hx);
+        axis(lo1, hi1, &g.y0, &g.inv_hy, &hy);
+        g.kx = (float)(hx * hx * Sconst[0]); g.ky = (float)(hy * hy * Sconst[N + 1]);
+        if (g.x0 != tv.grid.x0 || g.y0 != tv.grid.y0 || g.inv_hx != tv.grid.inv_hx || g.inv_hy != tv.grid.inv_hy) grid_dirty = true;
+        tv.grid = g;
+        grid_have_extents = true;
+    }
+    // (re)link every node of the tree, on `st`
+    int grid_rebuild(cudaStream_t st, int count_ub) {
+        if (!grid_active()) return LQ_OK;
+        LQ_CUDA(cudaMemsetAsync(g_head.p, 0xff, g_head.n * sizeof(int), st));
+        LQ_CUDA(cudaMemsetAsync(g_next.p, 0xfe, g_next.n * sizeof(int), st));        // GRID_PENDING
+        LQ_CUDA(cudaMemsetAsync(g_bits.p, 0, g_bits.n * sizeof(unsigned), st));
+        const int n = std::max(1, count_ub);
+        grid_insert_range_kernel<T><<<(n + 127) / 128, 128, 0, st>>>(tv, 0, tv.size, n); launches++;
+        LQ_CUDA(cudaGetLastError());
+        grid_dirty = false;
+        return LQ_OK;
+    }
+    int grid_sync(cudaStream_t st) { return (grid_active() && grid_dirty) ? grid_rebuild(st, size_ub) : LQ_OK; }
+    bool grid_active() const { return grid_ok && grid_opt == 1; }
 
     // Uniform grid over the obstacle table (see FeasPrim).  Zones of influence are axis-aligned boxes:
     // centre +- (obstacle extent + hull bounding radius + margin); the margin absorbs float rounding of
@@ -699,12 +766,34 @@ struct EngineImpl : lq_engine {
         }
         sp.tries = tries;
         have_sampling = true;
+        if (N >= 2) grid_extents(lo[0], hi[0], lo[1], hi[1]);
         return LQ_OK;
     }
 
+    // New tree = the seed alone (planner.py:172-173, tree.py:50-73).  The seed state rides in the kernel arguments:
+    // nothing is staged on the host, nothing waits -- everything is ordered on `st`, which the wave pipeline picks up.
     int reset(const double* x0, cudaStream_t st) override {
-        const int parent = -1, cost = 0;
-        return load_nodes(1, x0, &parent, &cost, st);
+        LQ_CUDA(cudaSetDevice(device));
+        SeedArgs<T, N> sa;
+        for (int d = 0; d < N; d++) sa.x[d] = (T)x0[d];
+        LQ_CUDA(cudaMemsetAsync(t_ignore.p, 0, (size_t)2 * cap, st)); ign_copy = 0;
+        LQ_CUDA(cudaMemsetAsync(t_owner.p, 0, cap, st));
+        seed_kernel<T, N><<<1, 32, 0, st>>>(tv, sa); launches++;
+        tree_scalars_kernel<T><<<1, 1, 0, st>>>(tv, 1, w_ctl.p); launches++;
+        init_gain_kernel<T, Sys, Lqr><<<1, 128, 0, st>>>(md, t_state.p, t_K.p, cap, 1); launches++;
+        LQ_CUDA(cudaGetLastError());
+        if (grid_ok) {
+            if (!grid_have_extents) { grid_extents(x0[0] - 50.0, x0[0] + 50.0, x0[1] - 50.0, x0[1] + 50.0); grid_have_extents = false; }
+            if (int r = grid_rebuild(st, 1)) return r;
+            if (!grid_active()) grid_dirty = true;
+        }
+        size_ub = 1; size_ub_exact = 1;
+        memset(&last_stats, 0, sizeof last_stats);
+        last_stats.tree_size = 1; last_stats.best_node = -1; last_stats.best_cost = -1;
+        q_head = q_tail = 0;
+        for (int k = 0; k < RING; k++) prof_open[k] = false;
+        sample_parity = 0; consumed_valid[0] = consumed_valid[1] = false;
+        return LQ_OK;
     }
 
     int load_nodes(int count, const double* state, const int* parent, const int* cost, cudaStream_t st) override {
@@ -728,6 +817,20 @@ struct EngineImpl : lq_engine {
         tree_scalars_kernel<T><<<1, 1, 0, st>>>(tv, count, w_ctl.p); launches++;
         init_gain_kernel<T, Sys, Lqr><<<(count + 127) / 128, 128, 0, st>>>(md, t_state.p, t_K.p, cap, count); launches++;
         LQ_CUDA(cudaGetLastError());
+        if (grid_ok) {
+            if (!grid_have_extents) {                 // no sample box yet: the loaded nodes' own bounding box
+                double b[4] = {state[0], state[0], state[1], state[1]};
+                for (int i = 0; i < count; i++) {
+                    const double x = state[(size_t)i * N], y = state[(size_t)i * N + 1];
+                    if (std::isfinite(x)) { b[0] = std::min(b[0], x); b[1] = std::max(b[1], x); }
+                    if (std::isfinite(y)) { b[2] = std::min(b[2], y); b[3] = std::max(b[3], y); }
+                }
+                grid_extents(b[0], b[1], b[2], b[3]);
+                grid_have_extents = false;            // a later sample box still takes over
+            }
+            if (int r = grid_rebuild(st, count)) return r;
+            if (!grid_active()) grid_dirty = true;       // not linked: switching the option on re-links first
+        }
         LQ_CUDA(cudaStreamSynchronize(st));     // host staging vectors die here
         size_ub = count; size_ub_exact = count;
         memset(&last_stats, 0, sizeof last_stats);
@@ -778,6 +881,25 @@ struct EngineImpl : lq_engine {
         T* pc = pcost_of(par); int* pi = pidx_of(par);
         // the erf masks of the shipped vehicles get compile-time kernels; anything else the generic one
         const int cmask = md.angle_mask == 0u ? 0 : (md.angle_mask == 4u && N >= 3 ? 4 : (md.angle_mask == 1u ? 1 : -1));
+        if (metric_diag && d_lo == nullptr && grid_active() && !grid_dirty &&
+            (long long)std::max(1, W) * Nub >= (long long)grid_min_kpairs * 1024) {
+            // indexed search (grid.cuh): one candidate per query in a single slot
+            constexpr bool EX = sizeof(T) == 8;
+            constexpr int GL = GRID_R, GB = 128;
+            sa.nqb = std::max(1, (W * GL + GB - 1) / GB); sa.nsplit = 1;
+            sa.slot0 = end_aligned ? slot_base - 1 : slot_base;
+#define LQ_NEAR_GRID(MM)                                                                                   \
+    nearest_grid_kernel<T, N, MM, EX, GL, GB><<<sa.nqb, GB, 0, st>>>(t_state.p, cap, ignp, sa, q, qstride, dmet, tv.grid, pc, pi, Wc)
+            if (cmask == 0) LQ_NEAR_GRID(0);
+            else if (cmask == 4) LQ_NEAR_GRID((N >= 3 ? 4 : 0));
+            else if (cmask == 1) LQ_NEAR_GRID(1);
+            else LQ_NEAR_GRID(-1);
+#undef LQ_NEAR_GRID
+            launches++;
+            if (nsplit_out) *nsplit_out = 1;
+            LQ_CUDA(cudaGetLastError());
+            return LQ_OK;
+        }
         if (metric_diag) {
             constexpr int QBIG = sizeof(T) == 4 ? 4 : 2;
             constexpr bool EX = sizeof(T) == 8;
@@ -884,6 +1006,9 @@ struct EngineImpl : lq_engine {
     int scan_target() const { return 148 * (near_ctas_per_sm > 0 ? near_ctas_per_sm : (N <= 6 ? 16 : 8)); }
     // the old-tree scan shares the GPU with the rollout chain of the wave before: more, shorter CTAs let the chain's
     // (higher-priority) CTAs in sooner (measured on C4: 32 per SM 9.06 ms per plan, 16: 9.26, 8: 9.47)
+    // pipelined waves keep two scans in flight, which fills the machine by itself: one resident set of CTAs per scan,
+    // longer node chunks per CTA (measured on whole C4 plans, profiles/README.md: 8 per SM 6.57 ms, 16: 6.73, 4: 6.91)
+    int pipelined_scan_target() const { return 148 * (near_ctas_per_sm > 0 ? near_ctas_per_sm : 8); }
     int old_scan_target() const { return near_ctas_per_sm > 0 ? 148 * near_ctas_per_sm : 2 * scan_target(); }
 
     int nearest(const void* d_q, int W, int use_ignore, int* d_idx, void* d_cost, cudaStream_t st) override {
@@ -891,6 +1016,7 @@ struct EngineImpl : lq_engine {
         if (W < 1 || W > Wc) LQ_FAIL(LQ_ERR_ARG, "W=%d outside 1..wave_capacity=%d", W, Wc);
         const T* q = (const T*)d_q;
         int qstride = W;
+        if (int r = grid_sync(st)) return r;
         if (!metric_diag) {     // dense search reads S in the wave layout: restride the queries
             for (int d = 0; d < N; d++)
                 LQ_CUDA(cudaMemcpyAsync(w_samples.p + (size_t)d * Wc, q + (size_t)d * W, W * sizeof(T), cudaMemcpyDeviceToDevice, st));
@@ -993,16 +1119,17 @@ struct EngineImpl : lq_engine {
         return launch_steer_x_l<1>(W, slot, par, slot_lo, nslots, use_ignore, dst, flags, use_stop_word, st, copy, d_vis, xpar);
     }
 
-    int launch_sample(uint64_t seed, uint32_t wave, int slot, int par, int count_ub, cudaStream_t st) {
+    int launch_sample(uint64_t seed, uint32_t wave, int slot, int par, int count_ub, cudaStream_t st,
+                      int first_known = 0, int count_known = -1) {
         constexpr int TL = 16;                       // >= tries_capacity
         const long long threads = (long long)std::max(1, count_ub) * TL;
         const WaveSlot* ws = &w_ctl.p->ring[slot];
         if (threads >= 148LL * 8 * 128) {
             sample_kernel<T, Sys, Lqr, TL, 128><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(
-                md, sp, seed, wave, ws, samples_of(par), Wc, tries_of(par));
+                md, sp, seed, wave, ws, samples_of(par), Wc, tries_of(par), first_known, count_known);
         } else {
             sample_kernel<T, Sys, Lqr, TL, 32><<<(unsigned)((threads + 31) / 32), 32, 0, st>>>(
-                md, sp, seed, wave, ws, samples_of(par), Wc, tries_of(par));
+                md, sp, seed, wave, ws, samples_of(par), Wc, tries_of(par), first_known, count_known);
         }
         launches++;
         LQ_CUDA(cudaGetLastError());
@@ -1049,6 +1176,7 @@ struct EngineImpl : lq_engine {
         const int slot = 0, par = cur_parity;
         const int ps = q_tail % RING;
         if (prof_on) cudaEventRecord(pev[ps][1], st);
+        if (int r = grid_sync(st)) return r;
         if (int r = launch_metric(samples_of(par), Wc, count, nullptr, par, st)) return r;
         int nsplit = 1;
         // stepwise: one scan over the whole tree (n_old = 0), written to the "delta" slots
@@ -1207,7 +1335,7 @@ struct EngineImpl : lq_engine {
         if (!prof_on || !prof_open[ps]) return;
         float ms = 0;
         auto el = [&](int a, int b) { ms = 0; cudaEventElapsedTime(&ms, pev[ps][a], pev[ps][b]); return (double)ms; };
-        prof_ms[0] += el(0, 1); prof_ms[1] += el(1, 2); prof_ms[2] += el(3, 4) - 0.0; prof_ms[3] += el(4, 5); prof_ms[4] += el(5, 6);
+        prof_ms[0] += el(0, 1); prof_ms[1] += el(prof_scan_ev[ps] ? prof_scan_ev[ps] : 1, 2); prof_ms[2] += el(3, 4) - 0.0; prof_ms[3] += el(4, 5); prof_ms[4] += el(5, 6);
         prof_work[0] += (double)local_count * size_before;
         prof_work[1] += (double)local_count * size_before * N * sizeof(T);
         prof_work[2] += local_count; prof_work[3] += 1;
@@ -1262,6 +1390,8 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(cudaStreamCreateWithPriority(&s_chain2, cudaStreamNonBlocking, hi));
         for (auto& e : ev_commit) LQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& e : ev_scan) LQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : ev_steer) LQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : ev_samp) LQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         LQ_CUDA(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
         LQ_CUDA(cudaEventCreate(&ev_begin));
         LQ_CUDA(cudaEventCreate(&ev_end));
@@ -1297,6 +1427,7 @@ struct EngineImpl : lq_engine {
         last_my_seg = rank;
 
         // the chain stream picks up after the caller's stream (reset / goal / sampling uploads)
+        if (int r = grid_sync(st)) return r;
         LQ_CUDA(cudaEventRecord(ev_in, st));
         LQ_CUDA(cudaStreamWaitEvent(s_chain, ev_in, 0));
         *h_stop = 0;
@@ -1342,17 +1473,38 @@ struct EngineImpl : lq_engine {
                 // other stream meanwhile.
                 cudaStream_t sc = (k & 1) ? s_chain2 : s_chain;
                 const int copy = k & 1;
-                if (prof_on) cudaEventRecord(pev[ps][0], sc);
-                if (int r = launch_sample(a->seed, a->wave_ctr0 + (uint32_t)k, slot, par, cub, sc)) return r;
+                // The sampler reads nothing of the tree (planner.py:201-211), only the wave's size.  Once the policy has
+                // reached its top size (it is monotone in the tree size), and for waves 0 and 1, the host knows that size
+                // itself: the sampler then runs on the side stream as soon as the sample buffer's last reader (the
+                // rollouts two waves back) is done, off the wave's chain.  After a stop the slot says 0 samples and the
+                // rollout kernel ignores what was drawn.
+                const int n_known = n_start[exact_upto];
+                const bool ahead = sample_ahead && (pol.fixed > 0 || k < 2 || policy_wave(pol, n_known) >= pol.wmax);
+                if (ahead) {
+                    const int wk = k < 2 ? policy_wave(pol, n0) : (pol.fixed > 0 ? pol.fixed : pol.wmax);
+                    int first_k = 0, count_k = 0;
+                    policy_slice(wk, rank, world, &first_k, &count_k);
+                    if (k >= 2) LQ_CUDA(cudaStreamWaitEvent(s_scan, ev_steer[(k - 2) % EVR], 0));
+                    if (prof_on) cudaEventRecord(pev[ps][0], s_scan);
+                    if (int r = launch_sample(a->seed, a->wave_ctr0 + (uint32_t)k, slot, par, cub, s_scan, first_k, count_k)) return r;
+                    if (prof_on) cudaEventRecord(pev[ps][1], s_scan);
+                    LQ_CUDA(cudaEventRecord(ev_samp[k % EVR], s_scan));
+                    LQ_CUDA(cudaStreamWaitEvent(sc, ev_samp[k % EVR], 0));
+                } else {
+                    if (prof_on) cudaEventRecord(pev[ps][0], sc);
+                    if (int r = launch_sample(a->seed, a->wave_ctr0 + (uint32_t)k, slot, par, cub, sc)) return r;
+                    if (prof_on) cudaEventRecord(pev[ps][1], sc);
+                }
+                if (prof_on) { cudaEventRecord(pev[ps][7], sc); prof_scan_ev[ps] = 7; }
                 if (int r = launch_metric(samples_of(par), Wc, cub, d_count, par, sc)) return r;
-                if (prof_on) cudaEventRecord(pev[ps][1], sc);
                 int ns = 0;
                 if (int r = launch_scan(samples_of(par), Wc, cub, d_count, nullptr, d_nold, n_old_ub, nullptr, use_ignore, par,
-                                        MAX_SPLIT_OLD, true, MAX_SPLIT_OLD, scan_target(), sc, &ns, copy)) return r;
+                                        MAX_SPLIT_OLD, true, MAX_SPLIT_OLD, pipelined_scan_target(), sc, &ns, copy)) return r;
                 if (int r = launch_reduce(par, MAX_SPLIT_OLD - ns, ns, cub, d_count, sc)) return r;
                 if (prof_on) { cudaEventRecord(pev[ps][2], sc); cudaEventRecord(pev[ps][3], sc); cudaEventRecord(pev[ps][4], sc); }
                 const ExDst dst = next_dst(par);
                 if (int r = launch_steer_x(cub, slot, par, MAX_SPLIT_OLD - 1, 1, use_ignore, dst, 0, true, sc, copy, d_nold, par)) return r;
+                LQ_CUDA(cudaEventRecord(ev_steer[k % EVR], sc));
                 if (prof_on) cudaEventRecord(pev[ps][5], sc);
                 if (k >= 1) LQ_CUDA(cudaStreamWaitEvent(sc, ev_commit[(k - 1) % EVR], 0));
                 const char* segs = seg_of(par);
@@ -1370,7 +1522,7 @@ struct EngineImpl : lq_engine {
             if (prof_on) cudaEventRecord(pev[ps][0], s_scan);
             if (int r = launch_sample(a->seed, a->wave_ctr0 + (uint32_t)k, slot, par, cub, s_scan)) return r;
             if (int r = launch_metric(samples_of(par), Wc, cub, d_count, par, s_scan)) return r;
-            if (prof_on) cudaEventRecord(pev[ps][1], s_scan);
+            if (prof_on) { cudaEventRecord(pev[ps][1], s_scan); prof_scan_ev[ps] = 1; }
             int ns_old = 0, ns_new = 0;
             if (spec) {
                 if (int r = launch_scan(samples_of(par), Wc, cub, d_count, nullptr, d_nold, n_old_ub, nullptr, use_ignore, par,
@@ -1554,6 +1706,7 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(cudaMemcpy(t_owner.p + sz, &own, 1, cudaMemcpyHostToDevice));
         // the reference stores lqr=None for this node (planner.py:299); K = lqr(state, 0) keeps it steerable
         init_gain_kernel<T, Sys, Lqr><<<1, 32, 0, st>>>(md, t_state.p + sz, t_K.p + sz, cap, 1); launches++;
+        if (grid_active() && !grid_dirty) { grid_insert_range_kernel<T><<<1, 32, 0, st>>>(tv, sz, nullptr, 1); launches++; }
         const int nsz = sz + 1;
         LQ_CUDA(cudaMemcpyAsync(tv.size, &nsz, sizeof(int), cudaMemcpyHostToDevice, st));
         LQ_CUDA(cudaStreamSynchronize(st));
@@ -1790,6 +1943,19 @@ struct EngineImpl : lq_engine {
         case LQ_OPT_FORCE_RESCAN: force_rescan = value != 0; return LQ_OK;
         case LQ_OPT_STAGE_TABLES: stage_tables_on = value != 0; return LQ_OK;
         case LQ_OPT_PDL: pdl_on = value != 0; return LQ_OK;
+        case LQ_OPT_SAMPLE_AHEAD: sample_ahead = value != 0; return LQ_OK;
+        case LQ_OPT_NEAREST_GRID:
+            if (value < 0 || value > 1) LQ_FAIL(LQ_ERR_ARG, "indexed search must be 0 or 1");
+            if (value != grid_opt) {
+                if (q_head != q_tail) LQ_FAIL(LQ_ERR_STATE, "waves are in flight");
+                grid_opt = value;
+                tv.grid.on = grid_active() ? 1 : 0;
+                if (tv.grid.on) grid_dirty = true;       // nothing was linked while it was off
+            }
+            return LQ_OK;
+        case LQ_OPT_GRID_MIN_KPAIRS:
+            if (value < 0) LQ_FAIL(LQ_ERR_ARG, "threshold must be >= 0");
+            grid_min_kpairs = value; return LQ_OK;
         case LQ_OPT_STEER_BLOCK:
             if (value != 0 && value != 32 && value != 128) LQ_FAIL(LQ_ERR_ARG, "rollout CTA size must be 0 (auto), 32 or 128");
             steer_block = value; return LQ_OK;
@@ -1806,6 +1972,9 @@ struct EngineImpl : lq_engine {
         case LQ_OPT_STAGE_TABLES: *value = stage_tables_on; return LQ_OK;
         case LQ_OPT_STEER_BLOCK: *value = steer_block; return LQ_OK;
         case LQ_OPT_PDL: *value = pdl_on; return LQ_OK;
+        case LQ_OPT_SAMPLE_AHEAD: *value = sample_ahead; return LQ_OK;
+        case LQ_OPT_NEAREST_GRID: *value = grid_active() ? 1 : 0; return LQ_OK;
+        case LQ_OPT_GRID_MIN_KPAIRS: *value = grid_min_kpairs; return LQ_OK;
         default: LQ_FAIL(LQ_ERR_ARG, "unknown option %d", option);
         }
     }

@@ -44,11 +44,14 @@ __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(
 template <typename T, class Sys, class Lqr, int TL, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 sample_kernel(Model<T, Sys, Lqr> md, SamplerParams<T, Sys::N> sp, uint64_t seed, uint32_t wave,
-              const WaveSlot* __restrict__ ws, T* __restrict__ samples, int sstride, int* __restrict__ tries_used) {
+              const WaveSlot* __restrict__ ws, T* __restrict__ samples, int sstride, int* __restrict__ tries_used,
+              int first_known, int count_known) {
     constexpr int N = Sys::N, M = Sys::M;
     const int j = (blockIdx.x * BLOCK + threadIdx.x) / TL;
     const int t = threadIdx.x % TL;
-    const int first = ws->first, count = ws->count;          // this rank's slice of the wave (device-resident)
+    // this rank's slice of the wave: device-resident, or -- when the host already knows the wave's size for sure and
+    // samples it ahead of the commit that would write the slot -- passed in (count_known >= 0)
+    const int first = count_known >= 0 ? first_known : ws->first, count = count_known >= 0 ? count_known : ws->count;
     if (j >= count) return;                                  // whole groups leave together
     const uint32_t g = (uint32_t)(first + j);
     T x[N], u0[M];

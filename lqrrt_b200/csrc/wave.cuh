@@ -107,7 +107,26 @@ struct ExDst {
     unsigned seq;                  // wave sequence number the flags are raised to
 };
 
+// Spatial index of the tree over two position-like state dims (csrc/grid.cuh): GRID_F x GRID_F fine cells, each the
+// head of a singly linked list of the nodes inside it (`next`, by node id), occupancy bitmaps of the fine cells and of
+// the GRID_C x GRID_C coarse cells (GRID_R x GRID_R fine cells each).  Border cells stand for everything beyond them.
+// Nodes are linked in by whoever appends them (commit kernel, load / append paths); lists are only ever prepended to,
+// with the link written before the head is published, so a search may walk them while a commit is appending.
+constexpr int GRID_F = 256, GRID_C = 32, GRID_R = GRID_F / GRID_C;
+struct GridView {
+    int* head;          // [GRID_F * GRID_F], -1 = empty
+    int* next;          // [cap]
+    unsigned* fine;     // [GRID_F * GRID_F / 32] occupancy bits, cell = fy * GRID_F + fx
+    unsigned* coarse;   // [GRID_C * GRID_C / 32]
+    float x0, y0;       // origin of cell (0, 0)
+    float inv_hx, inv_hy;   // cells per state unit
+    float kx, ky;       // metric cost of one cell width squared: hx^2 S_xx, hy^2 S_yy
+    int dx, dy;         // the two state dims
+    int on;             // 0: no index is kept
+};
+
 template <typename T> struct TreeView {
+    GridView grid;
     T* state;          // [N][cap]
     T* K;              // [M*N][cap]
     int* parent;       // [cap]

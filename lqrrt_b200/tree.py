@@ -218,7 +218,7 @@ class Tree(object):
                 x_full.extend(self._long_edges[node][0]); u_full.extend(self._long_edges[node][1])
             else:
                 L = int(el[k])
-                x_full.extend(hx[k, i].copy() for i in range(L)); u_full.extend(hu[k, i].copy() for i in range(L))
+                x_full.extend(hx[k, :L].copy()); u_full.extend(hu[k, :L].copy())      # rows of one copy per edge
         return ids, x_full, u_full
 
     def trajectory(self, IDs):

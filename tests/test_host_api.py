@@ -141,7 +141,7 @@ def test_bench_cli_defaults():
         argparse.ArgumentParser.parse_args = orig
         sys.argv = argv
     ns = captured['ns']
-    assert (ns.gpus, ns.config, ns.impl, ns.wave, ns.growth, ns.nearest, ns.prefetch, ns.lag) == (1, 'c4', 'ours', 8192, 2.0, None, None, 2)
+    assert (ns.gpus, ns.config, ns.impl, ns.wave, ns.growth, ns.nearest, ns.prefetch, ns.lag) == (1, 'c4', 'ours', 16384, 2.0, None, None, 2)
     assert ns.steps >= 1 and ns.warmup >= 3
 
 
