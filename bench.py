@@ -86,7 +86,7 @@ def workload_name(prob, name):
         'c3': "C3 demo_boat_novice 6-DoF boat, 50 circular obstacles, tree grown to max_nodes",
         'c2': "C2 demo_car 5-state car, 20 box obstacles, tree grown to max_nodes",
         'c1': "C1 2-state pendulum swing-up, FD-Riccati lqr, 1 forbidden region, tree grown to max_nodes",
-        'c5': "C5 12-state double integrator, 5000 spheres, FD-Riccati lqr, tree grown to 1M nodes",
+        'c5': "C5 12-state double integrator, 5000 spheres, FD-Jacobian + Riccati lqr (Jacobians snapped to 0.025), tree grown to 1M nodes",
         'c5k': "C5 12-state double integrator, 5000 spheres, constant LQR gain, tree grown to 1M nodes",
     }.get(name, prob.name)
 
@@ -95,28 +95,78 @@ def workload_name(prob, name):
 # clocks
 # ---------------------------------------------------------------------------------------------
 class ClockSampler(object):
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in-process every 2 ms (a 100k-node plan
+    takes ~7 ms, nvidia-smi takes ~40 ms per call), nvidia-smi as the fallback where NVML cannot be loaded."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.rows = []            # (sm MHz, max MHz, hw_slowdown, hw_thermal, sw_thermal, sw_power_cap)
+        self.source = None
         self.stop = threading.Event()
         self.th = threading.Thread(target=self.run, daemon=True)
 
-    def run(self):
+    def physical_index(self):
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        if vis:
+            ids = [v.strip() for v in vis.split(',') if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
+
+    def open_nvml(self):
+        """NVML set-up (tens of ms) happens before the timed region, not inside the sampling thread."""
+        import pynvml as nv
+        nv.nvmlInit()
+        self.nv = nv
+        self.h = nv.nvmlDeviceGetHandleByIndex(self.physical_index())
+        self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        self.reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.sample_nvml()
+        self.rows = []
+
+    def sample_nvml(self):
+        nv = self.nv
+        r = int(self.reasons(self.h))
+        self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)), self.mx,
+                          bool(r & nv.nvmlClocksThrottleReasonHwSlowdown), bool(r & nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                          bool(r & nv.nvmlClocksThrottleReasonSwThermalSlowdown), bool(r & nv.nvmlClocksThrottleReasonSwPowerCap)))
+
+    def run_nvml(self):
+        self.source = 'nvml'
+        while not self.stop.is_set():
+            self.sample_nvml()
+            self.stop.wait(0.002)
+
+    def run_smi(self):
+        self.source = 'nvidia-smi'
         while not self.stop.is_set():
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                out = subprocess.run(['nvidia-smi', '-i', str(self.physical_index()), '--query-gpu=' + self.Q,
                                       '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
                 parts = [p.strip() for p in out.strip().split(',')]
                 if len(parts) >= 6:
-                    self.rows.append(parts)
+                    self.rows.append((float(parts[0]), float(parts[1])) + tuple(p.lower().startswith('active') for p in parts[2:6]))
             except Exception:
                 pass
-            self.stop.wait(0.1)
+            self.stop.wait(0.05)
+
+    def run(self):
+        try:
+            if self.nv is None:
+                raise RuntimeError("no NVML")
+            self.run_nvml()
+        except Exception:
+            if not self.stop.is_set():
+                self.run_smi()
 
     def __enter__(self):
+        self.nv = None
+        try:
+            self.open_nvml()
+        except Exception:
+            self.nv = None
         self.th.start()
         return self
 
@@ -126,14 +176,12 @@ class ClockSampler(object):
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        sm = sorted(float(r[0]) for r in self.rows)
-        reasons = []
-        for k, nm in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
-            if any(r[2 + k].lower().startswith('active') for r in self.rows):
-                reasons.append(nm)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = [nm for k, nm in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"))
+                   if any(r[2 + k] for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.rows[0][1], "reasons": reasons,
+                "samples": len(self.rows), "source": self.source}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -275,6 +323,35 @@ def tree_digest(tree):
     return h.hexdigest()[:16]
 
 
+def scan_alone(planner, prob, launches=20):
+    """The nearest-neighbour scan by itself: saturated searches (one full wave of fresh queries) of the tree the last timed
+    step grew, back to back on the launching stream with nothing else on the GPU, CUDA events around them.  Inside the
+    pipeline two waves' scans share the machine with each other and with rollouts and commits, so the per-stage event
+    times there are not kernel durations."""
+    import torch
+    eng = planner._engine
+    n = eng.n
+    size = int(planner.tree.size)
+    W = int(planner._wave_capacity())
+    ss = np.array(prob.sample_space, dtype=np.float64)
+    Q = ss[:, 0] + (ss[:, 1] - ss[:, 0]) * np.random.RandomState(0).rand(W, n)
+    dt = torch.float32 if eng.dtype == 'f32' else torch.float64
+    q = torch.tensor(np.ascontiguousarray(Q.T), dtype=dt, device='cuda')
+    idx = torch.empty(W, dtype=torch.int32, device='cuda')
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        eng.nearest(q.data_ptr(), W, False, idx.data_ptr(), None, st)
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(launches):
+        eng.nearest(q.data_ptr(), W, False, idx.data_ptr(), None, st)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / launches
+    return {"queries": W, "tree_size": size, "launches": launches, "ms_per_launch": ms,
+            "pairs_per_s": W * float(size) / (ms * 1e-3)}
+
+
 def goal_leg(prob, args, comm, local, plans):
     """Plans that actually reach the goal: the same obstacle field with the goal-reaching wave policy (waves of at most
     `--plan-wave` samples -- depth grows one edge per wave and the goal is >= 130 edges away), stopping at the first
@@ -372,6 +449,7 @@ def run_gpu_arm(args):
         barrier()
     prof = planner._engine.profile_read()
     digest = tree_digest(planner.tree)
+    alone = scan_alone(planner, prob) if not hasattr(prob.system.lqr, 'steps') else None     # (state-dependent metrics: in-pipeline figure only)
     schedule_used = planner.stats.get('schedule')
 
     tot_dev = float(np.sum(dev_ms)) / 1e3
@@ -405,7 +483,9 @@ def run_gpu_arm(args):
         fp32_peak = 148 * 128 * 2 * sm_hz / 1e12                 # TFLOP/s of the FP32 pipes at the clock of this run
         near_s = (prof['ms']['nearest_old'] + prof['ms']['nearest_delta']) / 1e3
         pairs_per_s = prof['pairs'] / near_s if near_s > 0 else 0.0
-        achieved = pairs_per_s * flops_per_pair / 1e12
+        achieved_pipe = pairs_per_s * flops_per_pair / 1e12
+        # primary figure: the scan alone on the GPU (scan_alone); the in-pipeline figure (overlapped stage times) beside it
+        achieved = alone['pairs_per_s'] * flops_per_pair / 1e12 if alone else achieved_pipe
         hbm_eff = prof['nearest_bytes'] / near_s / 1e9 if near_s > 0 else 0.0
         stage_total = sum(prof['ms'].values())
         traffic, traffic_file = ncu_traffic()
@@ -448,9 +528,18 @@ def run_gpu_arm(args):
             "roofline": {"bound": "fp32_pipe", "kernel": "nearest_diag_pk_kernel" if packed else "nearest_diag_kernel",
                          "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
                          "peak_source": "148 SMs x 128 FP32 lanes x 2 x SM clock sampled during this run ({:.0f} MHz)".format(sm_hz / 1e6),
-                         "flops_per_pair": flops_per_pair, "pairs_per_s": pairs_per_s, "kernel_seconds": near_s,
+                         "measured_on": ("{launches} saturated launches ({queries} queries x {tree_size} nodes) after the timed steps, nothing "
+                                         "else on the GPU, CUDA events on the launching stream".format(**alone)) if alone else
+                                        "per-stage CUDA events inside the pipeline",
+                         "alone": alone,
+                         "flops_per_pair": flops_per_pair, "pairs_per_s": alone['pairs_per_s'] if alone else pairs_per_s,
+                         "fma_pipe_frac": (alone['pairs_per_s'] if alone else pairs_per_s) * pipe_cycles_per_pair / (148 * 128 * sm_hz),
+                         "in_pipeline": {"achieved": achieved_pipe, "frac": achieved_pipe / fp32_peak if fp32_peak else None,
+                                         "pairs_per_s": pairs_per_s, "kernel_seconds": near_s,
+                                         "fma_pipe_frac": pairs_per_s * pipe_cycles_per_pair / (148 * 128 * sm_hz),
+                                         "note": "sum of event-bracketed scan stages over the timed steps; with pipelined waves two scans "
+                                                 "(and the other wave's rollouts / commit) share the GPU, so these seconds overlap each other"},
                          "share_of_device_time": (near_s * 1e3 / stage_total) if stage_total else None,
-                         "fma_pipe_frac": pairs_per_s * pipe_cycles_per_pair / (148 * 128 * sm_hz),
                          "fma_pipe_cycles_per_pair": pipe_cycles_per_pair,
                          "hbm_effective_gbs": hbm_eff, "hbm_peak_gbs": hbm, "hbm_effective_frac": hbm_eff / hbm if hbm else None,
                          "hbm_peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",

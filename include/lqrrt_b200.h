@@ -318,8 +318,16 @@ enum { LQ_OPT_NEAREST_KERNEL = 1, LQ_OPT_SAMPLE_PREFETCH = 2,
         * time, and loses to the brute-force scan; kept for sparse, wide trees. */
        LQ_OPT_NEAREST_GRID = 9,
        LQ_OPT_GRID_MIN_KPAIRS = 10,
-       LQ_OPT_SAMPLE_AHEAD = 11         /* pipelined waves: 1 (default) = once the wave size is known to the host (top of the
-                                           policy, fixed waves) the sampler runs on a side stream ahead of the wave's chain */ };
+       LQ_OPT_SAMPLE_AHEAD = 11,        /* pipelined waves: 1 (default) = once the wave size is known to the host (top of the
+                                           policy, fixed waves) the sampler runs on a side stream ahead of the wave's chain */
+       /* State-dependent lqr providers (FD-Jacobian + Riccati) whose metric S = lqr(x, 0).S (planner.py:348) does not in
+        * fact depend on x: lq_set_sampling probes S at 12 points of the sample box; if all agree with their mean within
+        * the finite-difference noise of the dtype (3e-2 relative in float32, 1e-7 in float64) and no state dim wraps, that
+        * mean is THE metric: factored S = U^T U on the host, the tree keeps z = U v, and the search is the diagonal scan
+        * over z (cost = |U q - U v|^2) instead of one Riccati sweep per sample plus a dense scan.  1 (default) = do so;
+        * 0 = always evaluate S per sample.  Unlike the other options this one changes float32 results within that noise
+        * (it removes it); lq_get_option reports whether it is in effect. */
+       LQ_OPT_WHITEN_METRIC = 12 };
 enum { LQ_NEAREST_SCALAR = 0, LQ_NEAREST_PACKED = 1,
        /* tuning variants, same results: 8 queries per thread (best on the 12-state scan), and the two-level
         * argmin with one-lane-at-a-time arithmetic */

@@ -22,7 +22,7 @@ LQ_F32, LQ_F64 = 0, 1
 LQ_OPT_NEAREST_KERNEL, LQ_OPT_SAMPLE_PREFETCH = 1, 2
 LQ_OPT_NEAREST_CTAS_PER_SM = 3
 LQ_OPT_SPECULATIVE_SCAN, LQ_OPT_FORCE_RESCAN, LQ_OPT_STAGE_TABLES, LQ_OPT_STEER_BLOCK, LQ_OPT_PDL = 4, 5, 6, 7, 8
-LQ_OPT_NEAREST_GRID, LQ_OPT_GRID_MIN_KPAIRS, LQ_OPT_SAMPLE_AHEAD = 9, 10, 11
+LQ_OPT_NEAREST_GRID, LQ_OPT_GRID_MIN_KPAIRS, LQ_OPT_SAMPLE_AHEAD, LQ_OPT_WHITEN_METRIC = 9, 10, 11, 12
 NEAREST_KERNELS = {'scalar': 0, 'packed': 1, 'packed_q8': 2, 'two_level': 3, 'prefix': 4}
 
 

@@ -196,6 +196,14 @@ commit_x_kernel(TreeView<T> tv, WaveCtl* __restrict__ ctl, int wave_k,
         for (int c = 0; c < 2; c++) { const int q = lane + 32 * c; if (q < nu) du[q] = eu[c]; }
         for (int q = lane + 128; q < nx; q += 32) dx[q] = sx[q];                                         // long edges
         for (int q = lane + 64; q < nu; q += 32) du[q] = su[q];
+        if (tv.zstate) {                             // whitened copy: lane i computes z_i = sum_{j >= i} U_ij x_j, ascending j
+            T a = T(0);                              // (the order and the fmas of nearest.cuh whiten_apply: same bits)
+            for (int jj = 0; jj < N; jj++) {
+                const T xj = __shfl_sync(0xffffffffu, rv[0], jj);
+                if (lane < N && jj >= lane) a = fma(__ldg(tv.U + lane * N + jj), xj, a);
+            }
+            if (lane < N) tv.zstate[(size_t)lane * tv.cap + node] = a;
+        }
         if (lane == 0) {
             const int c = pc + L;
             tv.parent[node] = par; tv.cost[node] = c; tv.edge_len[node] = L; tv.owner[node] = (uint8_t)sg;

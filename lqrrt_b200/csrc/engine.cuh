@@ -267,6 +267,15 @@ struct EngineImpl : lq_engine {
     int grid_opt = 0;                      // lq_set_option(LQ_OPT_NEAREST_GRID)
     int grid_min_kpairs = 16384;           // lq_set_option(LQ_OPT_GRID_MIN_KPAIRS)
     DiagMetric<T, N> dmet;
+    // State-dependent providers whose metric turns out NOT to depend on the state over the sample box (FD-Riccati on
+    // linear dynamics: config C5) are searched through a whitened copy of the tree with the diagonal scans
+    // (nearest.cuh whiten_apply): S = mean of the probes = U^T U, cost = |U q - U v|^2.
+    DevBuf<T> t_z, w_U, w_zq;
+    DiagMetric<T, N> dmet_w;               // identity metric on the whitened copy
+    bool whiten_on = false, z_dirty = false;
+    int whiten_opt = 1;                    // lq_set_option(LQ_OPT_WHITEN_METRIC)
+    double whiten_box[2 * N];              // the sample box the probes were drawn from
+    bool whiten_probed = false;
     double Sconst[N * N];
     StagePlan stage_plan;
 
@@ -315,7 +324,7 @@ struct EngineImpl : lq_engine {
     cudaStream_t q_stream[RING] = {};
     cudaStream_t last_stream = nullptr;
     // the device-scheduled driver's own streams: rollout chain (high priority) and scan / sampler (low priority)
-    cudaStream_t s_chain = nullptr, s_scan = nullptr, s_chain2 = nullptr;
+    cudaStream_t s_chain = nullptr, s_scan = nullptr, s_chain2 = nullptr, s_samp = nullptr;
     static constexpr int EVR = 8;
     cudaEvent_t ev_commit[EVR] = {}, ev_scan[EVR] = {}, ev_in = nullptr, ev_begin = nullptr, ev_end = nullptr;
     cudaEvent_t ev_steer[EVR] = {}, ev_samp[EVR] = {};     // pipelined waves: sampler ahead of the chain
@@ -350,6 +359,7 @@ struct EngineImpl : lq_engine {
         if (s_chain) cudaStreamDestroy(s_chain);
         if (s_scan) cudaStreamDestroy(s_scan);
         if (s_chain2) cudaStreamDestroy(s_chain2);
+        if (s_samp) cudaStreamDestroy(s_samp);
     }
 
     template <typename U>
@@ -509,6 +519,7 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(w_xs.alloc((size_t)2 * Wc * H * N)); LQ_CUDA(w_us.alloc((size_t)2 * Wc * H * M));
         LQ_CUDA(w_len.alloc(Wc)); LQ_CUDA(w_tries.alloc((size_t)2 * Wc)); LQ_CUDA(w_pick.alloc(Wc));
         LQ_CUDA(w_misc.alloc(8)); LQ_CUDA(w_hor.alloc(1));
+        LQ_CUDA(cudaMemset(w_misc.p, 0, 8 * sizeof(int)));      // [4] = completion counter of closest_kernel (zero between launches)
         { const int h0 = c->hfactor ? c->hspan_lo : c->horizon_iters; LQ_CUDA(cudaMemcpy(w_hor.p, &h0, sizeof(int), cudaMemcpyHostToDevice)); }
         md.horizon = w_hor.p;
         LQ_CUDA(w_goal.alloc(2 * LQ_MAX_N));
@@ -566,6 +577,7 @@ struct EngineImpl : lq_engine {
         // lists and cut the divergence of thread-per-sample rollouts; without obstacle tables one lane is enough
         steer_lanes = obs_work > 0 ? 8 : 1;
         if (Lqr::COOP) steer_lanes = 32;       // a warp per sample shares the Riccati sweep (measured 1.7x over 8 lanes on C5)
+        tv.zstate = nullptr; tv.U = nullptr;
         memset(&tv.grid, 0, sizeof tv.grid);
         grid_ok = metric_diag && N >= 2 && !(md.angle_mask & 3u) && Sconst[0] > 0 && Sconst[N + 1] > 0;
         if (grid_ok) {
@@ -614,6 +626,80 @@ struct EngineImpl : lq_engine {
     }
     int grid_sync(cudaStream_t st) { return (grid_active() && grid_dirty) ? grid_rebuild(st, size_ub) : LQ_OK; }
     bool grid_active() const { return grid_ok && grid_opt == 1; }
+
+    // ---- state-independent metric of a state-dependent provider ---------------------
+    bool whiten_active() const { return whiten_on && whiten_opt != 0; }
+    T* zq_of(int par) { return w_zq.p + (size_t)par * N * Wc; }
+    // Probe S = lqr(x, 0).S (planner.py:348) at the centre of the sample box and at points spread over it.  If every probe
+    // agrees with their mean to within the finite-difference noise of the arithmetic (float32 differences at |x| ~ 50
+    // are noisy at the 1e-3 level; float64 at 1e-11), the metric is that mean for every sample: factor it, keep z = U v.
+    int whiten_probe(const double* lo, const double* hi) {
+        if (Lqr::CONST_METRIC || md.angle_mask != 0u || whiten_opt == 0) return LQ_OK;
+        bool same = whiten_probed;
+        for (int i = 0; i < N && same; i++) same = whiten_box[2 * i] == lo[i] && whiten_box[2 * i + 1] == hi[i];
+        if (same) return LQ_OK;
+        for (int i = 0; i < N; i++) { whiten_box[2 * i] = lo[i]; whiten_box[2 * i + 1] = hi[i]; }
+        whiten_probed = true;
+        constexpr int P = 12;
+        std::vector<double> x((size_t)P * N), u((size_t)P * M, 0.0), S((size_t)P * N * N), K((size_t)P * M * N);
+        uint64_t rng = 0x9E3779B97F4A7C15ull;
+        for (int p = 0; p < P; p++)
+            for (int i = 0; i < N; i++) {
+                rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+                const double r = p == 0 ? 0.5 : (double)(rng >> 11) / 9007199254740992.0;
+                const double a = std::isfinite(lo[i]) ? lo[i] : 0.0, b = std::isfinite(hi[i]) ? hi[i] : a;
+                x[(size_t)p * N + i] = a + (b - a) * r;
+            }
+        if (int r = eval_lqr(P, x.data(), u.data(), S.data(), K.data())) return r;
+        double mean[N * N];
+        double scale = 0, dev = 0;
+        for (int k = 0; k < N * N; k++) {
+            double m = 0;
+            for (int p = 0; p < P; p++) m += S[(size_t)p * N * N + k];
+            mean[k] = m / P;
+        }
+        for (int a = 0; a < N; a++)
+            for (int b = a + 1; b < N; b++) mean[a * N + b] = mean[b * N + a] = 0.5 * (mean[a * N + b] + mean[b * N + a]);
+        for (int k = 0; k < N * N; k++) {
+            if (!std::isfinite(mean[k])) { whiten_on = false; tv.zstate = nullptr; return LQ_OK; }
+            scale = std::max(scale, std::fabs(mean[k]));
+            for (int p = 0; p < P; p++) dev = std::max(dev, std::fabs(S[(size_t)p * N * N + k] - mean[k]));
+        }
+        const double tol = sizeof(T) == 4 ? 3e-2 : 1e-7;
+        bool ok = scale > 0 && dev <= tol * scale;
+        // Cholesky S = C C^T; U = C^T (upper triangular), so that e^T S e = |U e|^2
+        double C[N * N] = {0};
+        for (int i = 0; i < N && ok; i++)
+            for (int j = 0; j <= i; j++) {
+                double a = mean[i * N + j];
+                for (int k = 0; k < j; k++) a -= C[i * N + k] * C[j * N + k];
+                if (i == j) { if (!(a > 1e-12 * scale)) { ok = false; break; } C[i * N + i] = std::sqrt(a); }
+                else C[i * N + j] = a / C[j * N + j];
+            }
+        if (!ok) { whiten_on = false; tv.zstate = nullptr; tv.U = nullptr; return LQ_OK; }
+        std::vector<T> Uh((size_t)N * N, T(0));
+        for (int i = 0; i < N; i++)
+            for (int j = i; j < N; j++) Uh[(size_t)i * N + j] = (T)C[j * N + i];
+        if (!t_z.p) { LQ_CUDA(t_z.alloc((size_t)N * cap)); LQ_CUDA(w_zq.alloc((size_t)2 * N * Wc)); }
+        if (int r = upload(w_U, Uh)) return r;
+        for (int i = 0; i < N; i++) { dmet_w.w[i] = T(1); dmet_w.period[i] = (T)6.283185307179586; dmet_w.sdiag[i] = T(1); }
+        dmet_w.angle_mask = 0u; dmet_w.exact = sizeof(T) == 8 ? 1 : 0;
+        for (int k = 0; k < N * N; k++) Sconst[k] = mean[k];
+        tv.zstate = t_z.p; tv.U = w_U.p;
+        whiten_on = true; z_dirty = true;
+        return LQ_OK;
+    }
+    int whiten_range(int first, const int* d_size, int count_ub, cudaStream_t st) {
+        const int n = std::max(1, count_ub);
+        whiten_range_kernel<T, N><<<(n + 127) / 128, 128, 0, st>>>(t_state.p, t_z.p, w_U.p, cap, first, d_size, n); launches++;
+        LQ_CUDA(cudaGetLastError());
+        return LQ_OK;
+    }
+    int whiten_sync(cudaStream_t st) {
+        if (!whiten_on || !z_dirty) return LQ_OK;
+        z_dirty = false;
+        return whiten_range(0, tv.size, size_ub, st);
+    }
 
     // Uniform grid over the obstacle table (see FeasPrim).  Zones of influence are axis-aligned boxes:
     // centre +- (obstacle extent + hull bounding radius + margin); the margin absorbs float rounding of
@@ -767,7 +853,7 @@ struct EngineImpl : lq_engine {
         sp.tries = tries;
         have_sampling = true;
         if (N >= 2) grid_extents(lo[0], hi[0], lo[1], hi[1]);
-        return LQ_OK;
+        return whiten_probe(lo, hi);
     }
 
     // New tree = the seed alone (planner.py:172-173, tree.py:50-73).  The seed state rides in the kernel arguments:
@@ -782,6 +868,7 @@ struct EngineImpl : lq_engine {
         tree_scalars_kernel<T><<<1, 1, 0, st>>>(tv, 1, w_ctl.p); launches++;
         init_gain_kernel<T, Sys, Lqr><<<1, 128, 0, st>>>(md, t_state.p, t_K.p, cap, 1); launches++;
         LQ_CUDA(cudaGetLastError());
+        if (whiten_on) { if (int r = whiten_range(0, nullptr, 1, st)) return r; z_dirty = false; }
         if (grid_ok) {
             if (!grid_have_extents) { grid_extents(x0[0] - 50.0, x0[0] + 50.0, x0[1] - 50.0, x0[1] + 50.0); grid_have_extents = false; }
             if (int r = grid_rebuild(st, 1)) return r;
@@ -817,6 +904,7 @@ struct EngineImpl : lq_engine {
         tree_scalars_kernel<T><<<1, 1, 0, st>>>(tv, count, w_ctl.p); launches++;
         init_gain_kernel<T, Sys, Lqr><<<(count + 127) / 128, 128, 0, st>>>(md, t_state.p, t_K.p, cap, count); launches++;
         LQ_CUDA(cudaGetLastError());
+        if (whiten_on) { if (int r = whiten_range(0, nullptr, count, st)) return r; z_dirty = false; }
         if (grid_ok) {
             if (!grid_have_extents) {                 // no sample box yet: the loaded nodes' own bounding box
                 double b[4] = {state[0], state[0], state[1], state[1]};
@@ -900,7 +988,17 @@ struct EngineImpl : lq_engine {
             LQ_CUDA(cudaGetLastError());
             return LQ_OK;
         }
-        if (metric_diag) {
+        // a state-independent dense metric goes through the diagonal scans on the whitened copy: queries first
+        const bool whitened = !metric_diag && whiten_active() && !z_dirty;
+        const T* scan_state = t_state.p;
+        const DiagMetric<T, N>& dmet = whitened ? dmet_w : this->dmet;
+        if (whitened) {
+            whiten_queries_kernel<T, N><<<(std::max(1, W) + 127) / 128, 128, 0, st>>>(q, qstride, W, d_count, w_U.p, zq_of(par), Wc);
+            launches++;
+            LQ_CUDA(cudaGetLastError());
+            q = zq_of(par); qstride = Wc; scan_state = t_z.p;
+        }
+        if (metric_diag || whitened) {
             constexpr int QBIG = sizeof(T) == 4 ? 4 : 2;
             constexpr bool EX = sizeof(T) == 8;
             plan(QBIG);
@@ -910,7 +1008,7 @@ struct EngineImpl : lq_engine {
             if (!big) plan(1);
 #define LQ_NEAR_DIAG(QQ, MM)                                                                              \
     nearest_diag_kernel<T, N, QQ, NEAR_BLOCK, MM, EX><<<sa.nqb * sa.nsplit, NEAR_BLOCK, 0, st>>>(         \
-        t_state.p, cap, ignp, sa, q, qstride, dmet, pc, pi, Wc)
+        scan_state, cap, ignp, sa, q, qstride, dmet, pc, pi, Wc)
 #define LQ_NEAR_DIAG_M(QQ)                                  \
     do {                                                    \
         if (cmask == 0) LQ_NEAR_DIAG(QQ, 0);                \
@@ -920,7 +1018,7 @@ struct EngineImpl : lq_engine {
     } while (0)
 #define LQ_NEAR_PK(QQ, MB, PK, MM)                                                                         \
     nearest_diag_pk_kernel<N, QQ, NEAR_BLOCK, MM, 8, MB, PK><<<sa.nqb * sa.nsplit, NEAR_BLOCK, 0, st>>>(    \
-        t_state.p, cap, ignp, sa, q, qstride, dmet, pc, pi, Wc)
+        scan_state, cap, ignp, sa, q, qstride, dmet, pc, pi, Wc)
 #define LQ_NEAR_PK_M(QQ, MB, PK)                                  \
     do {                                                          \
         plan(QQ);                                                 \
@@ -944,7 +1042,7 @@ struct EngineImpl : lq_engine {
                                 plan(4);
 #define LQ_NEAR_PFX(MM)                                                                                   \
     nearest_diag_prefix_kernel<N, 4, NEAR_BLOCK, MM, PFX><<<sa.nqb * sa.nsplit, NEAR_BLOCK, 0, st>>>(       \
-        t_state.p, cap, ignp, sa, q, qstride, dmet, pc, pi, Wc)
+        scan_state, cap, ignp, sa, q, qstride, dmet, pc, pi, Wc)
                                 if (cmask == 0) LQ_NEAR_PFX(0); else LQ_NEAR_PFX((N >= 3 ? 4 : 0));
 #undef LQ_NEAR_PFX
                                 break;
@@ -981,7 +1079,7 @@ struct EngineImpl : lq_engine {
 
     // S = lqr(sample, 0).S per query for state-dependent providers (planner.py:348), into parity `par`
     int launch_metric(const T* q, int qstride, int W, const int* d_count, int par, cudaStream_t st) {
-        if (metric_diag || Lqr::CONST_METRIC) return LQ_OK;
+        if (metric_diag || Lqr::CONST_METRIC || whiten_active()) return LQ_OK;
         if (W < 1) return LQ_OK;
         if (Lqr::COOP) {
             constexpr int ML = 8;
@@ -1017,15 +1115,18 @@ struct EngineImpl : lq_engine {
         const T* q = (const T*)d_q;
         int qstride = W;
         if (int r = grid_sync(st)) return r;
-        if (!metric_diag) {     // dense search reads S in the wave layout: restride the queries
+        if (int r = whiten_sync(st)) return r;
+        if (!metric_diag && !whiten_active()) {     // dense search reads S in the wave layout: restride the queries
             for (int d = 0; d < N; d++)
                 LQ_CUDA(cudaMemcpyAsync(w_samples.p + (size_t)d * Wc, q + (size_t)d * W, W * sizeof(T), cudaMemcpyDeviceToDevice, st));
             q = w_samples.p; qstride = Wc;
             if (int r = launch_metric(q, qstride, W, nullptr, 0, st)) return r;
         }
         int nsplit = 1;
+        // a full wave of queries fills the machine with one resident set of CTAs (ncu: 474 us at 8 per SM against 547 us
+        // at 16 for 8192 queries x 1e5 nodes); small batches need the finer split
         if (int r = launch_scan(q, qstride, W, nullptr, nullptr, tv.size, size_ub, tv.n_ignored2[ign_copy], use_ignore, 0, 0, false, MAX_SPLIT,
-                                scan_target(), st, &nsplit, ign_copy)) return r;
+                                W >= 4096 ? pipelined_scan_target() : scan_target(), st, &nsplit, ign_copy)) return r;
         nearest_finalize_kernel<T><<<(W + 127) / 128, 128, 0, st>>>(pcost_of(0), pidx_of(0), Wc, nsplit, W, d_idx, (T*)d_cost);
         launches++;
         LQ_CUDA(cudaGetLastError());
@@ -1092,6 +1193,8 @@ struct EngineImpl : lq_engine {
         PartialsIn<T> pin{pcost_of(par) + (size_t)slot_lo * Wc, pidx_of(par) + (size_t)slot_lo * Wc, Wc, nslots};
         NearMetric<T, N> nm;
         nm.dmet = dmet; nm.dmet.angle_mask = md.angle_mask; nm.Spacked = sp_of(par); nm.diag = metric_diag ? 1 : 0;
+        nm.zstate = nullptr; nm.U = nullptr;
+        if (!metric_diag && whiten_active()) { nm.dmet = dmet_w; nm.diag = 2; nm.zstate = t_z.p; nm.U = w_U.p; }
         const int* stopw = use_stop_word ? d_stop : nullptr;
         int block = steer_block;
         if (block != 32 && block != 128) block = (threads >= 148LL * 2 * 128 && !(Lqr::COOP && LANES > 1)) ? 128 : 32;
@@ -1177,6 +1280,7 @@ struct EngineImpl : lq_engine {
         const int ps = q_tail % RING;
         if (prof_on) cudaEventRecord(pev[ps][1], st);
         if (int r = grid_sync(st)) return r;
+        if (int r = whiten_sync(st)) return r;
         if (int r = launch_metric(samples_of(par), Wc, count, nullptr, par, st)) return r;
         int nsplit = 1;
         // stepwise: one scan over the whole tree (n_old = 0), written to the "delta" slots
@@ -1388,6 +1492,9 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(cudaStreamCreateWithPriority(&s_chain, cudaStreamNonBlocking, hi));
         LQ_CUDA(cudaStreamCreateWithPriority(&s_scan, cudaStreamNonBlocking, lo));
         LQ_CUDA(cudaStreamCreateWithPriority(&s_chain2, cudaStreamNonBlocking, hi));
+        // the sampler that runs ahead of a pipelined wave's chain: short, and the wave's scan waits for it, so it must not
+        // queue behind the long rollout kernels of the other chain (measured on C5, where a low-priority sampler starved)
+        LQ_CUDA(cudaStreamCreateWithPriority(&s_samp, cudaStreamNonBlocking, hi));
         for (auto& e : ev_commit) LQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& e : ev_scan) LQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& e : ev_steer) LQ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1428,6 +1535,7 @@ struct EngineImpl : lq_engine {
 
         // the chain stream picks up after the caller's stream (reset / goal / sampling uploads)
         if (int r = grid_sync(st)) return r;
+        if (int r = whiten_sync(st)) return r;
         LQ_CUDA(cudaEventRecord(ev_in, st));
         LQ_CUDA(cudaStreamWaitEvent(s_chain, ev_in, 0));
         *h_stop = 0;
@@ -1435,6 +1543,7 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(cudaEventRecord(ev_begin, s_chain));
         LQ_CUDA(cudaStreamWaitEvent(s_scan, ev_begin, 0));         // waves 0 and 1 start from the initial control block
         LQ_CUDA(cudaStreamWaitEvent(s_chain2, ev_begin, 0));
+        LQ_CUDA(cudaStreamWaitEvent(s_samp, ev_begin, 0));
 
         // host mirror of the schedule as upper bounds (they only shape grids): Nub[k] >= N_k, the tree size wave k
         // starts from, and Wub[k] >= W_k = policy(N_{k-1}) (W_0 = W_1 = policy(N_0))
@@ -1484,11 +1593,11 @@ struct EngineImpl : lq_engine {
                     const int wk = k < 2 ? policy_wave(pol, n0) : (pol.fixed > 0 ? pol.fixed : pol.wmax);
                     int first_k = 0, count_k = 0;
                     policy_slice(wk, rank, world, &first_k, &count_k);
-                    if (k >= 2) LQ_CUDA(cudaStreamWaitEvent(s_scan, ev_steer[(k - 2) % EVR], 0));
-                    if (prof_on) cudaEventRecord(pev[ps][0], s_scan);
-                    if (int r = launch_sample(a->seed, a->wave_ctr0 + (uint32_t)k, slot, par, cub, s_scan, first_k, count_k)) return r;
-                    if (prof_on) cudaEventRecord(pev[ps][1], s_scan);
-                    LQ_CUDA(cudaEventRecord(ev_samp[k % EVR], s_scan));
+                    if (k >= 2) LQ_CUDA(cudaStreamWaitEvent(s_samp, ev_steer[(k - 2) % EVR], 0));
+                    if (prof_on) cudaEventRecord(pev[ps][0], s_samp);
+                    if (int r = launch_sample(a->seed, a->wave_ctr0 + (uint32_t)k, slot, par, cub, s_samp, first_k, count_k)) return r;
+                    if (prof_on) cudaEventRecord(pev[ps][1], s_samp);
+                    LQ_CUDA(cudaEventRecord(ev_samp[k % EVR], s_samp));
                     LQ_CUDA(cudaStreamWaitEvent(sc, ev_samp[k % EVR], 0));
                 } else {
                     if (prof_on) cudaEventRecord(pev[ps][0], sc);
@@ -1605,7 +1714,7 @@ struct EngineImpl : lq_engine {
             rd++;
         }
         if (rc != LQ_OK) {                                       // leave nothing in flight behind an error
-            cudaStreamSynchronize(s_scan); cudaStreamSynchronize(s_chain2); cudaStreamSynchronize(s_chain);
+            cudaStreamSynchronize(s_scan); cudaStreamSynchronize(s_samp); cudaStreamSynchronize(s_chain2); cudaStreamSynchronize(s_chain);
             return rc;
         }
         if (lag2 && enq > 0) {                                   // the last commit may sit on the second chain stream
@@ -1613,6 +1722,7 @@ struct EngineImpl : lq_engine {
         }
         LQ_CUDA(cudaEventRecord(ev_end, s_chain));
         LQ_CUDA(cudaStreamSynchronize(s_scan));
+        LQ_CUDA(cudaStreamSynchronize(s_samp));
         LQ_CUDA(cudaStreamSynchronize(s_chain2));
         LQ_CUDA(cudaStreamSynchronize(s_chain));
         LQ_CUDA(cudaStreamWaitEvent(st, ev_end, 0));            // later work on the caller's stream sees the finished tree
@@ -1643,7 +1753,7 @@ struct EngineImpl : lq_engine {
             for (int j = 0; j < N; j++) fm.S[i * N + j] = (colmask && colmask[j]) ? T(0) : (T)S[i * N + j];
         }
         fm.angle_mask = md.angle_mask;
-        closest_kernel<T, N><<<1, 1024, 0, st>>>(t_state.p, cap, tv.size, fm, w_misc.p + 1); launches++;
+        closest_kernel<T, N><<<CLOSEST_CTAS, CLOSEST_BLOCK, 0, st>>>(t_state.p, cap, tv.size, fm, w_misc.p + 1, pcost_of(0), pidx_of(0), (unsigned*)(w_misc.p + 4)); launches++;
         LQ_CUDA(cudaGetLastError());
         LQ_CUDA(cudaMemcpyAsync(h_misc + 1, w_misc.p + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         LQ_CUDA(cudaStreamSynchronize(st));
@@ -1706,6 +1816,7 @@ struct EngineImpl : lq_engine {
         LQ_CUDA(cudaMemcpy(t_owner.p + sz, &own, 1, cudaMemcpyHostToDevice));
         // the reference stores lqr=None for this node (planner.py:299); K = lqr(state, 0) keeps it steerable
         init_gain_kernel<T, Sys, Lqr><<<1, 32, 0, st>>>(md, t_state.p + sz, t_K.p + sz, cap, 1); launches++;
+        if (whiten_on && !z_dirty) { if (int r = whiten_range(sz, nullptr, 1, st)) return r; }
         if (grid_active() && !grid_dirty) { grid_insert_range_kernel<T><<<1, 32, 0, st>>>(tv, sz, nullptr, 1); launches++; }
         const int nsz = sz + 1;
         LQ_CUDA(cudaMemcpyAsync(tv.size, &nsz, sizeof(int), cudaMemcpyHostToDevice, st));
@@ -1781,7 +1892,7 @@ struct EngineImpl : lq_engine {
                 for (int j = 0; j < N; j++) fm.S[i * N + j] = (colmask && colmask[j]) ? T(0) : (T)S[i * N + j];
             }
             fm.angle_mask = md.angle_mask;
-            closest_kernel<T, N><<<1, 1024, 0, st>>>(t_state.p, cap, tv.size, fm, d_node); launches++;
+            closest_kernel<T, N><<<CLOSEST_CTAS, CLOSEST_BLOCK, 0, st>>>(t_state.p, cap, tv.size, fm, d_node, pcost_of(0), pidx_of(0), (unsigned*)(w_misc.p + 4)); launches++;
         } else {
             LQ_CUDA(cudaMemcpyAsync(d_node, &node, sizeof(int), cudaMemcpyHostToDevice, st));
         }
@@ -1944,6 +2055,9 @@ struct EngineImpl : lq_engine {
         case LQ_OPT_STAGE_TABLES: stage_tables_on = value != 0; return LQ_OK;
         case LQ_OPT_PDL: pdl_on = value != 0; return LQ_OK;
         case LQ_OPT_SAMPLE_AHEAD: sample_ahead = value != 0; return LQ_OK;
+        case LQ_OPT_WHITEN_METRIC:
+            if (q_head != q_tail) LQ_FAIL(LQ_ERR_STATE, "waves are in flight");
+            whiten_opt = value != 0; return LQ_OK;
         case LQ_OPT_NEAREST_GRID:
             if (value < 0 || value > 1) LQ_FAIL(LQ_ERR_ARG, "indexed search must be 0 or 1");
             if (value != grid_opt) {
@@ -1973,6 +2087,7 @@ struct EngineImpl : lq_engine {
         case LQ_OPT_STEER_BLOCK: *value = steer_block; return LQ_OK;
         case LQ_OPT_PDL: *value = pdl_on; return LQ_OK;
         case LQ_OPT_SAMPLE_AHEAD: *value = sample_ahead; return LQ_OK;
+        case LQ_OPT_WHITEN_METRIC: *value = whiten_active() ? 1 : 0; return LQ_OK;
         case LQ_OPT_NEAREST_GRID: *value = grid_active() ? 1 : 0; return LQ_OK;
         case LQ_OPT_GRID_MIN_KPAIRS: *value = grid_min_kpairs; return LQ_OK;
         default: LQ_FAIL(LQ_ERR_ARG, "unknown option %d", option);

@@ -390,19 +390,30 @@ template <typename T, class Sys> struct FdRiccatiLqr {
     // shared memory and split every product by output element; finite-difference columns are split the
     // same way.  Each output is accumulated in ascending k exactly as in solve(), so both forms agree.
     static constexpr bool COOP = true;
-    // A, B, P, BtP, G, Rhs/K, AmBK, AtP
-    static constexpr int COOP_SCALARS = N * N + N * M + N * N + M * N + M * M + M * N + N * N + N * N;
+    // one solve: A, B, P, BtP, G, Rhs/K, AmBK, AtP.  A group's slice holds COOP_SLOTS of them: the solve in progress and
+    // the one before, so that a rollout whose Jacobian alternates between two values (an axis that saturates every
+    // other step: saturated -> its gain row is zero -> no effort -> unsaturated -> ...) runs each sweep once.
+    static constexpr int SLOT_SCALARS = N * N + N * M + N * N + M * N + M * M + M * N + N * N + N * N;
+    static constexpr int COOP_SLOTS = 2;
+    static constexpr int COOP_SCALARS = SLOT_SCALARS * COOP_SLOTS;
     T Q[N * N], R[M * M];
     T eps;
     int steps;
+    // snap > 0: every finite-difference Jacobian entry is rounded to the nearest multiple of `snap` before the sweep.
+    // For dynamics that are (piecewise) linear with entries on that grid this removes the finite-difference noise, and
+    // the gain becomes a function of a handful of distinct Jacobians -- which is what lets a rollout keep its gain
+    // while the Jacobian does not change (gain_coop below).  0 = the Jacobian as differenced.
+    T snap;
     __host__ int unpack(const double* p, int count) {
-        if (count != N * N + M * M + 2) return -1;
+        if (count != N * N + M * M + 2 && count != N * N + M * M + 3) return -1;
         int k = 0;
         for (int i = 0; i < N * N; i++) Q[i] = (T)p[k++];
         for (int i = 0; i < M * M; i++) R[i] = (T)p[k++];
         eps = (T)p[k++]; steps = (int)p[k++];
+        snap = count == N * N + M * M + 3 ? (T)p[k++] : T(0);
         return 0;
     }
+    __device__ __forceinline__ T snapped(T v) const { return snap > T(0) ? rint_t(v / snap) * snap : v; }
 
     __device__ void solve(const Sys& sys, T dt, const T* x, const T* u, T* P, T* K) const {
         T A[N * N], Bm[N * M];
@@ -418,7 +429,7 @@ template <typename T, class Sys> struct FdRiccatiLqr {
             sys.step(xp, up, dt, fp);
             sys.step(xm, um, dt, fm);
 #pragma unroll
-            for (int i = 0; i < N; i++) A[i * N + j] = (fp[i] - fm[i]) * inv2e;
+            for (int i = 0; i < N; i++) A[i * N + j] = snapped((fp[i] - fm[i]) * inv2e);
         }
         for (int j = 0; j < M; j++) {
             T xp[N], xm[N], up[M], um[M], fp[N], fm[N];
@@ -430,7 +441,7 @@ template <typename T, class Sys> struct FdRiccatiLqr {
             sys.step(xp, up, dt, fp);
             sys.step(xm, um, dt, fm);
 #pragma unroll
-            for (int i = 0; i < N; i++) Bm[i * M + j] = (fp[i] - fm[i]) * inv2e;
+            for (int i = 0; i < N; i++) Bm[i * M + j] = snapped((fp[i] - fm[i]) * inv2e);
         }
 #pragma unroll
         for (int i = 0; i < N * N; i++) P[i] = Q[i];
@@ -512,13 +523,15 @@ template <typename T, class Sys> struct FdRiccatiLqr {
     static constexpr int A_OFF = 0, B_OFF = A_OFF + N * N, P_OFF = B_OFF + N * M, BTP_OFF = P_OFF + N * N,
                          G_OFF = BTP_OFF + M * N, K_OFF = G_OFF + M * M, AMBK_OFF = K_OFF + M * N,
                          ATP_OFF = AMBK_OFF + N * N;
+    // memo (may be null): the group's rollout-long note of which slots hold finished solves (bit s = slot s valid, bit 2 =
+    // the slot used last).  If the new Jacobian equals a held one bit for bit, that slot's P and K are what the sweep
+    // would produce again: it is skipped, the result is identical by construction.  Returns the slot that holds P and K.
     template <class Sync>
-    __device__ void solve_coop(const Sys& sys, T dt, const T* x, const T* u, T* sm, int lane, int lanes, Sync sync) const {
-        T* A = sm + A_OFF; T* Bm = sm + B_OFF; T* P = sm + P_OFF; T* BtP = sm + BTP_OFF;
-        T* G = sm + G_OFF; T* K = sm + K_OFF; T* AmBK = sm + AMBK_OFF; T* AtP = sm + ATP_OFF;
+    __device__ int solve_coop(const Sys& sys, T dt, const T* x, const T* u, T* sm, int lane, int lanes, Sync sync,
+                              int* memo = nullptr) const {
         const T inv2e = T(1) / (T(2) * eps);
-        sync();                                        // previous users of the slice are done
-        for (int j = lane; j < N + M; j += lanes) {    // finite-difference columns of [A | B]
+        // finite-difference column j of [A | B] into v
+        auto fd_column = [&](int j, T (&v)[N]) {
             T xp[N], xm[N], up[M], um[M], fp[N], fm[N];
 #pragma unroll
             for (int i = 0; i < N; i++) { xp[i] = x[i]; xm[i] = x[i]; }
@@ -530,14 +543,49 @@ template <typename T, class Sys> struct FdRiccatiLqr {
             for (int i = 0; i < M; i++) if (N + i == j) { up[i] += eps; um[i] -= eps; }
             sys.step(xp, up, dt, fp);
             sys.step(xm, um, dt, fm);
+#pragma unroll
+            for (int i = 0; i < N; i++) v[i] = snapped((fp[i] - fm[i]) * inv2e);
+        };
+        auto put_column = [&](T* slot, int j, const T (&v)[N]) {
             if (j < N) {
 #pragma unroll
-                for (int i = 0; i < N; i++) A[i * N + j] = (fp[i] - fm[i]) * inv2e;
+                for (int i = 0; i < N; i++) slot[A_OFF + i * N + j] = v[i];
             } else {
 #pragma unroll
-                for (int i = 0; i < N; i++) Bm[i * M + (j - N)] = (fp[i] - fm[i]) * inv2e;
+                for (int i = 0; i < N; i++) slot[B_OFF + i * M + (j - N)] = v[i];
+            }
+        };
+        int slot = 0;
+        sync();                                        // previous users of the slice are done
+        if (memo && lanes >= N + M) {                  // one column per lane: compare before anything is overwritten
+            const int state = *memo;
+            T v[N];
+            bool m0 = (state & 1) != 0, m1 = (state & 2) != 0;
+            if (lane < N + M) {
+                fd_column(lane, v);
+#pragma unroll
+                for (int i = 0; i < N; i++) {
+                    const int off = lane < N ? A_OFF + i * N + lane : B_OFF + i * M + (lane - N);
+                    if (m0) m0 = sm[off] == v[i];
+                    if (m1) m1 = sm[SLOT_SCALARS + off] == v[i];
+                }
+            }
+            m0 = sync.all(m0); m1 = sync.all(m1);      // every lane of the group takes the same branch
+            if (m0) { *memo = (state & 3); return 0; }
+            if (m1) { *memo = (state & 3) | 4; return 1; }
+            slot = !(state & 1) ? 0 : (!(state & 2) ? 1 : ((state & 4) ? 0 : 1));     // an empty slot, else not the last used
+            *memo = ((state & 3) | (1 << slot)) & 3 | (slot << 2);
+            sm += slot * SLOT_SCALARS;
+            if (lane < N + M) put_column(sm, lane, v);
+        } else {
+            for (int j = lane; j < N + M; j += lanes) {
+                T v[N];
+                fd_column(j, v);
+                put_column(sm, j, v);
             }
         }
+        T* A = sm + A_OFF; T* Bm = sm + B_OFF; T* P = sm + P_OFF; T* BtP = sm + BTP_OFF;
+        T* G = sm + G_OFF; T* K = sm + K_OFF; T* AmBK = sm + AMBK_OFF; T* AtP = sm + ATP_OFF;
         for (int e = lane; e < N * N; e += lanes) P[e] = Q[e];
         sync();
         for (int it = 0; it < steps; it++) {
@@ -641,12 +689,14 @@ template <typename T, class Sys> struct FdRiccatiLqr {
             }
             sync();
         }
+        return slot;
     }
     template <class Sync>
-    __device__ void gain_coop(const Sys& sys, T dt, const T* x, const T* u, T* K, T* sm, int lane, int lanes, Sync sync) const {
-        solve_coop(sys, dt, x, u, sm, lane, lanes, sync);
+    __device__ void gain_coop(const Sys& sys, T dt, const T* x, const T* u, T* K, T* sm, int lane, int lanes, Sync sync,
+                              int* memo = nullptr) const {
+        const int slot = solve_coop(sys, dt, x, u, sm, lane, lanes, sync, memo);
 #pragma unroll
-        for (int e = 0; e < M * N; e++) K[e] = sm[K_OFF + e];
+        for (int e = 0; e < M * N; e++) K[e] = sm[slot * SLOT_SCALARS + K_OFF + e];
     }
 
     __device__ void gain(const Sys& sys, T dt, const T* x, const T* u, T* K) const {

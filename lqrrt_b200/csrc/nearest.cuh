@@ -551,6 +551,50 @@ reduce_partials_kernel(T* __restrict__ pcost, int* __restrict__ pidx, int pstrid
     }
 }
 
+// ---- constant dense metric through the diagonal scans ---------------------------------------------------------
+// cost = e^T S e with S = U^T U (U upper triangular, from a host-side Cholesky factorisation) is |U e|^2 = |U q - U v|^2:
+// the tree keeps z = U v next to v, a wave's queries are transformed once, and the scan is the identity-metric
+// diagonal scan over z.  One function produces every z (commit, load, seed, queries), with explicit fmas in a fixed
+// order, so equal inputs give equal bits wherever they are transformed.
+template <typename T, int N>
+__device__ __forceinline__ void whiten_apply(const T* __restrict__ U, const T (&x)[N], T (&z)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        T a = T(0);
+#pragma unroll
+        for (int j = i; j < N; j++) a = fma(__ldg(U + i * N + j), x[j], a);
+        z[i] = a;
+    }
+}
+
+// z rows of nodes [first, *d_size) (or first + count_ub when d_size is null)
+template <typename T, int N>
+__global__ void whiten_range_kernel(const T* __restrict__ state, T* __restrict__ zstate, const T* __restrict__ U, int cap,
+                                    int first, const int* __restrict__ d_size, int count_ub) {
+    const int i = first + blockIdx.x * blockDim.x + threadIdx.x;
+    const int hi = d_size ? *d_size : first + count_ub;
+    if (i >= hi) return;
+    T x[N], z[N];
+#pragma unroll
+    for (int d = 0; d < N; d++) x[d] = state[(size_t)d * cap + i];
+    whiten_apply<T, N>(U, x, z);
+#pragma unroll
+    for (int d = 0; d < N; d++) zstate[(size_t)d * cap + i] = z[d];
+}
+
+template <typename T, int N>
+__global__ void whiten_queries_kernel(const T* __restrict__ q, int qstride, int W, const int* __restrict__ d_count,
+                                      const T* __restrict__ U, T* __restrict__ zq, int zstride) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= (d_count ? min(*d_count, W) : W)) return;
+    T x[N], z[N];
+#pragma unroll
+    for (int d = 0; d < N; d++) x[d] = q[(size_t)d * qstride + j];
+    whiten_apply<T, N>(U, x, z);
+#pragma unroll
+    for (int d = 0; d < N; d++) zq[(size_t)d * zstride + j] = z[d];
+}
+
 // Per-query metric for state-dependent providers (planner.py:348: S = lqr(x, 0)[0]
 // at the sample), packed for nearest_dense_kernel.
 template <typename T, class Sys, class Lqr>
@@ -577,15 +621,22 @@ __global__ void metric_kernel(Sys sys, Lqr lqr, T dt, const T* __restrict__ quer
 template <typename T, int N>
 struct FullMetric { T S[N * N]; T x[N]; uint32_t angle_mask; };
 
+// Closest-to-guide (planner.py:313-318) over the whole tree: CLOSEST_CTAS CTAs take interleaved node blocks, each
+// leaves its lexicographic (cost, index) minimum in scratch, the last one to finish merges them.  `counter` must be
+// zero on entry and is zero again on exit.
+constexpr int CLOSEST_CTAS = 64, CLOSEST_BLOCK = 256;
 template <typename T, int N>
-__global__ void closest_kernel(const T* __restrict__ state, int cap, const int* __restrict__ d_size,
-                               FullMetric<T, N> fm, int* __restrict__ out) {
-    __shared__ T sc[1024];
-    __shared__ int si[1024];
+__global__ void __launch_bounds__(CLOSEST_BLOCK)
+closest_kernel(const T* __restrict__ state, int cap, const int* __restrict__ d_size,
+               FullMetric<T, N> fm, int* __restrict__ out, T* __restrict__ pc, int* __restrict__ pi,
+               unsigned* __restrict__ counter) {
+    __shared__ T sc[CLOSEST_BLOCK];
+    __shared__ int si[CLOSEST_BLOCK];
+    __shared__ bool s_last;
     const int size = *d_size;
     T best = Num<T>::inf();
     int b = -1;
-    for (int node = threadIdx.x; node < size; node += blockDim.x) {
+    for (int node = blockIdx.x * CLOSEST_BLOCK + threadIdx.x; node < size; node += gridDim.x * CLOSEST_BLOCK) {
         T e[N];
 #pragma unroll
         for (int d = 0; d < N; d++) {
@@ -602,17 +653,32 @@ __global__ void closest_kernel(const T* __restrict__ state, int cap, const int* 
         }
         if (b < 0 || c < best) { best = c; b = node; }
     }
-    sc[threadIdx.x] = best; si[threadIdx.x] = b;
-    __syncthreads();
-    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-        if (threadIdx.x < s) {
-            const T c2 = sc[threadIdx.x + s]; const int i2 = si[threadIdx.x + s];
-            const T c1 = sc[threadIdx.x]; const int i1 = si[threadIdx.x];
-            if (i2 >= 0 && (i1 < 0 || c2 < c1 || (c2 == c1 && i2 < i1))) { sc[threadIdx.x] = c2; si[threadIdx.x] = i2; }
-        }
+    auto reduce = [&]() {
+        sc[threadIdx.x] = best; si[threadIdx.x] = b;
         __syncthreads();
+        for (int s = CLOSEST_BLOCK / 2; s > 0; s >>= 1) {
+            if (threadIdx.x < s) {
+                const T c2 = sc[threadIdx.x + s]; const int i2 = si[threadIdx.x + s];
+                const T c1 = sc[threadIdx.x]; const int i1 = si[threadIdx.x];
+                if (i2 >= 0 && (i1 < 0 || c2 < c1 || (c2 == c1 && i2 < i1))) { sc[threadIdx.x] = c2; si[threadIdx.x] = i2; }
+            }
+            __syncthreads();
+        }
+    };
+    reduce();
+    if (threadIdx.x == 0) {
+        pc[blockIdx.x] = sc[0]; pi[blockIdx.x] = si[0];
+        __threadfence();
+        s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
     }
-    if (threadIdx.x == 0) *out = si[0] < 0 ? 0 : si[0];
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    best = Num<T>::inf(); b = -1;
+    if (threadIdx.x < gridDim.x) { best = __ldcg(&pc[threadIdx.x]); b = __ldcg(&pi[threadIdx.x]); }
+    __syncthreads();
+    reduce();
+    if (threadIdx.x == 0) { *out = si[0] < 0 ? 0 : si[0]; *counter = 0; }
 }
 
 }  // namespace lq

@@ -62,14 +62,20 @@ struct GroupSync {
     __device__ __forceinline__ void operator()() const {
         if (LANES > 1) cg::tiled_partition<LANES>(cg::this_thread_block()).sync();
     }
+    __device__ __forceinline__ bool all(bool p) const {
+        if (LANES > 1) return cg::tiled_partition<LANES>(cg::this_thread_block()).all(p);
+        return p;
+    }
 };
 
 // K = lqr(x, u).K, cooperatively when the provider supports it (FD-Jacobian + Riccati) and the group has lanes.
+// have_prev: the group's rollout-long note that its shared-memory slice holds the previous solve (FD-Riccati: a gain is
+// kept while the Jacobian does not change, models.cuh solve_coop)
 template <typename T, class Sys, class Lqr, int LANES>
 __device__ __forceinline__ void group_gain(const Model<T, Sys, Lqr>& md, const T* x, const T* u, T* K, T s, T c,
-                                           T* coop, int lane) {
+                                           T* coop, int lane, int* have_prev = nullptr) {
     if constexpr (Lqr::COOP && LANES > 1) {
-        md.lqr.gain_coop(md.sys, md.dt, x, u, K, coop, lane, LANES, GroupSync<LANES>());
+        md.lqr.gain_coop(md.sys, md.dt, x, u, K, coop, lane, LANES, GroupSync<LANES>(), have_prev);
     } else {
         md.lqr.gain_sc(md.sys, md.dt, x, u, K, s, c);
     }
@@ -100,6 +106,7 @@ __device__ __forceinline__ void rollout(const Model<T, Sys, Lqr>& md, const Feas
     if (HD >= 0) { sincos_t(x[HD < 0 ? 0 : HD], &sh, &ch); sincos_t(xt[HD < 0 ? 0 : HD], &sg, &cg); }
 
     int len = 0, nrec = 0, i = 0;
+    int have_prev = 0;           // nothing of this rollout in the provider's shared-memory slice yet
     // every rollout of a wave starts from the same planner-level horizon (frozen at wave start)
     const bool adaptive = md.hfactor != 0;
     int hor = adaptive ? *md.horizon : md.H;
@@ -147,7 +154,7 @@ __device__ __forceinline__ void rollout(const Model<T, Sys, Lqr>& md, const Feas
             for (int r = 0; r < M; r++) urow[nrec * M + r] = u[r];
         }
         nrec += 1;
-        group_gain<T, Sys, Lqr, LANES>(md, x, u, K, sh, ch, coop, lane);   // planner.py:436
+        group_gain<T, Sys, Lqr, LANES>(md, x, u, K, sh, ch, coop, lane, &have_prev);   // planner.py:436
     }
 
     // The node is the last KEPT state and its gain is lqr(xnew, u_seq[-1]).K (planner.py:256-257).  Without an
@@ -162,7 +169,7 @@ __device__ __forceinline__ void rollout(const Model<T, Sys, Lqr>& md, const Feas
         for (int r = 0; r < M; r++) uk[r] = urow[(len - 1) * M + r];
         T s2 = T(0), c2 = T(1);
         if (HD >= 0) sincos_t(x[HD < 0 ? 0 : HD], &s2, &c2);
-        group_gain<T, Sys, Lqr, LANES>(md, x, uk, K, s2, c2, coop, lane);
+        group_gain<T, Sys, Lqr, LANES>(md, x, uk, K, s2, c2, coop, lane, &have_prev);
     }
     len_out = len;
     vote_out = vote;
@@ -211,7 +218,9 @@ template <typename T, int N>
 struct NearMetric {
     DiagMetric<T, N> dmet;
     const T* Spacked;        // per-query packed S (dense metrics), [NS][sstride]
-    int diag;
+    int diag;                // 1: diagonal metric on the states; 2: identity metric on the whitened copy (dmet = identity)
+    const T* zstate;         // diag == 2: z = U v per node, [N][cap]
+    const T* U;
 };
 
 // One query's brute-force scan by its own group of LANES threads: the exact arithmetic of the K1 kernels
@@ -226,10 +235,18 @@ __device__ __noinline__ int rescan_nearest(const T* __restrict__ tstate, int cap
     constexpr int NS = N * (N + 1) / 2;
     const uint32_t mask = nm.dmet.angle_mask;
     T q[N], S[NS];
+    if (nm.diag == 2) tstate = nm.zstate;            // the scan searched the whitened copy: so does this
     if (nm.diag) {
+        T xw[N];
+        if (nm.diag == 2) {
+            whiten_apply<T, N>(nm.U, xq, xw);
+        } else {
+#pragma unroll
+            for (int d = 0; d < N; d++) xw[d] = xq[d];
+        }
 #pragma unroll
         for (int d = 0; d < N; d++) {
-            T v = xq[d];
+            T v = xw[d];
             if (!EXACT) { if (mask & (1u << d)) v = reduce_period(v); v = prescale(v, nm.dmet.w[d]); }
             q[d] = v;
         }

@@ -127,6 +127,10 @@ struct GridView {
 
 template <typename T> struct TreeView {
     GridView grid;
+    // Whitened copy of the states (nullptr: none): z = U x with S = U^T U for a metric S that does not depend on the
+    // state, so that cost = |U (q - v)|^2 and the diagonal scans serve a constant dense metric (nearest.cuh whiten_apply)
+    T* zstate;         // [N][cap]
+    const T* U;        // [N][N] row-major, upper triangular
     T* state;          // [N][cap]
     T* K;              // [M*N][cap]
     int* parent;       // [cap]

@@ -231,18 +231,24 @@ class FDRiccatiLqr(Lqr):
     the reference, SURVEY.md M2 -- parity unpinned): central-difference
     Jacobians of the device dynamics about (x, u), then `steps` backward
     iterations of the discrete Riccati recursion from P = Q;  S = P_0, K = K_0
-    with  u = K erf(xtar, x)  (sign convention of planner.py:386-387)."""
+    with  u = K erf(xtar, x)  (sign convention of planner.py:386-387).
+    `snap` > 0 rounds every Jacobian entry to the nearest multiple of it before the
+    sweep: for (piecewise) linear dynamics whose entries lie on that grid this removes
+    the finite-difference noise (float32 differences at |x| ~ 50 are noisy at the 1e-3
+    level) and lets a rollout keep its gain while the Jacobian does not change."""
     kind = LQR_FD_RICCATI
 
-    def __init__(self, Q, R, steps=20, eps=1e-3):
+    def __init__(self, Q, R, steps=20, eps=1e-3, snap=0.0):
         self.Q = _f64(Q); self.R = _f64(R)
-        self.steps = int(steps); self.eps = float(eps)
+        self.steps = int(steps); self.eps = float(eps); self.snap = float(snap)
         if self.steps < 1:
             raise ValueError("steps must be >= 1")
+        if self.snap < 0:
+            raise ValueError("snap must be >= 0")
 
     def blob(self, n, m):
         return np.concatenate((_f64(self.Q, (n, n)).ravel(), _f64(self.R, (m, m)).ravel(),
-                               [self.eps, float(self.steps)]))
+                               [self.eps, float(self.steps), self.snap]))
 
 
 # =============================================================================
@@ -629,14 +635,16 @@ def pendulum2(tau_max=5.0, region=((1.2, -1.0), (1.8, 1.0)), Q=(10.0, 1.0), R=(1
     return System(dyn, lqr, Erf([0]), Feasibility(prims), dt_hint=0.01, name='pendulum2')
 
 
-def double_integrator(axes=6, spheres=(), a_max=1.0, steps=20, eps=1e-3, riccati=True, v_max=3.0):
+def double_integrator(axes=6, spheres=(), a_max=1.0, steps=20, eps=1e-3, riccati=True, v_max=3.0, snap=0.025):
     """Config C5: accelerations saturate at a_max inside the dynamics (SURVEY.md's
     "|u| <= 1 via is_feasible" would reject every rollout whose first LQR effort exceeds 1, i.e. nearly all
     of them, so the limit is applied where the demos apply theirs); speeds beyond v_max are infeasible."""
     dyn = DoubleIntegratorDynamics(axes, a_max=a_max)
     n, m = dyn.nstates, dyn.ncontrols
     if riccati:
-        lqr = FDRiccatiLqr(np.eye(n), np.eye(m), steps=steps, eps=eps)
+        # the true Jacobian entries (1, dt = 0.1, 0, and dt / 2 where a difference straddles the saturation) are
+        # multiples of 0.025: snapping restores them from the noisy differences
+        lqr = FDRiccatiLqr(np.eye(n), np.eye(m), steps=steps, eps=eps, snap=snap)
     else:
         K = np.hstack((np.eye(m), 1.7 * np.eye(m)))
         lqr = ConstantLqr(np.eye(n), K)

@@ -198,7 +198,7 @@ class Planner(object):
         from ._native import LQ_OPT_NEAREST_KERNEL, LQ_OPT_SAMPLE_PREFETCH, LQ_OPT_NEAREST_CTAS_PER_SM, NEAREST_KERNELS
         self._engine.set_option(LQ_OPT_NEAREST_KERNEL, NEAREST_KERNELS[self.nearest_kernel])
         self._engine.set_option(LQ_OPT_SAMPLE_PREFETCH, int(self.prefetch_active))
-        for env, opt in (('LQRRT_SPEC', 4), ('LQRRT_STEER_BLOCK', 7), ('LQRRT_SCAN_CTAS', LQ_OPT_NEAREST_CTAS_PER_SM), ('LQRRT_STAGE', 6), ('LQRRT_PDL', 8), ('LQRRT_GRID', 9), ('LQRRT_GRID_MIN', 10), ('LQRRT_SAMPLE_AHEAD', 11)):
+        for env, opt in (('LQRRT_SPEC', 4), ('LQRRT_STEER_BLOCK', 7), ('LQRRT_SCAN_CTAS', LQ_OPT_NEAREST_CTAS_PER_SM), ('LQRRT_STAGE', 6), ('LQRRT_PDL', 8), ('LQRRT_GRID', 9), ('LQRRT_GRID_MIN', 10), ('LQRRT_SAMPLE_AHEAD', 11), ('LQRRT_WHITEN', 12)):
             if os.environ.get(env):                          # experiments (tools/gpu_*.sh): issue-level options only
                 self._engine.set_option(opt, int(os.environ[env]))
         for opt, val in self.engine_options.items():

@@ -175,6 +175,9 @@ def fd_riccati_lqr(spec, dynamics, dt):
     def lqr(x, u):
         u = np.zeros(spec.R.shape[0]) + np.asarray(u, dtype=np.float64)
         A, B = fd_jacobians(dynamics, np.asarray(x, dtype=np.float64), u, dt, spec.eps)
+        snap = float(getattr(spec, 'snap', 0.0))
+        if snap > 0:                              # Jacobian entries on a grid (csrc/models.cuh FdRiccatiLqr::snapped)
+            A = np.rint(A / snap) * snap; B = np.rint(B / snap) * snap
         return riccati_sweep(A, B, spec.Q, spec.R, spec.steps)
     return lqr
 

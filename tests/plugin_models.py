@@ -34,7 +34,7 @@ def dint2_pair(riccati, seed=0, spheres=60):
     base = configs.c5_double_integrator(seed, count=0, axes=2, max_nodes=4000, riccati=riccati)
     b = base.system
     dyn = plugin.UserDynamics(4, 2, DINT2_STEP, params=[b.dynamics.a_max], name='dint2')
-    lqr = models.FDRiccatiLqr(b.lqr.Q, b.lqr.R, steps=b.lqr.steps, eps=b.lqr.eps) if riccati \
+    lqr = models.FDRiccatiLqr(b.lqr.Q, b.lqr.R, steps=b.lqr.steps, eps=b.lqr.eps, snap=b.lqr.snap) if riccati \
         else models.ConstantLqr(b.lqr.S, b.lqr.K)
     rng = np.random.RandomState(seed)
     circles = np.column_stack((5 + 90 * rng.rand(spheres, 2), 1 + 2 * rng.rand(spheres)))

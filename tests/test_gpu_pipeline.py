@@ -114,6 +114,12 @@ def test_pipelined_waves_do_not_depend_on_issue_options(cuda_device, name, dtype
     _same(base, _grow(prob, dtype, 'device', {nat.LQ_OPT_STAGE_TABLES: 0}, lag=2))
     _same(base, _grow(prob, dtype, 'device', {nat.LQ_OPT_STEER_BLOCK: 32}, lag=2))
     _same(base, _grow(prob, dtype, 'device', {nat.LQ_OPT_STEER_BLOCK: 128}, lag=2))
+    # ... with the sampler on the wave's own chain instead of ahead of it on the side stream, and other scan grid targets
+    _same(base, _grow(prob, dtype, 'device', {nat.LQ_OPT_SAMPLE_AHEAD: 0}, lag=2))
+    _same(base, _grow(prob, dtype, 'device', {nat.LQ_OPT_NEAREST_CTAS_PER_SM: 3}, lag=2))
+    # ... and with larger waves, where the policy reaches its top size and the sampler really runs ahead
+    big = _grow(prob, dtype, 'device', lag=2, max_nodes=12000, wave_max=2048)
+    _same(big, _grow(prob, dtype, 'device', {nat.LQ_OPT_SAMPLE_AHEAD: 0}, lag=2, max_nodes=12000, wave_max=2048))
     gb = [0.9, 0.9] + [0] * (prob.nstates - 2)
     a = _grow(prob, dtype, 'device', goal_bias=gb, lag=2, max_nodes=5000, wave_max=128)
     b = _grow(prob, dtype, 'device', {nat.LQ_OPT_FORCE_RESCAN: 1}, goal_bias=gb, lag=2, max_nodes=5000, wave_max=128)
