@@ -1084,7 +1084,7 @@ struct EngineImpl : lq_engine {
         if (Lqr::COOP) {
             constexpr int ML = 8;
             metric_coop_kernel<T, Sys, Lqr, ML><<<(unsigned)(((long long)W * ML + 31) / 32), 32,
-                                                  (32 / ML) * Lqr::COOP_SCALARS * sizeof(T), st>>>(md, q, qstride, W, d_count, sp_of(par));
+                                                  (32 / ML) * Lqr::SLOT_SCALARS * sizeof(T), st>>>(md, q, qstride, W, d_count, sp_of(par));
         } else {
             metric_kernel<T, Sys, Lqr><<<(W + 63) / 64, 64, 0, st>>>(md.sys, md.lqr, md.dt, q, qstride, W, d_count, sp_of(par));
         }

@@ -311,6 +311,7 @@ template <typename T, class Sys> struct PdRotatedLqr {
     static constexpr bool CONST_METRIC = true;
     static constexpr bool COOP = false;
     static constexpr int COOP_SCALARS = 0;
+    static constexpr int SLOT_SCALARS = 0;
     T kp[M * M], kd[M * M], S[N * N];
     __host__ int unpack(const double* p, int count) {
         if (count != 2 * M * M + N * N) return -1;
@@ -359,6 +360,7 @@ template <typename T, class Sys> struct ConstantLqr {
     static constexpr bool CONST_METRIC = true;
     static constexpr bool COOP = false;
     static constexpr int COOP_SCALARS = 0;
+    static constexpr int SLOT_SCALARS = 0;
     T S[N * N], K0[M * N];
     __host__ int unpack(const double* p, int count) {
         if (count != N * N + M * N) return -1;

@@ -435,7 +435,7 @@ metric_coop_kernel(Model<T, Sys, Lqr> md, const T* __restrict__ queries, int qst
                    const int* __restrict__ d_count, T* __restrict__ Spacked) {
     constexpr int N = Sys::N, M = Sys::M;
     extern __shared__ __align__(16) unsigned char coop_raw[];
-    T* coop = reinterpret_cast<T*>(coop_raw) + (size_t)(threadIdx.x / LANES) * Lqr::COOP_SCALARS;
+    T* coop = reinterpret_cast<T*>(coop_raw) + (size_t)(threadIdx.x / LANES) * Lqr::SLOT_SCALARS;     // one solve per query: one slot
     const int j = (blockIdx.x * 32 + threadIdx.x) / LANES;
     const int lane = threadIdx.x % LANES;
     if (j >= (d_count ? min(*d_count, W) : W)) return;

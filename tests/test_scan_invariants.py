@@ -1,6 +1,6 @@
 """
 CPU checks of the two floating-point facts the filtered nearest scans rest on (csrc/nearest.cuh
-nearest_diag_prefix_kernel; tools/tc_filter/tc_filter.cu):
+nearest_diag_prefix_kernel; csrc/grid.cuh relies on fact 1 as well):
 
 1. the float32 cost chain c <- fma(e, e, c) never decreases, so the cost of the leading dims is a lower bound of
    the full cost in floating point, not only in real arithmetic;
