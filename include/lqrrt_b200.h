@@ -47,7 +47,10 @@ enum { LQ_SYS_BOAT = 1,              /* demos/demo_boat_{novice,intermediate,adv
 /* (S, K) = lqr(x, u) -- reference contract planner.py:39-42 */
 enum { LQ_LQR_PD_ROTATED = 1,        /* demo_boat_novice.py:86-103, demo_car.py:95-113 */
        LQ_LQR_CONSTANT = 2,          /* demo_pendulum.py:119-126 */
-       LQ_LQR_FD_RICCATI = 3         /* north_star's built-in provider (not in the reference) */ };
+       LQ_LQR_FD_RICCATI = 3         /* north_star's built-in provider (not in the reference): central-difference Jacobians of
+                                        the device dynamics, `steps` backward Riccati iterations from P = Q.
+                                        lqr_params = Q (n x n), R (m x m), eps, steps[, snap]: snap > 0 rounds every Jacobian
+                                        entry to a multiple of snap before the sweep (0 / absent: as differenced) */ };
 
 /* is_feasible(x, u) primitives -- reference contract constraints.py:29,53-61 */
 enum { LQ_FEAS_STATE_BOX = 1,        /* demo_boat_advanced.py:211-213 */

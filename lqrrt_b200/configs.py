@@ -215,12 +215,13 @@ def c5_double_integrator(seed=0, count=5000, axes=6, max_nodes=1E6, riccati=True
     n = 2 * axes
     x0 = np.zeros(n); goal = np.concatenate((80.0 * np.ones(axes), np.zeros(axes)))
     spheres = random_spheres(rng, count, 5.0, 95.0, 1.0, 3.0, x0, goal, 4.0) if count else ()
-    system = models.double_integrator(axes, spheres, a_max=1.0, riccati=riccati)
+    dt = 0.1
+    system = models.double_integrator(axes, spheres, a_max=1.0, riccati=riccati, snap=dt / 4)
     gb = [4.0] * axes + [np.inf] * axes
     ss = [(0, 100)] * axes + [(-2, 2)] * axes
     tol = [2.0] * axes + [np.inf] * axes
     return Problem('c5_double_integrator', system, x0, goal, gb, tol, ss, [0.1] * axes + [0] * axes,
-                   horizon=2, dt=0.1, FPR=0.5, max_nodes=max_nodes, min_time=60, max_time=60, obs=spheres)
+                   horizon=2, dt=dt, FPR=0.5, max_nodes=max_nodes, min_time=60, max_time=60, obs=spheres)
 
 
 BY_NAME = {

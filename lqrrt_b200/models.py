@@ -635,15 +635,15 @@ def pendulum2(tau_max=5.0, region=((1.2, -1.0), (1.8, 1.0)), Q=(10.0, 1.0), R=(1
     return System(dyn, lqr, Erf([0]), Feasibility(prims), dt_hint=0.01, name='pendulum2')
 
 
-def double_integrator(axes=6, spheres=(), a_max=1.0, steps=20, eps=1e-3, riccati=True, v_max=3.0, snap=0.025):
+def double_integrator(axes=6, spheres=(), a_max=1.0, steps=20, eps=1e-3, riccati=True, v_max=3.0, snap=0.0):
     """Config C5: accelerations saturate at a_max inside the dynamics (SURVEY.md's
     "|u| <= 1 via is_feasible" would reject every rollout whose first LQR effort exceeds 1, i.e. nearly all
     of them, so the limit is applied where the demos apply theirs); speeds beyond v_max are infeasible."""
     dyn = DoubleIntegratorDynamics(axes, a_max=a_max)
     n, m = dyn.nstates, dyn.ncontrols
     if riccati:
-        # the true Jacobian entries (1, dt = 0.1, 0, and dt / 2 where a difference straddles the saturation) are
-        # multiples of 0.025: snapping restores them from the noisy differences
+        # the true Jacobian entries are 1, dt, 0, and dt / 2 where a difference straddles the saturation: with
+        # snap = dt / 4 (what configs.c5_double_integrator passes) snapping restores them from the noisy differences
         lqr = FDRiccatiLqr(np.eye(n), np.eye(m), steps=steps, eps=eps, snap=snap)
     else:
         K = np.hstack((np.eye(m), 1.7 * np.eye(m)))
