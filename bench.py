@@ -29,7 +29,9 @@ Philox seed (different samples, same obstacle field), so nothing is cached betwe
           reference by tests/test_oracle_*.py) where oracle/_ref did not travel, `kind` says which
 
 --impl reference times that CPU implementation on all host cores (one independent replica per core, different
-seeds, nodes/s summed) and prints the same JSON shape.
+seeds, nodes/s summed; every step a bounded sample so that the whole run stays within a few minutes) and prints the
+same JSON shape.  `config` is the same object in both arms (the workload and how the GPU arm expands it); what a run
+measured besides the metric (waves, samples, yield, plan statistics) is under `run`.
 """
 import argparse
 import hashlib
@@ -89,6 +91,27 @@ def workload_name(prob, name):
         'c5': "C5 12-state double integrator, 5000 spheres, FD-Jacobian + Riccati lqr (Jacobians snapped to 0.025), tree grown to 1M nodes",
         'c5k': "C5 12-state double integrator, 5000 spheres, constant LQR gain, tree grown to 1M nodes",
     }.get(name, prob.name)
+
+
+def static_config(args, prob, world):
+    """What both arms of the benchmark print as `config`: the workload and how the GPU arm expands it -- nothing measured
+    (per-run figures go under `run`), so the two lines carry the same object."""
+    wave_max = args.wave * world if args.scaling == 'weak' else args.wave
+    lag = args.lag
+    nearest = args.nearest or os.environ.get('LQRRT_NEAREST') or 'packed'
+    return {"workload": workload_name(prob, args.config), "max_nodes": int(prob.max_nodes),
+            "wave": "adaptive clamp({:g}*N, 32, {}), wave k sized from the tree wave k-1 started with".format(args.growth, wave_max),
+            "wave_per_gpu_max": wave_max // world, "schedule": args.schedule or 'device',
+            "lag": "{} ({})".format(lag, "pipelined waves: wave k searches the tree committed by wave k-2" if lag == 2
+                                    else "wave k searches the tree committed by wave k-1"),
+            "sampler": "philox4x32-10 on device, new seed per step", "nearest_kernel": nearest,
+            "note": "throughput workload: the tree is filled to max_nodes with the largest waves; tree depth grows by "
+                    "at most one edge per wave, so it fills before the 283 m-away goal is reached -- the `plan` "
+                    "object times the goal-reaching policy on the same field.  The reference arm (--impl reference) runs "
+                    "the reference's sequential loop (one sample per iteration) on the same obstacle field for a bounded "
+                    "wall budget; it stays at N ~ 1e2-1e3 nodes and cannot reach max_nodes (BASELINE.md section 2)",
+            "l2": "tree states (<= 2.4 MB) and obstacle tables are L2-resident by design; every step "
+                  "grows a new tree from new samples (no reuse between timed steps)"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -276,8 +299,10 @@ def run_reference_arm(args):
     prob = make_problem(args.config)
     cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
     cores = max(1, min(cores, 64))
-    budget = float(args.cpu_seconds)
     steps = max(1, args.steps)
+    # every step is a bounded sample of the workload; the whole run stays within a few minutes whatever --steps is
+    budget = min(float(args.cpu_seconds), max(2.0, 120.0 / steps))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
     per = []
     kind = 'port'
     ctx = mp.get_context('fork')
@@ -296,11 +321,11 @@ def run_reference_arm(args):
         else "oracle port of the reference loop (oracle/_ref absent on this box)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(prob, args.config), "implementation": what,
-                   "note": "sequential expand loop (one sample per iteration); trees stay at N~1e2-1e3 within the budget, "
-                           "the reference cannot reach 100k nodes (BASELINE.md section 2)"},
+        "config": static_config(args, prob, world),
+        "run": {"implementation": what, "seconds_per_replica_per_step": budget,
+                "note": "sequential expand loop (one sample per iteration); trees stay at N~1e2-1e3 within the budget"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
                          "sample": "{} independent replicas x {:.0f} s of sequential growth from an empty tree, summed".format(cores, budget)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -505,21 +530,12 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": tot_dev / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "tree_digest": digest,
-            "config": {"workload": workload_name(prob, args.config), "max_nodes": int(prob.max_nodes),
-                       "wave": "adaptive clamp({:g}*N, 32, {}), wave k sized from the tree wave k-1 started with".format(args.growth, wave_max),
-                       "wave_per_gpu_max": wave_max // world, "schedule": schedule_used,
-                       "lag": "{} ({})".format(planner.stats.get('lag'), "pipelined waves: wave k searches the tree committed by wave k-2"
-                                               if planner.stats.get('lag') == 2 else "wave k searches the tree committed by wave k-1"),
-                       "waves_per_step": float(np.mean(waves)), "samples_per_step": float(np.mean(samples)),
-                       "yield": total_nodes / float(np.sum(samples)), "sampler": "philox4x32-10 on device, new seed per step",
-                       "nearest_kernel": planner.nearest_kernel,
-                       "plans_reaching_goal": "{}/{}".format(reached, args.steps), "plan_depth_edges": float(np.mean(depth)),
-                       "plan_duration_s": float(np.mean(plan_T)),
-                       "note": "throughput workload: the tree is filled to max_nodes with the largest waves; tree depth grows by "
-                               "at most one edge per wave, so it fills before the 283 m-away goal is reached -- the `plan` "
-                               "object times the goal-reaching policy on the same field",
-                       "l2": "tree states (<= 2.4 MB) and obstacle tables are L2-resident by design; every step "
-                             "grows a new tree from new samples (no reuse between timed steps)"},
+            "config": static_config(args, prob, world),
+            "run": {"schedule": schedule_used, "lag": planner.stats.get('lag'), "nearest_kernel": planner.nearest_kernel,
+                    "waves_per_step": float(np.mean(waves)), "samples_per_step": float(np.mean(samples)),
+                    "yield": total_nodes / float(np.sum(samples)),
+                    "plans_reaching_goal": "{}/{}".format(reached, args.steps), "plan_depth_edges": float(np.mean(depth)),
+                    "plan_duration_s": float(np.mean(plan_T))},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
                     "ms_per_step": tot_host / args.steps * 1e3,
                     "host_ms_per_step": dict(zip(("setup", "wave_loop", "closeout"), (phases / args.steps * 1e3).round(3).tolist())),
