@@ -173,3 +173,30 @@ def test_device_schedule_rule_mirrors_the_host_rule():
                 assert first == pos
                 pos += count
             assert pos == W
+
+
+def test_reference_arm_prints_the_gpu_arms_config():
+    """Both arms of bench.py carry the same `config` object (what is measured per run lives under `run`), and the reference
+    arm is a bounded sample: one line, metric / unit / direction of the GPU arm, no GPU touched."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0',
+                          '--cpu-seconds', '2'], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip().startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['metric'] == 'tree_expansions_per_s' and d['unit'] == 'nodes/s'
+    assert d['higher_is_better'] is True and d['value'] > 0 and d['gpu_launches'] == 0
+    assert d['e2e']['value'] == d['value'] and d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
+    assert d['cpu_baseline']['kind'] in ('reference', 'port') and d['cpu_baseline']['cores'] >= 1
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('bench_mod2', os.path.join(root, 'bench.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    import argparse
+    ns = argparse.Namespace(wave=16384, scaling='strong', lag=2, nearest=None, growth=2.0, schedule=None, config='c4')
+    assert d['config'] == mod.static_config(ns, mod.make_problem('c4'), 1)
