@@ -642,8 +642,9 @@ def double_integrator(axes=6, spheres=(), a_max=1.0, steps=20, eps=1e-3, riccati
     dyn = DoubleIntegratorDynamics(axes, a_max=a_max)
     n, m = dyn.nstates, dyn.ncontrols
     if riccati:
-        # the true Jacobian entries are 1, dt, 0, and dt / 2 where a difference straddles the saturation: with
-        # snap = dt / 4 (what configs.c5_double_integrator passes) snapping restores them from the noisy differences
+        # the true Jacobian entries are 1, dt and 0 (and anything between 0 and dt where a difference straddles the
+        # saturation): with snap = dt / 4 (what configs.c5_double_integrator passes) snapping restores them from the
+        # noisy differences
         lqr = FDRiccatiLqr(np.eye(n), np.eye(m), steps=steps, eps=eps, snap=snap)
     else:
         K = np.hstack((np.eye(m), 1.7 * np.eye(m)))

@@ -38,3 +38,46 @@ def test_pendulum_gain_swings_toward_target():
     assert S.shape == (2, 2) and K.shape == (1, 2)
     assert np.all(np.linalg.eigvalsh((S + S.T) / 2) > 0)
     assert K[0, 0] > 0 and K[0, 1] > 0
+
+
+def test_snapped_jacobians_are_the_exact_ones_on_the_double_integrator():
+    """`FDRiccatiLqr(snap=dt / 4)` (config C5): every true Jacobian entry of the saturating double integrator lies on that
+    grid -- 1, dt, 0 -- so snapping turns the differenced Jacobian into the analytic one exactly, at any state and for
+    every saturation pattern, and the gains are those of the analytic Jacobian (this is what the float32 engine relies on
+    to see the float64 Jacobian).  Where a central difference straddles the saturation (|u| within eps of a_max) the
+    slope is anything between 0 and dt; it lands on one of the five grid values in between."""
+    dt, axes = 0.1, 3
+    system = models.double_integrator(axes, a_max=1.0, snap=dt / 4)
+    dyn, lqr, _, _ = om.make_callbacks(system, dt)
+    spec = system.lqr
+    rng = np.random.RandomState(3)
+    patterns = set()
+    for trial in range(40):
+        x = 200.0 * (rng.rand(2 * axes) - 0.5)                     # large |x|: where differencing is noisiest
+        u = 4.0 * (rng.rand(axes) - 0.5)
+        if trial == 0:
+            u[:] = 0.0
+        if trial == 1:
+            u[0] = 1.0 + 0.4e-3                                    # the difference straddles the saturation: slope 0.3 dt
+        A, B = om.fd_jacobians(dyn, x, u, dt, spec.eps)
+        As = np.rint(A / spec.snap) * spec.snap; Bs = np.rint(B / spec.snap) * spec.snap
+        A0 = np.eye(2 * axes); A0[:axes, axes:] = dt * np.eye(axes)
+        straddle = (np.abs(u) + spec.eps > 1.0) & (np.abs(u) - spec.eps < 1.0)
+        slope = np.where(np.abs(u) + spec.eps <= 1.0, 1.0, 0.0)
+        for i in np.nonzero(straddle)[0]:                          # (a_max - (|u| - eps)) / (2 eps), snapped
+            slope[i] = np.rint((1.0 - (abs(u[i]) - spec.eps)) / (2 * spec.eps) * dt / spec.snap) * spec.snap / dt
+        B0 = np.zeros((2 * axes, axes)); B0[axes:] = dt * np.diag(slope)
+        assert np.abs(As - A0).max() < 1e-15 and np.abs(Bs - B0).max() < 1e-15
+        assert trial != 1 or abs(Bs[axes, 0] - 0.025) < 1e-15
+        S, K = lqr(x, u)
+        S0, K0 = om.riccati_sweep(A0, B0, spec.Q, spec.R, spec.steps)
+        assert np.abs(S - S0).max() < 1e-12 and np.abs(K - K0).max() < 1e-12
+        patterns.add(tuple(slope))
+    assert len(patterns) > 4                                       # several saturation patterns, each with its own gain
+
+
+def test_snap_off_is_the_plain_provider():
+    sysm = models.pendulum2()
+    assert sysm.lqr.snap == 0.0 and len(sysm.lqr.blob(2, 1)) == 2 * 2 + 1 + 3
+    with np.testing.assert_raises(ValueError):
+        models.FDRiccatiLqr(np.eye(2), np.eye(1), snap=-1.0)
